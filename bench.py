@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: MHD Jacobian (+residual) assembly Mcells/s and Krylov SpMV GB/s.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle restatement on the host cores
+
+Workload at N=1: BASELINE.json configs[1] -- Hunt duct nc=(64,64), Ha=1000 (12 288 cells, 732 690 dofs,
+146 981 976 nnz), Q2/P1disc/RT1/Q1disc, 27-point Gauss, convection :newton with a seeded random state
+(mirrors main.jl:137-141).  N>1: weak scaling, 64x64x3 cells per GPU, Cartesian (px,py,1) partition
+(hunt_mesher.jl:116-118), ghost-cell redundant integration, halo exchange + all-reduce over NCCL.
+
+One step = one linearisation of the nonlinear problem at a given state: residual!(b,op,x) + jacobian!(A,op,x)
+(what every Newton iteration of solve!(xh,solver,op) does, main.jl:275).  `value` = cells/s with x resident in
+HBM; `e2e` = the same through the host-buffer API (H2D of x, D2H of the residual inside the timed region; the
+matrix stays on the device behind the handle, as a PETSc Mat would).  The SpMV leg is reported under "spmv".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NC_PER_GPU = (64, 64)
+HA = 1000.0
+PARTS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}
+
+
+def algorithmic_bytes_jacobian(ncells, nnz, nentries):
+    """8 B per stored value (written once) + 4 B per scattered entry (int32 scatter map)
+    + 1740 B per cell (8 nodes x 24 B + 129 ids x 4 B + 129 state x 8 B)."""
+    return 8 * nnz + 4 * nentries + 1740 * ncells
+
+
+def algorithmic_bytes_spmv(nrows, ncols, nnz):
+    """12 B/nnz (value + int32 column) + y + x once + rowptr."""
+    return 12 * nnz + 8 * nrows + 8 * ncols + 4 * (nrows + 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [t.strip() for t in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_case(nparts, rank):
+    """Hunt cfg2-per-GPU mesh, FE spaces, (partitioned) operator inputs."""
+    import gridapmhd_jl_b200  # noqa: F401
+    from gridapmhd_jl_b200.applications import hunt_params, setup_spaces
+
+    px, py = PARTS[nparts]
+    nc = (NC_PER_GPU[0] * px, NC_PER_GPU[1] * py)
+    params = hunt_params(nc=nc, B=(0.0, HA, 0.0), solver="badia2024", convection="newton")
+    fes = setup_spaces(params)
+    return params, fes, nc
+
+
+def run_reference(args):
+    """CPU arm: the oracle's C restatement (oracle/mhd_oracle.c, OpenMP over cells/rows) on the box's host cores,
+    same config/metric; each step is a bounded sample of the workload (cells [0,nsample))."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import gridapmhd_jl_b200  # noqa: F401
+    from oracle import mhd_oracle as O
+    from oracle.c_oracle import COracle
+
+    params, fes, nc = build_case(1, 0)
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    co = COracle(fes, prm)
+    ncells = fes.mesh.ncells
+    # pattern restricted to the sampled cells keeps the symbolic cost bounded
+    nsample = min(ncells, args.ref_cells)
+    gids = fes.cell_global_ids()[:nsample]
+    rp, cv = O.symbolic_csr(gids, fes.ndofs)
+    x = np.random.default_rng(1234).random(fes.ndofs)
+    nz = np.zeros(len(cv))
+    times = []
+    for it in range(args.warmup + args.steps):
+        nz[:] = 0.0
+        t0 = time.perf_counter()
+        co.residual(x, 0, nsample)
+        co.jacobian_values(x, rp, cv, 0, nsample, out=nz)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    val = nsample / t / 1e6
+    # SpMV on the sampled matrix
+    v = np.random.default_rng(1).standard_normal(fes.ndofs)
+    ts = []
+    for it in range(3 + 10):
+        t0 = time.perf_counter()
+        co.spmv(rp, cv, nz, v)
+        if it >= 3:
+            ts.append(time.perf_counter() - t0)
+    spmv_gbs = (16 * len(cv) + 8 * 2 * fes.ndofs + 8 * (fes.ndofs + 1)) / float(np.mean(ts)) / 1e9
+    line = {
+        "impl": "reference", "metric": "mhd_assembly_jacobian_plus_residual", "value": val, "unit": "Mcells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3 * (ncells / nsample),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Hunt duct nc=({nc[0]},{nc[1]},3) Ha={HA:g} Q2/P1disc/RT1/Q1disc 27-pt Gauss, convection newton",
+                   "ncells": ncells, "ndofs": fes.ndofs},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": co.threads, "kind": "port",
+                         "sample": f"cells [0,{nsample}) of {ncells}: residual + Jacobian re-assembly into sorted CSR "
+                                   f"(C/OpenMP restatement of the algorithm, not Gridap/Julia)"},
+        "spmv": {"value": spmv_gbs, "unit": "GB/s", "note": "int64 CSR of the sampled cells, OpenMP"},
+        "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(fes, params, seconds=12.0):
+    """Bounded CPU sample for the cpu_baseline object (rank 0, N=1)."""
+    from oracle import mhd_oracle as O
+    from oracle.c_oracle import COracle
+
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    co = COracle(fes, prm)
+    nsample = min(fes.mesh.ncells, 2048)
+    gids = fes.cell_global_ids()[:nsample]
+    rp, cv = O.symbolic_csr(gids, fes.ndofs)
+    x = np.random.default_rng(1234).random(fes.ndofs)
+    nz = np.zeros(len(cv))
+    co.jacobian_values(x, rp, cv, 0, min(nsample, 256), out=nz)  # warm-up
+    reps, t_total = 0, 0.0
+    while t_total < seconds and reps < 20:
+        nz[:] = 0.0
+        t0 = time.perf_counter()
+        co.residual(x, 0, nsample)
+        co.jacobian_values(x, rp, cv, 0, nsample, out=nz)
+        t_total += time.perf_counter() - t0
+        reps += 1
+    return {"value": nsample * reps / t_total / 1e6, "unit": "Mcells/s", "cores": co.threads, "kind": "port",
+            "sample": f"{reps} x cells [0,{nsample}) of {fes.mesh.ncells}: residual + Jacobian re-assembly into sorted "
+                      f"CSR, C/OpenMP restatement (oracle/mhd_oracle.c), {t_total:.1f} s of CPU work"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import gridapmhd_jl_b200  # noqa: F401
+    from gridapmhd_jl_b200 import lib as L
+    from gridapmhd_jl_b200.feoperator import B200FEOperator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    L.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    params, fes_global, nc = build_case(world, rank)
+    if world > 1:
+        from gridapmhd_jl_b200.host.partition import distribute_operator
+
+        op, part = distribute_operator(fes_global, params, PARTS[world], rank, world, dist)
+        fes = part.fes
+    else:
+        op = B200FEOperator(fes_global, params["fluid"])
+        fes = fes_global
+    t0 = time.perf_counter()
+    A = op.allocate_jacobian()
+    L.check(L.load().mhd_device_synchronize())
+    t_symbolic = time.perf_counter() - t0
+    nentries, nexcl = op.scatter_stats()
+    ncells_owned = fes.mesh.ncells if world == 1 else part.nowned_cells
+    ncells_local = fes.mesh.ncells
+    ncells_global = fes_global.mesh.ncells
+
+    rng = np.random.default_rng(1234 + rank)
+    x_host = torch.from_numpy(rng.random(op.ncols)).pin_memory()
+    r_host = torch.empty(op.nrows, dtype=torch.float64).pin_memory()
+    x_dev = x_host.cuda()
+    r_dev = torch.empty(op.nrows, dtype=torch.float64, device="cuda")
+    v_dev = torch.from_numpy(rng.standard_normal(op.ncols)).cuda()
+    y_dev = torch.empty(op.nrows, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        op.residual_b(r_dev, x_dev)
+        op.jacobian_b(A, x_dev)
+
+    def step_host():
+        op.residual_b(r_host.numpy(), x_host.numpy())
+        op.jacobian_b(A, x_host.numpy())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.load().mhd_profile_enable(1)
+    L.load().mhd_profile_reset()
+    l0 = L.launch_count()
+    ms_step = timed(step_device, args.steps, args.warmup)
+    launches = (L.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    jac_ms, jac_n = L.profile_get("jacobian")
+    res_ms, res_n = L.profile_get("residual")
+    L.load().mhd_profile_reset()
+    ms_spmv = timed(lambda: op.spmv(v_dev, y_dev), max(args.steps, 20), max(args.warmup, 3))
+    spmv_ms, spmv_n = L.profile_get("spmv")
+    L.load().mhd_profile_enable(0)
+    # host wall-clock for the e2e leg (host buffers; copies inside): CUDA events bracket it too
+    ms_e2e = timed(step_host, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    jac_kernel_ms = jac_ms / max(jac_n, 1)
+    jac_bytes = algorithmic_bytes_jacobian(ncells_local, op.nnz, nentries)
+    jac_gbs = jac_bytes / (jac_kernel_ms * 1e-3) / 1e9
+    spmv_kernel_ms = spmv_ms / max(spmv_n, 1)
+    spmv_bytes = algorithmic_bytes_spmv(op.nrows, op.ncols, op.nnz)
+    spmv_gbs = spmv_bytes / (spmv_kernel_ms * 1e-3) / 1e9
+
+    value = ncells_global / (ms_step * 1e-3) / 1e6
+    e2e = ncells_global / (ms_e2e * 1e-3) / 1e6
+    line = {
+        "metric": "mhd_assembly_jacobian_plus_residual", "value": value, "unit": "Mcells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Hunt duct nc=({nc[0]},{nc[1]},3) Ha={HA:g} Q2/P1disc/RT1/Q1disc 27-pt Gauss, convection newton, "
+                               f"seeded random state; step = residual! + jacobian! (one Newton linearisation)",
+                   "ncells": ncells_global, "ncells_per_gpu": ncells_owned, "ndofs_local": op.ncols, "nnz_local": op.nnz,
+                   "partition": list(PARTS[world]), "l2_policy": "working set >> L2 (nzval+map = %.2f GB per GPU)" % ((8 * op.nnz + 2 * nentries) / 1e9),
+                   "symbolic_s": t_symbolic, "scatter_entries": nentries, "exclusive_entries": nexcl},
+        "e2e": {"value": e2e, "unit": "Mcells/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * 8 * op.ncols,
+                "d2h_bytes_per_step": 8 * op.nrows},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "jacobian_kernel", "bound": "hbm", "achieved": jac_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": jac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": jac_kernel_ms,
+                     "algorithmic_bytes": jac_bytes, "jacobian_only_Mcells_s": ncells_local / (jac_kernel_ms * 1e-3) / 1e6},
+        "residual": {"kernel_ms": res_ms / max(res_n, 1)},
+        "spmv": {"value": spmv_gbs * world, "unit": "GB/s", "ms": ms_spmv, "kernel_ms": spmv_kernel_ms,
+                 "roofline": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
+                              "traffic": None, "algorithmic_bytes": spmv_bytes}},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(fes_global, params)
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            tr = json.load(open(traffic_file))
+            line["roofline"]["traffic"] = tr.get("jacobian_kernel_dram_bytes")
+            line["spmv"]["roofline"]["traffic"] = tr.get("spmv_dram_bytes")
+        print(json.dumps(line))
+    op.destroy()
+    if world > 1:
+        L.load().mhd_comm_finalize()
+        dist.destroy_process_group()
+    L.finalize()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-cells", type=int, default=1536, help="cells per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""Drivers mirroring `GridapMHD.hunt(;kwargs...)` (src/Applications/hunt.jl:1-304) and `main(params)`
+(src/main.jl:122-169) for the part of the call stack that reaches the hot path.
+
+Only what configures the path is restated: reduced quantities (hunt.jl:115-136), mesh (hunt.jl:140-143),
+params[:fluid]/[:bcs] (hunt.jl:149-193), the timed sections of `main` (`solve`, `residual`, `jacobian`;
+main.jl:144-165).  VTK/BSON output and the analytical error norms stay with the Julia host.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from .feoperator import B200FEOperator, B200LinearSolver, B200SolverOptions, FluidParams, NewtonSolver
+from .host.fespaces import FESpaces, setup_fe_spaces
+from .host.mesh import HexMesh, hunt_generate_base_mesh
+
+
+def hunt_reduced_quantities(nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.0, 0.0, 1.0), L=1.0, u0=1.0,
+                            formulation="cfd"):
+    """hunt.jl:115-136.  Returns (alpha, beta, gamma, fbar, Bbar, Re, Ha, N)."""
+    B0 = math.sqrt(sum(b * b for b in B))
+    Re = u0 * L / nu
+    Ha = B0 * L * math.sqrt(sigma / (rho * nu))
+    N = Ha**2 / Re
+    fbar = tuple((L / (rho * u0**2)) * x for x in f)
+    Bbar = tuple(b / B0 for b in B)
+    if formulation == "cfd":
+        alpha, beta, gamma = 1.0, 1.0 / Re, N
+    elif formulation == "mhd":
+        alpha, beta, gamma = 1.0 / N, 1.0 / Ha**2, 1.0
+        fbar = tuple(x / N for x in fbar)
+    else:
+        raise ValueError("Unknown formulation")
+    return alpha, beta, gamma, fbar, Bbar, Re, Ha, N
+
+
+def hunt_params(nc=(4, 4), nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.0, 0.0, 1.0), zeta_u=0.0, zeta_j=0.0,
+                L=1.0, u0=1.0, formulation="cfd", convection="newton", BL_adapted=True, kmap_x=1, kmap_y=1,
+                solver="julia", nz=3, periodic_z=True, z_extent=(0.0, 0.1)):
+    """params Dict of `_hunt` (hunt.jl:88-193).  NOTE: `_hunt` never forwards its `convection` kwarg into
+    params[:fluid] (hunt.jl:149-158), so the reference effectively runs Hunt with the `params_fluid` default
+    `:newton` (parameters.jl:717); that is the default here too."""
+    alpha, beta, gamma, fbar, Bbar, Re, Ha, N = hunt_reduced_quantities(nu, rho, sigma, B, f, L, u0, formulation)
+    mesh = hunt_generate_base_mesh(nc, L=L, tw=0.0, Ha=Ha, kmap_x=kmap_x, kmap_y=kmap_y, BL_adapted=BL_adapted, nz=nz,
+                                   periodic_z=periodic_z, z_extent=z_extent)
+    return {
+        "model": mesh,
+        "fluid": FluidParams(alpha=alpha, beta=beta, gamma=gamma, sigma=1.0, zeta_u=zeta_u, zeta_j=zeta_j, B=Bbar,
+                             f=fbar, convection=convection),
+        "bcs": {"u": {"tags": ("noslip",) + (("zwalls",) if not periodic_z else ()), "values": None},
+                "j": {"tags": ("insulating",)}},
+        "solver": solver,
+        "info": {"Re": Re, "Ha": Ha, "N": N, "ncells": mesh.ncells},
+    }
+
+
+def setup_spaces(params) -> FESpaces:
+    """`setup_fe_spaces(params)` (src/fespaces.jl:13-46) on the host."""
+    bcs = params["bcs"]
+    utags = tuple(bcs["u"]["tags"])
+    uvals = bcs["u"].get("values")
+    if uvals is None:
+        uvals = (None,) * len(utags)
+    return setup_fe_spaces(params["model"], u_tags=utags, u_values=tuple(uvals), j_tags=tuple(bcs["j"]["tags"]),
+                           solver=params.get("solver", "julia"))
+
+
+def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts: B200SolverOptions | None = None,
+         newton_maxiter=10, newton_rtol=1e-6, verbose=False):
+    """`main(params;output)` (src/main.jl:122-169): FE spaces -> FE operator -> [solve] -> [residual] -> [jacobian],
+    with the PTimer sections of the reference (`fe_spaces`, `solve`, `residual`, `jacobian`) as wall-clock seconds."""
+    from . import lib as L
+
+    times = {}
+    t0 = time.perf_counter()
+    fes = setup_spaces(params)
+    times["fe_spaces"] = time.perf_counter() - t0
+    op = B200FEOperator(fes, params["fluid"])
+    x = np.zeros(fes.ndofs)  # initial_guess(::Val{:zero}) main.jl:302
+    out = {"fes": fes, "op": op}
+    if solve:
+        t0 = time.perf_counter()
+        nls = NewtonSolver(B200LinearSolver(solver_opts), maxiter=newton_maxiter, rtol=newton_rtol, verbose=verbose)
+        x = nls.solve_b(x, op)
+        L.check(L.load().mhd_device_synchronize())
+        times["solve"] = time.perf_counter() - t0
+        out["newton_log"] = nls.log
+    if res_assemble:
+        t0 = time.perf_counter()
+        out["residual"] = op.residual(x)
+        times["residual"] = time.perf_counter() - t0
+    if jac_assemble:
+        t0 = time.perf_counter()
+        out["jacobian"] = op.jacobian(x)
+        L.check(L.load().mhd_device_synchronize())
+        times["jacobian"] = time.perf_counter() - t0
+    out["x"] = x
+    out["times"] = times
+    return out
+
+
+def hunt(**kwargs):
+    """`hunt(;kwargs...)`: build params, call `main`, return the info dict (hunt.jl:282-303 subset)."""
+    main_keys = ("solve", "res_assemble", "jac_assemble", "solver_opts", "newton_maxiter", "newton_rtol", "verbose")
+    mk = {k: kwargs.pop(k) for k in main_keys if k in kwargs}
+    params = hunt_params(**kwargs)
+    out = main(params, **mk)
+    fes = out["fes"]
+    info = dict(params["info"])
+    info.update({"ndofs_u": fes.nfree["u"], "ndofs_p": fes.nfree["p"], "ndofs_j": fes.nfree["j"],
+                 "ndofs_phi": fes.nfree["phi"], "ndofs": fes.ndofs})
+    for k, v in out["times"].items():
+        info[f"time_{k}"] = v
+    return info, out

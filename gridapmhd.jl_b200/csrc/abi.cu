@@ -1,0 +1,527 @@
+// C ABI entry points of libmhdb200.so (see include/mhdb200.h for the contract of each function).
+#include <stdarg.h>
+
+#include "common.h"
+
+namespace mhd {
+
+cudaStream_t g_stream = 0;
+int g_device = -1;
+int64_t g_launches = 0;
+int g_nranks = 1, g_rank = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+  return MHD_E_CUDA;
+}
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+bool g_prof_on = false;
+struct ProfSlot {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double total_ms = 0.0;
+  int64_t count = 0;
+  cudaEvent_t cur = nullptr;
+};
+static ProfSlot g_prof[PROF_N];
+
+void prof_begin(int which) {
+  if (!g_prof_on) return;
+  cudaEvent_t e0;
+  cudaEventCreate(&e0);
+  cudaEventRecord(e0, g_stream);
+  g_prof[which].cur = e0;
+}
+void prof_end(int which) {
+  if (!g_prof_on || !g_prof[which].cur) return;
+  cudaEvent_t e1;
+  cudaEventCreate(&e1);
+  cudaEventRecord(e1, g_stream);
+  g_prof[which].pending.push_back({g_prof[which].cur, e1});
+  g_prof[which].cur = nullptr;
+}
+static void prof_collect() {
+  cudaStreamSynchronize(g_stream);
+  for (int w = 0; w < PROF_N; w++) {
+    for (auto& pr : g_prof[w].pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        g_prof[w].total_ms += ms;
+        g_prof[w].count++;
+      }
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    g_prof[w].pending.clear();
+  }
+}
+
+}  // namespace mhd
+
+using namespace mhd;
+
+extern "C" {
+
+const char* mhd_last_error_string(void) { return g_err; }
+
+int mhd_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return MHD_OK;
+}
+int mhd_profile_reset(void) {
+  prof_collect();
+  for (int w = 0; w < PROF_N; w++) {
+    g_prof[w].total_ms = 0.0;
+    g_prof[w].count = 0;
+  }
+  return MHD_OK;
+}
+int mhd_profile_get(const char* name, double* total_ms, int64_t* launches) {
+  MHD_CHECK(name != nullptr, MHD_E_INVALID, "null name");
+  int w = !strcmp(name, "jacobian") ? PROF_JAC : !strcmp(name, "residual") ? PROF_RES : !strcmp(name, "spmv") ? PROF_SPMV : -1;
+  MHD_CHECK(w >= 0, MHD_E_INVALID, "unknown profile slot '%s'", name);
+  prof_collect();
+  if (total_ms) *total_ms = g_prof[w].total_ms;
+  if (launches) *launches = g_prof[w].count;
+  return MHD_OK;
+}
+
+int mhd_init(int device_ordinal) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("mhd_init: no CUDA device available (%s); libmhdb200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return MHD_E_CUDA;
+  }
+  MHD_CHECK(device_ordinal >= 0 && device_ordinal < n, MHD_E_INVALID, "mhd_init: device %d out of range [0,%d)",
+            device_ordinal, n);
+  MHD_CUDA(cudaSetDevice(device_ordinal));
+  g_device = device_ordinal;
+  g_launches = 0;
+  MHD_CUDA(cudaFree(0));
+  return MHD_OK;
+}
+
+int mhd_finalize(void) {
+  if (g_device >= 0) cudaStreamSynchronize(g_stream);
+  g_device = -1;
+  g_stream = 0;
+  return MHD_OK;
+}
+
+int mhd_set_stream(void* s) {
+  g_stream = (cudaStream_t)s;
+  return MHD_OK;
+}
+
+int mhd_device_synchronize(void) {
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CUDA(cudaSetDevice(g_device));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  return MHD_OK;
+}
+
+int mhd_kernel_launch_count(int64_t* count) {
+  *count = g_launches;
+  return MHD_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+
+static int check_ready(const mhd_operator* op) {
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(op != nullptr, MHD_E_INVALID, "null operator handle");
+  MHD_CUDA(cudaSetDevice(g_device));
+  return 0;
+}
+
+int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const mhd_layout_t* lay,
+                        const mhd_params_t* prm, mhd_operator_t** out) {
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(mesh && tab && lay && prm && out, MHD_E_INVALID, "mhd_operator_create: null argument");
+  MHD_CHECK(tab->nq == NQ, MHD_E_INVALID, "mhd_operator_create: nq=%d, only the 27-point rule (q=5) is supported",
+            tab->nq);
+  MHD_CHECK(mesh->ncells > 0 && mesh->nnodes > 0, MHD_E_INVALID, "mhd_operator_create: empty mesh");
+  MHD_CHECK(mesh->index_base == 0 || mesh->index_base == 1, MHD_E_INVALID, "index_base must be 0 or 1");
+  MHD_CHECK(prm->convection >= 0 && prm->convection <= 2, MHD_E_INVALID, "invalid convection mode %d", prm->convection);
+  MHD_CUDA(cudaSetDevice(g_device));
+  // field_order must be a permutation
+  int seen[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    int f = lay->field_order[i];
+    MHD_CHECK(f >= 0 && f < 4 && !seen[f], MHD_E_INVALID, "field_order is not a permutation of 0..3");
+    seen[f] = 1;
+  }
+  mhd_operator* op = new mhd_operator();
+  op->ncells = mesh->ncells;
+  op->nnodes = mesh->nnodes;
+  op->prm = *prm;
+  int64_t own = 0, gh = 0, dir = 0;
+  for (int i = 0; i < 4; i++) {
+    op->nfree[i] = lay->nfree[i];
+    op->nowned[i] = lay->nowned[i] > 0 || lay->nfree[i] == 0 ? lay->nowned[i] : lay->nfree[i];
+    op->ndir[i] = lay->ndir[i];
+    op->field_order[i] = lay->field_order[i];
+    if (op->nowned[i] > op->nfree[i] || op->nfree[i] < 0 || op->ndir[i] < 0) {
+      delete op;
+      set_error("inconsistent nfree/nowned/ndir for field %d", i);
+      return MHD_E_INVALID;
+    }
+  }
+  for (int i = 0; i < 4; i++) {
+    int f = op->field_order[i];
+    op->own_off[f] = own;
+    own += op->nowned[f];
+  }
+  for (int i = 0; i < 4; i++) {
+    int f = op->field_order[i];
+    op->ghost_off[f] = own + gh;
+    gh += op->nfree[f] - op->nowned[f];
+  }
+  for (int f = 0; f < 4; f++) {
+    op->dir_off[f] = dir;
+    dir += op->ndir[f];
+  }
+  op->nrows = own;
+  op->ncols = own + gh;
+  op->ndir_total = dir;
+  if (op->ncols >= (int64_t)INT32_MAX) {
+    delete op;
+    set_error("local vector length %lld exceeds int32 column indices", (long long)op->ncols);
+    return MHD_E_CAPACITY;
+  }
+
+  // ---- host-side translation of the signed per-field ids into one int32 table
+  const int nd[4] = {NU, NP, NJ, NF};
+  const int lo[4] = {OFF_U, OFF_P, OFF_J, OFF_F};
+  std::vector<int32_t> gids((size_t)op->ncells * NLOC);
+  for (int f = 0; f < 4; f++) {
+    const int32_t* cd = lay->cell_dofs[f];
+    if (!cd) {
+      delete op;
+      set_error("cell_dofs[%d] is null", f);
+      return MHD_E_INVALID;
+    }
+    for (int64_t c = 0; c < op->ncells; c++) {
+      for (int k = 0; k < nd[f]; k++) {
+        int32_t id = cd[c * nd[f] + k];
+        int32_t g;
+        if (id > 0) {
+          if (id > op->nfree[f]) {
+            delete op;
+            set_error("cell %lld field %d: dof id %d > nfree %lld", (long long)c, f, id, (long long)op->nfree[f]);
+            return MHD_E_INVALID;
+          }
+          g = id <= op->nowned[f] ? (int32_t)(op->own_off[f] + id - 1)
+                                  : (int32_t)(op->ghost_off[f] + (id - 1 - op->nowned[f]));
+        } else if (id < 0) {
+          if (-id > op->ndir[f]) {
+            delete op;
+            set_error("cell %lld field %d: Dirichlet id %d beyond ndir %lld", (long long)c, f, id, (long long)op->ndir[f]);
+            return MHD_E_INVALID;
+          }
+          g = -(int32_t)(op->dir_off[f] + (-id - 1)) - 1;
+        } else {
+          delete op;
+          set_error("cell %lld field %d: dof id 0 is invalid (ids are 1-based, signed)", (long long)c, f);
+          return MHD_E_INVALID;
+        }
+        gids[(size_t)c * NLOC + lo[f] + k] = g;
+      }
+    }
+  }
+  std::vector<int32_t> cn((size_t)op->ncells * 8);
+  for (size_t i = 0; i < cn.size(); i++) {
+    int32_t v = mesh->cell_nodes[i] - mesh->index_base;
+    if (v < 0 || v >= mesh->nnodes) {
+      delete op;
+      set_error("cell_nodes[%zu]=%d out of range", i, mesh->cell_nodes[i]);
+      return MHD_E_INVALID;
+    }
+    cn[i] = v;
+  }
+  std::vector<double> dirv((size_t)(dir > 0 ? dir : 1), 0.0);
+  for (int f = 0; f < 4; f++)
+    if (op->ndir[f] > 0 && lay->dir_values[f]) memcpy(&dirv[op->dir_off[f]], lay->dir_values[f], op->ndir[f] * sizeof(double));
+
+  int rc = 0;
+#define CR(x) if (!rc) rc = (x)
+  CR(dev_alloc(&op->d_coords, op->nnodes * 3));
+  CR(dev_alloc(&op->d_cell_nodes, op->ncells * 8));
+  CR(dev_alloc(&op->d_gids, op->ncells * NLOC));
+  CR(dev_alloc(&op->d_jsign, op->ncells * NJ));
+  CR(dev_alloc(&op->d_dir, dir));
+  CR(dev_alloc(&op->d_x, op->ncols));
+  CR(dev_alloc(&op->d_y, op->ncols));
+  CR(h2d(op->d_coords, mesh->coords, op->nnodes * 3));
+  CR(h2d(op->d_cell_nodes, cn.data(), op->ncells * 8));
+  CR(h2d(op->d_gids, gids.data(), op->ncells * NLOC));
+  CR(h2d(op->d_jsign, lay->j_sign, op->ncells * NJ));
+  CR(h2d(op->d_dir, dirv.data(), dir));
+  CR(pack_tables(op, tab));
+  CR(ensure_red(op, 4096 + 65 * 1024));
+  if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+#undef CR
+  if (rc) {
+    mhd_operator_destroy(op);
+    return rc;
+  }
+  *out = op;
+  return MHD_OK;
+}
+
+int mhd_operator_destroy(mhd_operator_t* op) {
+  if (!op) return MHD_OK;
+  if (g_device >= 0) cudaSetDevice(g_device);
+  cudaStreamSynchronize(g_stream);
+  cudaFree(op->d_coords);
+  cudaFree(op->d_cell_nodes);
+  cudaFree(op->d_gids);
+  cudaFree(op->d_jsign);
+  cudaFree(op->d_dir);
+  cudaFree(op->d_tables);
+  cudaFree(op->d_rowptr);
+  cudaFree(op->d_colval);
+  cudaFree(op->d_nzval);
+  cudaFree(op->d_map);
+  cudaFree(op->d_x);
+  cudaFree(op->d_y);
+  cudaFree(op->d_red);
+  cudaFree(op->halo.d_send_idx);
+  cudaFree(op->halo.d_recv_idx);
+  cudaFree(op->halo.d_send_buf);
+  cudaFree(op->halo.d_recv_buf);
+  delete op;
+  return MHD_OK;
+}
+
+int mhd_operator_set_params(mhd_operator_t* op, const mhd_params_t* prm) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(prm && prm->convection >= 0 && prm->convection <= 2, MHD_E_INVALID, "invalid params");
+  op->prm = *prm;
+  return MHD_OK;
+}
+
+int mhd_operator_symbolic(mhd_operator_t* op, int64_t* nrows, int64_t* ncols, int64_t* nnz) {
+  MHD_TRY(check_ready(op));
+  if (!op->has_symbolic) MHD_TRY(symbolic_build(op));
+  if (nrows) *nrows = op->nrows;
+  if (ncols) *ncols = op->ncols;
+  if (nnz) *nnz = op->nnz;
+  return MHD_OK;
+}
+
+int mhd_operator_get_scatter_stats(mhd_operator_t* op, int64_t* nentries, int64_t* nexclusive) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_operator_symbolic must be called first");
+  if (nentries) *nentries = op->nentries;
+  if (nexclusive) *nexclusive = op->nexclusive;
+  return MHD_OK;
+}
+
+int mhd_operator_get_csr(mhd_operator_t* op, void* rowptr, void* colval, int index_bytes, int base) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_operator_symbolic must be called first");
+  MHD_CHECK(index_bytes == 4 || index_bytes == 8, MHD_E_INVALID, "index_bytes must be 4 or 8");
+  MHD_CHECK(base == 0 || base == 1, MHD_E_INVALID, "base must be 0 or 1");
+  MHD_CHECK(index_bytes == 8 || op->nnz + base < (int64_t)INT32_MAX, MHD_E_CAPACITY, "nnz does not fit 32-bit indices");
+  std::vector<int64_t> rp(op->nrows + 1);
+  std::vector<int32_t> cv((size_t)op->nnz);
+  MHD_TRY(d2h(rp.data(), op->d_rowptr, op->nrows + 1));
+  MHD_TRY(d2h(cv.data(), op->d_colval, op->nnz));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  if (index_bytes == 8) {
+    int64_t* r = (int64_t*)rowptr;
+    int64_t* c = (int64_t*)colval;
+    for (int64_t i = 0; i <= op->nrows; i++) r[i] = rp[i] + base;
+    for (int64_t i = 0; i < op->nnz; i++) c[i] = (int64_t)cv[i] + base;
+  } else {
+    int32_t* r = (int32_t*)rowptr;
+    int32_t* c = (int32_t*)colval;
+    for (int64_t i = 0; i <= op->nrows; i++) r[i] = (int32_t)(rp[i] + base);
+    for (int64_t i = 0; i < op->nnz; i++) c[i] = cv[i] + base;
+  }
+  return MHD_OK;
+}
+
+int mhd_operator_device_ptrs(mhd_operator_t* op, void** rowptr, void** colval, void** nzval) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_operator_symbolic must be called first");
+  if (rowptr) *rowptr = op->d_rowptr;
+  if (colval) *colval = op->d_colval;
+  if (nzval) *nzval = op->d_nzval;
+  return MHD_OK;
+}
+
+// ---- helpers: bring a vector argument to the device / back
+static int in_vec(mhd_operator* op, const double* p, int64_t n, double* staging, const double** d) {
+  MHD_CHECK(p != nullptr, MHD_E_INVALID, "null vector argument");
+  if (is_device_ptr(p)) {
+    *d = p;
+  } else {
+    MHD_TRY(h2d(staging, p, n));
+    *d = staging;
+  }
+  return 0;
+}
+
+int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_jacobian: call mhd_operator_symbolic first");
+  const double* dx;
+  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+  MHD_TRY(launch_jacobian(op, dx));
+  if (nzval_out) return mhd_get_nzval(op, nzval_out);
+  if (!is_device_ptr(x)) MHD_CUDA(cudaStreamSynchronize(g_stream));
+  return MHD_OK;
+}
+
+int mhd_get_nzval(mhd_operator_t* op, double* out) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic && out, MHD_E_STATE, "mhd_get_nzval: no matrix / null output");
+  if (is_device_ptr(out)) {
+    MHD_CUDA(cudaMemcpyAsync(out, op->d_nzval, op->nnz * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+  } else {
+    MHD_TRY(d2h(out, op->d_nzval, op->nnz));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return MHD_OK;
+}
+
+int mhd_set_nzval(mhd_operator_t* op, const double* v) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic && v, MHD_E_STATE, "mhd_set_nzval: no pattern / null input");
+  MHD_CUDA(cudaMemcpyAsync(op->d_nzval, v, op->nnz * sizeof(double), cudaMemcpyDefault, g_stream));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  return MHD_OK;
+}
+
+int mhd_residual(mhd_operator_t* op, const double* x, double* r_out) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(r_out != nullptr, MHD_E_INVALID, "mhd_residual: null output");
+  const double* dx;
+  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+  bool dev_out = is_device_ptr(r_out);
+  double* dr = dev_out ? r_out : op->d_y;
+  MHD_TRY(launch_residual(op, dx, dr));
+  if (!dev_out) {
+    MHD_TRY(d2h(r_out, dr, op->nrows));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return MHD_OK;
+}
+
+int mhd_spmv(mhd_operator_t* op, const double* x, double* y) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_spmv: no matrix");
+  MHD_CHECK(y != nullptr, MHD_E_INVALID, "mhd_spmv: null output");
+  const double* dx;
+  bool xdev = is_device_ptr(x);
+  if (g_nranks > 1 && xdev) {
+    // the halo exchange writes the ghost section of x: needs a mutable device vector
+    MHD_TRY(halo_exchange(op, const_cast<double*>(x)));
+    dx = x;
+  } else {
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    if (g_nranks > 1) MHD_TRY(halo_exchange(op, op->d_x));
+  }
+  bool dev_out = is_device_ptr(y);
+  double* dy = dev_out ? y : op->d_y;
+  MHD_TRY(launch_spmv(op, dx, dy));
+  if (!dev_out) {
+    MHD_TRY(d2h(y, dy, op->nrows));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return MHD_OK;
+}
+
+int mhd_dot(mhd_operator_t* op, const double* x, const double* y, double* result) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(result != nullptr, MHD_E_INVALID, "mhd_dot: null result");
+  const double *dx, *dy;
+  MHD_TRY(in_vec(op, x, op->nrows, op->d_x, &dx));
+  MHD_TRY(in_vec(op, y, op->nrows, op->d_y, &dy));
+  MHD_TRY(ensure_red(op, 4096));
+  bool dev_out = is_device_ptr(result);
+  double* dres = dev_out ? result : op->d_red + 2048;
+  MHD_TRY(launch_dot(op, op->nrows, dx, dy, dres));
+  if (g_nranks > 1) MHD_TRY(allreduce_sum(dres, 1));
+  if (!dev_out) {
+    MHD_TRY(d2h(result, dres, 1));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return MHD_OK;
+}
+
+int mhd_axpy(mhd_operator_t* op, double a, const double* x, double* y) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(x && y, MHD_E_INVALID, "mhd_axpy: null argument");
+  bool ydev = is_device_ptr(y);
+  const double* dx;
+  MHD_TRY(in_vec(op, x, op->nrows, op->d_x, &dx));
+  double* dy = y;
+  if (!ydev) {
+    MHD_TRY(h2d(op->d_y, y, op->nrows));
+    dy = op->d_y;
+  }
+  MHD_TRY(launch_axpy(op->nrows, a, dx, dy));
+  if (!ydev) {
+    MHD_TRY(d2h(y, dy, op->nrows));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  return MHD_OK;
+}
+
+int mhd_multi_dot_axpy(mhd_operator_t* op, int32_t k, const double* V, int64_t ldv, double* w, double* h) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(k >= 1 && k <= 64 && V && w && h && ldv >= op->nrows, MHD_E_INVALID, "mhd_multi_dot_axpy: bad arguments");
+  bool vdev = is_device_ptr(V), wdev = is_device_ptr(w), hdev = is_device_ptr(h);
+  MHD_CHECK(vdev == wdev, MHD_E_INVALID, "mhd_multi_dot_axpy: V and w must live in the same memory space");
+  double *dV = nullptr, *dw = nullptr;
+  int rc = 0;
+  if (!vdev) {
+    rc = dev_alloc(&dV, (int64_t)k * ldv);
+    if (!rc) rc = dev_alloc(&dw, op->nrows);
+    if (!rc) rc = h2d(dV, V, (int64_t)k * ldv);
+    if (!rc) rc = h2d(dw, w, op->nrows);
+  } else {
+    dV = const_cast<double*>(V);
+    dw = w;
+  }
+  if (!rc) rc = ensure_red(op, 4096 + (int64_t)k * 1024);
+  double* dh = hdev ? h : op->d_red + 2048;
+  if (!rc) rc = launch_multi_dot(op, op->nrows, k, dV, ldv, dw, dh);
+  if (!rc && g_nranks > 1) rc = allreduce_sum(dh, k);
+  if (!rc) rc = launch_multi_axpy(op->nrows, k, dV, ldv, dh, -1.0, dw);
+  if (!rc && !hdev) rc = d2h(h, dh, k);
+  if (!rc && !vdev) rc = d2h(w, dw, op->nrows);
+  if (!rc && (!vdev || !hdev) && cudaStreamSynchronize(g_stream) != cudaSuccess)
+    rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+  if (!vdev) {
+    cudaFree(dV);
+    cudaFree(dw);
+  }
+  return rc;
+}
+
+}  // extern "C"

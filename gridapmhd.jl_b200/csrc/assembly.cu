@@ -1,0 +1,689 @@
+// FP64 sm_100a assembly kernels: cell-wise integration of the Jacobian and residual of the inductionless MHD
+// H1-HDiv weak form, scattered into CSR / the residual vector through the precomputed map.
+//
+// Integrands: jac_fluid_h1_hdiv (src/weakforms.jl:283-312), res_fluid_h1_hdiv (src/weakforms.jl:255-281),
+// conv (weakforms.jl:670), local projection (weakforms.jl:672-681).  Notation of SURVEY.md Appendix A.
+//
+// Design (one persistent CTA per SM slot, one cell at a time):
+//   prep   : geometry Jacobians at the 27 Gauss points (registers -> smem), physical gradients of the Q2 basis,
+//            Piola-mapped RT basis, all pre-scaled by sqrt(w_q |det J_q|) so every block is a plain product
+//            sum_k A[k][m] B[k][n] of two shared-memory panels;
+//   blocks : register-tiled FP64 panel products (4x4 per thread) into a shared staging buffer;
+//   scatter: row-major sweep of each block section of the 16-bit scatter map (coalesced map reads, runs of
+//            consecutive nnz), plain stores for single-contribution nnz, RED.ADD.F64 otherwise.
+#include "common.h"
+
+namespace mhd {
+
+int pack_tables(mhd_operator* op, const mhd_tables_t* t) {
+  MHD_CHECK(t->w && t->geo_grad && t->u_val && t->u_grad && t->p_val && t->j_val && t->j_div && t->phi_val,
+            MHD_E_INVALID, "mhd_tables_t has a null table");
+  std::vector<double> h(T_TOTAL);
+  memcpy(&h[T_W], t->w, NQ * sizeof(double));
+  memcpy(&h[T_GG], t->geo_grad, NQ * 24 * sizeof(double));
+  memcpy(&h[T_NU], t->u_val, NQ * 27 * sizeof(double));
+  memcpy(&h[T_DNU], t->u_grad, NQ * 81 * sizeof(double));
+  memcpy(&h[T_PP], t->p_val, NQ * 4 * sizeof(double));
+  memcpy(&h[T_PSI], t->j_val, NQ * 108 * sizeof(double));
+  memcpy(&h[T_DPSI], t->j_div, NQ * 36 * sizeof(double));
+  memcpy(&h[T_CHI], t->phi_val, NQ * 8 * sizeof(double));
+  MHD_TRY(dev_alloc(&op->d_tables, T_TOTAL));
+  MHD_TRY(h2d(op->d_tables, h.data(), T_TOTAL));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  return 0;
+}
+
+struct KParams {
+  double alpha, beta, gamma, sigma, zeta_u, zeta_j;
+  double B[3], f[3], g[3];
+};
+
+constexpr int NT = 256;  // threads per CTA
+
+// ---- shared-memory plan (doubles)
+constexpr int LDN = 28;                       // padded leading dimension of 27-wide panels
+constexpr int S_G = 0;                        // [81][28]  sqrt(w) dN_a/dx_i, row = q*3+i
+constexpr int S_UG = S_G + 81 * LDN;          // [27][28]  sqrt(w) (u_q . grad N_b)
+constexpr int S_XB = S_G;                     // [27][108] sqrt(w) (psi_m x B)_c, row q, col c*36+m (aliases G,UG)
+constexpr int S_N = S_UG + 27 * LDN;          // [27][28]  sqrt(w) N_a
+constexpr int S_PSI = S_N + 27 * LDN;         // [81][36]  sqrt(w) Piola(psi_m)_i, row = q*3+i
+constexpr int S_DIV = S_PSI + 81 * 36;        // [27][36]  sqrt(w) div psi_m   (contiguous after PSI)
+constexpr int S_PP = S_DIV + 27 * 36;         // [27][4]
+constexpr int S_CHI = S_PP + 27 * 4;          // [27][8]
+constexpr int S_T = S_CHI + 27 * 8;           // [27][9]   (d_d u_c)(q), index d*3+c
+constexpr int S_ST = S_T + 244;               // staging
+constexpr int ST_SIZE = 2070 + 2187;
+constexpr int S_J = S_ST + ST_SIZE;           // [27][9]
+constexpr int S_INV = S_J + 243;              // [27][9]
+constexpr int S_DET = S_INV + 243;            // [27]
+constexpr int S_SW = S_DET + 27;              // [27]
+constexpr int S_X = S_SW + 27;                // [8][3]
+constexpr int S_U = S_X + 24;                 // [129] local state
+constexpr int S_SG = S_U + 130;               // [36] sign
+constexpr int S_E = S_SG + 36;                // [4][81]
+constexpr int S_MI = S_E + 324;               // [16]
+constexpr int S_UQ = S_MI + 16;               // [27][3] u at q (unweighted)
+constexpr int S_SC = S_UQ + 82;               // [108] scale vector for the jj product
+constexpr int S_END = S_SC + 108;
+constexpr int SMEM_BYTES = S_END * 8 + NLOC * 8 /*row starts*/ + 132 * 4 /*gids*/;
+
+// staging sub-buffers of phase 1
+constexpr int ST_D = 0;      // [81][4]  D[(c,a)][k] = sum_q w pi_k d_c N_a
+constexpr int ST_S = 324;    // [27][27]
+constexpr int ST_C = 1053;   // [27][27]
+constexpr int ST_JF = 1782;  // [36][8]
+constexpr int ST_NW = 2070;  // [3][27][27]
+
+// ---------------------------------------------------------------------------------------------
+// register-tiled panel product:  C[batch][m][n] = sum_k A[k*lda + m] * (sc ? sc[k*scs] : 1) * B[k*ldb + n]
+// tile t -> thread (t + toff) % NT.  store(batch, m, n, value) is called for in-range entries.
+template <int M, int N, int TM, int TN, bool SCALE, class Store>
+__device__ __forceinline__ void panel_product(int nbatch, const double* __restrict__ A, int lda, int a_bs,
+                                              const double* __restrict__ B, int ldb, int b_bs, int K,
+                                              const double* __restrict__ sc, int scs, int sc_bs, int toff,
+                                              Store store) {
+  constexpr int MT = (M + TM - 1) / TM, NTL = (N + TN - 1) / TN;
+  const int ntiles = nbatch * MT * NTL;
+  int t0 = (int)threadIdx.x - toff;
+  t0 %= NT;
+  if (t0 < 0) t0 += NT;
+  for (int t = t0; t < ntiles; t += NT) {
+    const int batch = t / (MT * NTL);
+    const int r = t - batch * (MT * NTL);
+    const int m0 = (r / NTL) * TM, n0 = (r % NTL) * TN;
+    const double* a = A + batch * a_bs + m0;
+    const double* b = B + batch * b_bs + n0;
+    const double* s = SCALE ? sc + batch * sc_bs : nullptr;
+    double acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+#pragma unroll 3
+    for (int k = 0; k < K; k++) {
+      double av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) av[i] = a[k * lda + i];
+#pragma unroll
+      for (int j = 0; j < TN; j++) bv[j] = b[k * ldb + j];
+      if (SCALE) {
+        const double sk = s[k * scs];
+#pragma unroll
+        for (int i = 0; i < TM; i++) av[i] *= sk;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+      for (int j = 0; j < TN; j++)
+        if (m0 + i < M && n0 + j < N) store(batch, m0 + i, n0 + j, acc[i][j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct CellCtx {
+  double* sm;
+  long long* row;  // [129] nnz offset of each local row (-1: dropped)
+  int32_t* gid;    // [129]
+};
+
+// loads + geometry + mapped bases.  NEED_STATE: 0 none, 1 u only, 2 all fields
+template <int NEED_STATE>
+__device__ __forceinline__ void cell_prep(const CellCtx& cx, int64_t cell, const double* __restrict__ tab,
+                                          const double* __restrict__ coords, const int32_t* __restrict__ cell_nodes,
+                                          const int32_t* __restrict__ gids, const int8_t* __restrict__ jsign,
+                                          const double* __restrict__ dirv, const double* __restrict__ x) {
+  double* sm = cx.sm;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < NLOC; i += NT) {
+    const int32_t g = gids[cell * NLOC + i];
+    cx.gid[i] = g;
+    if (NEED_STATE == 2 || (NEED_STATE == 1 && i < NU)) sm[S_U + i] = g >= 0 ? x[g] : dirv[-g - 1];
+  }
+  if (tid < 24) sm[S_X + tid] = coords[(int64_t)cell_nodes[cell * 8 + tid / 3] * 3 + tid % 3];
+  if (tid >= 32 && tid < 32 + NJ) sm[S_SG + tid - 32] = (double)jsign[cell * NJ + tid - 32];
+  __syncthreads();
+  if (tid < NQ) {
+    const int q = tid;
+    double J[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) J[i][k] = 0.0;
+    for (int v = 0; v < 8; v++) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double xv = sm[S_X + v * 3 + i];
+#pragma unroll
+        for (int k = 0; k < 3; k++) J[i][k] = fma(xv, tab[T_GG + (q * 8 + v) * 3 + k], J[i][k]);
+      }
+    }
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double id = 1.0 / det;
+    // inv[k][i] = d xi_k / d x_i  (inverse of J[i][k])
+    double inv[3][3];
+    inv[0][0] = c00 * id;
+    inv[1][0] = c01 * id;
+    inv[2][0] = c02 * id;
+    inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        sm[S_J + q * 9 + i * 3 + k] = J[i][k];
+        sm[S_INV + q * 9 + k * 3 + i] = inv[k][i];
+      }
+    sm[S_DET + q] = det;
+    sm[S_SW + q] = sqrt(tab[T_W + q] * fabs(det));
+  }
+  __syncthreads();
+  // Q2 panels
+  for (int idx = tid; idx < NQ * LDN; idx += NT) {
+    const int q = idx / LDN, a = idx - q * LDN;
+    if (a < 27) {
+      const double sw = sm[S_SW + q];
+      const double d0 = tab[T_DNU + (q * 27 + a) * 3 + 0], d1 = tab[T_DNU + (q * 27 + a) * 3 + 1],
+                   d2 = tab[T_DNU + (q * 27 + a) * 3 + 2];
+      const double* inv = sm + S_INV + q * 9;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+        sm[S_G + (q * 3 + i) * LDN + a] = sw * (d0 * inv[0 * 3 + i] + d1 * inv[1 * 3 + i] + d2 * inv[2 * 3 + i]);
+      sm[S_N + q * LDN + a] = sw * tab[T_NU + q * 27 + a];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) sm[S_G + (q * 3 + i) * LDN + a] = 0.0;
+      sm[S_N + q * LDN + a] = 0.0;
+      sm[S_UG + q * LDN + a] = 0.0;
+    }
+  }
+  // RT panels (contravariant Piola + sign flip)
+  for (int idx = tid; idx < NQ * NJ; idx += NT) {
+    const int q = idx / NJ, m = idx - q * NJ;
+    const double s = sm[S_SG + m] * sm[S_SW + q] / sm[S_DET + q];
+    const double p0 = tab[T_PSI + (q * 36 + m) * 3 + 0], p1 = tab[T_PSI + (q * 36 + m) * 3 + 1],
+                 p2 = tab[T_PSI + (q * 36 + m) * 3 + 2];
+    const double* J = sm + S_J + q * 9;
+#pragma unroll
+    for (int i = 0; i < 3; i++) sm[S_PSI + (q * 3 + i) * NJ + m] = s * (J[i * 3 + 0] * p0 + J[i * 3 + 1] * p1 + J[i * 3 + 2] * p2);
+    sm[S_DIV + q * NJ + m] = s * tab[T_DPSI + q * 36 + m];
+  }
+  for (int idx = tid; idx < NQ * 4; idx += NT) sm[S_PP + idx] = sm[S_SW + idx / 4] * tab[T_PP + idx];
+  for (int idx = tid; idx < NQ * 8; idx += NT) sm[S_CHI + idx] = sm[S_SW + idx / 8] * tab[T_CHI + idx];
+  if (NEED_STATE >= 1) {
+    // u at the quadrature points (unweighted)
+    if (tid < 81) {
+      const int q = tid / 3, i = tid - q * 3;
+      double s = 0.0;
+      for (int a = 0; a < 27; a++) s = fma(tab[T_NU + q * 27 + a], sm[S_U + i * 27 + a], s);
+      sm[S_UQ + tid] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void scatter_entry(double* __restrict__ nz, long long rowstart, uint16_t code, double v) {
+  if (code == MAP_SKIP) return;
+  double* p = nz + rowstart + (code & 0x7FFF);
+  if (code & MAP_EXCL) *p = v;
+  else atomicAdd(p, v);
+}
+
+// =============================================================================================
+// Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0.
+template <int CONV, bool ZU>
+__global__ void __launch_bounds__(NT, 2)
+jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
+                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
+                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
+                const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ map, double* __restrict__ nz,
+                KParams P) {
+  extern __shared__ __align__(16) double smem[];
+  CellCtx cx;
+  cx.sm = smem;
+  cx.row = (long long*)(smem + S_END);
+  cx.gid = (int32_t*)(cx.row + NLOC);
+  double* sm = smem;
+  const int tid = threadIdx.x;
+  double* St = sm + S_ST;
+
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    __syncthreads();  // previous cell's scatter done before its tables are overwritten
+    cell_prep<(CONV > 0 ? 1 : 0)>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    for (int i = tid; i < NLOC; i += NT) {
+      const int32_t g = cx.gid[i];
+      cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
+    }
+    if (CONV > 0) {
+      // UG[q][b] = sqrt(w) u_q . grad N_b ;  T[q][d*3+c] = d_d u_c (unweighted)
+      for (int idx = tid; idx < NQ * 27; idx += NT) {
+        const int q = idx / 27, b = idx - q * 27;
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) s = fma(sm[S_UQ + q * 3 + i], sm[S_G + (q * 3 + i) * LDN + b], s);
+        sm[S_UG + q * LDN + b] = s;
+      }
+      if (CONV == 2) {
+        for (int idx = tid; idx < NQ * 9; idx += NT) {
+          const int q = idx / 9, dc = idx - q * 9, d = dc / 3, c = dc - d * 3;
+          double s = 0.0;
+          for (int b = 0; b < 27; b++) s = fma(sm[S_G + (q * 3 + d) * LDN + b], sm[S_U + c * 27 + b], s);
+          sm[S_T + idx] = s / sm[S_SW + q];
+        }
+      }
+    }
+    if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
+    __syncthreads();
+
+    // ---------------- phase 1: up, S, C, j-phi (+ pressure mass matrix)
+    // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]   (batch = c)
+    panel_product<27, 4, 4, 4, false>(3, sm + S_G, 3 * LDN, LDN, sm + S_PP, 4, 0, NQ, nullptr, 0, 0, 0,
+                                      [&](int c, int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
+    // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b]
+    panel_product<27, 27, 2, 4, false>(1, sm + S_G, LDN, 0, sm + S_G, LDN, 0, 81, nullptr, 0, 0, 21,
+                                       [&](int, int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
+    if (CONV > 0)
+      panel_product<27, 27, 4, 4, false>(1, sm + S_N, LDN, 0, sm + S_UG, LDN, 0, NQ, nullptr, 0, 0, 21 + 98,
+                                         [&](int, int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
+    // JF[m][l] = sum_q Div[q][m] Chi[q][l]
+    panel_product<36, 8, 4, 4, false>(1, sm + S_DIV, NJ, 0, sm + S_CHI, 8, 0, NQ, nullptr, 0, 0, 21 + 98 + 49,
+                                      [&](int, int m, int l, double v) { St[ST_JF + m * 8 + l] = v; });
+    if (ZU && tid >= NT - 16) {
+      const int kl = tid - (NT - 16), k = kl >> 2, l = kl & 3;
+      double s = 0.0;
+      for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
+      sm[S_MI + kl] = s;
+    }
+    __syncthreads();
+    if (ZU) {
+      if (tid == 0) {
+        // in-place inverse of the SPD 4x4 mass matrix (Gauss-Jordan, no pivoting)
+        double a[4][8];
+        for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) {
+            a[i][j] = sm[S_MI + i * 4 + j];
+            a[i][4 + j] = i == j ? 1.0 : 0.0;
+          }
+        for (int p = 0; p < 4; p++) {
+          const double ip = 1.0 / a[p][p];
+          for (int j = 0; j < 8; j++) a[p][j] *= ip;
+          for (int i = 0; i < 4; i++)
+            if (i != p) {
+              const double f = a[i][p];
+              for (int j = 0; j < 8; j++) a[i][j] -= f * a[p][j];
+            }
+        }
+        for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) sm[S_MI + i * 4 + j] = a[i][4 + j];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < 324; idx += NT) {
+        const int k = idx / 81, i = idx - k * 81;
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < 4; l++) s = fma(sm[S_MI + k * 4 + l], St[ST_D + i * 4 + l], s);
+        sm[S_E + k * 81 + i] = s;
+      }
+      __syncthreads();
+    }
+    const uint16_t* cmap = map + cell * NENT_PAD;
+    // up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(d,b)] = -D
+    for (int e = tid; e < NU * NP; e += NT) {
+      const int i = e >> 2;
+      scatter_entry(nz, cx.row[i], cmap[SEC_UP + e], -St[ST_D + e]);
+    }
+    for (int e = tid; e < NP * NU; e += NT) {
+      const int k = e / NU, i = e - k * NU;
+      scatter_entry(nz, cx.row[OFF_P + k], cmap[SEC_PU + e], -St[ST_D + i * 4 + k]);
+    }
+    // j-phi: -sigma JF[m][l] ; phi-j: -JF[m][l]
+    for (int e = tid; e < NJ * NF; e += NT) {
+      const int m = e >> 3;
+      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JF + e], -P.sigma * St[ST_JF + e]);
+    }
+    for (int e = tid; e < NF * NJ; e += NT) {
+      const int l = e / NJ, m = e - l * NJ;
+      scatter_entry(nz, cx.row[OFF_F + l], cmap[SEC_FJ + e], -St[ST_JF + m * 8 + l]);
+    }
+    // uu
+    if (CONV < 2) {
+      if (!ZU) {
+        for (int idx = tid; idx < 3 * 729; idx += NT) {
+          const int c = idx / 729, ab = idx - c * 729, a = ab / 27, b = ab - a * 27;
+          const int li = c * 27 + a, lj = c * 27 + b;
+          double v = P.beta * St[ST_S + ab];
+          if (CONV > 0) v = fma(P.alpha, St[ST_C + ab], v);
+          scatter_entry(nz, cx.row[li], cmap[SEC_UU + li * NU + lj], v);
+        }
+      } else {
+        for (int e = tid; e < NU * NU; e += NT) {
+          const int li = e / NU, lj = e - li * NU;
+          const int c = li / 27, a = li - c * 27, d = lj / 27, b = lj - d * 27;
+          double v = 0.0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) v = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], v);
+          v *= P.zeta_u;
+          if (c == d) {
+            v = fma(P.beta, St[ST_S + a * 27 + b], v);
+            if (CONV > 0) v = fma(P.alpha, St[ST_C + a * 27 + b], v);
+          }
+          scatter_entry(nz, cx.row[li], cmap[SEC_UU + e], v);
+        }
+      }
+    } else {
+      // Newton: NW[c][d][a][b] = sum_q N[q][a] (d_d u_c)(q) N[q][b], one row component c at a time
+      for (int c = 0; c < 3; c++) {
+        __syncthreads();
+        panel_product<27, 27, 4, 4, true>(3, sm + S_N, LDN, 0, sm + S_N, LDN, 0, NQ, sm + S_T + c, 9, 3, c * 147,
+                                          [&](int d, int a, int b, double v) { St[ST_NW + d * 729 + a * 27 + b] = v; });
+        __syncthreads();
+        for (int idx = tid; idx < 27 * NU; idx += NT) {
+          const int a = idx / NU, lj = idx - a * NU, d = lj / 27, b = lj - d * 27;
+          const int li = c * 27 + a;
+          double v = P.alpha * St[ST_NW + d * 729 + a * 27 + b];
+          if (ZU) {
+            double z = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
+            v = fma(P.zeta_u, z, v);
+          }
+          if (c == d) {
+            v = fma(P.beta, St[ST_S + a * 27 + b], v);
+            v = fma(P.alpha, St[ST_C + a * 27 + b], v);
+          }
+          scatter_entry(nz, cx.row[li], cmap[SEC_UU + li * NU + lj], v);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: uj / ju.  XB[q][c*36+m] = sqrt(w) (psi_m x B)_c (overwrites G, UG)
+    for (int idx = tid; idx < NQ * NJ; idx += NT) {
+      const int q = idx / NJ, m = idx - q * NJ;
+      const double p0 = sm[S_PSI + (q * 3 + 0) * NJ + m], p1 = sm[S_PSI + (q * 3 + 1) * NJ + m],
+                   p2 = sm[S_PSI + (q * 3 + 2) * NJ + m];
+      sm[S_XB + q * 108 + 0 * 36 + m] = p1 * P.B[2] - p2 * P.B[1];
+      sm[S_XB + q * 108 + 1 * 36 + m] = p2 * P.B[0] - p0 * P.B[2];
+      sm[S_XB + q * 108 + 2 * 36 + m] = p0 * P.B[1] - p1 * P.B[0];
+    }
+    __syncthreads();
+    // R[c][a][m] = sum_q N[q][a] XB[q][c*36+m]
+    panel_product<27, 36, 4, 4, false>(3, sm + S_N, LDN, 0, sm + S_XB, 108, 36, NQ, nullptr, 0, 0, 0,
+                                       [&](int c, int a, int m, double v) { St[(c * 27 + a) * NJ + m] = v; });
+    __syncthreads();
+    // K_uj[(c,a)][m] = -gamma R ; K_ju[m][(d,b)] = +sigma R[d][b][m]
+    for (int e = tid; e < NU * NJ; e += NT) {
+      const int i = e / NJ;
+      scatter_entry(nz, cx.row[i], cmap[SEC_UJ + e], -P.gamma * St[e]);
+    }
+    for (int e = tid; e < NJ * NU; e += NT) {
+      const int m = e / NU, i = e - m * NU;
+      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JU + e], P.sigma * St[i * NJ + m]);
+    }
+    __syncthreads();
+
+    // ---------------- phase 4: jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div  (K = 81 or 108, contiguous panels)
+    if (P.zeta_j != 0.0)
+      panel_product<36, 36, 2, 4, true>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 108, sm + S_SC, 1, 0, 0,
+                                        [&](int, int m, int n, double v) { St[m * NJ + n] = v; });
+    else
+      panel_product<36, 36, 2, 4, false>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 81, nullptr, 0, 0, 0,
+                                         [&](int, int m, int n, double v) { St[m * NJ + n] = v; });
+    __syncthreads();
+    for (int e = tid; e < NJ * NJ; e += NT) {
+      const int m = e / NJ;
+      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JJ + e], St[e]);
+    }
+  }
+}
+
+// =============================================================================================
+// Residual kernel: res_fluid_h1_hdiv (src/weakforms.jl:255-281)
+template <int CONV, bool ZU>
+__global__ void __launch_bounds__(NT, 2)
+residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
+                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
+                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
+                double* __restrict__ r, KParams P) {
+  extern __shared__ __align__(16) double smem[];
+  CellCtx cx;
+  cx.sm = smem;
+  cx.row = (long long*)(smem + S_END);
+  cx.gid = (int32_t*)(cx.row + NLOC);
+  double* sm = smem;
+  const int tid = threadIdx.x;
+  // per-q coefficient tables in the staging area
+  double* Fu = sm + S_ST;         // [27][3]  coefficient of N'[q][a] in r_u[(c,a)]
+  double* Gu = Fu + 81;           // [27][9]  coefficient of G'[(q,d)][a], index d*3+c
+  double* Fj = Gu + 243;          // [27][3]  coefficient of Psi'[(q,i)][m]
+  double* Dj = Fj + 81;           // [27]     coefficient of Div'[q][m]
+  double* Dv = Dj + 27;           // [27]     sqrt(w) div u
+  double* Jd = Dv + 27;           // [27]     sqrt(w) div j
+  double* Pq = Jd + 27;           // [27]     sqrt(w) p
+  double* Gq = Pq + 27;           // [27][9]  sqrt(w) d_d u_c
+  double* Pr = Gq + 243;          // [27]     sqrt(w) Pi_p(div u)
+  double* Rh = Pr + 27;           // [4] rhs / coefficients of the projection
+
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    __syncthreads();
+    cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    const double* U = sm + S_U;
+    // gradients of u, div u, p at q
+    for (int idx = tid; idx < NQ * 9; idx += NT) {
+      const int q = idx / 9, dc = idx - q * 9, d = dc / 3, c = dc - d * 3;
+      double s = 0.0;
+      for (int b = 0; b < 27; b++) s = fma(sm[S_G + (q * 3 + d) * LDN + b], U[c * 27 + b], s);
+      Gq[idx] = s;
+    }
+    if (tid < NQ) {
+      const int q = tid;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) s = fma(sm[S_PP + q * 4 + k], U[OFF_P + k], s);
+      Pq[q] = s;
+      double dj = 0.0;
+      for (int m = 0; m < NJ; m++) dj = fma(sm[S_DIV + q * NJ + m], U[OFF_J + m], dj);
+      Jd[q] = dj;
+    }
+    __syncthreads();
+    if (tid < NQ) Dv[tid] = Gq[tid * 9 + 0] + Gq[tid * 9 + 4] + Gq[tid * 9 + 8];
+    __syncthreads();
+    if (ZU) {
+      if (tid < 16) {
+        const int k = tid >> 2, l = tid & 3;
+        double s = 0.0;
+        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
+        sm[S_MI + tid] = s;
+      }
+      if (tid >= 32 && tid < 36) {
+        const int k = tid - 32;
+        double s = 0.0;
+        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], Dv[q], s);
+        Rh[k] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double a[4][5];
+        for (int i = 0; i < 4; i++) {
+          for (int j = 0; j < 4; j++) a[i][j] = sm[S_MI + i * 4 + j];
+          a[i][4] = Rh[i];
+        }
+        for (int p = 0; p < 4; p++) {
+          const double ip = 1.0 / a[p][p];
+          for (int j = 0; j < 5; j++) a[p][j] *= ip;
+          for (int i = 0; i < 4; i++)
+            if (i != p) {
+              const double f = a[i][p];
+              for (int j = 0; j < 5; j++) a[i][j] -= f * a[p][j];
+            }
+        }
+        for (int i = 0; i < 4; i++) Rh[i] = a[i][4];
+      }
+      __syncthreads();
+      if (tid < NQ) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s = fma(sm[S_PP + tid * 4 + k], Rh[k], s);
+        Pr[tid] = s;
+      }
+      __syncthreads();
+    }
+    if (tid < NQ) {
+      const int q = tid;
+      const double sw = sm[S_SW + q];
+      // weighted u, j, phi at q
+      double uq[3], jq[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        uq[i] = sm[S_UQ + q * 3 + i] * sw;
+        double s = 0.0;
+        for (int m = 0; m < NJ; m++) s = fma(sm[S_PSI + (q * 3 + i) * NJ + m], U[OFF_J + m], s);
+        jq[i] = s;
+      }
+      double fq = 0.0;
+#pragma unroll
+      for (int l = 0; l < 8; l++) fq = fma(sm[S_CHI + q * 8 + l], U[OFF_F + l], fq);
+      const double jxB[3] = {jq[1] * P.B[2] - jq[2] * P.B[1], jq[2] * P.B[0] - jq[0] * P.B[2], jq[0] * P.B[1] - jq[1] * P.B[0]};
+      const double uxB[3] = {uq[1] * P.B[2] - uq[2] * P.B[1], uq[2] * P.B[0] - uq[0] * P.B[2], uq[0] * P.B[1] - uq[1] * P.B[0]};
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double v = -P.gamma * jxB[c] - sw * P.f[c];
+        if (CONV > 0) {
+          // sqrt(w) (u . grad) u_c = sum_d u_d (sqrt(w) d_d u_c)
+          double cv = 0.0;
+#pragma unroll
+          for (int d = 0; d < 3; d++) cv = fma(sm[S_UQ + q * 3 + d], Gq[q * 9 + d * 3 + c], cv);
+          v = fma(P.alpha, cv, v);
+        }
+        Fu[q * 3 + c] = v;
+        Fj[q * 3 + c] = jq[c] - P.sigma * uxB[c] - sw * P.g[c];
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double v = P.beta * Gq[q * 9 + d * 3 + c];
+          if (d == c) {
+            v -= Pq[q];
+            if (ZU) v = fma(P.zeta_u, Pr[q], v);
+          }
+          Gu[q * 9 + d * 3 + c] = v;
+        }
+      Dj[q] = P.zeta_j * Jd[q] - P.sigma * fq;
+    }
+    __syncthreads();
+    // rows
+    if (tid < NLOC) {
+      const int i = tid;
+      double s = 0.0;
+      if (i < NU) {
+        const int c = i / 27, a = i - c * 27;
+        for (int q = 0; q < NQ; q++) {
+          s = fma(sm[S_N + q * LDN + a], Fu[q * 3 + c], s);
+#pragma unroll
+          for (int d = 0; d < 3; d++) s = fma(sm[S_G + (q * 3 + d) * LDN + a], Gu[q * 9 + d * 3 + c], s);
+        }
+      } else if (i < OFF_J) {
+        const int k = i - OFF_P;
+        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], Dv[q], s);
+        s = -s;
+      } else if (i < OFF_F) {
+        const int m = i - OFF_J;
+        for (int q = 0; q < NQ; q++) {
+#pragma unroll
+          for (int d = 0; d < 3; d++) s = fma(sm[S_PSI + (q * 3 + d) * NJ + m], Fj[q * 3 + d], s);
+          s = fma(sm[S_DIV + q * NJ + m], Dj[q], s);
+        }
+      } else {
+        const int l = i - OFF_F;
+        for (int q = 0; q < NQ; q++) s = fma(sm[S_CHI + q * 8 + l], Jd[q], s);
+        s = -s;
+      }
+      const int32_t g = cx.gid[i];
+      if (g >= 0 && g < nrows) atomicAdd(&r[g], s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static KParams make_kparams(const mhd_params_t& p) {
+  KParams k;
+  k.alpha = p.alpha; k.beta = p.beta; k.gamma = p.gamma; k.sigma = p.sigma; k.zeta_u = p.zeta_u; k.zeta_j = p.zeta_j;
+  for (int i = 0; i < 3; i++) { k.B[i] = p.B[i]; k.f[i] = p.f[i]; k.g[i] = p.g[i]; }
+  return k;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, g_device);
+  return g_sm_count ? g_sm_count : 148;
+}
+
+template <class Kern>
+static int set_smem(Kern k) {
+  MHD_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return 0;
+}
+
+int launch_jacobian(mhd_operator* op, const double* d_x) {
+  MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), g_stream));
+  const KParams P = make_kparams(op->prm);
+  const int conv = op->prm.convection;
+  const bool zu = op->prm.zeta_u != 0.0;
+  const int64_t grid64 = (int64_t)sm_count() * 2;
+  const unsigned grid = (unsigned)(op->ncells < grid64 ? op->ncells : grid64);
+#define JK(C, Z)                                                                                             \
+  do {                                                                                                       \
+    MHD_TRY(set_smem(jacobian_kernel<C, Z>));                                                                \
+    jacobian_kernel<C, Z><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
+        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, P);  \
+  } while (0)
+  prof_begin(PROF_JAC);
+  if (conv == 0 && !zu) JK(0, false);
+  else if (conv == 0 && zu) JK(0, true);
+  else if (conv == 1 && !zu) JK(1, false);
+  else if (conv == 1 && zu) JK(1, true);
+  else if (conv == 2 && !zu) JK(2, false);
+  else JK(2, true);
+#undef JK
+  prof_end(PROF_JAC);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_residual(mhd_operator* op, const double* d_x, double* d_r) {
+  MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
+  const KParams P = make_kparams(op->prm);
+  const int conv = op->prm.convection;
+  const bool zu = op->prm.zeta_u != 0.0;
+  const int64_t grid64 = (int64_t)sm_count() * 2;
+  const unsigned grid = (unsigned)(op->ncells < grid64 ? op->ncells : grid64);
+#define RK(C, Z)                                                                                             \
+  do {                                                                                                       \
+    MHD_TRY(set_smem(residual_kernel<C, Z>));                                                                \
+    residual_kernel<C, Z><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
+        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, d_r, P);                                   \
+  } while (0)
+  prof_begin(PROF_RES);
+  if (conv == 0 && !zu) RK(0, false);
+  else if (conv == 0 && zu) RK(0, true);
+  else if (!zu) RK(1, false);   // picard and newton share the residual
+  else RK(1, true);
+#undef RK
+  prof_end(PROF_RES);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mhd

@@ -1,0 +1,540 @@
+// Device-resident flexible GMRES + block-triangular preconditioner.
+//
+// Stands behind the Gridap LinearSolver seam (symbolic_setup / numerical_setup! / solve!) that GridapMHD fills
+// at src/main.jl:181-190 and src/Solvers/badia2024.jl:2-48:
+//   FGMRESSolver(m,P;maxiter=m,rtol,atol)           -> Fgmres below: the whole restart cycle is enqueued on the
+//                                                      stream; Hessenberg/Givens/convergence live in device memory
+//                                                      (one tiny kernel per Arnoldi step), no host round trip.
+//   BlockTriangularSolver([uj p phi], :upper)       -> apply_block_tri: exact cell-block inverses of the
+//                                                      discontinuous p / phi mass matrices (badia2024.jl:11-15,23-24)
+//                                                      and an inner Jacobi-preconditioned GMRES on the (u,j) block
+//                                                      (the reference uses LU/MUMPS there, badia2024.jl:22).
+// Orthogonalisation is classical Gram-Schmidt with one re-orthogonalisation pass (2 fused multi-dots per step
+// instead of the j+1 dependent dots of the reference's modified Gram-Schmidt: SURVEY.md 5.8).
+#include <functional>
+
+#include "common.h"
+
+namespace mhd {
+
+constexpr int MAXM = 64;
+
+struct KrylovScalars {  // lives in device memory
+  double H[(MAXM + 1) * MAXM];
+  double cs[MAXM], sn[MAXM], g[MAXM + 1], y[MAXM];
+  double h[MAXM + 2];   // fresh Gram-Schmidt coefficients (pass 1)
+  double h2[MAXM + 2];  // pass 2
+  double hn;            // ||w||^2 after orthogonalisation
+  double beta;          // current residual norm
+  double beta2;         // scratch: squared norm
+  double tol;
+  double inv;           // scaling for the next basis vector
+  double hist[4 * MAXM + 2];
+  int done;             // converged (or breakdown): later steps of the cycle become no-ops
+  int k;                // Arnoldi steps taken in this cycle
+  int iters;            // total iterations
+};
+
+__global__ void k_cycle_begin(KrylovScalars* S, double rtol, double atol, int first, int total_hist) {
+  // S->beta2 holds ||r||^2
+  const double beta = sqrt(S->beta2);
+  S->beta = beta;
+  if (first) {
+    S->tol = fmax(atol, rtol * beta);
+    S->iters = 0;
+    S->hist[0] = beta;
+  }
+  S->k = 0;
+  S->done = (beta <= S->tol) ? 1 : 0;
+  S->g[0] = beta;
+  for (int i = 1; i <= MAXM; i++) S->g[i] = 0.0;
+  for (int i = 0; i < MAXM; i++) S->y[i] = 0.0;
+  S->inv = beta > 0.0 ? 1.0 / beta : 0.0;
+}
+
+// V = done ? 0 : inv * w
+__global__ void __launch_bounds__(256) k_scale_to(int64_t n, const KrylovScalars* __restrict__ S, const double* __restrict__ w,
+                                                   double* __restrict__ v) {
+  const double a = S->done ? 0.0 : S->inv;
+  const bool dead = S->done != 0;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) v[i] = dead ? 0.0 : a * w[i];
+}
+
+__global__ void k_add_h(KrylovScalars* S, int j) {
+  const int i = threadIdx.x;
+  if (i <= j) S->h[i] += S->h2[i];
+}
+
+// one Arnoldi step's scalar work: new Hessenberg column, Givens rotations, residual estimate
+__global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
+  if (S->done) return;
+  double* H = S->H;
+  const double hn = sqrt(fmax(S->hn, 0.0));
+  for (int i = 0; i <= j; i++) H[i * MAXM + j] = S->h[i];
+  H[(j + 1) * MAXM + j] = hn;
+  for (int i = 0; i < j; i++) {
+    const double t = S->cs[i] * H[i * MAXM + j] + S->sn[i] * H[(i + 1) * MAXM + j];
+    H[(i + 1) * MAXM + j] = -S->sn[i] * H[i * MAXM + j] + S->cs[i] * H[(i + 1) * MAXM + j];
+    H[i * MAXM + j] = t;
+  }
+  const double a = H[j * MAXM + j], b = H[(j + 1) * MAXM + j];
+  const double d = hypot(a, b);
+  if (d == 0.0) {  // exact breakdown: stop
+    S->done = 1;
+    return;
+  }
+  S->cs[j] = a / d;
+  S->sn[j] = b / d;
+  H[j * MAXM + j] = d;
+  H[(j + 1) * MAXM + j] = 0.0;
+  S->g[j + 1] = -S->sn[j] * S->g[j];
+  S->g[j] = S->cs[j] * S->g[j];
+  S->beta = fabs(S->g[j + 1]);
+  S->k = j + 1;
+  S->iters += 1;
+  if (S->iters < 4 * MAXM + 2) S->hist[S->iters] = S->beta;
+  S->inv = hn > 0.0 ? 1.0 / hn : 0.0;
+  if (S->beta <= S->tol || hn == 0.0 || S->iters >= maxiter) S->done = 1;
+}
+
+__global__ void k_back_substitute(KrylovScalars* S) {
+  const int k = S->k;
+  for (int i = 0; i < MAXM; i++) S->y[i] = 0.0;
+  for (int i = k - 1; i >= 0; i--) {
+    double s = S->g[i];
+    for (int l = i + 1; l < k; l++) s -= S->H[i * MAXM + l] * S->y[l];
+    S->y[i] = s / S->H[i * MAXM + i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sub(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = a[i] - b[i];
+}
+__global__ void __launch_bounds__(256) k_mul(int64_t n, const double* __restrict__ d, const double* __restrict__ v, double* __restrict__ z) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) z[i] = d[i] * v[i];
+}
+
+static unsigned vgrid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+using VecOp = std::function<int(const double*, double*)>;
+
+// FGMRES on the rows [0,n) of an operator given as a matvec closure. Vectors handed to matvec have `ld` entries
+// (owned rows + ghost section) so that the halo exchange can fill the ghosts.
+struct Fgmres {
+  mhd_operator* op = nullptr;
+  int64_t n = 0, ld = 0;
+  int m = 15;
+  double *V = nullptr, *Z = nullptr, *w = nullptr, *t = nullptr;
+  KrylovScalars* S = nullptr;
+  bool flexible = true;
+
+  int init(mhd_operator* op_, int64_t n_, int64_t ld_, int m_, bool flexible_) {
+    op = op_; n = n_; ld = ld_; m = m_; flexible = flexible_;
+    MHD_CHECK(m >= 1 && m <= MAXM, MHD_E_INVALID, "restart length %d outside [1,%d]", m, MAXM);
+    MHD_TRY(dev_alloc(&V, (int64_t)(m + 1) * ld));
+    MHD_TRY(dev_alloc(&Z, (int64_t)(flexible ? m : 1) * ld));
+    MHD_TRY(dev_alloc(&w, ld));
+    MHD_TRY(dev_alloc(&t, ld));
+    MHD_TRY(dev_alloc(&S, 1));
+    MHD_CUDA(cudaMemsetAsync(V, 0, (size_t)(m + 1) * ld * 8, g_stream));
+    MHD_CUDA(cudaMemsetAsync(Z, 0, (size_t)(flexible ? m : 1) * ld * 8, g_stream));
+    MHD_CUDA(cudaMemsetAsync(w, 0, (size_t)ld * 8, g_stream));
+    MHD_CUDA(cudaMemsetAsync(t, 0, (size_t)ld * 8, g_stream));
+    MHD_CUDA(cudaMemsetAsync(S, 0, sizeof(KrylovScalars), g_stream));
+    return 0;
+  }
+  void release() {
+    cudaFree(V); cudaFree(Z); cudaFree(w); cudaFree(t); cudaFree(S);
+    V = Z = w = t = nullptr; S = nullptr;
+  }
+
+  // squared norm of v[0..n) into *d_out (device), all-reduced
+  int norm2(const double* v, double* d_out) {
+    MHD_TRY(launch_multi_dot(op, n, 1, v, ld, v, d_out));
+    return allreduce_sum(d_out, 1);
+  }
+
+  // one restart cycle, fully enqueued. x (ld entries) is updated in place.
+  int cycle(const VecOp& matvec, const VecOp& precond, const double* b, double* x, double rtol, double atol, int maxiter,
+            bool first, bool zero_guess) {
+    // r = b - A x
+    if (zero_guess && first) {
+      MHD_CUDA(cudaMemcpyAsync(w, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, g_stream));
+    } else {
+      MHD_TRY(matvec(x, t));
+      k_sub<<<vgrid(n), 256, 0, g_stream>>>(n, b, t, w);
+      MHD_LAUNCH_CHECK();
+    }
+    MHD_TRY(norm2(w, &S->beta2));
+    k_cycle_begin<<<1, 1, 0, g_stream>>>(S, rtol, atol, first ? 1 : 0, 0);
+    MHD_LAUNCH_CHECK();
+    k_scale_to<<<vgrid(n), 256, 0, g_stream>>>(n, S, w, V);
+    MHD_LAUNCH_CHECK();
+    for (int j = 0; j < m; j++) {
+      double* Vj = V + (int64_t)j * ld;
+      double* Zj = flexible ? Z + (int64_t)j * ld : Z;
+      MHD_TRY(precond(Vj, Zj));
+      MHD_TRY(matvec(Zj, w));
+      // CGS2: h = V^T w ; w -= V h ; h2 = V^T w ; w -= V h2 ; h += h2
+      MHD_TRY(launch_multi_dot(op, n, j + 1, V, ld, w, S->h));
+      MHD_TRY(allreduce_sum(S->h, j + 1));
+      MHD_TRY(launch_multi_axpy(n, j + 1, V, ld, S->h, -1.0, w));
+      MHD_TRY(launch_multi_dot(op, n, j + 1, V, ld, w, S->h2));
+      MHD_TRY(allreduce_sum(S->h2, j + 1));
+      MHD_TRY(launch_multi_axpy(n, j + 1, V, ld, S->h2, -1.0, w));
+      k_add_h<<<1, 64, 0, g_stream>>>(S, j);
+      MHD_LAUNCH_CHECK();
+      MHD_TRY(norm2(w, &S->hn));
+      k_arnoldi_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
+      MHD_LAUNCH_CHECK();
+      k_scale_to<<<vgrid(n), 256, 0, g_stream>>>(n, S, w, V + (int64_t)(j + 1) * ld);
+      MHD_LAUNCH_CHECK();
+    }
+    k_back_substitute<<<1, 1, 0, g_stream>>>(S);
+    MHD_LAUNCH_CHECK();
+    if (flexible) {
+      MHD_TRY(launch_multi_axpy(n, m, Z, ld, S->y, 1.0, x));
+    } else {
+      // x += P^{-1} (V y)
+      MHD_CUDA(cudaMemsetAsync(w, 0, (size_t)n * 8, g_stream));
+      MHD_TRY(launch_multi_axpy(n, m, V, ld, S->y, 1.0, w));
+      MHD_TRY(precond(w, t));
+      MHD_TRY(launch_axpy(n, 1.0, t, x));
+    }
+    return 0;
+  }
+};
+
+}  // namespace mhd
+
+using namespace mhd;
+
+struct mhd_solver {
+  mhd_operator* op = nullptr;
+  mhd_solver_opts_t opts;
+  Fgmres outer, inner;
+  double* d_dinv = nullptr;     // [nrows] Jacobi
+  double* d_minv_p = nullptr;   // [ncells*16] inverse P1disc mass blocks
+  double* d_minv_f = nullptr;   // [ncells*64] inverse Q1disc mass blocks
+  double *d_b = nullptr, *d_x = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr;
+  int64_t n_uj = 0;
+  bool setup_done = false;
+};
+
+namespace mhd {
+
+__global__ void __launch_bounds__(256)
+k_extract_dinv(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+               const double* __restrict__ nzval, double* __restrict__ dinv) {
+  for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < nrows; r += (int64_t)gridDim.x * 256) {
+    double d = 0.0;
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo <= hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      const int32_t c = colval[mid];
+      if (c == r) { d = nzval[mid]; break; }
+      if (c < r) lo = mid + 1; else hi = mid - 1;
+    }
+    dinv[r] = d != 0.0 ? 1.0 / d : 1.0;
+  }
+}
+
+// inverse cell mass blocks of the discontinuous p (4x4) and phi (8x8) spaces: M[k][l] = sum_q w |det J| b_k b_l
+constexpr int TM_W = T_W, TM_GG = T_GG, TM_PP = T_PP, TM_CHI = T_CHI;
+
+template <int NB>
+__device__ void invert_spd(double* a /* NB x 2NB */) {
+  for (int p = 0; p < NB; p++) {
+    const double ip = 1.0 / a[p * 2 * NB + p];
+    for (int j = 0; j < 2 * NB; j++) a[p * 2 * NB + j] *= ip;
+    for (int i = 0; i < NB; i++)
+      if (i != p) {
+        const double f = a[i * 2 * NB + p];
+        if (f != 0.0)
+          for (int j = 0; j < 2 * NB; j++) a[i * 2 * NB + j] -= f * a[p * 2 * NB + j];
+      }
+  }
+}
+
+__global__ void __launch_bounds__(64)
+k_mass_inverses(int64_t ncells, const double* __restrict__ tab, const double* __restrict__ coords,
+                const int32_t* __restrict__ cell_nodes, double* __restrict__ minv_p, double* __restrict__ minv_f) {
+  const int64_t cell = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (cell >= ncells) return;
+  double X[8][3];
+  for (int v = 0; v < 8; v++)
+    for (int i = 0; i < 3; i++) X[v][i] = coords[(int64_t)cell_nodes[cell * 8 + v] * 3 + i];
+  double Mp[4][8], Mf[8][16];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) Mp[i][j] = (j - 4 == i) ? 1.0 : 0.0;
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 16; j++) Mf[i][j] = (j - 8 == i) ? 1.0 : 0.0;
+  for (int q = 0; q < 27; q++) {
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int v = 0; v < 8; v++)
+      for (int i = 0; i < 3; i++)
+        for (int k = 0; k < 3; k++) J[i][k] += X[v][i] * tab[TM_GG + (q * 8 + v) * 3 + k];
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const double w = tab[TM_W + q] * fabs(det);
+    for (int k = 0; k < 4; k++)
+      for (int l = 0; l < 4; l++) Mp[k][l] += w * tab[TM_PP + q * 4 + k] * tab[TM_PP + q * 4 + l];
+    for (int k = 0; k < 8; k++)
+      for (int l = 0; l < 8; l++) Mf[k][l] += w * tab[TM_CHI + q * 8 + k] * tab[TM_CHI + q * 8 + l];
+  }
+  invert_spd<4>(&Mp[0][0]);
+  invert_spd<8>(&Mf[0][0]);
+  for (int k = 0; k < 4; k++) for (int l = 0; l < 4; l++) minv_p[cell * 16 + k * 4 + l] = Mp[k][4 + l];
+  for (int k = 0; k < 8; k++) for (int l = 0; l < 8; l++) minv_f[cell * 64 + k * 8 + l] = Mf[k][8 + l];
+}
+
+// z[rows of the cell's p and phi dofs] = (1/alpha) M^{-1} v
+__global__ void __launch_bounds__(128)
+k_apply_mass_inverses(int64_t ncells, int64_t nrows, const int32_t* __restrict__ gids, const double* __restrict__ minv_p,
+                      const double* __restrict__ minv_f, double inv_alpha_p, double inv_alpha_f,
+                      const double* __restrict__ v, double* __restrict__ z) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t cell = t / 12;
+  const int r = (int)(t - cell * 12);
+  if (cell >= ncells) return;
+  const int32_t* g = gids + cell * NLOC;
+  if (r < 4) {
+    const int32_t row = g[OFF_P + r];
+    if (row < 0 || row >= nrows) return;
+    double s = 0.0;
+    for (int l = 0; l < 4; l++) s = fma(minv_p[cell * 16 + r * 4 + l], v[g[OFF_P + l]], s);
+    z[row] = inv_alpha_p * s;
+  } else {
+    const int k = r - 4;
+    const int32_t row = g[OFF_F + k];
+    if (row < 0 || row >= nrows) return;
+    double s = 0.0;
+    for (int l = 0; l < 8; l++) s = fma(minv_f[cell * 64 + k * 8 + l], v[g[OFF_F + l]], s);
+    z[row] = inv_alpha_f * s;
+  }
+}
+
+// SpMV over the first nr rows only (block row of the block-ordered matrix)
+__global__ void __launch_bounds__(256)
+k_spmv_rows(int64_t nr, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+            const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t row = warp0; row < nr; row += nwarps) {
+    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    double s = 0.0;
+    for (int64_t p = lo + lane; p < hi; p += 32) s = fma(nzval[p], __ldg(x + colval[p]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+static int spmv_rows(mhd_operator* op, int64_t nr, const double* x, double* y) {
+  if (nr == 0) return 0;
+  int64_t blocks = (nr + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_spmv_rows<<<(unsigned)blocks, 256, 0, g_stream>>>(nr, op->d_rowptr, op->d_colval, op->d_nzval, x, y);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mhd
+
+extern "C" {
+
+int mhd_solver_default_opts(mhd_solver_opts_t* o) {
+  MHD_CHECK(o != nullptr, MHD_E_INVALID, "null opts");
+  o->m = 15;             // niter_ls (src/parameters.jl:268)
+  o->maxiter = 15;       // FGMRESSolver(m,P;maxiter=m) (badia2024.jl:40)
+  o->rtol = 1e-7;        // nl_rtol/10 (badia2024.jl:37) with nl_rtol = 1e-6 (parameters.jl:269)
+  o->atol = 1e-8;        // parameters.jl:270
+  o->precond = MHD_PC_BLOCK_TRI;
+  o->uj_inner_its = 30;
+  o->uj_inner_restart = 30;
+  o->alpha_p = -1.0;     // -1/(beta+zeta_u); the host overrides with the actual fluid parameters
+  o->alpha_phi = -1.0;   // -1/(1+zeta_j)
+  return MHD_OK;
+}
+
+int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_solver_t** out) {
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(op && opts && out, MHD_E_INVALID, "mhd_solver_create: null argument");
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_solver_create: call mhd_operator_symbolic first");
+  MHD_CHECK(opts->precond >= 0 && opts->precond <= 2, MHD_E_INVALID, "unknown preconditioner %d", opts->precond);
+  MHD_CHECK(opts->m >= 1 && opts->m <= MAXM && opts->maxiter >= 1, MHD_E_INVALID, "bad m/maxiter");
+  MHD_CUDA(cudaSetDevice(g_device));
+  if (opts->precond == MHD_PC_BLOCK_TRI) {
+    MHD_CHECK(op->field_order[0] == MHD_FIELD_U && op->field_order[1] == MHD_FIELD_J && op->field_order[2] == MHD_FIELD_P &&
+                  op->field_order[3] == MHD_FIELD_PHI,
+              MHD_E_INVALID, "block-triangular preconditioner needs field_order (u,j,p,phi) = ([u,j],p,phi) blocks");
+    MHD_CHECK(opts->alpha_p != 0.0 && opts->alpha_phi != 0.0, MHD_E_INVALID, "alpha_p/alpha_phi must be nonzero");
+    MHD_CHECK(opts->uj_inner_its >= 1 && opts->uj_inner_restart >= 1 && opts->uj_inner_restart <= MAXM, MHD_E_INVALID,
+              "bad inner iteration counts");
+  }
+  mhd_solver* s = new mhd_solver();
+  s->op = op;
+  s->opts = *opts;
+  s->n_uj = op->nowned[MHD_FIELD_U] + op->nowned[MHD_FIELD_J];
+  int rc = 0;
+#define CR(x) if (!rc) rc = (x)
+  CR(s->outer.init(op, op->nrows, op->ncols, opts->m, true));
+  CR(dev_alloc(&s->d_dinv, op->nrows));
+  CR(dev_alloc(&s->d_b, op->ncols));
+  CR(dev_alloc(&s->d_x, op->ncols));
+  CR(dev_alloc(&s->d_t1, op->ncols));
+  CR(dev_alloc(&s->d_t2, op->ncols));
+  CR(dev_alloc(&s->d_t3, op->ncols));
+  if (!rc) {
+    cudaMemsetAsync(s->d_x, 0, op->ncols * 8, g_stream);
+    cudaMemsetAsync(s->d_b, 0, op->ncols * 8, g_stream);
+    cudaMemsetAsync(s->d_t1, 0, op->ncols * 8, g_stream);
+    cudaMemsetAsync(s->d_t2, 0, op->ncols * 8, g_stream);
+    cudaMemsetAsync(s->d_t3, 0, op->ncols * 8, g_stream);
+  }
+  if (opts->precond == MHD_PC_BLOCK_TRI) {
+    const int mi = opts->uj_inner_restart < opts->uj_inner_its ? opts->uj_inner_restart : opts->uj_inner_its;
+    CR(s->inner.init(op, s->n_uj, op->ncols, mi, false));
+    CR(dev_alloc(&s->d_minv_p, op->ncells * 16));
+    CR(dev_alloc(&s->d_minv_f, op->ncells * 64));
+    if (!rc) {
+      k_mass_inverses<<<(unsigned)((op->ncells + 63) / 64), 64, 0, g_stream>>>(op->ncells, op->d_tables, op->d_coords,
+                                                                               op->d_cell_nodes, s->d_minv_p, s->d_minv_f);
+      g_launches++;
+      if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "k_mass_inverses", __FILE__, __LINE__);
+    }
+  }
+#undef CR
+  if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+  if (rc) {
+    mhd_solver_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return MHD_OK;
+}
+
+int mhd_solver_destroy(mhd_solver_t* s) {
+  if (!s) return MHD_OK;
+  if (g_device >= 0) cudaSetDevice(g_device);
+  cudaStreamSynchronize(g_stream);
+  s->outer.release();
+  s->inner.release();
+  cudaFree(s->d_dinv); cudaFree(s->d_minv_p); cudaFree(s->d_minv_f);
+  cudaFree(s->d_b); cudaFree(s->d_x); cudaFree(s->d_t1); cudaFree(s->d_t2); cudaFree(s->d_t3);
+  delete s;
+  return MHD_OK;
+}
+
+int mhd_solver_setup(mhd_solver_t* s) {
+  MHD_CHECK(s != nullptr, MHD_E_INVALID, "null solver");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CUDA(cudaSetDevice(g_device));
+  mhd_operator* op = s->op;
+  k_extract_dinv<<<vgrid(op->nrows), 256, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, s->d_dinv);
+  MHD_LAUNCH_CHECK();
+  s->setup_done = true;
+  return MHD_OK;
+}
+
+int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, double* resnorm, double* res_history) {
+  MHD_CHECK(s && b && x, MHD_E_INVALID, "mhd_solve: null argument");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(s->setup_done, MHD_E_STATE, "mhd_solve: call mhd_solver_setup after mhd_jacobian");
+  MHD_CUDA(cudaSetDevice(g_device));
+  mhd_operator* op = s->op;
+  const int64_t n = op->nrows;
+  const mhd_solver_opts_t& o = s->opts;
+  const bool bdev = is_device_ptr(b), xdev = is_device_ptr(x);
+  // the solve works on library-owned vectors with a ghost section
+  MHD_CUDA(cudaMemcpyAsync(s->d_b, b, n * 8, bdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
+  MHD_CUDA(cudaMemcpyAsync(s->d_x, x, n * 8, xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
+
+  VecOp matvec = [op](const double* v, double* y) -> int {
+    MHD_TRY(halo_exchange(op, const_cast<double*>(v)));
+    return launch_spmv(op, v, y);
+  };
+  // (u,j)-block operator: rows [0,n_uj), p/phi entries of the input are kept at zero by construction
+  const int64_t nuj = s->n_uj;
+  VecOp matvec_uj = [op, nuj](const double* v, double* y) -> int {
+    MHD_TRY(halo_exchange(op, const_cast<double*>(v)));
+    return spmv_rows(op, nuj, v, y);
+  };
+  double* dinv = s->d_dinv;
+  VecOp jacobi_uj = [dinv, nuj](const double* v, double* z) -> int {
+    k_mul<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, dinv, v, z);
+    MHD_LAUNCH_CHECK();
+    return 0;
+  };
+  VecOp precond;
+  if (o.precond == MHD_PC_NONE) {
+    precond = [n](const double* v, double* z) -> int {
+      MHD_CUDA(cudaMemcpyAsync(z, v, n * 8, cudaMemcpyDeviceToDevice, g_stream));
+      return 0;
+    };
+  } else if (o.precond == MHD_PC_JACOBI) {
+    precond = [dinv, n](const double* v, double* z) -> int {
+      k_mul<<<vgrid(n), 256, 0, g_stream>>>(n, dinv, v, z);
+      MHD_LAUNCH_CHECK();
+      return 0;
+    };
+  } else {
+    // upper block-triangular solve (badia2024.jl:25-31): phi, p first, then the (u,j) block with the coupling
+    precond = [s, op, n, nuj, &matvec_uj, &jacobi_uj](const double* v, double* z) -> int {
+      const mhd_solver_opts_t& oo = s->opts;
+      MHD_CUDA(cudaMemsetAsync(z, 0, (size_t)op->ncols * 8, g_stream));
+      k_apply_mass_inverses<<<(unsigned)((op->ncells * 12 + 127) / 128), 128, 0, g_stream>>>(
+          op->ncells, n, op->d_gids, s->d_minv_p, s->d_minv_f, 1.0 / oo.alpha_p, 1.0 / oo.alpha_phi, v, z);
+      MHD_LAUNCH_CHECK();
+      // t1 = A [0; z_p; z_phi] restricted to the (u,j) rows ; rhs = v_uj - t1
+      MHD_TRY(halo_exchange(op, z));
+      MHD_TRY(spmv_rows(op, nuj, z, s->d_t1));
+      k_sub<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, v, s->d_t1, s->d_t2);
+      MHD_LAUNCH_CHECK();
+      // inner GMRES on A_uj with Jacobi (zero initial guess); d_t3 = solution with zero p/phi/ghost entries
+      MHD_CUDA(cudaMemsetAsync(s->d_t3, 0, (size_t)op->ncols * 8, g_stream));
+      int done_its = 0;
+      bool first = true;
+      while (done_its < oo.uj_inner_its) {
+        MHD_TRY(s->inner.cycle(matvec_uj, jacobi_uj, s->d_t2, s->d_t3, 1e-2, 0.0, oo.uj_inner_its, first, true));
+        done_its += s->inner.m;
+        first = false;
+      }
+      MHD_CUDA(cudaMemcpyAsync(z, s->d_t3, (size_t)nuj * 8, cudaMemcpyDeviceToDevice, g_stream));
+      return 0;
+    };
+  }
+
+  KrylovScalars hs;
+  int total = 0;
+  bool first = true;
+  int rc = 0;
+  while (true) {
+    rc = s->outer.cycle(matvec, precond, s->d_b, s->d_x, o.rtol, o.atol, o.maxiter, first, false);
+    if (rc) return rc;
+    first = false;
+    MHD_CUDA(cudaMemcpyAsync(&hs, s->outer.S, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, g_stream));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    total = hs.iters;
+    if (hs.beta <= hs.tol || total >= o.maxiter || hs.k == 0) break;
+  }
+  if (iters) *iters = total;
+  if (resnorm) *resnorm = hs.beta;
+  if (res_history) {
+    const int nh = total + 1 < 4 * MAXM + 2 ? total + 1 : 4 * MAXM + 2;
+    for (int i = 0; i < nh; i++) res_history[i] = hs.hist[i];
+  }
+  MHD_CUDA(cudaMemcpyAsync(x, s->d_x, n * 8, xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g_stream));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  if (hs.beta > hs.tol) {
+    set_error("FGMRES stopped at %d iterations with residual %.3e > tol %.3e", total, hs.beta, hs.tol);
+    return MHD_E_NOTCONV;
+  }
+  return MHD_OK;
+}
+
+}  // extern "C"

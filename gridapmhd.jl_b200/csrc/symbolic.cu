@@ -1,0 +1,379 @@
+// Symbolic phase on the GPU: CSR sparsity + the cell-entry -> nnz scatter map, once per mesh.
+//
+// Stands behind Gridap's symbolic_loop_matrix!/nz_allocation/create_from_nz (reached through
+// SparseMatrixAssembler at src/main.jl:222,231): every (row,col) pair of the 8 touched blocks of every cell is
+// inserted (explicit zeros kept), Dirichlet rows/cols dropped, columns sorted and unique within a row.
+//
+// Algorithm (all data-parallel, no global sort):
+//   1. row -> (cell,local row) incidence lists (count, scan, fill)
+//   2. one warp per row: gather the candidate columns of its incident cells into shared memory, bitonic sort,
+//      unique -> row length (pass 1) and column values (pass 2)
+//   3. one CTA per cell: binary-search each touched entry in its row -> 16-bit row-relative position;
+//      count contributions per nnz and flag the nnz that receive exactly one (plain store instead of atomic).
+#include "common.h"
+
+namespace mhd {
+
+// ---- which local columns a local row couples to (the 8 touched blocks of jac_fluid_h1_hdiv,
+//      src/weakforms.jl:311): u-row: u,p,j | p-row: u | j-row: u,j,phi | phi-row: j
+__device__ __forceinline__ bool coupled(int li, int lj) {
+  int fi = li < OFF_P ? 0 : (li < OFF_J ? 1 : (li < OFF_F ? 2 : 3));
+  int fj = lj < OFF_P ? 0 : (lj < OFF_J ? 1 : (lj < OFF_F ? 2 : 3));
+  // 4 bits per row field: coupled column fields (bit fj): u:0b0111 p:0b0001 j:0b1101 phi:0b0100
+  const unsigned m = 0x4D17u;
+  return (m >> (fi * 4 + fj)) & 1u;
+}
+
+// canonical entry e -> (li, lj)
+__device__ __forceinline__ void entry_to_lilj(int e, int& li, int& lj) {
+  if (e < SEC_UP) { li = e / NU; lj = e % NU; }
+  else if (e < SEC_PU) { e -= SEC_UP; li = e / NP; lj = OFF_P + e % NP; }
+  else if (e < SEC_UJ) { e -= SEC_PU; li = OFF_P + e / NU; lj = e % NU; }
+  else if (e < SEC_JU) { e -= SEC_UJ; li = e / NJ; lj = OFF_J + e % NJ; }
+  else if (e < SEC_JJ) { e -= SEC_JU; li = OFF_J + e / NU; lj = e % NU; }
+  else if (e < SEC_JF) { e -= SEC_JJ; li = OFF_J + e / NJ; lj = OFF_J + e % NJ; }
+  else if (e < SEC_FJ) { e -= SEC_JF; li = OFF_J + e / NF; lj = OFF_F + e % NF; }
+  else { e -= SEC_FJ; li = OFF_F + e / NJ; lj = OFF_J + e % NJ; }
+}
+
+// ---------------------------------------------------------------- exclusive scan (int32 counts -> int64 offsets)
+constexpr int SCAN_B = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_B * SCAN_ITEMS;
+
+template <class TIn>
+__global__ void scan_tile_sums(const TIn* in, int64_t n, int64_t* sums) {
+  __shared__ int64_t sh[SCAN_B];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int64_t s = 0;
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    int64_t idx = base + (int64_t)i * SCAN_B + threadIdx.x;
+    if (idx < n) s += (int64_t)in[idx];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = SCAN_B / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = sh[0];
+}
+
+// out[i] = tile_offset + exclusive prefix inside the tile; writes out[n] = total when last tile
+template <class TIn>
+__global__ void scan_apply(const TIn* in, int64_t n, const int64_t* tile_off, int64_t* out) {
+  __shared__ int64_t sh[SCAN_B];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int64_t v[SCAN_ITEMS];
+  int64_t s = 0;
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? (int64_t)in[idx] : 0;
+    s += v[i];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 256 thread sums
+  for (int o = 1; o < SCAN_B; o <<= 1) {
+    int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int64_t run = tile_off[blockIdx.x] + sh[threadIdx.x] - s;
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = run;
+    run += v[i];
+    if (idx == n - 1) out[n] = run;
+  }
+}
+
+// exclusive scan of n counts into out[0..n] (out[n] = total). Recursive over tile sums.
+template <class TIn>
+static int exclusive_scan(const TIn* d_in, int64_t n, int64_t* d_out) {
+  if (n == 0) {
+    MHD_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int64_t), g_stream));
+    return 0;
+  }
+  int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t *d_sums = nullptr, *d_offs = nullptr;
+  MHD_TRY(dev_alloc(&d_sums, ntiles));
+  MHD_TRY(dev_alloc(&d_offs, ntiles + 1));
+  int rc = 0;
+  if (ntiles == 1) {  // base case: a single tile starts at offset 0
+    if (cudaMemsetAsync(d_offs, 0, 2 * sizeof(int64_t), g_stream) != cudaSuccess)
+      rc = cuda_fail(cudaGetLastError(), "memset", __FILE__, __LINE__);
+  } else {
+    scan_tile_sums<TIn><<<(unsigned)ntiles, SCAN_B, 0, g_stream>>>(d_in, n, d_sums);
+    g_launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "scan_tile_sums", __FILE__, __LINE__);
+    if (!rc) rc = exclusive_scan<int64_t>(d_sums, ntiles, d_offs);
+  }
+  if (!rc) {
+    scan_apply<TIn><<<(unsigned)ntiles, SCAN_B, 0, g_stream>>>(d_in, n, d_offs, d_out);
+    g_launches++;
+    if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "scan_apply", __FILE__, __LINE__);
+  }
+  cudaStreamSynchronize(g_stream);
+  cudaFree(d_sums);
+  cudaFree(d_offs);
+  return rc;
+}
+
+// ---------------------------------------------------------------- 1. row incidence
+__global__ void count_incidence(const int32_t* gids, int64_t nent, int64_t nrows, int32_t* cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nent) return;
+  int32_t g = gids[i];
+  if (g >= 0 && g < nrows) atomicAdd(&cnt[g], 1);
+}
+
+__global__ void fill_incidence(const int32_t* gids, int64_t nent, int64_t nrows, const int64_t* inc_ptr,
+                               int32_t* cursor, int64_t* inc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nent) return;
+  int32_t g = gids[i];
+  if (g >= 0 && g < nrows) {
+    int32_t k = atomicAdd(&cursor[g], 1);
+    inc[inc_ptr[g] + k] = i;  // i = cell*129 + li
+  }
+}
+
+// ---------------------------------------------------------------- 2. per-row sort/unique
+constexpr int ROW_CAP = 4096;       // candidate columns per row held in shared memory
+constexpr int ROW_WARPS = 2;        // warps (= rows) per CTA
+
+template <bool FILL>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+row_columns(const int32_t* __restrict__ gids, const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ inc,
+            int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ rowptr,
+            int32_t* __restrict__ colval, int* __restrict__ overflow) {
+  __shared__ int32_t buf[ROW_WARPS][ROW_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp;
+  if (row >= nrows) return;
+  int32_t* b = buf[warp];
+  int n = 0;
+  for (int64_t p = inc_ptr[row]; p < inc_ptr[row + 1]; p++) {
+    int64_t ci = inc[p];
+    int64_t cell = ci / NLOC;
+    int li = (int)(ci % NLOC);
+    const int32_t* g = gids + cell * NLOC;
+    for (int base = 0; base < NLOC; base += 32) {
+      int lj = base + lane;
+      int32_t c = -1;
+      if (lj < NLOC && coupled(li, lj)) c = g[lj];
+      unsigned m = __ballot_sync(0xffffffffu, c >= 0);
+      if (c >= 0) {
+        int pos = n + __popc(m & ((1u << lane) - 1));
+        if (pos < ROW_CAP) b[pos] = c;
+      }
+      n += __popc(m);
+    }
+  }
+  if (n > ROW_CAP) {
+    if (lane == 0) atomicExch(overflow, 1);
+    return;
+  }
+  // pad to a power of two and bitonic-sort inside the warp
+  int np2 = 32;
+  while (np2 < n) np2 <<= 1;
+  for (int i = n + lane; i < np2; i += 32) b[i] = INT32_MAX;
+  __syncwarp();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < np2; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          int32_t a = b[i], c = b[ixj];
+          bool up = (i & k) == 0;
+          if ((a > c) == up) { b[i] = c; b[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // unique
+  int64_t out0 = FILL ? rowptr[row] : 0;
+  int count = 0;
+  for (int base = 0; base < n; base += 32) {
+    int i = base + lane;
+    bool keep = i < n && (i == 0 || b[i] != b[i - 1]);
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (FILL && keep) colval[out0 + count + __popc(m & ((1u << lane) - 1))] = b[i];
+    count += __popc(m);
+  }
+  if (!FILL && lane == 0) row_len[row] = count;
+}
+
+// ---------------------------------------------------------------- 3. scatter map
+__global__ void __launch_bounds__(256)
+build_map(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+          int64_t nrows, uint16_t* __restrict__ map, uint8_t* __restrict__ contrib) {
+  __shared__ int32_t g[NLOC];
+  int64_t cell = blockIdx.x;
+  for (int i = threadIdx.x; i < NLOC; i += blockDim.x) g[i] = gids[cell * NLOC + i];
+  __syncthreads();
+  uint16_t* m = map + cell * NENT_PAD;
+  for (int e = threadIdx.x; e < NENT_PAD; e += blockDim.x) {
+    uint16_t code = MAP_SKIP;
+    if (e < NENT) {
+      int li, lj;
+      entry_to_lilj(e, li, lj);
+      int32_t r = g[li], c = g[lj];
+      if (r >= 0 && r < nrows && c >= 0) {
+        int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1, base = lo;
+        while (lo < hi) {
+          int64_t mid = (lo + hi) >> 1;
+          if (colval[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        code = (uint16_t)(lo - base);
+        // saturating contribution counter (1 byte per nnz)
+        uint32_t* word = (uint32_t*)(contrib + (lo & ~(int64_t)3));
+        unsigned sh = (unsigned)(lo & 3) * 8;
+        uint32_t old = *word;
+        if (((old >> sh) & 0xFF) < 2) {
+          // CAS loop: increment the byte, saturate at 2
+          uint32_t assumed;
+          do {
+            assumed = old;
+            uint32_t bval = (assumed >> sh) & 0xFF;
+            if (bval >= 2) break;
+            old = atomicCAS(word, assumed, assumed + (1u << sh));
+          } while (old != assumed);
+        }
+      }
+    }
+    m[e] = code;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+flag_exclusive(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ contrib,
+               uint16_t* __restrict__ map, unsigned long long* __restrict__ stats) {
+  __shared__ int32_t g[NLOC];
+  int64_t cell = blockIdx.x;
+  for (int i = threadIdx.x; i < NLOC; i += blockDim.x) g[i] = gids[cell * NLOC + i];
+  __syncthreads();
+  uint16_t* m = map + cell * NENT_PAD;
+  unsigned nent = 0, nex = 0;
+  for (int e = threadIdx.x; e < NENT; e += blockDim.x) {
+    uint16_t code = m[e];
+    if (code == MAP_SKIP) continue;
+    int li, lj;
+    entry_to_lilj(e, li, lj);
+    int64_t idx = rowptr[g[li]] + code;
+    nent++;
+    if (contrib[idx] == 1) {
+      m[e] = code | MAP_EXCL;
+      nex++;
+    }
+  }
+  // block reduce the two counters
+  for (int o = 16; o > 0; o >>= 1) {
+    nent += __shfl_down_sync(0xffffffffu, nent, o);
+    nex += __shfl_down_sync(0xffffffffu, nex, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&stats[0], (unsigned long long)nent);
+    atomicAdd(&stats[1], (unsigned long long)nex);
+  }
+}
+
+__global__ void max_row_len(const int32_t* row_len, int64_t nrows, int* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = i < nrows ? row_len[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+int symbolic_build(mhd_operator* op) {
+  const int64_t nent = op->ncells * NLOC;
+  const int64_t nrows = op->nrows;
+  int32_t *d_cnt = nullptr, *d_cursor = nullptr, *d_rowlen = nullptr;
+  int64_t *d_incptr = nullptr, *d_inc = nullptr;
+  int* d_flags = nullptr;  // [0] overflow, [1] max row length
+  uint8_t* d_contrib = nullptr;
+  unsigned long long* d_stats = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(g_stream);
+    cudaFree(d_cnt); cudaFree(d_cursor); cudaFree(d_rowlen); cudaFree(d_incptr); cudaFree(d_inc);
+    cudaFree(d_flags); cudaFree(d_contrib); cudaFree(d_stats);
+  };
+#define SY(x) do { if (!rc) rc = (x); } while (0)
+#define SYC(x) do { if (!rc) { cudaError_t _e = (x); if (_e != cudaSuccess) rc = cuda_fail(_e, #x, __FILE__, __LINE__); } } while (0)
+#define SYL() do { if (!rc) { g_launches++; cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) rc = cuda_fail(_e, "launch", __FILE__, __LINE__); } } while (0)
+  SY(dev_alloc(&d_cnt, nrows));
+  SY(dev_alloc(&d_cursor, nrows));
+  SY(dev_alloc(&d_rowlen, nrows));
+  SY(dev_alloc(&d_incptr, nrows + 1));
+  SY(dev_alloc(&d_flags, 2));
+  SY(dev_alloc(&d_stats, 2));
+  SYC(cudaMemsetAsync(d_cnt, 0, nrows * sizeof(int32_t), g_stream));
+  SYC(cudaMemsetAsync(d_cursor, 0, nrows * sizeof(int32_t), g_stream));
+  SYC(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), g_stream));
+  SYC(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), g_stream));
+  const unsigned gb = (unsigned)((nent + 255) / 256);
+  if (!rc) { count_incidence<<<gb, 256, 0, g_stream>>>(op->d_gids, nent, nrows, d_cnt); SYL(); }
+  SY(exclusive_scan<int32_t>(d_cnt, nrows, d_incptr));
+  int64_t ninc = 0;
+  SY(d2h(&ninc, d_incptr + nrows, 1));
+  SYC(cudaStreamSynchronize(g_stream));
+  SY(dev_alloc(&d_inc, ninc));
+  if (!rc) { fill_incidence<<<gb, 256, 0, g_stream>>>(op->d_gids, nent, nrows, d_incptr, d_cursor, d_inc); SYL(); }
+  const unsigned rb = (unsigned)((nrows + ROW_WARPS - 1) / ROW_WARPS);
+  if (!rc) {
+    row_columns<false><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, d_rowlen, nullptr, nullptr, d_flags);
+    SYL();
+  }
+  if (!rc) { max_row_len<<<(unsigned)((nrows + 255) / 256), 256, 0, g_stream>>>(d_rowlen, nrows, d_flags + 1); SYL(); }
+  int flags[2] = {0, 0};
+  SY(d2h(flags, d_flags, 2));
+  SYC(cudaStreamSynchronize(g_stream));
+  if (!rc && flags[0]) {
+    set_error("symbolic: a row couples to more than %d candidate columns (vertex valence too high)", ROW_CAP);
+    rc = MHD_E_CAPACITY;
+  }
+  if (!rc && flags[1] > MAX_ROW_NNZ) {
+    set_error("symbolic: row length %d exceeds the 15-bit scatter-map limit %d", flags[1], MAX_ROW_NNZ);
+    rc = MHD_E_CAPACITY;
+  }
+  cudaFree(op->d_rowptr); op->d_rowptr = nullptr;
+  SY(dev_alloc(&op->d_rowptr, nrows + 1));
+  SY(exclusive_scan<int32_t>(d_rowlen, nrows, op->d_rowptr));
+  int64_t nnz = 0;
+  SY(d2h(&nnz, op->d_rowptr + nrows, 1));
+  SYC(cudaStreamSynchronize(g_stream));
+  cudaFree(op->d_colval); op->d_colval = nullptr;
+  cudaFree(op->d_nzval); op->d_nzval = nullptr;
+  cudaFree(op->d_map); op->d_map = nullptr;
+  SY(dev_alloc(&op->d_colval, nnz));
+  SY(dev_alloc(&op->d_nzval, nnz));
+  SY(dev_alloc(&op->d_map, op->ncells * NENT_PAD));
+  SY(dev_alloc(&d_contrib, (nnz + 3) / 4 * 4 + 4));
+  SYC(cudaMemsetAsync(op->d_nzval, 0, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double), g_stream));
+  SYC(cudaMemsetAsync(d_contrib, 0, (size_t)((nnz + 3) / 4 * 4 + 4), g_stream));
+  if (!rc) {
+    row_columns<true><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, nullptr, op->d_rowptr, op->d_colval, d_flags);
+    SYL();
+  }
+  if (!rc) { build_map<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_gids, op->d_rowptr, op->d_colval, nrows, op->d_map, d_contrib); SYL(); }
+  if (!rc) { flag_exclusive<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_gids, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
+  unsigned long long stats[2] = {0, 0};
+  SY(d2h(stats, d_stats, 2));
+  SYC(cudaStreamSynchronize(g_stream));
+  cleanup();
+  if (rc) return rc;
+  op->nnz = nnz;
+  op->nentries = (int64_t)stats[0];
+  op->nexclusive = (int64_t)stats[1];
+  op->has_symbolic = true;
+  return 0;
+#undef SY
+#undef SYC
+#undef SYL
+}
+
+}  // namespace mhd

@@ -1,0 +1,172 @@
+/* mhdb200.h -- C ABI of libmhdb200.so: B200 (sm_100a) assembly + Krylov kernels for the
+ * inductionless-MHD H1-HDiv hot path of GridapMHD.jl.
+ *
+ * This is the drop-in boundary a Julia host reaches with `ccall` (see INTEGRATION.md and
+ * julia/GridapMHDB200.jl).  Each entry point cites the reference interface it stands behind
+ * (paths relative to the GridapMHD.jl checkout).
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, <0 = error class (MHD_E_*); text via mhd_last_error_string().
+ *     The library never aborts/exits (GridapPETSc precedent: src/Solvers/petsc.jl:16-27 @check_error_code).
+ *   - handles are opaque, created and destroyed explicitly (no finalizer-driven frees; hunt.jl:204).
+ *   - host arrays are BORROWED for the duration of the call only; the library copies what it keeps.
+ *   - every `double*` / `const double*` vector argument of the compute calls may be a HOST pointer or a
+ *     DEVICE pointer (detected with cudaPointerGetAttributes).  Host pointers: H2D copy, compute, D2H copy,
+ *     stream synchronised on return.  Device pointers: work is enqueued on the library stream and the call
+ *     returns without synchronising.
+ *   - cell->dof ids are Gridap's: per field, 1-based, signed; id<0 is a Dirichlet dof and -id (1-based)
+ *     indexes the field's Dirichlet-value array.  Vertex ids in `cell_nodes` use `index_base`.
+ *   - global vector layout: fields concatenated in `field_order` (src/fespaces.jl:4-9 _multi_field_style).
+ *   - emitted CSR: sorted column indices, explicit zeros kept, Dirichlet rows/cols dropped
+ *     (Gridap SparseMatrixAssembler semantics, src/main.jl:222-223).
+ */
+#ifndef MHDB200_H
+#define MHDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHD_OK 0
+#define MHD_E_INVALID (-1)   /* bad argument / inconsistent tables */
+#define MHD_E_CUDA (-2)      /* CUDA runtime error (sticky async errors surface at the next sync) */
+#define MHD_E_STATE (-3)     /* call order violated (e.g. jacobian before symbolic) */
+#define MHD_E_CAPACITY (-4)  /* a size limit of the implementation was exceeded */
+#define MHD_E_COMM (-5)      /* NCCL / communicator error */
+#define MHD_E_NOTCONV (-6)   /* iterative solve hit maxiter without meeting the tolerance */
+
+enum { MHD_FIELD_U = 0, MHD_FIELD_P = 1, MHD_FIELD_J = 2, MHD_FIELD_PHI = 3 };
+enum { MHD_CONV_NONE = 0, MHD_CONV_PICARD = 1, MHD_CONV_NEWTON = 2 }; /* src/parameters.jl:721 */
+
+typedef struct mhd_operator mhd_operator_t;
+typedef struct mhd_solver mhd_solver_t;
+
+/* Mesh: what Gridap's UnstructuredGrid holds (node coordinates + cell node ids, HEX8, lexicographic local
+ * vertex order x fastest).  Geometry is the trilinear map of the 8 vertices. */
+typedef struct {
+  int64_t nnodes;
+  const double* coords;      /* [nnodes*3] */
+  int64_t ncells;
+  const int32_t* cell_nodes; /* [ncells*8] */
+  int32_t index_base;        /* 0 or 1 */
+} mhd_mesh_t;
+
+/* Reference-element tables at the nq cell quadrature points (src/parameters.jl:436-441,521-525,617-639:
+ * Q2 vector Lagrangian, P1disc, RT1, Q1disc, Quadrature(HEX,5) => nq = 27).  The kernels are basis-agnostic:
+ * they only consume these numbers.  u is vector-valued with local dof = a + 27*c (component-major). */
+typedef struct {
+  int32_t nq;             /* must be 27 */
+  const double* w;        /* [nq] reference weights */
+  const double* geo_grad; /* [nq*8*3]  d(trilinear vertex function v)/d xi_k */
+  const double* u_val;    /* [nq*27]   scalar Q2 basis */
+  const double* u_grad;   /* [nq*27*3] reference gradients */
+  const double* p_val;    /* [nq*4] */
+  const double* j_val;    /* [nq*36*3] reference RT basis (contravariant Piola applied by the kernel) */
+  const double* j_div;    /* [nq*36]   reference divergence */
+  const double* phi_val;  /* [nq*8] */
+} mhd_tables_t;
+
+/* FE-space layout: what setup_fe_spaces (src/fespaces.jl:13-46) produces. */
+typedef struct {
+  const int32_t* cell_dofs[4]; /* per field [ncells*ndofs_f] signed 1-based; ndofs = 81,4,36,8 */
+  const int8_t* j_sign;        /* [ncells*36] +1/-1 sign flips of the RT face dofs */
+  int64_t nfree[4];            /* free dofs per field (local numbering: owned first, then ghosts) */
+  int64_t nowned[4];           /* owned free dofs per field; == nfree on a single GPU */
+  int64_t ndir[4];             /* Dirichlet dofs per field */
+  const double* dir_values[4]; /* [ndir_f] Dirichlet values (may be NULL when ndir_f == 0) */
+  int32_t field_order[4];      /* field ids in the order they appear in the global vector */
+} mhd_layout_t;
+
+/* retrieve_fluid_params (src/weakforms.jl:71-83), constant coefficients. */
+typedef struct {
+  double alpha, beta, gamma, sigma, zeta_u, zeta_j;
+  double B[3], f[3], g[3];
+  int32_t convection; /* MHD_CONV_* */
+} mhd_params_t;
+
+/* FGMRES + preconditioner options (src/Solvers/badia2024.jl:32-45, src/parameters.jl:259-271). */
+enum { MHD_PC_NONE = 0, MHD_PC_JACOBI = 1, MHD_PC_BLOCK_TRI = 2 };
+typedef struct {
+  int32_t m;            /* restart length (niter_ls, default 15) */
+  int32_t maxiter;      /* total Krylov iterations (reference: == m) */
+  double rtol, atol;    /* relative (to ||b - A x0||) and absolute tolerance */
+  int32_t precond;      /* MHD_PC_* */
+  int32_t uj_inner_its; /* MHD_PC_BLOCK_TRI: inner GMRES iterations on the (u,j) block */
+  int32_t uj_inner_restart;
+  double alpha_p, alpha_phi; /* scalings of the p / phi mass blocks (badia2024.jl:11-12) */
+} mhd_solver_opts_t;
+
+/* ---- library lifetime (GridapPETSc.with(args=...) do ... end; src/Applications/hunt.jl:202-206) ---- */
+int mhd_init(int device_ordinal);
+int mhd_finalize(void);
+int mhd_set_stream(void* cuda_stream); /* stream all later calls enqueue on (default: legacy stream 0) */
+int mhd_device_synchronize(void);
+const char* mhd_last_error_string(void);
+
+/* ---- multi-GPU: one process per GPU; rank 0 creates the id, the host broadcasts it (MPI / torch.distributed).
+ * Replaces PartitionedArrays' MPI backend (with_mpi, src/Applications/hunt.jl:22-24). ---- */
+int mhd_comm_get_unique_id(void* id128 /* 128 bytes out */);
+int mhd_comm_init(int rank, int nranks, const void* id128);
+int mhd_comm_finalize(void);
+
+/* ---- operator: stands behind _fe_operator / FEOperator(res,jac,U,V,assem) (src/main.jl:207-233) ---- */
+int mhd_operator_create(const mhd_mesh_t*, const mhd_tables_t*, const mhd_layout_t*, const mhd_params_t*,
+                        mhd_operator_t** out);
+int mhd_operator_destroy(mhd_operator_t*);
+int mhd_operator_set_params(mhd_operator_t*, const mhd_params_t*); /* continuation: src/main.jl:243-260 */
+
+/* Ghost exchange plan of the operator's vectors (PartitionedArrays consistent!/PVector):
+ * for neighbour k: send x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned local ids, 0-based) and receive into
+ * local ids recv_idx[recv_ptr[k]..) (ghost ids). */
+int mhd_operator_set_halo(mhd_operator_t*, int32_t nneigh, const int32_t* neigh_ranks, const int64_t* send_ptr,
+                          const int32_t* send_idx, const int64_t* recv_ptr, const int32_t* recv_idx);
+
+/* symbolic phase: symbolic_loop_matrix! + nz_allocation of Gridap's assembler (called through
+ * allocate_jacobian; src/main.jl:222,163).  Builds rowptr/colval and the cell-entry -> nnz scatter map. */
+int mhd_operator_symbolic(mhd_operator_t*, int64_t* nrows, int64_t* ncols, int64_t* nnz);
+/* copy the pattern out: index_bytes 4|8, base 0|1 (SparseMatrixCSR{0,Float64,PetscInt} / 1-based Int64;
+ * src/parameters.jl:224,235) */
+int mhd_operator_get_csr(mhd_operator_t*, void* rowptr, void* colval, int index_bytes, int base);
+int mhd_operator_get_scatter_stats(mhd_operator_t*, int64_t* nentries, int64_t* nexclusive);
+
+/* numeric phase: jacobian!(A,op,x) / residual!(b,op,x) (Gridap NonlinearOperator API used by
+ * solve!(xh,solver,op), src/main.jl:275; and jacobian(op,xh)/residual(op,xh), src/main.jl:158,163).
+ * x: [n local] free values.  nzval_out: [nnz] or NULL (values stay on the device behind the handle). */
+int mhd_jacobian(mhd_operator_t*, const double* x, double* nzval_out);
+int mhd_residual(mhd_operator_t*, const double* x, double* r_out);
+int mhd_get_nzval(mhd_operator_t*, double* nzval_out);          /* D2H (or D2D) copy of the current values */
+int mhd_set_nzval(mhd_operator_t*, const double* nzval);        /* tests: load values assembled elsewhere */
+
+/* ---- Krylov building blocks: mul!(y,A,x), dot, axpy! on PVector/PSparseMatrix as used by
+ * GridapSolvers FGMRES (src/Solvers/badia2024.jl:40).  n = local length (rows for dot/axpy). ---- */
+int mhd_spmv(mhd_operator_t*, const double* x, double* y); /* y = A x (halo exchange first when ranks>1) */
+int mhd_dot(mhd_operator_t*, const double* x, const double* y, double* result /* host or device */);
+int mhd_axpy(mhd_operator_t*, double a, const double* x, double* y); /* y += a x */
+/* fused Gram-Schmidt step of FGMRES: h[i] = <w, V_i>, i<k (one pass), then w -= sum h[i] V_i.
+ * V: k vectors of leading dimension ldv (device or host); h: k doubles out. */
+int mhd_multi_dot_axpy(mhd_operator_t*, int32_t k, const double* V, int64_t ldv, double* w, double* h);
+
+/* ---- linear solver: symbolic_setup/numerical_setup/numerical_setup!/solve! of a Gridap LinearSolver
+ * (seam: _solver / get_block_solver, src/main.jl:181-190, src/Solvers/gridap.jl:2-3). ---- */
+int mhd_solver_default_opts(mhd_solver_opts_t*);
+int mhd_solver_create(mhd_operator_t*, const mhd_solver_opts_t*, mhd_solver_t** out);
+int mhd_solver_setup(mhd_solver_t*); /* numerical_setup!: refresh preconditioner data after mhd_jacobian */
+int mhd_solve(mhd_solver_t*, const double* b, double* x /* in: x0, out: solution */, int32_t* iters,
+              double* resnorm, double* res_history /* nullable, maxiter+1 doubles */);
+int mhd_solver_destroy(mhd_solver_t*);
+
+/* ---- introspection for tests / benches ---- */
+int mhd_operator_device_ptrs(mhd_operator_t*, void** rowptr_i64, void** colval_i32, void** nzval_f64);
+int mhd_kernel_launch_count(int64_t* count); /* kernels launched by the library since mhd_init */
+/* CUDA-event timing of the named kernels on the library stream ("jacobian", "residual", "spmv"): enable, run,
+ * then read the accumulated device time and launch count (synchronises the stream). */
+int mhd_profile_enable(int on);
+int mhd_profile_get(const char* name, double* total_ms, int64_t* launches);
+int mhd_profile_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHDB200_H */

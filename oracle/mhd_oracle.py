@@ -207,33 +207,41 @@ def symbolic_csr(gids: np.ndarray, n: int):
     Returns rowptr[int64 n+1], colval[int64 nnz] with sorted columns."""
     mask = touched_mask()
     li, lj = np.nonzero(mask)
-    keys = []
-    chunk = 4096
+    P = None
+    chunk = 8192
     for s in range(0, gids.shape[0], chunk):
         g = gids[s : s + chunk]
         r = g[:, li]
         c = g[:, lj]
         ok = (r >= 0) & (c >= 0)
-        keys.append(np.unique(r[ok] * n + c[ok]))
-    keys = np.unique(np.concatenate(keys))
-    rows = keys // n
-    cols = keys % n
-    rowptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(rowptr, rows + 1, 1)
-    return np.cumsum(rowptr), cols.astype(np.int64)
+        Pi = sp.coo_matrix((np.ones(int(ok.sum()), dtype=np.int8), (r[ok], c[ok])), shape=(n, n)).tocsr()
+        Pi.sum_duplicates()
+        Pi.data[:] = 1
+        P = Pi if P is None else P + Pi
+    P.sum_duplicates()
+    P.sort_indices()
+    return P.indptr.astype(np.int64), P.indices.astype(np.int64)
 
 
-def assemble_matrix(K: np.ndarray, gids: np.ndarray, n: int) -> sp.csr_matrix:
+def assemble_matrix(K: np.ndarray, gids: np.ndarray, n: int, pattern=None) -> sp.csr_matrix:
+    """Scatter-add dense cell matrices into CSR on the symbolic pattern (explicit zeros kept)."""
+    if pattern is None:
+        pattern = symbolic_csr(gids, n)
+    rowptr, colval = pattern
+    keyP = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr)) * n + colval
     mask = touched_mask()
     li, lj = np.nonzero(mask)
-    r = gids[:, li]
-    c = gids[:, lj]
-    v = K[:, li, lj]
-    ok = (r >= 0) & (c >= 0)
-    A = sp.coo_matrix((v[ok], (r[ok], c[ok])), shape=(n, n)).tocsr()
-    A.sum_duplicates()
-    A.sort_indices()
-    return A
+    data = np.zeros(len(colval))
+    chunk = 2048
+    for s in range(0, gids.shape[0], chunk):
+        g = gids[s : s + chunk]
+        r = g[:, li]
+        c = g[:, lj]
+        v = K[s : s + chunk][:, li, lj]
+        ok = (r >= 0) & (c >= 0)
+        pos = np.searchsorted(keyP, r[ok] * n + c[ok])
+        np.add.at(data, pos, v[ok])
+    return sp.csr_matrix((data, colval.copy(), rowptr.copy()), shape=(n, n))
 
 
 def assemble_vector(R: np.ndarray, gids: np.ndarray, n: int) -> np.ndarray:
@@ -243,38 +251,21 @@ def assemble_vector(R: np.ndarray, gids: np.ndarray, n: int) -> np.ndarray:
     return out
 
 
-def jacobian(fes, x, prm: FluidParams, chunk: int = 2048) -> sp.csr_matrix:
+def jacobian(fes, x, prm: FluidParams, chunk: int = 2048, pattern=None) -> sp.csr_matrix:
     """`jacobian(op,xh)` (src/main.jl:163): assembled Jacobian in CSR (0-based, sorted, explicit zeros kept)."""
     X = fes.mesh.cell_coords()
     st = fes.cell_state(x)
     gids = fes.cell_global_ids()
     n = fes.ndofs
-    A = None
+    if pattern is None:
+        pattern = symbolic_csr(gids, n)
+    rowptr, colval = pattern
+    data = np.zeros(len(colval))
     for s in range(0, X.shape[0], chunk):
         sl = slice(s, s + chunk)
         K = cell_jacobians(fes.tables, X[sl], st[sl], fes.j_sign[sl], prm)
-        Ai = assemble_matrix(K, gids[sl], n)
-        A = Ai if A is None else A + Ai
-    # A + Ai drops nothing structurally except exact cancellations are kept as explicit entries by scipy's
-    # binop only if nonzero; rebuild on the symbolic pattern to keep explicit zeros
-    rowptr, colval = symbolic_csr(gids, n)
-    P = sp.csr_matrix((np.zeros(len(colval)), colval, rowptr), shape=(n, n))
-    out = _add_on_pattern(P, A)
-    return out
-
-
-def _add_on_pattern(P: sp.csr_matrix, A: sp.csr_matrix) -> sp.csr_matrix:
-    """Values of A scattered onto the (super-)pattern P."""
-    n = P.shape[0]
-    A = A.tocsr()
-    A.sort_indices()
-    keyP = np.repeat(np.arange(n, dtype=np.int64), np.diff(P.indptr)) * n + P.indices
-    keyA = np.repeat(np.arange(n, dtype=np.int64), np.diff(A.indptr)) * n + A.indices
-    pos = np.searchsorted(keyP, keyA)
-    assert np.all(keyP[pos] == keyA)
-    data = np.zeros(len(keyP))
-    data[pos] = A.data
-    return sp.csr_matrix((data, P.indices.copy(), P.indptr.copy()), shape=P.shape)
+        data += assemble_matrix(K, gids[sl], n, pattern).data
+    return sp.csr_matrix((data, colval.copy(), rowptr.copy()), shape=(n, n))
 
 
 def residual(fes, x, prm: FluidParams, chunk: int = 4096) -> np.ndarray:

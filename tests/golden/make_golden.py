@@ -1,0 +1,34 @@
+"""Generates the committed golden fixtures with the CPU oracle (run from the repo root:
+`python tests/golden/make_golden.py`).  The reference (Julia/Gridap) cannot run in the build container, so the
+vectors come from oracle/mhd_oracle.py, which is itself pinned to the reference's published Hunt norms
+(tests/test_oracle_pins.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import gridapmhd_jl_b200  # noqa: E402,F401
+from gridapmhd_jl_b200.applications import hunt_params, setup_spaces  # noqa: E402
+from oracle import mhd_oracle as O  # noqa: E402
+
+
+def main():
+    params = hunt_params(nc=(3, 3), B=(0.0, 20.0, 0.0))
+    fes = setup_spaces(params)
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    rng = np.random.default_rng(20261017)
+    x = rng.random(fes.ndofs)
+    v = rng.standard_normal(fes.ndofs)
+    A = O.jacobian(fes, x, prm)
+    r = O.residual(fes, x, prm)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hunt_nc3_ha20.npz")
+    np.savez_compressed(out, x=x, v=v, rowptr=A.indptr.astype(np.int64), colval=A.indices.astype(np.int64), nzval=A.data,
+                        residual=r, Av=A @ v, ndofs=np.array([fes.nfree[f] for f in ("u", "p", "j", "phi")]))
+    print("wrote", out, os.path.getsize(out), "bytes; nnz", A.nnz)
+
+
+if __name__ == "__main__":
+    main()
