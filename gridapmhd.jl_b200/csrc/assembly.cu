@@ -51,8 +51,9 @@ constexpr int S_DIV = S_PSI + 81 * 36;        // [27][36]  sqrt(w) div psi_m   (
 constexpr int S_PP = S_DIV + 27 * 36;         // [27][4]
 constexpr int S_CHI = S_PP + 27 * 4;          // [27][8]
 constexpr int S_T = S_CHI + 27 * 8;           // [27][9]   (d_d u_c)(q), index d*3+c
-constexpr int S_ST = S_T + 244;               // staging
-constexpr int ST_SIZE = 2070 + 2187;
+constexpr int LDT = 10;                       // padded row of the velocity-gradient table
+constexpr int S_ST = S_T + 27 * LDT + 2;      // staging
+constexpr int ST_SIZE = 2070 + 1296;
 constexpr int S_J = S_ST + ST_SIZE;           // [27][9]
 constexpr int S_INV = S_J + 243;              // [27][9]
 constexpr int S_DET = S_INV + 243;            // [27]
@@ -72,17 +73,23 @@ constexpr int ST_D = 0;      // [81][4]  D[(c,a)][k] = sum_q w pi_k d_c N_a
 constexpr int ST_S = 324;    // [27][27]
 constexpr int ST_C = 1053;   // [27][27]
 constexpr int ST_JF = 1782;  // [36][8]
-constexpr int ST_NW = 2070;  // [3][27][27]
+constexpr int ST_JJ = 2070;  // [36][36]   (uj/ju results reuse [0,2916) after phase 0 is scattered)
 
 // ---------------------------------------------------------------------------------------------
 // register-tiled panel product:  C[batch][m][n] = sum_k A[k*lda + m] * (sc ? sc[k*scs] : 1) * B[k*ldb + n]
-// tile t -> thread (t + toff) % NT.  store(batch, m, n, value) is called for in-range entries.
+// A thread owns TM x TN outputs arranged as PAIRS of adjacent rows/columns: rows {2(tm + MT*p), +1}, p < TM/2 and
+// columns {2(tn + NTL*p), +1}, p < TN/2.  Adjacent lanes therefore read adjacent 16-byte words of a panel row
+// (LDS.128, bank-conflict free) while lanes that share tm read the same A word (broadcast).  Panels need
+// lda >= TM*MT, ldb >= TN*NTL (even) and 16-byte aligned rows.  tile t -> thread (t + toff) % NT.
+// store(batch, m, n, value) is called for in-range entries.
 template <int M, int N, int TM, int TN, bool SCALE, class Store>
 __device__ __forceinline__ void panel_product(int nbatch, const double* __restrict__ A, int lda, int a_bs,
                                               const double* __restrict__ B, int ldb, int b_bs, int K,
                                               const double* __restrict__ sc, int scs, int sc_bs, int toff,
                                               Store store) {
+  static_assert(TM % 2 == 0 && TN % 2 == 0, "tiles are built from pairs");
   constexpr int MT = (M + TM - 1) / TM, NTL = (N + TN - 1) / TN;
+  constexpr int PM = TM / 2, PN = TN / 2;
   const int ntiles = nbatch * MT * NTL;
   int t0 = (int)threadIdx.x - toff;
   t0 %= NT;
@@ -90,9 +97,9 @@ __device__ __forceinline__ void panel_product(int nbatch, const double* __restri
   for (int t = t0; t < ntiles; t += NT) {
     const int batch = t / (MT * NTL);
     const int r = t - batch * (MT * NTL);
-    const int m0 = (r / NTL) * TM, n0 = (r % NTL) * TN;
-    const double* a = A + batch * a_bs + m0;
-    const double* b = B + batch * b_bs + n0;
+    const int tm = r / NTL, tn = r - tm * NTL;
+    const double* a = A + batch * a_bs + 2 * tm;
+    const double* b = B + batch * b_bs + 2 * tn;
     const double* s = SCALE ? sc + batch * sc_bs : nullptr;
     double acc[TM][TN];
 #pragma unroll
@@ -103,9 +110,17 @@ __device__ __forceinline__ void panel_product(int nbatch, const double* __restri
     for (int k = 0; k < K; k++) {
       double av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < TM; i++) av[i] = a[k * lda + i];
+      for (int p = 0; p < PM; p++) {
+        const double2 v = *reinterpret_cast<const double2*>(a + k * lda + 2 * MT * p);
+        av[2 * p] = v.x;
+        av[2 * p + 1] = v.y;
+      }
 #pragma unroll
-      for (int j = 0; j < TN; j++) bv[j] = b[k * ldb + j];
+      for (int p = 0; p < PN; p++) {
+        const double2 v = *reinterpret_cast<const double2*>(b + k * ldb + 2 * NTL * p);
+        bv[2 * p] = v.x;
+        bv[2 * p + 1] = v.y;
+      }
       if (SCALE) {
         const double sk = s[k * scs];
 #pragma unroll
@@ -119,8 +134,36 @@ __device__ __forceinline__ void panel_product(int nbatch, const double* __restri
 #pragma unroll
     for (int i = 0; i < TM; i++)
 #pragma unroll
-      for (int j = 0; j < TN; j++)
-        if (m0 + i < M && n0 + j < N) store(batch, m0 + i, n0 + j, acc[i][j]);
+      for (int j = 0; j < TN; j++) {
+        const int m = 2 * (tm + MT * (i / 2)) + (i & 1), n = 2 * (tn + NTL * (j / 2)) + (j & 1);
+        if (m < M && n < N) store(batch, m, n, acc[i][j]);
+      }
+  }
+}
+
+// Unrolled scatter sweep: U map codes are loaded before any of them is used (memory-level parallelism; the sweep
+// is otherwise bound by the latency of the 2-byte map loads).  getcode(e) reads the map code of sweep entry e,
+// f(e, rowstart&, value&) supplies the nnz row offset and the value.
+template <int U, class G, class F>
+__device__ __forceinline__ void scatter_generic(double* __restrict__ nz, int count, G getcode, F f) {
+  for (int base = 0; base < count; base += NT * U) {
+    uint16_t c[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int e = base + k * NT + (int)threadIdx.x;
+      c[k] = e < count ? getcode(e) : MAP_SKIP;
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      if (c[k] == MAP_SKIP) continue;
+      const int e = base + k * NT + (int)threadIdx.x;
+      long long rowstart;
+      double v;
+      f(e, rowstart, v);
+      double* p = nz + rowstart + (c[k] & 0x7FFF);
+      if (c[k] & MAP_EXCL) *p = v;
+      else atomicAdd(p, v);
+    }
   }
 }
 
@@ -279,26 +322,35 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
           const int q = idx / 9, dc = idx - q * 9, d = dc / 3, c = dc - d * 3;
           double s = 0.0;
           for (int b = 0; b < 27; b++) s = fma(sm[S_G + (q * 3 + d) * LDN + b], sm[S_U + c * 27 + b], s);
-          sm[S_T + idx] = s / sm[S_SW + q];
+          sm[S_T + q * LDT + dc] = s / sm[S_SW + q];
         }
       }
     }
     if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
     __syncthreads();
 
-    // ---------------- phase 1: up, S, C, j-phi (+ pressure mass matrix)
+    // ---------------- phase 0: D (up), j-phi, jj, S, C (+ pressure mass matrix), all independent panel products
     // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]   (batch = c)
     panel_product<27, 4, 4, 4, false>(3, sm + S_G, 3 * LDN, LDN, sm + S_PP, 4, 0, NQ, nullptr, 0, 0, 0,
                                       [&](int c, int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
-    // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b]
-    panel_product<27, 27, 2, 4, false>(1, sm + S_G, LDN, 0, sm + S_G, LDN, 0, 81, nullptr, 0, 0, 21,
-                                       [&](int, int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
-    if (CONV > 0)
-      panel_product<27, 27, 4, 4, false>(1, sm + S_N, LDN, 0, sm + S_UG, LDN, 0, NQ, nullptr, 0, 0, 21 + 98,
-                                         [&](int, int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
     // JF[m][l] = sum_q Div[q][m] Chi[q][l]
-    panel_product<36, 8, 4, 4, false>(1, sm + S_DIV, NJ, 0, sm + S_CHI, 8, 0, NQ, nullptr, 0, 0, 21 + 98 + 49,
+    panel_product<36, 8, 4, 4, false>(1, sm + S_DIV, NJ, 0, sm + S_CHI, 8, 0, NQ, nullptr, 0, 0, 21,
                                       [&](int, int m, int l, double v) { St[ST_JF + m * 8 + l] = v; });
+    // jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div  (K = 81 or 108: Psi and Div panels are contiguous)
+    if (P.zeta_j != 0.0)
+      panel_product<36, 36, 2, 4, true>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 108, sm + S_SC, 1, 0, 39,
+                                        [&](int, int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
+    else
+      panel_product<36, 36, 2, 4, false>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 81, nullptr, 0, 0, 39,
+                                         [&](int, int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
+    if (CONV < 2) {
+      // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b] ; C[a][b] = sum_q N[q][a] UG[q][b]
+      panel_product<27, 27, 2, 4, false>(1, sm + S_G, LDN, 0, sm + S_G, LDN, 0, 81, nullptr, 0, 0, 39 + 162,
+                                         [&](int, int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
+      if (CONV > 0)
+        panel_product<27, 27, 4, 4, false>(1, sm + S_N, LDN, 0, sm + S_UG, LDN, 0, NQ, nullptr, 0, 0, 39 + 162 + 98,
+                                           [&](int, int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
+    }
     if (ZU && tid >= NT - 16) {
       const int kl = tid - (NT - 16), k = kl >> 2, l = kl & 3;
       double s = 0.0;
@@ -338,77 +390,134 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       __syncthreads();
     }
     const uint16_t* cmap = map + cell * NENT_PAD;
-    // up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(d,b)] = -D
-    for (int e = tid; e < NU * NP; e += NT) {
-      const int i = e >> 2;
-      scatter_entry(nz, cx.row[i], cmap[SEC_UP + e], -St[ST_D + e]);
-    }
-    for (int e = tid; e < NP * NU; e += NT) {
-      const int k = e / NU, i = e - k * NU;
-      scatter_entry(nz, cx.row[OFF_P + k], cmap[SEC_PU + e], -St[ST_D + i * 4 + k]);
-    }
-    // j-phi: -sigma JF[m][l] ; phi-j: -JF[m][l]
-    for (int e = tid; e < NJ * NF; e += NT) {
-      const int m = e >> 3;
-      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JF + e], -P.sigma * St[ST_JF + e]);
-    }
-    for (int e = tid; e < NF * NJ; e += NT) {
-      const int l = e / NJ, m = e - l * NJ;
-      scatter_entry(nz, cx.row[OFF_F + l], cmap[SEC_FJ + e], -St[ST_JF + m * 8 + l]);
-    }
-    // uu
-    if (CONV < 2) {
-      if (!ZU) {
-        for (int idx = tid; idx < 3 * 729; idx += NT) {
-          const int c = idx / 729, ab = idx - c * 729, a = ab / 27, b = ab - a * 27;
-          const int li = c * 27 + a, lj = c * 27 + b;
-          double v = P.beta * St[ST_S + ab];
-          if (CONV > 0) v = fma(P.alpha, St[ST_C + ab], v);
-          scatter_entry(nz, cx.row[li], cmap[SEC_UU + li * NU + lj], v);
-        }
-      } else {
-        for (int e = tid; e < NU * NU; e += NT) {
-          const int li = e / NU, lj = e - li * NU;
-          const int c = li / 27, a = li - c * 27, d = lj / 27, b = lj - d * 27;
-          double v = 0.0;
+    const long long* row = cx.row;
+
+    // ---------------- uu
+    if (CONV == 2) {
+      // Newton: a thread owns the 2x2 (a,b) node tile of all 9 component blocks:
+      //   K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term]
+      // accumulated in registers and scattered straight from them (no staging, no extra barrier).
+      if (tid < 196) {
+        const int ta = tid / 14, tb = tid - ta * 14;
+        const double* Ga = sm + S_G + 2 * ta;
+        const double* Gb = sm + S_G + 2 * tb;
+        const double* Na = sm + S_N + 2 * ta;
+        const double* Nb = sm + S_N + 2 * tb;
+        const double* Ub = sm + S_UG + 2 * tb;
+        double sS[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, sC[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double nw[9][2][2];
 #pragma unroll
-          for (int k = 0; k < 4; k++) v = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], v);
-          v *= P.zeta_u;
-          if (c == d) {
-            v = fma(P.beta, St[ST_S + a * 27 + b], v);
-            if (CONV > 0) v = fma(P.alpha, St[ST_C + a * 27 + b], v);
+        for (int dc = 0; dc < 9; dc++) nw[dc][0][0] = nw[dc][0][1] = nw[dc][1][0] = nw[dc][1][1] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < NQ; q++) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            const double2 ga = *reinterpret_cast<const double2*>(Ga + (q * 3 + i) * LDN);
+            const double2 gb = *reinterpret_cast<const double2*>(Gb + (q * 3 + i) * LDN);
+            sS[0][0] = fma(ga.x, gb.x, sS[0][0]);
+            sS[0][1] = fma(ga.x, gb.y, sS[0][1]);
+            sS[1][0] = fma(ga.y, gb.x, sS[1][0]);
+            sS[1][1] = fma(ga.y, gb.y, sS[1][1]);
           }
-          scatter_entry(nz, cx.row[li], cmap[SEC_UU + e], v);
+          const double2 na = *reinterpret_cast<const double2*>(Na + q * LDN);
+          const double2 nb = *reinterpret_cast<const double2*>(Nb + q * LDN);
+          const double2 ub = *reinterpret_cast<const double2*>(Ub + q * LDN);
+          sC[0][0] = fma(na.x, ub.x, sC[0][0]);
+          sC[0][1] = fma(na.x, ub.y, sC[0][1]);
+          sC[1][0] = fma(na.y, ub.x, sC[1][0]);
+          sC[1][1] = fma(na.y, ub.y, sC[1][1]);
+          const double p00 = na.x * nb.x, p01 = na.x * nb.y, p10 = na.y * nb.x, p11 = na.y * nb.y;
+          const double* Tq = sm + S_T + q * LDT;
+#pragma unroll
+          for (int dc = 0; dc < 9; dc++) {
+            const double t = Tq[dc];
+            nw[dc][0][0] = fma(t, p00, nw[dc][0][0]);
+            nw[dc][0][1] = fma(t, p01, nw[dc][0][1]);
+            nw[dc][1][0] = fma(t, p10, nw[dc][1][0]);
+            nw[dc][1][1] = fma(t, p11, nw[dc][1][1]);
+          }
+        }
+        // 36 entries per thread, swept one column component d at a time: 12 map codes are loaded first, then
+        // the 12 values are scattered
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          uint16_t code[3][2][2];
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                const int a = 2 * ta + i, b = 2 * tb + j;
+                code[c][i][j] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
+              }
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                const uint16_t cd = code[c][i][j];
+                if (cd == MAP_SKIP) continue;
+                const int li = c * 27 + 2 * ta + i, lj = d * 27 + 2 * tb + j;
+                double v = P.alpha * nw[d * 3 + c][i][j];
+                if (c == d) v += P.beta * sS[i][j] + P.alpha * sC[i][j];
+                if (ZU) {
+                  double z = 0.0;
+#pragma unroll
+                  for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
+                  v = fma(P.zeta_u, z, v);
+                }
+                double* pz = nz + row[li] + (cd & 0x7FFF);
+                if (cd & MAP_EXCL) *pz = v;
+                else atomicAdd(pz, v);
+              }
         }
       }
+    } else if (!ZU) {
+      // only the three diagonal component blocks carry values: beta S + alpha C
+      scatter_generic<8>(nz, 3 * 729,
+          [&](int idx) { const int c = idx / 729, ab = idx - c * 729, a = ab / 27, b = ab - a * 27;
+                         return cmap[SEC_UU + (c * 27 + a) * NU + c * 27 + b]; },
+          [&](int idx, long long& rs, double& v) {
+            const int c = idx / 729, ab = idx - c * 729, a = ab / 27;
+            rs = row[c * 27 + a];
+            v = P.beta * St[ST_S + ab];
+            if (CONV > 0) v = fma(P.alpha, St[ST_C + ab], v);
+          });
     } else {
-      // Newton: NW[c][d][a][b] = sum_q N[q][a] (d_d u_c)(q) N[q][b], one row component c at a time
-      for (int c = 0; c < 3; c++) {
-        __syncthreads();
-        panel_product<27, 27, 4, 4, true>(3, sm + S_N, LDN, 0, sm + S_N, LDN, 0, NQ, sm + S_T + c, 9, 3, c * 147,
-                                          [&](int d, int a, int b, double v) { St[ST_NW + d * 729 + a * 27 + b] = v; });
-        __syncthreads();
-        for (int idx = tid; idx < 27 * NU; idx += NT) {
-          const int a = idx / NU, lj = idx - a * NU, d = lj / 27, b = lj - d * 27;
-          const int li = c * 27 + a;
-          double v = P.alpha * St[ST_NW + d * 729 + a * 27 + b];
-          if (ZU) {
+      scatter_generic<8>(nz, NU * NU, [&](int e) { return cmap[SEC_UU + e]; },
+          [&](int e, long long& rs, double& v) {
+            const int li = e / NU, lj = e - li * NU;
+            const int c = li / 27, a = li - c * 27, d = lj / 27, b = lj - d * 27;
             double z = 0.0;
 #pragma unroll
             for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
-            v = fma(P.zeta_u, z, v);
-          }
-          if (c == d) {
-            v = fma(P.beta, St[ST_S + a * 27 + b], v);
-            v = fma(P.alpha, St[ST_C + a * 27 + b], v);
-          }
-          scatter_entry(nz, cx.row[li], cmap[SEC_UU + li * NU + lj], v);
-        }
-      }
+            z *= P.zeta_u;
+            if (c == d) {
+              z = fma(P.beta, St[ST_S + a * 27 + b], z);
+              if (CONV > 0) z = fma(P.alpha, St[ST_C + a * 27 + b], z);
+            }
+            rs = row[li];
+            v = z;
+          });
     }
+    // ---------------- up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(d,b)] = -D
+    scatter_generic<2>(nz, NU * NP, [&](int e) { return cmap[SEC_UP + e]; },
+                       [&](int e, long long& rs, double& v) { rs = row[e >> 2]; v = -St[ST_D + e]; });
+    scatter_generic<2>(nz, NP * NU, [&](int e) { return cmap[SEC_PU + e]; },
+                       [&](int e, long long& rs, double& v) { const int k = e / NU, i = e - k * NU; rs = row[OFF_P + k]; v = -St[ST_D + i * 4 + k]; });
+    // ---------------- j-phi: -sigma JF[m][l] ; phi-j: -JF[m][l]
+    scatter_generic<2>(nz, NJ * NF, [&](int e) { return cmap[SEC_JF + e]; },
+                       [&](int e, long long& rs, double& v) { rs = row[OFF_J + (e >> 3)]; v = -P.sigma * St[ST_JF + e]; });
+    scatter_generic<2>(nz, NF * NJ, [&](int e) { return cmap[SEC_FJ + e]; },
+                       [&](int e, long long& rs, double& v) { const int l = e / NJ, m = e - l * NJ; rs = row[OFF_F + l]; v = -St[ST_JF + m * 8 + l]; });
+    // ---------------- jj
+    scatter_generic<6>(nz, NJ * NJ, [&](int e) { return cmap[SEC_JJ + e]; },
+                       [&](int e, long long& rs, double& v) { rs = row[OFF_J + e / NJ]; v = St[ST_JJ + e]; });
     __syncthreads();
 
-    // ---------------- phase 3: uj / ju.  XB[q][c*36+m] = sqrt(w) (psi_m x B)_c (overwrites G, UG)
+    // ---------------- uj / ju.  XB[q][c*36+m] = sqrt(w) (psi_m x B)_c (overwrites G, UG)
     for (int idx = tid; idx < NQ * NJ; idx += NT) {
       const int q = idx / NJ, m = idx - q * NJ;
       const double p0 = sm[S_PSI + (q * 3 + 0) * NJ + m], p1 = sm[S_PSI + (q * 3 + 1) * NJ + m],
@@ -423,28 +532,10 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
                                        [&](int c, int a, int m, double v) { St[(c * 27 + a) * NJ + m] = v; });
     __syncthreads();
     // K_uj[(c,a)][m] = -gamma R ; K_ju[m][(d,b)] = +sigma R[d][b][m]
-    for (int e = tid; e < NU * NJ; e += NT) {
-      const int i = e / NJ;
-      scatter_entry(nz, cx.row[i], cmap[SEC_UJ + e], -P.gamma * St[e]);
-    }
-    for (int e = tid; e < NJ * NU; e += NT) {
-      const int m = e / NU, i = e - m * NU;
-      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JU + e], P.sigma * St[i * NJ + m]);
-    }
-    __syncthreads();
-
-    // ---------------- phase 4: jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div  (K = 81 or 108, contiguous panels)
-    if (P.zeta_j != 0.0)
-      panel_product<36, 36, 2, 4, true>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 108, sm + S_SC, 1, 0, 0,
-                                        [&](int, int m, int n, double v) { St[m * NJ + n] = v; });
-    else
-      panel_product<36, 36, 2, 4, false>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 81, nullptr, 0, 0, 0,
-                                         [&](int, int m, int n, double v) { St[m * NJ + n] = v; });
-    __syncthreads();
-    for (int e = tid; e < NJ * NJ; e += NT) {
-      const int m = e / NJ;
-      scatter_entry(nz, cx.row[OFF_J + m], cmap[SEC_JJ + e], St[e]);
-    }
+    scatter_generic<12>(nz, NU * NJ, [&](int e) { return cmap[SEC_UJ + e]; },
+                        [&](int e, long long& rs, double& v) { rs = row[e / NJ]; v = -P.gamma * St[e]; });
+    scatter_generic<12>(nz, NJ * NU, [&](int e) { return cmap[SEC_JU + e]; },
+                        [&](int e, long long& rs, double& v) { const int m = e / NU, i = e - m * NU; rs = row[OFF_J + m]; v = P.sigma * St[i * NJ + m]; });
   }
 }
 
