@@ -283,15 +283,19 @@ __device__ __forceinline__ void scatter_entry(double* __restrict__ nz, long long
   else atomicAdd(p, v);
 }
 
+template <int CONV, bool ZU>
+__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, double* __restrict__ r, const KParams& P);
+
 // =============================================================================================
 // Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0.
-template <int CONV, bool ZU>
+// RES: also assemble the residual at the same state (residual_and_jacobian!), sharing the cell preparation.
+template <int CONV, bool ZU, bool RES>
 __global__ void __launch_bounds__(NT, 2)
 jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
                 const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
                 const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
                 const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ map, double* __restrict__ nz,
-                KParams P) {
+                double* __restrict__ rvec, KParams P) {
   extern __shared__ __align__(16) double smem[];
   CellCtx cx;
   cx.sm = smem;
@@ -303,10 +307,14 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();  // previous cell's scatter done before its tables are overwritten
-    cell_prep<(CONV > 0 ? 1 : 0)>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
     for (int i = tid; i < NLOC; i += NT) {
       const int32_t g = cx.gid[i];
       cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
+    }
+    if (RES) {
+      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, nrows, rvec, P);
+      __syncthreads();  // the residual's scratch lives in the staging area that phase 0 overwrites
     }
     if (CONV > 0) {
       // UG[q][b] = sqrt(w) u_q . grad N_b ;  T[q][d*3+c] = d_d u_c (unweighted)
@@ -540,19 +548,11 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
 }
 
 // =============================================================================================
-// Residual kernel: res_fluid_h1_hdiv (src/weakforms.jl:255-281)
+// Residual of one cell: res_fluid_h1_hdiv (src/weakforms.jl:255-281).  Needs cell_prep<2> (all panels + the full
+// local state); uses the first ~820 doubles of the staging area and leaves the panels untouched.
 template <int CONV, bool ZU>
-__global__ void __launch_bounds__(NT, 2)
-residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
-                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
-                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
-                double* __restrict__ r, KParams P) {
-  extern __shared__ __align__(16) double smem[];
-  CellCtx cx;
-  cx.sm = smem;
-  cx.row = (long long*)(smem + S_END);
-  cx.gid = (int32_t*)(cx.row + NLOC);
-  double* sm = smem;
+__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, double* __restrict__ r, const KParams& P) {
+  double* sm = cx.sm;
   const int tid = threadIdx.x;
   // per-q coefficient tables in the staging area
   double* Fu = sm + S_ST;         // [27][3]  coefficient of N'[q][a] in r_u[(c,a)]
@@ -565,10 +565,7 @@ residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
   double* Gq = Pq + 27;           // [27][9]  sqrt(w) d_d u_c
   double* Pr = Gq + 243;          // [27]     sqrt(w) Pi_p(div u)
   double* Rh = Pr + 27;           // [4] rhs / coefficients of the projection
-
-  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
-    __syncthreads();
-    cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+  {
     const double* U = sm + S_U;
     // gradients of u, div u, p at q
     for (int idx = tid; idx < NQ * 9; idx += NT) {
@@ -707,6 +704,24 @@ residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
   }
 }
 
+template <int CONV, bool ZU>
+__global__ void __launch_bounds__(NT, 2)
+residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
+                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
+                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
+                double* __restrict__ r, KParams P) {
+  extern __shared__ __align__(16) double smem[];
+  CellCtx cx;
+  cx.sm = smem;
+  cx.row = (long long*)(smem + S_END);
+  cx.gid = (int32_t*)(cx.row + NLOC);
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    __syncthreads();
+    cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    cell_residual<CONV, ZU>(cx, nrows, r, P);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 static KParams make_kparams(const mhd_params_t& p) {
   KParams k;
@@ -727,26 +742,30 @@ static int set_smem(Kern k) {
   return 0;
 }
 
-int launch_jacobian(mhd_operator* op, const double* d_x) {
+// d_r != nullptr: fused residual + Jacobian (residual_and_jacobian!)
+int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), g_stream));
+  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
   const KParams P = make_kparams(op->prm);
   const int conv = op->prm.convection;
   const bool zu = op->prm.zeta_u != 0.0;
   const int64_t grid64 = (int64_t)sm_count() * 2;
   const unsigned grid = (unsigned)(op->ncells < grid64 ? op->ncells : grid64);
-#define JK(C, Z)                                                                                             \
+#define JK(C, Z, R)                                                                                          \
   do {                                                                                                       \
-    MHD_TRY(set_smem(jacobian_kernel<C, Z>));                                                                \
-    jacobian_kernel<C, Z><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
-        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, P);  \
+    MHD_TRY(set_smem(jacobian_kernel<C, Z, R>));                                                             \
+    jacobian_kernel<C, Z, R><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
+        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, d_r, P); \
   } while (0)
+#define JKR(C, Z) do { if (d_r) JK(C, Z, true); else JK(C, Z, false); } while (0)
   prof_begin(PROF_JAC);
-  if (conv == 0 && !zu) JK(0, false);
-  else if (conv == 0 && zu) JK(0, true);
-  else if (conv == 1 && !zu) JK(1, false);
-  else if (conv == 1 && zu) JK(1, true);
-  else if (conv == 2 && !zu) JK(2, false);
-  else JK(2, true);
+  if (conv == 0 && !zu) JKR(0, false);
+  else if (conv == 0 && zu) JKR(0, true);
+  else if (conv == 1 && !zu) JKR(1, false);
+  else if (conv == 1 && zu) JKR(1, true);
+  else if (conv == 2 && !zu) JKR(2, false);
+  else JKR(2, true);
+#undef JKR
 #undef JK
   prof_end(PROF_JAC);
   MHD_LAUNCH_CHECK();

@@ -158,7 +158,7 @@ int d2h(T* h, const T* d, int64_t n) {
 int symbolic_build(mhd_operator* op);
 // assembly.cu
 int pack_tables(mhd_operator* op, const mhd_tables_t* t);
-int launch_jacobian(mhd_operator* op, const double* d_x);
+int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // krylov.cu
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);

@@ -11,6 +11,9 @@
 //                                                      (the reference uses LU/MUMPS there, badia2024.jl:22).
 // Orthogonalisation is classical Gram-Schmidt with one re-orthogonalisation pass (2 fused multi-dots per step
 // instead of the j+1 dependent dots of the reference's modified Gram-Schmidt: SURVEY.md 5.8).
+#include <cusolverDn.h>
+#include <dlfcn.h>
+
 #include <functional>
 
 #include "common.h"
@@ -214,6 +217,65 @@ struct Fgmres {
 
 using namespace mhd;
 
+// ---- cuSOLVER (dense LU of the (u,j) block), bound lazily like NCCL so the library has no link-time dependency
+namespace mhd {
+struct CusolverApi {
+  void* lib = nullptr;
+  cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*DgetrfBufferSize)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*Dgetrf)(cusolverDnHandle_t, int, int, double*, int, double*, int*, int*) = nullptr;
+  cusolverStatus_t (*Dgetrs)(cusolverDnHandle_t, cublasOperation_t, int, int, const double*, int, const int*, double*, int, int*) = nullptr;
+};
+static CusolverApi g_cs;
+static int load_cusolver() {
+  if (g_cs.lib) return 0;
+  const char* names[] = {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"};
+  void* lib = nullptr;
+  for (const char* n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  MHD_CHECK(lib != nullptr, MHD_E_INVALID, "cannot dlopen libcusolver.so.11 (needed for MHD_UJ_DENSE_LU): %s", dlerror());
+#define SYM(field, name)                                                              \
+  do {                                                                                \
+    *(void**)(&g_cs.field) = dlsym(lib, name);                                        \
+    MHD_CHECK(g_cs.field != nullptr, MHD_E_INVALID, "libcusolver lacks symbol %s", name); \
+  } while (0)
+  SYM(Create, "cusolverDnCreate");
+  SYM(Destroy, "cusolverDnDestroy");
+  SYM(SetStream, "cusolverDnSetStream");
+  SYM(DgetrfBufferSize, "cusolverDnDgetrf_bufferSize");
+  SYM(Dgetrf, "cusolverDnDgetrf");
+  SYM(Dgetrs, "cusolverDnDgetrs");
+#undef SYM
+  g_cs.lib = lib;
+  return 0;
+}
+#define MHD_CUSOLVER(call)                                             \
+  do {                                                                 \
+    cusolverStatus_t _s = (call);                                      \
+    if (_s != CUSOLVER_STATUS_SUCCESS) {                               \
+      set_error("cuSOLVER error %d in %s", (int)_s, #call);            \
+      return MHD_E_CUDA;                                               \
+    }                                                                  \
+  } while (0)
+
+// dense column-major copy of the leading n x n block of the CSR matrix
+__global__ void __launch_bounds__(256)
+k_csr_block_to_dense(int64_t n, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                     const double* __restrict__ nzval, double* __restrict__ D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  for (int64_t p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) {
+    const int32_t c = colval[p];
+    if (c < n) D[(int64_t)c * n + row] = nzval[p];
+  }
+}
+}  // namespace mhd
+
 struct mhd_solver {
   mhd_operator* op = nullptr;
   mhd_solver_opts_t opts;
@@ -224,6 +286,13 @@ struct mhd_solver {
   double *d_b = nullptr, *d_x = nullptr, *d_t1 = nullptr, *d_t2 = nullptr, *d_t3 = nullptr;
   int64_t n_uj = 0;
   bool setup_done = false;
+  // dense LU of the (u,j) block
+  cusolverDnHandle_t cs = nullptr;
+  double* d_dense = nullptr;
+  double* d_lu_work = nullptr;
+  int* d_ipiv = nullptr;
+  int* d_info = nullptr;
+  int lu_lwork = 0;
 };
 
 namespace mhd {
@@ -358,6 +427,8 @@ int mhd_solver_default_opts(mhd_solver_opts_t* o) {
   o->uj_inner_restart = 30;
   o->alpha_p = -1.0;     // -1/(beta+zeta_u); the host overrides with the actual fluid parameters
   o->alpha_phi = -1.0;   // -1/(1+zeta_j)
+  o->uj_solver = MHD_UJ_GMRES_JACOBI;
+  o->reserved = 0;
   return MHD_OK;
 }
 
@@ -375,6 +446,14 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
     MHD_CHECK(opts->alpha_p != 0.0 && opts->alpha_phi != 0.0, MHD_E_INVALID, "alpha_p/alpha_phi must be nonzero");
     MHD_CHECK(opts->uj_inner_its >= 1 && opts->uj_inner_restart >= 1 && opts->uj_inner_restart <= MAXM, MHD_E_INVALID,
               "bad inner iteration counts");
+    MHD_CHECK(opts->uj_solver == MHD_UJ_GMRES_JACOBI || opts->uj_solver == MHD_UJ_DENSE_LU, MHD_E_INVALID, "unknown uj_solver");
+    if (opts->uj_solver == MHD_UJ_DENSE_LU) {
+      MHD_CHECK(g_nranks == 1, MHD_E_INVALID, "MHD_UJ_DENSE_LU is a single-GPU option (the (u,j) block is distributed)");
+      MHD_CHECK(op->nowned[MHD_FIELD_U] + op->nowned[MHD_FIELD_J] <= 24576, MHD_E_CAPACITY,
+                "MHD_UJ_DENSE_LU: (u,j) block of %lld rows exceeds the dense limit 24576",
+                (long long)(op->nowned[MHD_FIELD_U] + op->nowned[MHD_FIELD_J]));
+      MHD_TRY(load_cusolver());
+    }
   }
   mhd_solver* s = new mhd_solver();
   s->op = op;
@@ -399,6 +478,16 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
   if (opts->precond == MHD_PC_BLOCK_TRI) {
     const int mi = opts->uj_inner_restart < opts->uj_inner_its ? opts->uj_inner_restart : opts->uj_inner_its;
     CR(s->inner.init(op, s->n_uj, op->ncols, mi, false));
+    if (opts->uj_solver == MHD_UJ_DENSE_LU) {
+      CR(dev_alloc(&s->d_dense, s->n_uj * s->n_uj));
+      CR(dev_alloc(&s->d_ipiv, s->n_uj));
+      CR(dev_alloc(&s->d_info, 1));
+      if (!rc && g_cs.Create(&s->cs) != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed"); rc = MHD_E_CUDA; }
+      if (!rc && g_cs.DgetrfBufferSize(s->cs, (int)s->n_uj, (int)s->n_uj, s->d_dense, (int)s->n_uj, &s->lu_lwork) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnDgetrf_bufferSize failed"); rc = MHD_E_CUDA;
+      }
+      CR(dev_alloc(&s->d_lu_work, s->lu_lwork));
+    }
     CR(dev_alloc(&s->d_minv_p, op->ncells * 16));
     CR(dev_alloc(&s->d_minv_f, op->ncells * 64));
     if (!rc) {
@@ -424,6 +513,8 @@ int mhd_solver_destroy(mhd_solver_t* s) {
   cudaStreamSynchronize(g_stream);
   s->outer.release();
   s->inner.release();
+  if (s->cs) g_cs.Destroy(s->cs);
+  cudaFree(s->d_dense); cudaFree(s->d_lu_work); cudaFree(s->d_ipiv); cudaFree(s->d_info);
   cudaFree(s->d_dinv); cudaFree(s->d_minv_p); cudaFree(s->d_minv_f);
   cudaFree(s->d_b); cudaFree(s->d_x); cudaFree(s->d_t1); cudaFree(s->d_t2); cudaFree(s->d_t3);
   delete s;
@@ -437,6 +528,18 @@ int mhd_solver_setup(mhd_solver_t* s) {
   mhd_operator* op = s->op;
   k_extract_dinv<<<vgrid(op->nrows), 256, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, s->d_dinv);
   MHD_LAUNCH_CHECK();
+  if (s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_DENSE_LU) {
+    const int64_t n = s->n_uj;
+    MHD_CUDA(cudaMemsetAsync(s->d_dense, 0, (size_t)n * n * 8, g_stream));
+    k_csr_block_to_dense<<<(unsigned)((n + 7) / 8), 256, 0, g_stream>>>(n, op->d_rowptr, op->d_colval, op->d_nzval, s->d_dense);
+    MHD_LAUNCH_CHECK();
+    MHD_CUSOLVER(g_cs.SetStream(s->cs, g_stream));
+    MHD_CUSOLVER(g_cs.Dgetrf(s->cs, (int)n, (int)n, s->d_dense, (int)n, s->d_lu_work, s->d_ipiv, s->d_info));
+    int info = 0;
+    MHD_TRY(d2h(&info, s->d_info, 1));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    MHD_CHECK(info == 0, MHD_E_INVALID, "dense LU of the (u,j) block failed: getrf info = %d", info);
+  }
   s->setup_done = true;
   return MHD_OK;
 }
@@ -495,6 +598,13 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
       MHD_TRY(spmv_rows(op, nuj, z, s->d_t1));
       k_sub<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, v, s->d_t1, s->d_t2);
       MHD_LAUNCH_CHECK();
+      if (oo.uj_solver == MHD_UJ_DENSE_LU) {
+        // exact solve with the LU factors (in place on the right-hand side)
+        MHD_CUSOLVER(g_cs.SetStream(s->cs, g_stream));
+        MHD_CUSOLVER(g_cs.Dgetrs(s->cs, CUBLAS_OP_N, (int)nuj, 1, s->d_dense, (int)nuj, s->d_ipiv, s->d_t2, (int)nuj, s->d_info));
+        MHD_CUDA(cudaMemcpyAsync(z, s->d_t2, (size_t)nuj * 8, cudaMemcpyDeviceToDevice, g_stream));
+        return 0;
+      }
       // inner GMRES on A_uj with Jacobi (zero initial guess); d_t3 = solution with zero p/phi/ghost entries
       MHD_CUDA(cudaMemsetAsync(s->d_t3, 0, (size_t)op->ncols * 8, g_stream));
       int done_its = 0;

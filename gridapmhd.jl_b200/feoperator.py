@@ -183,6 +183,13 @@ class B200FEOperator:
     def jacobian(self, x) -> B200Matrix:
         return self.jacobian_b(self.allocate_jacobian(), x)
 
+    def residual_and_jacobian_b(self, b, A: B200Matrix, x):
+        """residual_and_jacobian!(b,A,op,x): fused kernel (the per-cell geometry/basis preparation is shared)."""
+        assert A is self._A
+        xx = x if _is_torch(x) else _as_f64(x)
+        L.check(L.load().mhd_residual_and_jacobian(self.handle, L.ptr(xx), L.ptr(b)))
+        return b, A
+
     def residual_b(self, b, x):
         """residual!(b,op,x)"""
         xx = x if _is_torch(x) else _as_f64(x)
@@ -248,6 +255,7 @@ class B200SolverOptions:
     precond: str = "block_tri"
     uj_inner_its: int = 30
     uj_inner_restart: int = 30
+    uj_solver: str = "gmres_jacobi"  # or "dense_lu": exact (u,j)-block solve on the device, small problems only
 
 
 class B200LinearSolver:
@@ -279,6 +287,7 @@ class B200NumericalSetup:
         c.m, c.maxiter, c.rtol, c.atol = o.m, o.maxiter, o.rtol, o.atol
         c.precond = L.PRECOND[o.precond]
         c.uj_inner_its, c.uj_inner_restart = o.uj_inner_its, o.uj_inner_restart
+        c.uj_solver = L.UJ_SOLVER[o.uj_solver]
         c.alpha_p = -1.0 / (fl.beta + fl.zeta_u)  # badia2024.jl:11
         c.alpha_phi = -1.0 / (1.0 + fl.zeta_j)  # badia2024.jl:12
         h = C.c_void_p()
@@ -329,19 +338,19 @@ class NewtonSolver:
 
     def solve_b(self, x: np.ndarray, op: B200FEOperator):
         A = op.allocate_jacobian()
-        b = op.residual(x)
+        b = np.empty(op.nrows)
+        op.residual_and_jacobian_b(b, A, x)
         r0 = float(np.linalg.norm(b))
         self.log = [r0]
         ns = None
         for it in range(self.maxiter):
             if r0 == 0.0:
                 break
-            op.jacobian_b(A, x)
             ns = self.ls.symbolic_setup(A).numerical_setup() if ns is None else ns.numerical_setup_b(A)
             dx = np.zeros(op.nrows)
             ns.solve_b(dx, -b)
             x += dx
-            b = op.residual(x)
+            op.residual_and_jacobian_b(b, A, x)
             rn = float(np.linalg.norm(b))
             self.log.append(rn)
             if self.verbose:

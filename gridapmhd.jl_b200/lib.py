@@ -16,6 +16,7 @@ ERRORS = {-1: "MHD_E_INVALID", -2: "MHD_E_CUDA", -3: "MHD_E_STATE", -4: "MHD_E_C
 FIELD_IDS = {"u": 0, "p": 1, "j": 2, "phi": 3}
 CONVECTION = {"none": 0, "picard": 1, "newton": 2}
 PRECOND = {"none": 0, "jacobi": 1, "block_tri": 2}
+UJ_SOLVER = {"gmres_jacobi": 0, "dense_lu": 1}
 
 
 class MhdError(RuntimeError):
@@ -50,7 +51,7 @@ class mhd_params_t(C.Structure):
 class mhd_solver_opts_t(C.Structure):
     _fields_ = [("m", C.c_int32), ("maxiter", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("precond", C.c_int32), ("uj_inner_its", C.c_int32), ("uj_inner_restart", C.c_int32),
-                ("alpha_p", C.c_double), ("alpha_phi", C.c_double)]
+                ("alpha_p", C.c_double), ("alpha_phi", C.c_double), ("uj_solver", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every exported symbol of include/mhdb200.h with its signature (tests check the .so exports all of them)
@@ -74,6 +75,7 @@ SIGNATURES = {
     "mhd_operator_get_scatter_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mhd_jacobian": (C.c_int, [_P, _P, _P]),
     "mhd_residual": (C.c_int, [_P, _P, _P]),
+    "mhd_residual_and_jacobian": (C.c_int, [_P, _P, _P]),
     "mhd_get_nzval": (C.c_int, [_P, _P]),
     "mhd_set_nzval": (C.c_int, [_P, _P]),
     "mhd_spmv": (C.c_int, [_P, _P, _P]),

@@ -88,6 +88,10 @@ typedef struct {
 
 /* FGMRES + preconditioner options (src/Solvers/badia2024.jl:32-45, src/parameters.jl:259-271). */
 enum { MHD_PC_NONE = 0, MHD_PC_JACOBI = 1, MHD_PC_BLOCK_TRI = 2 };
+/* (u,j)-block solver of the block-triangular preconditioner: inner Jacobi-GMRES (any size, any rank count) or an
+ * exact dense LU on the device (cuSOLVER getrf/getrs; single GPU, n_uj <= 24576) -- the device stand-in for the
+ * reference's direct block solver on small problems. */
+enum { MHD_UJ_GMRES_JACOBI = 0, MHD_UJ_DENSE_LU = 1 };
 typedef struct {
   int32_t m;            /* restart length (niter_ls, default 15) */
   int32_t maxiter;      /* total Krylov iterations (reference: == m) */
@@ -96,6 +100,8 @@ typedef struct {
   int32_t uj_inner_its; /* MHD_PC_BLOCK_TRI: inner GMRES iterations on the (u,j) block */
   int32_t uj_inner_restart;
   double alpha_p, alpha_phi; /* scalings of the p / phi mass blocks (badia2024.jl:11-12) */
+  int32_t uj_solver;    /* MHD_UJ_*: how block_solvers[1] (LU/MUMPS in the reference, badia2024.jl:22) is realised */
+  int32_t reserved;
 } mhd_solver_opts_t;
 
 /* ---- library lifetime (GridapPETSc.with(args=...) do ... end; src/Applications/hunt.jl:202-206) ---- */
@@ -136,6 +142,8 @@ int mhd_operator_get_scatter_stats(mhd_operator_t*, int64_t* nentries, int64_t* 
  * x: [n local] free values.  nzval_out: [nnz] or NULL (values stay on the device behind the handle). */
 int mhd_jacobian(mhd_operator_t*, const double* x, double* nzval_out);
 int mhd_residual(mhd_operator_t*, const double* x, double* r_out);
+/* residual_and_jacobian!(b,A,op,x) (Gridap NonlinearOperator API): one fused kernel, the cell preparation is shared */
+int mhd_residual_and_jacobian(mhd_operator_t*, const double* x, double* r_out);
 int mhd_get_nzval(mhd_operator_t*, double* nzval_out);          /* D2H (or D2D) copy of the current values */
 int mhd_set_nzval(mhd_operator_t*, const double* nzval);        /* tests: load values assembled elsewhere */
 

@@ -342,7 +342,7 @@ def fgmres(A, b, x0=None, M=None, m=15, maxiter=15, rtol=1e-7, atol=1e-8):
     return x, it, np.array(hist)
 
 
-def newton_lu(fes, prm: FluidParams, x0=None, maxiter=10, rtol=1e-6, verbose=False):
+def newton_lu(fes, prm: FluidParams, x0=None, maxiter=10, rtol=1e-6, verbose=False, min_iters=1):
     """`_solver(::Val{:julia})` (src/main.jl:181-186): Newton with sparse LU, rtol 1e-6 on the residual norm."""
     x = np.zeros(fes.ndofs) if x0 is None else x0.copy()
     b = residual(fes, x, prm)
@@ -357,7 +357,7 @@ def newton_lu(fes, prm: FluidParams, x0=None, maxiter=10, rtol=1e-6, verbose=Fal
         hist.append(rn)
         if verbose:
             print(f"  newton it {it+1}: |r| = {rn:.3e} (rel {rn/r0:.3e})")
-        if rn <= rtol * r0 or rn < 1e-14:
+        if (rn <= rtol * r0 or rn < 1e-14) and it + 1 >= min_iters:  # extra iterations = iterative refinement
             break
     return x, hist
 
