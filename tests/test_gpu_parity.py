@@ -297,3 +297,20 @@ def test_fgmres_jacobi_inner_solver_reduces_residual(mhdlib):
         ns.solve_b(np.zeros(op.nrows), -b, raise_on_maxiter=True)
     ns.destroy()
     op.destroy()
+
+
+def test_multigpu_parity_when_two_gpus_are_visible(mhdlib):
+    """Spawns tests/multigpu_check.py under torchrun with 2 ranks (skipped on a single-GPU box; `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29511", os.path.join(here, "multigpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "MULTIGPU_OK 2" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
