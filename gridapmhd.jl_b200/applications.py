@@ -14,7 +14,7 @@ import numpy as np
 
 from .feoperator import B200FEOperator, B200LinearSolver, B200SolverOptions, FluidParams, NewtonSolver
 from .host.fespaces import FESpaces, setup_fe_spaces
-from .host.mesh import HexMesh, hunt_generate_base_mesh
+from .host.mesh import HexMesh, expansion_generate_mesh, hunt_generate_base_mesh
 
 
 def hunt_reduced_quantities(nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.0, 0.0, 1.0), L=1.0, u0=1.0,
@@ -51,6 +51,44 @@ def hunt_params(nc=(4, 4), nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.
                              f=fbar, convection=convection),
         "bcs": {"u": {"tags": ("noslip",) + (("zwalls",) if not periodic_z else ()), "values": None},
                 "j": {"tags": ("insulating",)}},
+        "solver": solver,
+        "info": {"Re": Re, "Ha": Ha, "N": N, "ncells": mesh.ncells},
+    }
+
+
+def u_inlet_parabolic(Z=4.0, b=0.2):
+    """`u_inlet(:parabolic,...)` (expansion.jl:385): 36 Z (y-1/Z)(y+1/Z)(z-bZ)(z+bZ) e_x."""
+
+    def fn(X):
+        y, z = X[:, 1], X[:, 2]
+        u = np.zeros_like(X)
+        u[:, 0] = 36.0 * Z * (y - 1.0 / Z) * (y + 1.0 / Z) * (z - b * Z) * (z + b * Z)
+        return u
+
+    return fn
+
+
+def expansion_params(level=1, Ha=1.0, N=1.0, zeta_u=0.0, zeta_j=0.0, formulation="mhd", convection="newton", Z=4.0, b=0.2,
+                     solver="julia", perturb=0.0, mesh=None):
+    """params Dict of `_expansion` (src/Applications/expansion.jl:40-181) for `solid_coupling=:none`,
+    `inlet=:parabolic`: :mhd scaling alpha=1/N, beta=1/Ha^2, gamma=1 (:112-123), B=(0,1,0), f=0 (:133-143), u Dirichlet on
+    ["inlet","wall"] = [u_in, 0] (:150-153), j.n = 0 on ["wall","inlet","outlet"] (:156-159).  The mesh is the p4est
+    base mesh of expansion_mesher.jl refined `level` times (stand-in for the missing Expansion_68k/749k.msh) unless a
+    `HexMesh` (e.g. from `read_gmsh41`) is passed."""
+    Re = Ha**2 / N
+    if formulation == "cfd":
+        alpha, beta, gamma = 1.0, 1.0 / Re, N
+    elif formulation == "mhd":
+        alpha, beta, gamma = 1.0 / N, 1.0 / Ha**2, 1.0
+    else:
+        raise ValueError("Unknown formulation")
+    mesh = mesh if mesh is not None else expansion_generate_mesh(level, perturb=perturb)
+    return {
+        "model": mesh,
+        "fluid": FluidParams(alpha=alpha, beta=beta, gamma=gamma, sigma=1.0, zeta_u=zeta_u, zeta_j=zeta_j, B=(0.0, 1.0, 0.0),
+                             f=(0.0, 0.0, 0.0), convection=convection),
+        "bcs": {"u": {"tags": ("inlet", "wall"), "values": (u_inlet_parabolic(Z, b), None)},
+                "j": {"tags": ("wall", "inlet", "outlet")}},
         "solver": solver,
         "info": {"Re": Re, "Ha": Ha, "N": N, "ncells": mesh.ncells},
     }

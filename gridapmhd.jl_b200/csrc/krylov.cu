@@ -1,6 +1,8 @@
 // Krylov building blocks on the device: CSR SpMV, dot, axpy and the fused Gram-Schmidt kernels of FGMRES.
 // Stand behind mul!(y,A,x) / dot / axpy-style broadcasts that GridapSolvers' FGMRES issues on PVector /
 // PSparseMatrix (configured at src/Solvers/badia2024.jl:36-40); all HBM-bandwidth bound.
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace mhd {
@@ -27,6 +29,7 @@ int ensure_red(mhd_operator* op, int64_t n) {
 // x gathered through the read-only path (x is tiny next to A and stays L2 resident).
 constexpr int SPMV_WARPS = 8;
 
+template <int U>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 spmv_warp_row(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
               const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y) {
@@ -35,30 +38,53 @@ spmv_warp_row(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* 
   const int64_t nwarps = (int64_t)gridDim.x * SPMV_WARPS;
   for (int64_t row = warp0; row < nrows; row += nwarps) {
     const int64_t lo = rowptr[row], hi = rowptr[row + 1];
-    double s0 = 0.0, s1 = 0.0;
-    int64_t p = lo + lane;
-    for (; p + 32 < hi; p += 64) {
-      const int32_t c0 = __ldg(colval + p), c1 = __ldg(colval + p + 32);
-      const double v0 = __ldg(nzval + p), v1 = __ldg(nzval + p + 32);
-      s0 = fma(v0, __ldg(x + c0), s0);
-      s1 = fma(v1, __ldg(x + c1), s1);
-    }
-    if (p < hi) s0 = fma(__ldg(nzval + p), __ldg(x + __ldg(colval + p)), s0);
-    double s = s0 + s1;
+    double s[U];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[row] = s;
+    for (int u = 0; u < U; u++) s[u] = 0.0;
+    int64_t p = lo + lane;
+    // U x 32 entries in flight per warp: all (col,val) loads are issued before the dependent x gathers
+    for (; p + 32 * (U - 1) < hi; p += 32 * U) {
+      int32_t c[U];
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        c[u] = __ldg(colval + p + 32 * u);
+        v[u] = __ldg(nzval + p + 32 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) s[u] = fma(v[u], __ldg(x + c[u]), s[u]);
+    }
+    for (; p < hi; p += 32) s[0] = fma(__ldg(nzval + p), __ldg(x + __ldg(colval + p)), s[0]);
+    double t = s[0];
+#pragma unroll
+    for (int u = 1; u < U; u++) t += s[u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) y[row] = t;
   }
 }
 
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y) {
   if (op->nrows == 0) return 0;
+  static int unroll = 0, ctas_per_sm = 0;
+  if (!unroll) {
+    const char* e = getenv("MHD_SPMV_UNROLL");
+    unroll = e ? atoi(e) : 4;
+    const char* g = getenv("MHD_SPMV_CTAS_PER_SM");
+    ctas_per_sm = g ? atoi(g) : 8;
+  }
   int64_t blocks = (op->nrows + SPMV_WARPS - 1) / SPMV_WARPS;
-  const int64_t cap = (int64_t)sms() * 8 * 4;
+  const int64_t cap = (int64_t)sms() * ctas_per_sm * 4;
   if (blocks > cap) blocks = cap;
   prof_begin(PROF_SPMV);
-  spmv_warp_row<<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval,
-                                                                     d_x, d_y);
+  if (unroll == 1)
+    spmv_warp_row<1><<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, d_x, d_y);
+  else if (unroll == 2)
+    spmv_warp_row<2><<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, d_x, d_y);
+  else if (unroll == 8)
+    spmv_warp_row<8><<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, d_x, d_y);
+  else
+    spmv_warp_row<4><<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, d_x, d_y);
   prof_end(PROF_SPMV);
   MHD_LAUNCH_CHECK();
   return 0;

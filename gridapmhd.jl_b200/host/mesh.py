@@ -223,6 +223,59 @@ def hunt_generate_base_mesh(nc, L=1.0, tw=0.0, Ha=10.0, kmap_x=1, kmap_y=1, BL_a
 
 
 # ----------------------------------------------------------------------------
+# Expansion (sudden expansion duct), src/Meshers/expansion_mesher.jl
+
+
+def expansion_generate_mesh(level: int = 0, perturb: float = 0.0, seed: int = 0) -> HexMesh:
+    """The 12-hex base mesh of `expansion_generate_base_mesh` (expansion_mesher.jl:92-118: 4 blocks refined (1,3,1),
+    mapped by `coordinate_transformation` :3-13) after `level` uniform refinements (what p4est produces there).
+
+    In physical coordinates the base mesh is the T-shaped union of boxes with X-grid {-8,-16/3,-8/3,0,8/3,16/3,8},
+    Y-grid {-1,-1/4,1/4,1} (the cubic y_stretch maps 0,1,2,3 to these), Z in [-1,1]; for X<0 only the inlet channel
+    |Y|<=1/4 exists.  Tags: `inlet` (X=-8), `outlet` (X=8), `wall` (rest of the boundary), cell tag `fluid`.
+    `perturb` > 0 moves interior vertices randomly by that fraction of the local cell size: general (non-affine)
+    trilinear hexes like the sheared cells of meshes/Expansion_710.msh."""
+    k = 2**level
+    nx, ny, nz = 6 * k, 3 * k, k
+    xs = np.linspace(-8.0, 8.0, nx + 1)
+    yb = np.array([-1.0, -0.25, 0.25, 1.0])
+    ys = np.concatenate([np.linspace(yb[i], yb[i + 1], k + 1)[:-1] for i in range(3)] + [[1.0]])
+    zs = np.linspace(-1.0, 1.0, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    coords = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def nid(i, j, l):
+        return i + (nx + 1) * (j + (ny + 1) * l)
+
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    keep = (I >= nx // 2) | ((J >= k) & (J < 2 * k))
+    I, J, K = I[keep], J[keep], K[keep]
+    cn = np.stack([nid(I + di, J + dj, K + dk) for dk in (0, 1) for dj in (0, 1) for di in (0, 1)], axis=1)
+    used, inv = np.unique(cn, return_inverse=True)
+    cn = inv.reshape(cn.shape)
+    coords = coords[used]
+    mesh = HexMesh(coords=coords, cell_nodes=cn, cell_verts=cn.copy())
+    build_topology(mesh)
+    _, fv = entity_vertices(mesh)
+    fx = coords[fv][:, :, 0]
+    bnd = mesh.face_ncells == 1
+    inlet = bnd & np.all(np.abs(fx + 8.0) < 1e-12, axis=1)
+    outlet = bnd & np.all(np.abs(fx - 8.0) < 1e-12, axis=1)
+    tag_from_boundary_faces(mesh, "inlet", inlet)
+    tag_from_boundary_faces(mesh, "outlet", outlet)
+    tag_from_boundary_faces(mesh, "wall", bnd & ~inlet & ~outlet)
+    tag_from_boundary_faces(mesh, "boundary", bnd)
+    mesh.cell_tags["fluid"] = np.ones(mesh.ncells, dtype=bool)
+    if perturb > 0.0:
+        interior = ~mesh.vertex_tags["boundary"]
+        h = np.array([16.0 / nx, 0.5 / k, 2.0 / nz])
+        rng = np.random.default_rng(seed)
+        mesh.coords = coords + interior[:, None] * (rng.random(coords.shape) - 0.5) * 2.0 * perturb * h
+    return mesh
+
+
+# ----------------------------------------------------------------------------
 # Gmsh 4.1 ASCII reader (hex8 + quad4 physical groups), Expansion meshes
 
 # gmsh hex8 node order (0,0,0),(1,0,0),(1,1,0),(0,1,0),(0,0,1),(1,0,1),(1,1,1),(0,1,1) -> lexicographic

@@ -314,3 +314,52 @@ def test_multigpu_parity_when_two_gpus_are_visible(mhdlib):
                           "127.0.0.1", "--master-port", "29511", os.path.join(here, "multigpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_OK 2" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_expansion_nonaffine_mesh_values(mhdlib):
+    """Expansion configuration (BASELINE configs 3/4 stand-in): p4est base mesh of expansion_mesher.jl refined once,
+    interior vertices perturbed -> general trilinear (non-affine) hexes, inhomogeneous inlet Dirichlet data,
+    j.n = 0 on the whole boundary, Newton convection."""
+    from gridapmhd_jl_b200.applications import expansion_params
+    from oracle import mhd_oracle as O
+
+    params = expansion_params(level=1, Ha=10.0, N=5.0, perturb=0.2, zeta_u=3.0, zeta_j=2.0)
+    fes = setup_spaces(params)
+    assert fes.mesh.ncells == 96 and np.abs(fes.dirichlet_values["u"]).max() > 1.0
+    op = B200FEOperator(fes, params["fluid"])
+    x = np.random.default_rng(5).random(fes.ndofs)
+    A = op.allocate_jacobian()
+    b = np.empty(op.nrows)
+    op.residual_and_jacobian_b(b, A, x)
+    Ao = O.jacobian(fes, x, oracle_params(params["fluid"]))
+    rowptr, colval = A.pattern()
+    assert np.array_equal(rowptr, Ao.indptr) and np.array_equal(colval, Ao.indices)
+    assert relerr(A.nzval(), Ao.data) < VAL_TOL
+    assert relerr(b, O.residual(fes, x, oracle_params(params["fluid"]))) < VAL_TOL
+    assert relerr(op.residual(x), b) < 1e-14
+    op.destroy()
+
+
+def test_expansion_newton_solve_matches_oracle(mhdlib):
+    """Full Newton solve of the (nonlinear, convection :newton) Expansion problem on the device against the oracle's
+    Newton + sparse LU on the same discrete problem: u, j within 1e-10; phi up to its constant null mode
+    (j.n = 0 on all of the boundary, no phi constraint: SURVEY.md Appendix G)."""
+    from gridapmhd_jl_b200.applications import expansion_params
+    from gridapmhd_jl_b200.feoperator import B200LinearSolver, B200SolverOptions, NewtonSolver
+    from oracle import mhd_oracle as O
+
+    params = expansion_params(level=1, Ha=10.0, N=5.0, perturb=0.15, zeta_u=20.0, zeta_j=20.0, solver="badia2024")
+    fes = setup_spaces(params)
+    op = B200FEOperator(fes, params["fluid"])
+    opts = B200SolverOptions(m=40, maxiter=40, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
+    nls = NewtonSolver(B200LinearSolver(opts), maxiter=12, rtol=1e-15)
+    x = nls.solve_b(np.zeros(fes.ndofs), op)
+    assert len(nls.log) >= 5 and nls.log[-1] < 1e-11 * nls.log[0], nls.log  # genuinely nonlinear: several Newton steps
+    xo, _ = O.newton_lu(fes, oracle_params(params["fluid"]), maxiter=12, rtol=1e-15, min_iters=8)
+    s, so = fes.split(x), fes.split(xo)
+    assert relerr(s["u"], so["u"]) < SOL_TOL
+    assert relerr(s["j"], so["j"]) < SOL_TOL
+    assert relerr(s["p"], so["p"]) < 1e-7
+    df = s["phi"] - so["phi"]
+    assert np.abs(df - df.mean()).max() < 1e-7 * max(1.0, np.abs(so["phi"]).max())
+    op.destroy()
