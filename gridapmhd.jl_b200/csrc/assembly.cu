@@ -168,6 +168,78 @@ __device__ __forceinline__ void scatter_generic(double* __restrict__ nz, int cou
 }
 
 // ---------------------------------------------------------------------------------------------
+// FP64 tensor-core path: mma.sync.m8n8k4 (DMMA).  Same peak rate as the FP64 FMA pipe on B200, but an 8x8x4 product
+// costs one operand word per lane and operand fragments are shared by all tiles of a warp's output block, which
+// halves the shared-memory wavefronts of the panel products (the kernel is L1TEX-bound, not FP64- or HBM-bound).
+#ifndef MHD_NO_MMA
+constexpr bool USE_MMA = true;
+#else
+constexpr bool USE_MMA = false;
+#endif
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// One warp computes the (8 MT) x (8 NTL) output block at (m0, n0) of  C = sum_k A[k][m] * sc[k] * B[k][n]
+// (panels k-major in shared memory).  Fragment loads are bank-conflict free for leading dimensions = 4 or 12 mod 16
+// (28, 36, 108, 4).  Rows/columns beyond M/N read neighbouring panel data and are discarded; k >= K contributes 0.
+template <int MT, int NTL, bool SCALE>
+__device__ __forceinline__ void warp_mma_acc(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                             int K, const double* __restrict__ sc, int scs, int m0, int n0,
+                                             double (&acc)[MT][NTL][2]) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+#pragma unroll
+  for (int i = 0; i < MT; i++)
+#pragma unroll
+    for (int j = 0; j < NTL; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const double* ap = A + m0 + lr;
+  const double* bp = B + n0 + lr;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const int kk = k0 + lk;
+    const bool valid = kk < K;
+    const int kc = valid ? kk : 0;
+    double a[MT], b[NTL];
+    const double s = SCALE ? sc[kc * scs] : 1.0;
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+      const double v = ap[kc * lda + 8 * i];
+      a[i] = valid ? v : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NTL; j++) {
+      const double v = bp[kc * ldb + 8 * j];
+      b[j] = valid ? (SCALE ? v * s : v) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+      for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+template <int MT, int NTL, bool SCALE, class Store>
+__device__ __forceinline__ void warp_mma_product(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                                 int K, const double* __restrict__ sc, int scs, int m0, int n0, int M, int N,
+                                                 Store store) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+  double acc[MT][NTL][2];
+  warp_mma_acc<MT, NTL, SCALE>(A, lda, B, ldb, K, sc, scs, m0, n0, acc);
+#pragma unroll
+  for (int i = 0; i < MT; i++)
+#pragma unroll
+    for (int j = 0; j < NTL; j++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int m = m0 + 8 * i + lr, n = n0 + 8 * j + 2 * lk + r;
+        if (m < M && n < N) store(m, n, acc[i][j][r]);
+      }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct CellCtx {
   double* sm;
   long long* row;  // [129] nnz offset of each local row (-1: dropped)
@@ -338,6 +410,41 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     __syncthreads();
 
     // ---------------- phase 0: D (up), j-phi, jj, S, C (+ pressure mass matrix), all independent panel products
+    if (USE_MMA) {
+      // 12 warp jobs, heaviest first, dealt round-robin to the 8 warps
+      const int warp = tid >> 5;
+      const bool zj = P.zeta_j != 0.0;
+      for (int job = warp; job < 12; job += 8) {
+        if (job < 2) {
+          // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b], two column halves
+          warp_mma_product<4, 2, false>(sm + S_G, LDN, sm + S_G, LDN, 81, nullptr, 0, 0, 16 * job, 27, 27,
+                                        [&](int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
+        } else if (job < 7) {
+          // jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous), one 8-column strip each
+          const int n0 = 8 * (job - 2);
+          if (zj)
+            warp_mma_product<5, 1, true>(sm + S_PSI, NJ, sm + S_PSI, NJ, 108, sm + S_SC, 1, 0, n0, NJ, NJ,
+                                         [&](int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
+          else
+            warp_mma_product<5, 1, false>(sm + S_PSI, NJ, sm + S_PSI, NJ, 81, nullptr, 0, 0, n0, NJ, NJ,
+                                          [&](int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
+        } else if (job == 7) {
+          // C[a][b] = sum_q N[q][a] UG[q][b]
+          if (CONV > 0)
+            warp_mma_product<4, 4, false>(sm + S_N, LDN, sm + S_UG, LDN, NQ, nullptr, 0, 0, 0, 27, 27,
+                                          [&](int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
+        } else if (job == 8) {
+          // JF[m][l] = sum_q Div[q][m] Chi[q][l]
+          warp_mma_product<5, 1, false>(sm + S_DIV, NJ, sm + S_CHI, 8, NQ, nullptr, 0, 0, 0, NJ, NF,
+                                        [&](int m, int l, double v) { St[ST_JF + m * 8 + l] = v; });
+        } else {
+          // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]
+          const int c = job - 9;
+          warp_mma_product<4, 1, false>(sm + S_G + c * LDN, 3 * LDN, sm + S_PP, 4, NQ, nullptr, 0, 0, 0, 27, NP,
+                                        [&](int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
+        }
+      }
+    } else {
     // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]   (batch = c)
     panel_product<27, 4, 4, 4, false>(3, sm + S_G, 3 * LDN, LDN, sm + S_PP, 4, 0, NQ, nullptr, 0, 0, 0,
                                       [&](int c, int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
@@ -351,13 +458,14 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     else
       panel_product<36, 36, 2, 4, false>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 81, nullptr, 0, 0, 39,
                                          [&](int, int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
-    if (CONV < 2) {
+    {
       // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b] ; C[a][b] = sum_q N[q][a] UG[q][b]
       panel_product<27, 27, 2, 4, false>(1, sm + S_G, LDN, 0, sm + S_G, LDN, 0, 81, nullptr, 0, 0, 39 + 162,
                                          [&](int, int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
       if (CONV > 0)
         panel_product<27, 27, 4, 4, false>(1, sm + S_N, LDN, 0, sm + S_UG, LDN, 0, NQ, nullptr, 0, 0, 39 + 162 + 98,
                                            [&](int, int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
+    }
     }
     if (ZU && tid >= NT - 16) {
       const int kl = tid - (NT - 16), k = kl >> 2, l = kl & 3;
@@ -401,7 +509,49 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     const long long* row = cx.row;
 
     // ---------------- uu
-    if (CONV == 2) {
+    if (CONV == 2 && USE_MMA) {
+      // Newton: K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term].
+      // 18 warp jobs = 9 component pairs x 2 column halves of the product N'^T diag(T_dc) N'; the accumulators are
+      // scattered straight from registers (16 map codes loaded first), S and C come from the staging buffer.
+      const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+      for (int job = warp; job < 18; job += 8) {
+        const int dc = job >> 1, half = job & 1, d = dc / 3, c = dc - d * 3;
+        double acc[4][2][2];
+        uint16_t code[4][2][2];
+        warp_mma_acc<4, 2, true>(sm + S_N, LDN, sm + S_N, LDN, NQ, sm + S_T + dc, LDT, 0, 16 * half, acc);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+              const int a = 8 * i + lr, b = 16 * half + 8 * j + 2 * lk + r;
+              code[i][j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
+            }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+              const uint16_t cd = code[i][j][r];
+              if (cd == MAP_SKIP) continue;
+              const int a = 8 * i + lr, b = 16 * half + 8 * j + 2 * lk + r;
+              const int li = c * 27 + a, lj = d * 27 + b;
+              double v = P.alpha * acc[i][j][r];
+              if (c == d) v += P.beta * St[ST_S + a * 27 + b] + P.alpha * St[ST_C + a * 27 + b];
+              if (ZU) {
+                double z = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
+                v = fma(P.zeta_u, z, v);
+              }
+              double* pz = nz + row[li] + (cd & 0x7FFF);
+              if (cd & MAP_EXCL) *pz = v;
+              else atomicAdd(pz, v);
+            }
+      }
+    } else     if (CONV == 2) {
       // Newton: a thread owns the 2x2 (a,b) node tile of all 9 component blocks:
       //   K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term]
       // accumulated in registers and scattered straight from them (no staging, no extra barrier).
@@ -536,8 +686,15 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     }
     __syncthreads();
     // R[c][a][m] = sum_q N[q][a] XB[q][c*36+m]
-    panel_product<27, 36, 4, 4, false>(3, sm + S_N, LDN, 0, sm + S_XB, 108, 36, NQ, nullptr, 0, 0, 0,
-                                       [&](int c, int a, int m, double v) { St[(c * 27 + a) * NJ + m] = v; });
+    if (USE_MMA) {
+      const int warp = tid >> 5;
+      if (warp < 7)
+        warp_mma_product<4, 2, false>(sm + S_N, LDN, sm + S_XB, 108, NQ, nullptr, 0, 0, 16 * warp, 27, 108,
+                                      [&](int a, int n, double v) { const int c = n / NJ; St[(c * 27 + a) * NJ + (n - c * NJ)] = v; });
+    } else {
+      panel_product<27, 36, 4, 4, false>(3, sm + S_N, LDN, 0, sm + S_XB, 108, 36, NQ, nullptr, 0, 0, 0,
+                                         [&](int c, int a, int m, double v) { St[(c * 27 + a) * NJ + m] = v; });
+    }
     __syncthreads();
     // K_uj[(c,a)][m] = -gamma R ; K_ju[m][(d,b)] = +sigma R[d][b][m]
     scatter_generic<12>(nz, NU * NJ, [&](int e) { return cmap[SEC_UJ + e]; },
