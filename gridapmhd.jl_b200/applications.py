@@ -38,12 +38,12 @@ def hunt_reduced_quantities(nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0
 
 def hunt_params(nc=(4, 4), nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.0, 0.0, 1.0), zeta_u=0.0, zeta_j=0.0,
                 L=1.0, u0=1.0, formulation="cfd", convection="newton", BL_adapted=True, kmap_x=1, kmap_y=1,
-                solver="julia", nz=3, periodic_z=True, z_extent=(0.0, 0.1)):
+                solver="julia", nz=3, periodic_z=True, z_extent=(0.0, 0.1), tw=0.0, sigma_w1=0.1, sigma_w2=10.0):
     """params Dict of `_hunt` (hunt.jl:88-193).  NOTE: `_hunt` never forwards its `convection` kwarg into
     params[:fluid] (hunt.jl:149-158), so the reference effectively runs Hunt with the `params_fluid` default
     `:newton` (parameters.jl:717); that is the default here too."""
     alpha, beta, gamma, fbar, Bbar, Re, Ha, N = hunt_reduced_quantities(nu, rho, sigma, B, f, L, u0, formulation)
-    mesh = hunt_generate_base_mesh(nc, L=L, tw=0.0, Ha=Ha, kmap_x=kmap_x, kmap_y=kmap_y, BL_adapted=BL_adapted, nz=nz,
+    mesh = hunt_generate_base_mesh(nc, L=L, tw=tw, Ha=Ha, kmap_x=kmap_x, kmap_y=kmap_y, BL_adapted=BL_adapted, nz=nz,
                                    periodic_z=periodic_z, z_extent=z_extent)
     return {
         "model": mesh,
@@ -52,6 +52,10 @@ def hunt_params(nc=(4, 4), nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.
         "bcs": {"u": {"tags": ("noslip",) + (("zwalls",) if not periodic_z else ()), "values": None},
                 "j": {"tags": ("insulating",)}},
         "solver": solver,
+        # params[:solid] (hunt.jl:168-176): sigma per cell = sigma_w1/sigma on solid_1, sigma_w2/sigma on solid_2; zeta = zeta_j
+        "solid": None if tw <= 0.0 else {"cells": mesh.cell_tags["solid"],
+                                         "sigma": np.where(mesh.cell_tags["solid_1"], sigma_w1 / sigma,
+                                                           np.where(mesh.cell_tags["solid_2"], sigma_w2 / sigma, 1.0))},
         "info": {"Re": Re, "Ha": Ha, "N": N, "ncells": mesh.ncells},
     }
 
@@ -101,8 +105,10 @@ def setup_spaces(params) -> FESpaces:
     uvals = bcs["u"].get("values")
     if uvals is None:
         uvals = (None,) * len(utags)
+    solid = params.get("solid")
     return setup_fe_spaces(params["model"], u_tags=utags, u_values=tuple(uvals), j_tags=tuple(bcs["j"]["tags"]),
-                           solver=params.get("solver", "julia"))
+                           solver=params.get("solver", "julia"), solid_cells=None if solid is None else solid["cells"],
+                           cell_sigma=None if solid is None else solid["sigma"])
 
 
 def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts: B200SolverOptions | None = None,

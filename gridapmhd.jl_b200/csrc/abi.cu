@@ -242,9 +242,14 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
           }
           g = -(int32_t)(op->dir_off[f] + (-id - 1)) - 1;
         } else {
-          delete op;
-          set_error("cell %lld field %d: dof id 0 is invalid (ids are 1-based, signed)", (long long)c, f);
-          return MHD_E_INVALID;
+          // id 0: the dof does not exist on this cell (u, p on solid cells).  Treated as a Dirichlet dof with value 0:
+          // one extra zero is appended to the Dirichlet-value array.
+          if (!(mesh->cell_solid && mesh->cell_solid[c] && (f == MHD_FIELD_U || f == MHD_FIELD_P))) {
+            delete op;
+            set_error("cell %lld field %d: dof id 0 is only valid for u/p on solid cells", (long long)c, f);
+            return MHD_E_INVALID;
+          }
+          g = -(int32_t)dir - 1;
         }
         gids[(size_t)c * NLOC + lo[f] + k] = g;
       }
@@ -260,7 +265,7 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
     }
     cn[i] = v;
   }
-  std::vector<double> dirv((size_t)(dir > 0 ? dir : 1), 0.0);
+  std::vector<double> dirv((size_t)dir + 1, 0.0);  // + the zero of the absent dofs
   for (int f = 0; f < 4; f++)
     if (op->ndir[f] > 0 && lay->dir_values[f]) memcpy(&dirv[op->dir_off[f]], lay->dir_values[f], op->ndir[f] * sizeof(double));
 
@@ -270,14 +275,21 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
   CR(dev_alloc(&op->d_cell_nodes, op->ncells * 8));
   CR(dev_alloc(&op->d_gids, op->ncells * NLOC));
   CR(dev_alloc(&op->d_jsign, op->ncells * NJ));
-  CR(dev_alloc(&op->d_dir, dir));
+  CR(dev_alloc(&op->d_dir, dir + 1));
   CR(dev_alloc(&op->d_x, op->ncols));
   CR(dev_alloc(&op->d_y, op->ncols));
   CR(h2d(op->d_coords, mesh->coords, op->nnodes * 3));
   CR(h2d(op->d_cell_nodes, cn.data(), op->ncells * 8));
   CR(h2d(op->d_gids, gids.data(), op->ncells * NLOC));
   CR(h2d(op->d_jsign, lay->j_sign, op->ncells * NJ));
-  CR(h2d(op->d_dir, dirv.data(), dir));
+  CR(h2d(op->d_dir, dirv.data(), dir + 1));
+  if (mesh->cell_solid) {
+    if (!mesh->cell_sigma && !rc) { set_error("cell_solid given without cell_sigma"); rc = MHD_E_INVALID; }
+    CR(dev_alloc(&op->d_cell_solid, op->ncells));
+    CR(dev_alloc(&op->d_cell_sigma, op->ncells));
+    CR(h2d(op->d_cell_solid, mesh->cell_solid, op->ncells));
+    CR(h2d(op->d_cell_sigma, mesh->cell_sigma, op->ncells));
+  }
   CR(pack_tables(op, tab));
   CR(ensure_red(op, 4096 + 65 * 1024));
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
@@ -298,6 +310,8 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_cell_nodes);
   cudaFree(op->d_gids);
   cudaFree(op->d_jsign);
+  cudaFree(op->d_cell_solid);
+  cudaFree(op->d_cell_sigma);
   cudaFree(op->d_dir);
   cudaFree(op->d_tables);
   cudaFree(op->d_rowptr);

@@ -36,6 +36,8 @@ int pack_tables(mhd_operator* op, const mhd_tables_t* t) {
 struct KParams {
   double alpha, beta, gamma, sigma, zeta_u, zeta_j;
   double B[3], f[3], g[3];
+  const uint8_t* cell_solid;  // null: no solid sub-domain
+  const double* cell_sigma;
 };
 
 constexpr int NT = 256;  // threads per CTA
@@ -164,6 +166,36 @@ __device__ __forceinline__ void scatter_generic(double* __restrict__ nz, int cou
       if (c[k] & MAP_EXCL) *p = v;
       else atomicAdd(p, v);
     }
+  }
+}
+
+// Split form of the sweep for single-pass sections (count <= U * NT): the map codes are fetched into registers
+// BEFORE the panel products that produce the values, so their global-load latency is hidden by the math.
+template <int U>
+struct Codes {
+  uint16_t c[U];
+};
+template <int U>
+__device__ __forceinline__ void load_codes(Codes<U>& cd, const uint16_t* __restrict__ codes, int count) {
+#pragma unroll
+  for (int k = 0; k < U; k++) {
+    const int e = k * NT + (int)threadIdx.x;
+    cd.c[k] = e < count ? __ldg(codes + e) : MAP_SKIP;
+  }
+}
+template <int U, class F>
+__device__ __forceinline__ void scatter_loaded(double* __restrict__ nz, const Codes<U>& cd, F f) {
+#pragma unroll
+  for (int k = 0; k < U; k++) {
+    const uint16_t c = cd.c[k];
+    if (c == MAP_SKIP) continue;
+    const int e = k * NT + (int)threadIdx.x;
+    long long rowstart;
+    double v;
+    f(e, rowstart, v);
+    double* p = nz + rowstart + (c & 0x7FFF);
+    if (c & MAP_EXCL) *p = v;
+    else atomicAdd(p, v);
   }
 }
 
@@ -356,7 +388,8 @@ __device__ __forceinline__ void scatter_entry(double* __restrict__ nz, long long
 }
 
 template <int CONV, bool ZU>
-__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, double* __restrict__ r, const KParams& P);
+__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, int64_t nrows, double* __restrict__ r,
+                                              const KParams& P);
 
 // =============================================================================================
 // Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0.
@@ -385,7 +418,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
     }
     if (RES) {
-      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, nrows, rvec, P);
+      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, cell, nrows, rvec, P);
       __syncthreads();  // the residual's scratch lives in the staging area that phase 0 overwrites
     }
     if (CONV > 0) {
@@ -408,6 +441,22 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     }
     if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
     __syncthreads();
+
+    const uint16_t* cmap = map + cell * NENT_PAD;
+    const long long* row = cx.row;
+    // solid cells (jac_solid_h1_hdiv, weakforms.jl:327-338): own conductivity, +phi div j instead of -div j phi; their
+    // u/p dofs are absent (map codes SKIP), so the u-related products are skipped
+    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+    const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
+    const double fj_sign = solid ? 1.0 : -1.0;
+    // map codes of the sections scattered right after phase 0, fetched now (latency hidden by the panel products)
+    Codes<2> c_up, c_pu, c_jf, c_fj;
+    Codes<6> c_jj;
+    load_codes(c_up, cmap + SEC_UP, NU * NP);
+    load_codes(c_pu, cmap + SEC_PU, NP * NU);
+    load_codes(c_jf, cmap + SEC_JF, NJ * NF);
+    load_codes(c_fj, cmap + SEC_FJ, NF * NJ);
+    load_codes(c_jj, cmap + SEC_JJ, NJ * NJ);
 
     // ---------------- phase 0: D (up), j-phi, jj, S, C (+ pressure mass matrix), all independent panel products
     if (USE_MMA) {
@@ -505,11 +554,11 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       }
       __syncthreads();
     }
-    const uint16_t* cmap = map + cell * NENT_PAD;
-    const long long* row = cx.row;
 
     // ---------------- uu
-    if (CONV == 2 && USE_MMA) {
+    if (solid) {
+      // no u block on solid cells
+    } else if (CONV == 2 && USE_MMA) {
       // Newton: K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term].
       // 18 warp jobs = 9 component pairs x 2 column halves of the product N'^T diag(T_dc) N'; the accumulators are
       // scattered straight from registers (16 map codes loaded first), S and C come from the staging buffer.
@@ -518,7 +567,6 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
         const int dc = job >> 1, half = job & 1, d = dc / 3, c = dc - d * 3;
         double acc[4][2][2];
         uint16_t code[4][2][2];
-        warp_mma_acc<4, 2, true>(sm + S_N, LDN, sm + S_N, LDN, NQ, sm + S_T + dc, LDT, 0, 16 * half, acc);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -528,6 +576,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
               const int a = 8 * i + lr, b = 16 * half + 8 * j + 2 * lk + r;
               code[i][j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
             }
+        warp_mma_acc<4, 2, true>(sm + S_N, LDN, sm + S_N, LDN, NQ, sm + S_T + dc, LDT, 0, 16 * half, acc);
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -661,18 +710,18 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
           });
     }
     // ---------------- up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(d,b)] = -D
-    scatter_generic<2>(nz, NU * NP, [&](int e) { return cmap[SEC_UP + e]; },
-                       [&](int e, long long& rs, double& v) { rs = row[e >> 2]; v = -St[ST_D + e]; });
-    scatter_generic<2>(nz, NP * NU, [&](int e) { return cmap[SEC_PU + e]; },
-                       [&](int e, long long& rs, double& v) { const int k = e / NU, i = e - k * NU; rs = row[OFF_P + k]; v = -St[ST_D + i * 4 + k]; });
+    scatter_loaded(nz, c_up, [&](int e, long long& rs, double& v) { rs = row[e >> 2]; v = -St[ST_D + e]; });
+    scatter_loaded(nz, c_pu, [&](int e, long long& rs, double& v) { const int k = e / NU, i = e - k * NU; rs = row[OFF_P + k]; v = -St[ST_D + i * 4 + k]; });
     // ---------------- j-phi: -sigma JF[m][l] ; phi-j: -JF[m][l]
-    scatter_generic<2>(nz, NJ * NF, [&](int e) { return cmap[SEC_JF + e]; },
-                       [&](int e, long long& rs, double& v) { rs = row[OFF_J + (e >> 3)]; v = -P.sigma * St[ST_JF + e]; });
-    scatter_generic<2>(nz, NF * NJ, [&](int e) { return cmap[SEC_FJ + e]; },
-                       [&](int e, long long& rs, double& v) { const int l = e / NJ, m = e - l * NJ; rs = row[OFF_F + l]; v = -St[ST_JF + m * 8 + l]; });
+    scatter_loaded(nz, c_jf, [&](int e, long long& rs, double& v) { rs = row[OFF_J + (e >> 3)]; v = -sig_c * St[ST_JF + e]; });
+    scatter_loaded(nz, c_fj, [&](int e, long long& rs, double& v) { const int l = e / NJ, m = e - l * NJ; rs = row[OFF_F + l]; v = fj_sign * St[ST_JF + m * 8 + l]; });
     // ---------------- jj
-    scatter_generic<6>(nz, NJ * NJ, [&](int e) { return cmap[SEC_JJ + e]; },
-                       [&](int e, long long& rs, double& v) { rs = row[OFF_J + e / NJ]; v = St[ST_JJ + e]; });
+    scatter_loaded(nz, c_jj, [&](int e, long long& rs, double& v) { rs = row[OFF_J + e / NJ]; v = St[ST_JJ + e]; });
+    // map codes of the uj / ju sections, fetched before the XB fill and the uj product
+    if (solid) continue;  // CTA-uniform: no uj / ju blocks on solid cells (the loop-top barrier follows)
+    Codes<12> c_uj, c_ju;
+    load_codes(c_uj, cmap + SEC_UJ, NU * NJ);
+    load_codes(c_ju, cmap + SEC_JU, NJ * NU);
     __syncthreads();
 
     // ---------------- uj / ju.  XB[q][c*36+m] = sqrt(w) (psi_m x B)_c (overwrites G, UG)
@@ -697,10 +746,8 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
     }
     __syncthreads();
     // K_uj[(c,a)][m] = -gamma R ; K_ju[m][(d,b)] = +sigma R[d][b][m]
-    scatter_generic<12>(nz, NU * NJ, [&](int e) { return cmap[SEC_UJ + e]; },
-                        [&](int e, long long& rs, double& v) { rs = row[e / NJ]; v = -P.gamma * St[e]; });
-    scatter_generic<12>(nz, NJ * NU, [&](int e) { return cmap[SEC_JU + e]; },
-                        [&](int e, long long& rs, double& v) { const int m = e / NU, i = e - m * NU; rs = row[OFF_J + m]; v = P.sigma * St[i * NJ + m]; });
+    scatter_loaded(nz, c_uj, [&](int e, long long& rs, double& v) { rs = row[e / NJ]; v = -P.gamma * St[e]; });
+    scatter_loaded(nz, c_ju, [&](int e, long long& rs, double& v) { const int m = e / NU, i = e - m * NU; rs = row[OFF_J + m]; v = sig_c * St[i * NJ + m]; });
   }
 }
 
@@ -708,9 +755,14 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
 // Residual of one cell: res_fluid_h1_hdiv (src/weakforms.jl:255-281).  Needs cell_prep<2> (all panels + the full
 // local state); uses the first ~820 doubles of the staging area and leaves the panels untouched.
 template <int CONV, bool ZU>
-__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, double* __restrict__ r, const KParams& P) {
+__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, int64_t nrows, double* __restrict__ r,
+                                              const KParams& P) {
   double* sm = cx.sm;
   const int tid = threadIdx.x;
+  // res_solid_h1_hdiv (weakforms.jl:314-325) on solid cells: sigma of the cell, +phi-test * div j; u = 0 there
+  const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+  const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
+  const double f_sign = solid ? 1.0 : -1.0;
   // per-q coefficient tables in the staging area
   double* Fu = sm + S_ST;         // [27][3]  coefficient of N'[q][a] in r_u[(c,a)]
   double* Gu = Fu + 81;           // [27][9]  coefficient of G'[(q,d)][a], index d*3+c
@@ -812,7 +864,7 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, 
           v = fma(P.alpha, cv, v);
         }
         Fu[q * 3 + c] = v;
-        Fj[q * 3 + c] = jq[c] - P.sigma * uxB[c] - sw * P.g[c];
+        Fj[q * 3 + c] = jq[c] - sig_c * uxB[c] - sw * P.g[c];
       }
 #pragma unroll
       for (int d = 0; d < 3; d++)
@@ -825,7 +877,7 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, 
           }
           Gu[q * 9 + d * 3 + c] = v;
         }
-      Dj[q] = P.zeta_j * Jd[q] - P.sigma * fq;
+      Dj[q] = P.zeta_j * Jd[q] - sig_c * fq;
     }
     __syncthreads();
     // rows
@@ -853,7 +905,7 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t nrows, 
       } else {
         const int l = i - OFF_F;
         for (int q = 0; q < NQ; q++) s = fma(sm[S_CHI + q * 8 + l], Jd[q], s);
-        s = -s;
+        s = f_sign * s;
       }
       const int32_t g = cx.gid[i];
       if (g >= 0 && g < nrows) atomicAdd(&r[g], s);
@@ -875,7 +927,7 @@ residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();
     cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
-    cell_residual<CONV, ZU>(cx, nrows, r, P);
+    cell_residual<CONV, ZU>(cx, cell, nrows, r, P);
   }
 }
 
@@ -884,6 +936,8 @@ static KParams make_kparams(const mhd_params_t& p) {
   KParams k;
   k.alpha = p.alpha; k.beta = p.beta; k.gamma = p.gamma; k.sigma = p.sigma; k.zeta_u = p.zeta_u; k.zeta_j = p.zeta_j;
   for (int i = 0; i < 3; i++) { k.B[i] = p.B[i]; k.f[i] = p.f[i]; k.g[i] = p.g[i]; }
+  k.cell_solid = nullptr;
+  k.cell_sigma = nullptr;
   return k;
 }
 
@@ -903,7 +957,9 @@ static int set_smem(Kern k) {
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), g_stream));
   if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
-  const KParams P = make_kparams(op->prm);
+  KParams P = make_kparams(op->prm);
+  P.cell_solid = op->d_cell_solid;
+  P.cell_sigma = op->d_cell_sigma;
   const int conv = op->prm.convection;
   const bool zu = op->prm.zeta_u != 0.0;
   const int64_t grid64 = (int64_t)sm_count() * 2;
@@ -931,7 +987,9 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
 
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r) {
   MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
-  const KParams P = make_kparams(op->prm);
+  KParams P = make_kparams(op->prm);
+  P.cell_solid = op->d_cell_solid;
+  P.cell_sigma = op->d_cell_sigma;
   const int conv = op->prm.convection;
   const bool zu = op->prm.zeta_u != 0.0;
   const int64_t grid64 = (int64_t)sm_count() * 2;

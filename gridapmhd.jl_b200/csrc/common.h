@@ -77,6 +77,8 @@ struct mhd_operator {
   int32_t* d_cell_nodes = nullptr; // [ncells*8] 0-based
   int32_t* d_gids = nullptr;       // [ncells*129] >=0 local free id (owned first, ghosts after); <0: -(dirichlet index+1)
   int8_t* d_jsign = nullptr;       // [ncells*36]
+  uint8_t* d_cell_solid = nullptr; // [ncells] or null
+  double* d_cell_sigma = nullptr;  // [ncells] or null
   double* d_dir = nullptr;         // [ndir_total]
   double* d_tables = nullptr;      // packed reference tables (see assembly.cu)
   int64_t* d_rowptr = nullptr;     // [nrows+1]

@@ -116,7 +116,10 @@ class B200FEOperator:
             self._keep.append(a)
             return a.ctypes.data
 
-        mesh = L.mhd_mesh_t(m.coords.shape[0], hold(m.coords, np.float64), m.ncells, hold(m.cell_nodes, np.int32), 0)
+        has_solid = fes.cell_solid is not None and bool(np.any(fes.cell_solid))
+        mesh = L.mhd_mesh_t(m.coords.shape[0], hold(m.coords, np.float64), m.ncells, hold(m.cell_nodes, np.int32), 0,
+                            hold(fes.cell_solid, np.uint8) if has_solid else None,
+                            hold(fes.cell_sigma, np.float64) if has_solid else None)
         tab = L.mhd_tables_t(T.nq, hold(T.w, np.float64), hold(T.geo_grad, np.float64), hold(T.nu, np.float64),
                              hold(T.dnu, np.float64), hold(T.pp, np.float64), hold(T.psi, np.float64),
                              hold(T.dpsi, np.float64), hold(T.chi, np.float64))

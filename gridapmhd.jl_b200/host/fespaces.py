@@ -60,6 +60,8 @@ class FESpaces:
     field_order: tuple = FIELD_ORDER["julia"]
     u_node_coords: np.ndarray | None = None  # [ncells,27,3] physical coordinates of the Q2 nodes
     cell_unodes: np.ndarray | None = None  # [ncells,27] global Q2 node labels
+    cell_solid: np.ndarray | None = None  # [ncells] bool: solid cells carry only j and phi (u, p ids are 0 = absent)
+    cell_sigma: np.ndarray | None = None  # [ncells] conductivity used on solid cells (params[:solid][:sigma])
     extra: dict = field(default_factory=dict)
 
     @property
@@ -92,7 +94,7 @@ class FESpaces:
             dv = self.dirichlet_values[f]
             free = x[np.where(ids > 0, ids - 1 + off[f], 0)]
             dirv = dv[np.where(ids < 0, -ids - 1, 0)] if len(dv) else np.zeros_like(free)
-            out.append(np.where(ids > 0, free, dirv))
+            out.append(np.where(ids > 0, free, np.where(ids < 0, dirv, 0.0)))  # id 0 = absent dof (value 0)
         return np.concatenate(out, axis=1)
 
     def split(self, x: np.ndarray) -> dict:
@@ -101,7 +103,8 @@ class FESpaces:
 
 
 def setup_fe_spaces(mesh: HexMesh, u_tags=("noslip",), u_values=(None,), j_tags=("insulating",),
-                    solver: str = "julia", tables: Tables | None = None) -> FESpaces:
+                    solver: str = "julia", tables: Tables | None = None, solid_cells: np.ndarray | None = None,
+                    cell_sigma: np.ndarray | None = None) -> FESpaces:
     """Build the four spaces. `u_values[i]` is None (zero) or a callable x[n,3] -> u[n,3] for tag i;
     where several tags meet on a node the later tag in the list wins (expansion.jl:150-153).
     Normal-flux Dirichlet values for j are zero (hunt.jl:182, expansion.jl:156-159)."""
@@ -123,24 +126,28 @@ def setup_fe_spaces(mesh: HexMesh, u_tags=("noslip",), u_values=(None,), j_tags=
         m = np.concatenate([mesh.vertex_tags[tag], mesh.edge_tags[tag], mesh.face_tags[tag], np.zeros(nc, dtype=bool)])
         node_dir |= m
         node_tagidx[m] = ti
-    node_ids, nfree_n, ndir_n, free_nodes, dir_nodes = _first_touch_numbering(unodes, node_dir)
+    fluid = np.ones(nc, dtype=bool) if solid_cells is None else ~np.asarray(solid_cells, dtype=bool)
+    # u and p live on the fluid triangulation only (fe_space_u/fe_space_p use params[:Omega_f], fespaces.jl:51,68)
+    node_ids_f, nfree_n, ndir_n, free_nodes, dir_nodes = _first_touch_numbering(unodes[fluid], node_dir)
+    node_ids = np.zeros(unodes.shape, dtype=np.int64)
+    node_ids[fluid] = node_ids_f
     comp = np.arange(3)
     # local dof a + 27 c ; global id 3*(node-1)+c+1, sign preserved
     sgn = np.sign(node_ids)
     base = 3 * (np.abs(node_ids) - 1)
-    cd_u = np.concatenate([sgn * (base + c + 1) for c in comp], axis=1)
+    cd_u = np.concatenate([np.where(sgn != 0, sgn * (base + c + 1), 0) for c in comp], axis=1)
     # node coordinates (trilinear map of the reference node positions)
     gv, _ = q1_tabulate(Q2_NODE_XI)
     node_xyz = np.einsum("av,cvi->cai", gv, X)
     dir_u = np.zeros(3 * ndir_n)
     if ndir_n:
         # coordinates and tag of each Dirichlet node (first cell occurrence)
-        flat = unodes.ravel()
+        flat = unodes[fluid].ravel()
         _, first = np.unique(flat, return_index=True)
         label_first = np.zeros(nnodes, dtype=np.int64)
         label_first[np.unique(flat)] = first
         fidx = label_first[dir_nodes]
-        xyz = node_xyz.reshape(-1, 3)[fidx]
+        xyz = node_xyz[fluid].reshape(-1, 3)[fidx]
         tix = node_tagidx[dir_nodes]
         vals = np.zeros((ndir_n, 3))
         for ti, fn in enumerate(u_values):
@@ -152,7 +159,8 @@ def setup_fe_spaces(mesh: HexMesh, u_tags=("noslip",), u_values=(None,), j_tags=
         dir_u = vals.reshape(-1)
 
     # ---- p, phi: cell-local
-    cd_p = 1 + 4 * np.arange(nc)[:, None] + np.arange(4)[None, :]
+    fnum = np.cumsum(fluid) - 1  # fluid cell counter
+    cd_p = np.where(fluid[:, None], 1 + 4 * fnum[:, None] + np.arange(4)[None, :], 0)
     cd_phi = 1 + 8 * np.arange(nc)[:, None] + np.arange(8)[None, :]
 
     # ---- j: 4 dofs per face (one per face vertex, matched across cells by global vertex id) + 12 interior
@@ -175,11 +183,13 @@ def setup_fe_spaces(mesh: HexMesh, u_tags=("noslip",), u_values=(None,), j_tags=
         mesh=mesh,
         tables=tables,
         cell_dofs={"u": cd_u, "p": cd_p, "j": cd_j, "phi": cd_phi},
-        nfree={"u": 3 * nfree_n, "p": 4 * nc, "j": nfree_j, "phi": 8 * nc},
+        nfree={"u": 3 * nfree_n, "p": 4 * int(fluid.sum()), "j": nfree_j, "phi": 8 * nc},
         ndir={"u": 3 * ndir_n, "p": 0, "j": ndir_j, "phi": 0},
         dirichlet_values={"u": dir_u, "p": np.zeros(0), "j": np.zeros(ndir_j), "phi": np.zeros(0)},
         j_sign=js,
         field_order=FIELD_ORDER[solver],
         u_node_coords=node_xyz,
         cell_unodes=unodes,
+        cell_solid=None if solid_cells is None else ~fluid,
+        cell_sigma=None if cell_sigma is None else np.asarray(cell_sigma, dtype=np.float64),
     )

@@ -203,8 +203,6 @@ def hunt_generate_base_mesh(nc, L=1.0, tw=0.0, Ha=10.0, kmap_x=1, kmap_y=1, BL_a
 
     Tags (CartesianDiscreteModel entity ids 1-26): `noslip` = every x/y wall (ids 1-20,23-26),
     `insulating` = x = -1 and x = +1 faces (25,26), `conducting` = y walls (23,24 + lower-dim)."""
-    if tw > 0.0:
-        raise NotImplementedError("solid walls (tw>0) are outside the round-1 scope")
     Lt = L + tw
     cmap = hunt_stretch_map(Lt, Ha, kmap_x, kmap_y, BL_adapted)
     domain = (-1.0, 1.0, -1.0, 1.0, z_extent[0], z_extent[1])
@@ -212,6 +210,26 @@ def hunt_generate_base_mesh(nc, L=1.0, tw=0.0, Ha=10.0, kmap_x=1, kmap_y=1, BL_a
     fm = _cartesian_face_masks(mesh, domain)
     xw = fm[(0, 0)] | fm[(0, 1)]
     yw = fm[(1, 0)] | fm[(1, 1)]
+    if tw > 0.0:
+        # hunt_add_tags!, tw > 0 branch (hunt_mesher.jl:60-93): cells whose vertices all lie beyond |x| > L are solid_1,
+        # beyond |y| > L solid_2; the fluid/solid interface is `noslip`; the outer x/y boundary is `insulating`
+        X = mesh.cell_coords()
+        tol = 1.0e-9
+        s1 = np.all((X[:, :, 0] > L - tol) | (X[:, :, 0] < -L + tol), axis=1)
+        s2 = np.all((X[:, :, 1] > L - tol) | (X[:, :, 1] < -L + tol), axis=1) & ~s1
+        solid = s1 | s2
+        mesh.cell_tags["solid_1"], mesh.cell_tags["solid_2"] = s1, s2
+        mesh.cell_tags["solid"], mesh.cell_tags["fluid"] = solid, ~solid
+        nsolid = np.zeros(mesh.nfaces, dtype=np.int64)
+        nfluid = np.zeros(mesh.nfaces, dtype=np.int64)
+        np.add.at(nsolid, mesh.cell_faces[solid].ravel(), 1)
+        np.add.at(nfluid, mesh.cell_faces[~solid].ravel(), 1)
+        tag_from_boundary_faces(mesh, "noslip", (nsolid > 0) & (nfluid > 0))
+        tag_from_boundary_faces(mesh, "insulating", xw | yw)
+        tag_from_boundary_faces(mesh, "conducting", np.zeros(mesh.nfaces, dtype=bool))
+        if not periodic_z:
+            tag_from_boundary_faces(mesh, "zwalls", fm[(2, 0)] | fm[(2, 1)])
+        return mesh
     tag_from_boundary_faces(mesh, "noslip", xw | yw)
     tag_from_boundary_faces(mesh, "insulating", xw)
     tag_from_boundary_faces(mesh, "conducting", yw)

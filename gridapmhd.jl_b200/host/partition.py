@@ -134,7 +134,9 @@ def partition_fespaces(fes: FESpaces, cell_part: np.ndarray, rank: int) -> Parti
         nowned[f] = no
     lfes = FESpaces(mesh=lmesh, tables=fes.tables, cell_dofs=cell_dofs, nfree=nfree, ndir=dict(fes.ndir),
                     dirichlet_values=fes.dirichlet_values, j_sign=fes.j_sign[me.cells], field_order=fes.field_order,
-                    u_node_coords=None if fes.u_node_coords is None else fes.u_node_coords[me.cells])
+                    u_node_coords=None if fes.u_node_coords is None else fes.u_node_coords[me.cells],
+                    cell_solid=None if fes.cell_solid is None else fes.cell_solid[me.cells],
+                    cell_sigma=None if fes.cell_sigma is None else fes.cell_sigma[me.cells])
     ps = PartitionedSpaces(fes=lfes, rank=rank, nparts=nparts, nowned=nowned, nowned_cells=me.nowned_cells, cells=me.cells,
                            own_global=me.owned, ghost_global=me.ghost)
     ps._global_offsets = fes.offsets

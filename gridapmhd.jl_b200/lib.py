@@ -27,7 +27,7 @@ class MhdError(RuntimeError):
 
 class mhd_mesh_t(C.Structure):
     _fields_ = [("nnodes", C.c_int64), ("coords", C.c_void_p), ("ncells", C.c_int64), ("cell_nodes", C.c_void_p),
-                ("index_base", C.c_int32)]
+                ("index_base", C.c_int32), ("cell_solid", C.c_void_p), ("cell_sigma", C.c_void_p)]
 
 
 class mhd_tables_t(C.Structure):

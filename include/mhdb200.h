@@ -15,7 +15,8 @@
  *     stream synchronised on return.  Device pointers: work is enqueued on the library stream and the call
  *     returns without synchronising.
  *   - cell->dof ids are Gridap's: per field, 1-based, signed; id<0 is a Dirichlet dof and -id (1-based)
- *     indexes the field's Dirichlet-value array.  Vertex ids in `cell_nodes` use `index_base`.
+ *     indexes the field's Dirichlet-value array; id 0 marks a dof that does not exist on that cell (u, p on solid
+ *     cells, whose spaces live on the fluid triangulation only).  Vertex ids in `cell_nodes` use `index_base`.
  *   - global vector layout: fields concatenated in `field_order` (src/fespaces.jl:4-9 _multi_field_style).
  *   - emitted CSR: sorted column indices, explicit zeros kept, Dirichlet rows/cols dropped
  *     (Gridap SparseMatrixAssembler semantics, src/main.jl:222-223).
@@ -51,6 +52,10 @@ typedef struct {
   int64_t ncells;
   const int32_t* cell_nodes; /* [ncells*8] */
   int32_t index_base;        /* 0 or 1 */
+  /* solid sub-domain (params[:solid], src/weakforms.jl:314-338; NULL when there is none): cells flagged 1 carry only
+   * j and phi -- their u and p dof ids are 0 (= absent) -- and use cell_sigma[cell] as conductivity. */
+  const uint8_t* cell_solid; /* [ncells] or NULL */
+  const double* cell_sigma;  /* [ncells] or NULL */
 } mhd_mesh_t;
 
 /* Reference-element tables at the nq cell quadrature points (src/parameters.jl:436-441,521-525,617-639:

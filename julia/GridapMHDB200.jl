@@ -26,6 +26,7 @@ end
 
 struct MhdMesh
   nnodes::Int64; coords::Ptr{Float64}; ncells::Int64; cell_nodes::Ptr{Int32}; index_base::Int32
+  cell_solid::Ptr{UInt8}; cell_sigma::Ptr{Float64}   # C_NULL without params[:solid]
 end
 struct MhdTables
   nq::Int32; w::Ptr{Float64}; geo_grad::Ptr{Float64}; u_val::Ptr{Float64}; u_grad::Ptr{Float64}

@@ -94,9 +94,11 @@ def _cross(a, B):
     )
 
 
-def cell_jacobians(T, X, state, j_sign, prm: FluidParams):
+def cell_jacobians(T, X, state, j_sign, prm: FluidParams, solid=None, sigma_c=None):
     """Dense cell matrices [nc,129,129] of `jac_fluid_h1_hdiv` (src/weakforms.jl:283-312).
-    rows = test functions, cols = trial functions; local order u(a+27c), p, j, phi."""
+    rows = test functions, cols = trial functions; local order u(a+27c), p, j, phi.
+    `solid` [nc] bool marks cells of `jac_solid_h1_hdiv` (:327-338): only jj, j-phi (sigma = sigma_c of the cell) and
+    phi-j with the OPPOSITE sign (+phi div j) are present; their u/p dofs are absent and dropped at assembly."""
     nc = X.shape[0]
     w, gN, psi, dpsi = mapped_bases(T, X, j_sign)
     N, Pp, Chi = T.nu, T.pp, T.chi
@@ -139,15 +141,20 @@ def cell_jacobians(T, X, state, j_sign, prm: FluidParams):
         Kjj += prm.zeta_j * np.einsum("cq,cqm,cqn->cmn", w, dpsi, dpsi)
     K[:, 85:121, 85:121] = Kjj
     # --- j-phi / phi-j
-    Kjf = -prm.sigma * np.einsum("cq,ql,cqm->cml", w, Chi, dpsi)
-    Kfj = -np.einsum("cq,ql,cqn->cln", w, Chi, dpsi)
-    K[:, 85:121, 121:129] = Kjf
-    K[:, 121:129, 85:121] = Kfj
+    sig = np.full(nc, prm.sigma) if solid is None else np.where(solid, sigma_c, prm.sigma)
+    sgn = np.ones(nc) if solid is None else np.where(solid, -1.0, 1.0)
+    JF = np.einsum("cq,ql,cqm->cml", w, Chi, dpsi)
+    K[:, 85:121, 121:129] = -sig[:, None, None] * JF
+    K[:, 121:129, 85:121] = -sgn[:, None, None] * np.transpose(JF, (0, 2, 1))
+    if solid is not None:
+        K[solid, :85, :] = 0.0
+        K[solid, :, :85] = 0.0
     return K
 
 
-def cell_residuals(T, X, state, j_sign, prm: FluidParams):
-    """Cell vectors [nc,129] of `res_fluid_h1_hdiv` (src/weakforms.jl:255-281)."""
+def cell_residuals(T, X, state, j_sign, prm: FluidParams, solid=None, sigma_c=None):
+    """Cell vectors [nc,129] of `res_fluid_h1_hdiv` (src/weakforms.jl:255-281); `solid` cells follow
+    `res_solid_h1_hdiv` (:314-325): j.s + zeta div j div s - sigma_c phi div s + phi-test * div j - s.g."""
     nc = X.shape[0]
     w, gN, psi, dpsi = mapped_bases(T, X, j_sign)
     N, Pp, Chi = T.nu, T.pp, T.chi
@@ -189,12 +196,16 @@ def cell_residuals(T, X, state, j_sign, prm: FluidParams):
     rj = np.einsum("cq,cqi,cqmi->cm", w, jq, psi)
     if prm.zeta_j != 0.0:
         rj += prm.zeta_j * np.einsum("cq,cq,cqm->cm", w, divj, dpsi)
-    rj -= prm.sigma * np.einsum("cq,cq,cqm->cm", w, fq, dpsi)
+    sig = np.full(nc, prm.sigma) if solid is None else np.where(solid, sigma_c, prm.sigma)
+    sgn = np.ones(nc) if solid is None else np.where(solid, -1.0, 1.0)
+    rj -= sig[:, None] * np.einsum("cq,cq,cqm->cm", w, fq, dpsi)
     rj -= prm.sigma * np.einsum("cq,cqi,cqmi->cm", w, uxB, psi)
     rj -= np.einsum("cq,i,cqmi->cm", w, g, psi)
     R[:, 85:121] = rj
     # phi rows
-    R[:, 121:129] = -np.einsum("cq,ql,cq->cl", w, Chi, divj)
+    R[:, 121:129] = -sgn[:, None] * np.einsum("cq,ql,cq->cl", w, Chi, divj)
+    if solid is not None:
+        R[solid, :85] = 0.0
     return R
 
 
@@ -263,7 +274,9 @@ def jacobian(fes, x, prm: FluidParams, chunk: int = 2048, pattern=None) -> sp.cs
     data = np.zeros(len(colval))
     for s in range(0, X.shape[0], chunk):
         sl = slice(s, s + chunk)
-        K = cell_jacobians(fes.tables, X[sl], st[sl], fes.j_sign[sl], prm)
+        solid = None if fes.cell_solid is None else fes.cell_solid[sl]
+        sigc = None if fes.cell_sigma is None else fes.cell_sigma[sl]
+        K = cell_jacobians(fes.tables, X[sl], st[sl], fes.j_sign[sl], prm, solid, sigc)
         data += assemble_matrix(K, gids[sl], n, pattern).data
     return sp.csr_matrix((data, colval.copy(), rowptr.copy()), shape=(n, n))
 
@@ -277,7 +290,9 @@ def residual(fes, x, prm: FluidParams, chunk: int = 4096) -> np.ndarray:
     out = np.zeros(n)
     for s in range(0, X.shape[0], chunk):
         sl = slice(s, s + chunk)
-        R = cell_residuals(fes.tables, X[sl], st[sl], fes.j_sign[sl], prm)
+        solid = None if fes.cell_solid is None else fes.cell_solid[sl]
+        sigc = None if fes.cell_sigma is None else fes.cell_sigma[sl]
+        R = cell_residuals(fes.tables, X[sl], st[sl], fes.j_sign[sl], prm, solid, sigc)
         out += assemble_vector(R, gids[sl], n)
     return out
 

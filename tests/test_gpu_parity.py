@@ -363,3 +363,34 @@ def test_expansion_newton_solve_matches_oracle(mhdlib):
     df = s["phi"] - so["phi"]
     assert np.abs(df - df.mean()).max() < 1e-7 * max(1.0, np.abs(so["phi"]).max())
     op.destroy()
+
+
+def test_hunt_solid_walls_values_and_solve(mhdlib):
+    """Hunt with conducting solid walls (reference test/seq/hunt_tests.jl:74-88: nc=(12,12), tw=0.2, kmap=3): u, p live
+    on the fluid cells only, solid cells use jac/res_solid_h1_hdiv (weakforms.jl:314-338) with per-cell sigma."""
+    from gridapmhd_jl_b200.feoperator import B200LinearSolver, B200SolverOptions, NewtonSolver
+    from oracle import mhd_oracle as O
+
+    params, fes = make_case(nc=(12, 12), B=(0.0, 50.0, 0.0), tw=0.2, BL_adapted=False, kmap_x=3, kmap_y=3, solver="badia2024",
+                            zeta_u=20.0, zeta_j=20.0)
+    assert fes.cell_solid.sum() == 132 and fes.nfree["u"] == 6498 and fes.nfree["p"] == 1200
+    op = B200FEOperator(fes, params["fluid"])
+    x = np.random.default_rng(21).random(fes.ndofs)
+    A = op.allocate_jacobian()
+    b = np.empty(op.nrows)
+    op.residual_and_jacobian_b(b, A, x)
+    Ao = O.jacobian(fes, x, oracle_params(params["fluid"]))
+    rowptr, colval = A.pattern()
+    assert np.array_equal(rowptr, Ao.indptr) and np.array_equal(colval, Ao.indices)
+    assert relerr(A.nzval(), Ao.data) < VAL_TOL
+    assert relerr(b, O.residual(fes, x, oracle_params(params["fluid"]))) < VAL_TOL
+    assert relerr(op.residual(x), b) < 1e-14
+    # solve (linear: the Hunt flow has no convection contribution)
+    opts = B200SolverOptions(m=30, maxiter=30, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
+    nls = NewtonSolver(B200LinearSolver(opts), maxiter=3, rtol=1e-16)
+    xs = nls.solve_b(np.zeros(fes.ndofs), op)
+    xo, _ = O.newton_lu(fes, oracle_params(params["fluid"]), min_iters=3)
+    s, so = fes.split(xs), fes.split(xo)
+    assert relerr(s["u"], so["u"]) < SOL_TOL
+    assert relerr(s["j"], so["j"]) < SOL_TOL
+    op.destroy()
