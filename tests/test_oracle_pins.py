@@ -220,3 +220,30 @@ def test_fgmres_oracle_converges_like_direct_solve():
     assert np.abs(su["u"] - sd["u"]).max() < 1e-8 * np.abs(sd["u"]).max()
     assert np.abs(su["j"] - sd["j"]).max() < 1e-8 * np.abs(sd["j"]).max()
     assert np.linalg.norm(A @ x - b) < 1e-8 * np.linalg.norm(b)
+
+
+def test_solid_subdomain_oracle_fd_and_structure():
+    """Solid walls (weakforms.jl:314-338): u/p rows exist only for fluid cells, the phi-row sign flips on solid cells,
+    per-cell sigma; the oracle Jacobian is the derivative of its residual."""
+    from gridapmhd_jl_b200.applications import hunt_params, setup_spaces
+
+    params = hunt_params(nc=(12, 12), B=(0.0, 20.0, 0.0), tw=0.2, BL_adapted=False, kmap_x=3, kmap_y=3, zeta_j=2.0)
+    fes = setup_spaces(params)
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    assert fes.cell_solid.sum() == 132 and set(np.unique(fes.cell_sigma)) == {0.1, 1.0, 10.0}
+    assert (fes.cell_dofs["u"][fes.cell_solid] == 0).all() and (fes.cell_dofs["p"][fes.cell_solid] == 0).all()
+    assert fes.nfree["p"] == 4 * int((~fes.cell_solid).sum())
+    rng = np.random.default_rng(0)
+    x, d = rng.random(fes.ndofs), rng.standard_normal(fes.ndofs)
+    A = O.jacobian(fes, x, prm)
+    eps = 1e-6
+    fd = (O.residual(fes, x + eps * d, prm) - O.residual(fes, x - eps * d, prm)) / (2 * eps)
+    assert np.abs(fd - A @ d).max() / np.abs(A @ d).max() < 1e-7
+    # phi-j block: K_phij = +K_jphi^T/sigma on fluid cells (both carry a minus sign), -K_jphi^T/sigma_c on solid cells
+    off = fes.offsets
+    K = O.cell_jacobians(fes.tables, fes.mesh.cell_coords(), fes.cell_state(x), fes.j_sign, prm, fes.cell_solid, fes.cell_sigma)
+    c_s, c_f = int(np.nonzero(fes.cell_solid)[0][0]), int(np.nonzero(~fes.cell_solid)[0][0])
+    assert np.allclose(K[c_s, 121:129, 85:121], -K[c_s, 85:121, 121:129].T / fes.cell_sigma[c_s])
+    assert np.allclose(K[c_f, 121:129, 85:121], +K[c_f, 85:121, 121:129].T / prm.sigma)
+    assert np.abs(K[c_s, 121:129, 85:121]).max() > 0
