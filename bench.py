@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
 
 import numpy as np  # noqa: E402
 
@@ -160,7 +162,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_leg(fes, params, seconds=12.0):
@@ -325,7 +327,8 @@ def run_ours(args):
             tr = json.load(open(traffic_file))
             line["roofline"]["traffic"] = tr.get("jacobian_kernel_dram_bytes")
             line["spmv"]["roofline"]["traffic"] = tr.get("spmv_dram_bytes")
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    barrier()  # nobody tears its inbox down while a neighbour may still push into it
     op.destroy()
     if world > 1:
         L.load().mhd_comm_finalize()

@@ -321,6 +321,13 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_x);
   cudaFree(op->d_y);
   cudaFree(op->d_red);
+  for (void* pm : op->halo.peer_mem)
+    if (pm) cudaIpcCloseMemHandle(pm);
+  cudaFree(op->halo.ipc_mem);
+  cudaFree(op->halo.d_dev);
+  cudaFree(op->halo.d_ghost_src);
+  cudaFree(op->halo.d_row_bits);
+  cudaFree(op->halo.d_err);
   cudaFree(op->halo.d_send_idx);
   cudaFree(op->halo.d_recv_idx);
   cudaFree(op->halo.d_send_buf);
@@ -465,19 +472,17 @@ int mhd_spmv(mhd_operator_t* op, const double* x, double* y) {
   MHD_TRY(check_ready(op));
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_spmv: no matrix");
   MHD_CHECK(y != nullptr, MHD_E_INVALID, "mhd_spmv: null output");
-  const double* dx;
-  bool xdev = is_device_ptr(x);
-  if (g_nranks > 1 && xdev) {
-    // the halo exchange writes the ghost section of x: needs a mutable device vector
-    MHD_TRY(halo_exchange(op, const_cast<double*>(x)));
-    dx = x;
+  // the NCCL halo path writes the ghost section of x: needs a mutable device vector
+  double* dx;
+  if (is_device_ptr(x)) {
+    dx = const_cast<double*>(x);
   } else {
-    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    if (g_nranks > 1) MHD_TRY(halo_exchange(op, op->d_x));
+    MHD_TRY(h2d(op->d_x, x, op->nrows));
+    dx = op->d_x;
   }
   bool dev_out = is_device_ptr(y);
   double* dy = dev_out ? y : op->d_y;
-  MHD_TRY(launch_spmv(op, dx, dy));
+  MHD_TRY(spmv_with_halo(op, op->nrows, dx, dy));
   if (!dev_out) {
     MHD_TRY(d2h(y, dy, op->nrows));
     MHD_CUDA(cudaStreamSynchronize(g_stream));

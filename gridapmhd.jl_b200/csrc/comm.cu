@@ -6,6 +6,7 @@
 // (same SONAME) is reused when the host process is Python.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -138,6 +139,119 @@ int mhd_comm_finalize(void) {
   }
   g_nranks = 1;
   g_rank = 0;
+  return MHD_OK;
+}
+
+__global__ void tag_ghost_rows(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                               long long* __restrict__ tagged) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nrows) return;
+  long long v = rowptr[r];
+  if (r < nrows && rowptr[r + 1] > rowptr[r] && colval[rowptr[r + 1] - 1] >= nrows) v |= 1ll << 62;  // sorted: ghosts are the tail
+  tagged[r] = v;
+}
+
+// ---- fused peer-memory halo: export this rank's inbox, connect to the neighbours' inboxes
+int mhd_operator_halo_ipc_export(mhd_operator_t* op, void* handle64) {
+  MHD_CHECK(op != nullptr && handle64 != nullptr, MHD_E_INVALID, "mhd_operator_halo_ipc_export: null argument");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CUDA(cudaSetDevice(g_device));
+  Halo& h = op->halo;
+  MHD_CHECK(h.nneigh > 0 && h.nneigh <= HALO_MAX_NEIGH, MHD_E_INVALID, "halo plan missing or more than %d neighbours", HALO_MAX_NEIGH);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+  if (!h.ipc_mem) {
+    const int64_t nghost = op->ncols - op->nrows;
+    const size_t bytes = HALO_FLAG_BYTES + 2 * (size_t)(nghost > 0 ? nghost : 1) * sizeof(double);
+    MHD_CUDA(cudaMalloc(&h.ipc_mem, bytes));
+    MHD_CUDA(cudaMemset(h.ipc_mem, 0, bytes));
+  }
+  cudaIpcMemHandle_t hd;
+  MHD_CUDA(cudaIpcGetMemHandle(&hd, h.ipc_mem));
+  memcpy(handle64, &hd, 64);
+  return MHD_OK;
+}
+
+int mhd_operator_halo_ipc_connect(mhd_operator_t* op, const void* handles, const int32_t* send_dst,
+                                  const int32_t* peer_slot, const int64_t* peer_nghost) {
+  MHD_CHECK(op && handles && send_dst && peer_slot && peer_nghost, MHD_E_INVALID, "mhd_operator_halo_ipc_connect: null argument");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CUDA(cudaSetDevice(g_device));
+  Halo& h = op->halo;
+  MHD_CHECK(h.ipc_mem != nullptr, MHD_E_STATE, "call mhd_operator_halo_ipc_export first");
+  HaloDev hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.nneigh = h.nneigh;
+  hd.nrecv = h.nrecv;
+  h.peer_mem.assign(h.nneigh, nullptr);
+  std::vector<int> push_neigh;
+  std::vector<int64_t> push_begin;
+  for (int k = 0; k < h.nneigh; k++) {
+    cudaIpcMemHandle_t hk;
+    memcpy(&hk, (const char*)handles + 64 * k, 64);
+    MHD_CUDA(cudaIpcOpenMemHandle(&h.peer_mem[k], hk, cudaIpcMemLazyEnablePeerAccess));
+    MHD_CHECK(peer_slot[k] >= 0 && peer_slot[k] < HALO_MAX_NEIGH, MHD_E_INVALID, "bad peer slot");
+    char* base = (char*)h.peer_mem[k];
+    for (int p = 0; p < 2; p++) {
+      hd.peer_inbox[p][k] = (double*)(base + HALO_FLAG_BYTES) + (int64_t)p * (peer_nghost[k] > 0 ? peer_nghost[k] : 1);
+      hd.peer_flag[p][k] = (unsigned*)base + p * HALO_MAX_NEIGH + peer_slot[k];
+    }
+    const int64_t nr = h.recv_ptr[k + 1] - h.recv_ptr[k];
+    hd.expected[k] = (unsigned)((nr + HALO_CHUNK - 1) / HALO_CHUNK);
+    hd.send_begin[k] = h.send_ptr[k];
+    for (int64_t b = h.send_ptr[k]; b < h.send_ptr[k + 1]; b += HALO_CHUNK) {
+      push_neigh.push_back(k);
+      push_begin.push_back(b);
+    }
+  }
+  hd.send_begin[h.nneigh] = h.send_ptr[h.nneigh];
+  hd.npush = (int)push_neigh.size();
+  for (int64_t i = 0; i < h.nsend; i++) {
+    int k = 0;
+    while (i >= h.send_ptr[k + 1]) k++;
+    MHD_CHECK(send_dst[i] >= 0 && send_dst[i] < peer_nghost[k], MHD_E_INVALID, "send_dst[%lld]=%d outside the neighbour's ghost range", (long long)i, send_dst[i]);
+  }
+  int* d_push_neigh = nullptr;
+  int64_t* d_push_begin = nullptr;
+  MHD_TRY(dev_alloc(&d_push_neigh, (int64_t)push_neigh.size()));
+  MHD_TRY(dev_alloc(&d_push_begin, (int64_t)push_begin.size()));
+  MHD_TRY(dev_alloc(&h.d_ghost_src, h.nsend));
+  MHD_TRY(dev_alloc(&h.d_err, 1));
+  MHD_TRY(h2d(d_push_neigh, push_neigh.data(), (int64_t)push_neigh.size()));
+  MHD_TRY(h2d(d_push_begin, push_begin.data(), (int64_t)push_begin.size()));
+  MHD_TRY(h2d(h.d_ghost_src, send_dst, h.nsend));
+  MHD_CUDA(cudaMemsetAsync(h.d_err, 0, sizeof(int), g_stream));
+  hd.send_idx = h.d_send_idx;
+  hd.push_neigh = d_push_neigh;
+  hd.push_begin = d_push_begin;
+  hd.my_flags = (const unsigned*)h.ipc_mem;
+  hd.my_inbox[0] = (const double*)((char*)h.ipc_mem + HALO_FLAG_BYTES);
+  hd.my_inbox[1] = hd.my_inbox[0] + (op->ncols - op->nrows > 0 ? op->ncols - op->nrows : 1);
+  MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_operator_halo_ipc_connect: call mhd_operator_symbolic first");
+  MHD_TRY(dev_alloc(&h.d_row_bits, op->nrows + 1));
+  tag_ghost_rows<<<(unsigned)((op->nrows + 256) / 256), 256, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, h.d_row_bits);
+  MHD_LAUNCH_CHECK();
+  hd.send_dst = h.d_ghost_src;
+  hd.rowptr_tagged = h.d_row_bits;
+  hd.err = h.d_err;
+  MHD_TRY(dev_alloc(&h.d_dev, 1));
+  MHD_CUDA(cudaMemcpyAsync(h.d_dev, &hd, sizeof(HaloDev), cudaMemcpyHostToDevice, g_stream));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  h.epoch = 0;
+  h.fused = getenv("MHD_HALO_NCCL") == nullptr;  // MHD_HALO_NCCL=1 keeps the NCCL send/recv path (A/B comparison)
+  return MHD_OK;
+}
+
+int mhd_operator_halo_status(mhd_operator_t* op, int32_t* fused, int32_t* timed_out) {
+  MHD_CHECK(op != nullptr, MHD_E_INVALID, "null operator");
+  if (fused) *fused = op->halo.fused ? 1 : 0;
+  if (timed_out) {
+    *timed_out = 0;
+    if (op->halo.d_err) {
+      int e = 0;
+      MHD_CUDA(cudaMemcpy(&e, op->halo.d_err, sizeof(int), cudaMemcpyDeviceToHost));
+      *timed_out = e;
+    }
+  }
   return MHD_OK;
 }
 

@@ -56,6 +56,36 @@ struct Halo {
   double* d_send_buf = nullptr;
   double* d_recv_buf = nullptr;
   int64_t nsend = 0, nrecv = 0;
+  // fused SpMV + halo over NVLink peer memory (see krylov.cu: spmv_fused_halo)
+  bool fused = false;
+  void* ipc_mem = nullptr;              // [flags 2 x 64 u32 | inbox parity 0 | inbox parity 1], exported with CUDA IPC
+  std::vector<void*> peer_mem;          // the neighbours' ipc_mem, opened with cudaIpcOpenMemHandle
+  struct HaloDev* d_dev = nullptr;      // device copy of the plan
+  int32_t* d_ghost_src = nullptr;       // [nsend] destination ghost slots on the neighbours (send_dst)
+  long long* d_row_bits = nullptr;      // [nrows+1] tagged copy of rowptr (bit 62: row has ghost columns)
+  int* d_err = nullptr;
+  unsigned epoch = 0;
+};
+
+constexpr int HALO_MAX_NEIGH = 64;
+constexpr int HALO_FLAG_BYTES = 2 * HALO_MAX_NEIGH * 4;
+constexpr int HALO_CHUNK = 2048;        // ghost values pushed per CTA
+
+struct HaloDev {
+  int nneigh, npush;
+  int64_t nrecv;
+  double* peer_inbox[2][HALO_MAX_NEIGH];     // where my values for neighbour k land (parity p), already offset
+  unsigned* peer_flag[2][HALO_MAX_NEIGH];    // my arrival counter inside neighbour k's memory
+  unsigned expected[HALO_MAX_NEIGH];         // CTAs neighbour k uses to push to me
+  int64_t send_begin[HALO_MAX_NEIGH + 1];
+  const int32_t* send_idx;
+  const int32_t* send_dst;                   // [nsend] ghost slot (ghost id - nrows) of each sent value on its neighbour
+  const int* push_neigh;                     // [npush] neighbour of each push CTA
+  const int64_t* push_begin;                 // [npush] first send-list entry of each push CTA
+  const unsigned* my_flags;                  // [2][HALO_MAX_NEIGH]
+  const double* my_inbox[2];
+  const long long* rowptr_tagged;            // rowptr copy with bit 62 set on rows that end with ghost columns (unused by the vote kernel)
+  int* err;
 };
 
 }  // namespace mhd
@@ -164,6 +194,8 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // krylov.cu
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);
+// y[0..nr) = (A x)[0..nr) including the ghost exchange (fused peer-memory kernel when connected, NCCL otherwise)
+int spmv_with_halo(mhd_operator* op, int64_t nr, double* d_x, double* d_y);
 int launch_dot(mhd_operator* op, int64_t n, const double* d_x, const double* d_y, double* d_out);
 int launch_axpy(int64_t n, double a, const double* d_x, double* d_y);
 int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int64_t ldv, const double* d_w, double* d_h);

@@ -90,6 +90,137 @@ int launch_spmv(mhd_operator* op, const double* d_x, double* d_y) {
   return 0;
 }
 
+// ---------------------------------------------------------------- fused SpMV + ghost exchange over NVLink peer memory
+// ONE kernel per product (replaces pack -> ncclSend/ncclRecv -> unpack -> SpMV):
+//   * the first `npush` CTAs store this rank's interface values straight into the neighbours' inboxes (peer-mapped
+//     memory, st.global over NVLink), fence, and bump an arrival counter inside the neighbour's memory;
+//   * all other CTAs run the warp-per-row SpMV.  Columns are sorted and ghost ids come last, so a row is computed from
+//     local x first and touches the inbox only at its tail; a warp waits (once) for the neighbours' counters when it
+//     meets its first ghost column.  Interior rows never wait: the exchange is overlapped with the bulk of the product.
+//   Inboxes are double-buffered by the parity of the product count and the counters are monotone (target = expected
+//   CTAs x use count), so nothing is ever reset and a fast neighbour cannot overwrite data still being read.
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y,
+                const HaloDev* __restrict__ H, int parity, unsigned round, int nowait) {
+  const int npush = H->npush;
+  if ((int)blockIdx.x < npush) {
+    // ---- push CTA: one chunk of the send list of one neighbour
+    const int k = H->push_neigh[blockIdx.x];
+    const int64_t b0 = H->push_begin[blockIdx.x];
+    const int64_t kend = H->send_begin[k + 1];
+    const int64_t b1 = b0 + HALO_CHUNK < kend ? b0 + HALO_CHUNK : kend;
+    double* dst = H->peer_inbox[parity][k];
+    // each value goes straight to its final ghost slot of the neighbour (send_dst = ghost id - nrows over there)
+    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[H->send_dst[i]] = x[H->send_idx[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd_system(H->peer_flag[parity][k], 1u);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)(blockIdx.x - npush) * SPMV_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)(gridDim.x - npush) * SPMV_WARPS;
+  // ghost column c lives at inbox[c - nrows]: one pointer select, one load, no branch in the gather
+  const double* xg = H->my_inbox[parity] - nrows;
+  const unsigned* fl = H->my_flags + parity * HALO_MAX_NEIGH;
+  const int nn = nowait ? 0 : H->nneigh;
+  bool arrived = false;
+  for (int64_t row = warp0; row < nr; row += nwarps) {
+    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    double s0 = 0.0, s1 = 0.0;
+    // warp-uniform trip count: the vote below is legal, and a row needs no extra load to learn that it has ghosts
+    for (int64_t base = lo; base < hi; base += 64) {
+      const int64_t p0 = base + lane, p1 = p0 + 32;
+      const bool ok0 = p0 < hi, ok1 = p1 < hi;
+      const int32_t c0 = ok0 ? __ldg(colval + p0) : 0, c1 = ok1 ? __ldg(colval + p1) : 0;
+      const double v0 = ok0 ? __ldg(nzval + p0) : 0.0, v1 = ok1 ? __ldg(nzval + p1) : 0.0;
+      const bool g0 = c0 >= nrows, g1 = c1 >= nrows;
+      if (!arrived && __any_sync(0xffffffffu, g0 || g1)) {
+        // first ghost column met by this warp: wait (once) until every neighbour's values have landed
+        if (lane == 0) {
+          for (int k = 0; k < nn; k++) {
+            const unsigned target = H->expected[k] * round;
+            unsigned spins = 0;
+            while (ld_volatile_u32(fl + k) < target) {
+              if (++spins > (1u << 28)) {  // never hang the GPU: report and go on
+                atomicExch(H->err, 1);
+                break;
+              }
+            }
+          }
+          // no __threadfence() here: a gpu-scope fence invalidates the SM's whole L1 (CCTL.IVALL) and with it the cached
+          // x entries of every warp on the SM.  The counters are read with ld.volatile (L2); inbox lines cannot be in
+          // L1 yet (L1 is empty at kernel start and nothing reads a ghost before this point).
+        }
+        __syncwarp();
+        arrived = true;
+      }
+      // L1 is invalidated at every kernel launch and no ghost is read before the arrival wait, so the cached path is safe
+      const double x0 = __ldg((g0 ? xg : x) + c0);
+      const double x1 = __ldg((g1 ? xg : x) + c1);
+      s0 = fma(v0, x0, s0);
+      s1 = fma(v1, x1, s1);
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+// SpMV over the first nr rows only (block row of the block-ordered matrix), local x (ghosts already in place)
+__global__ void __launch_bounds__(256)
+spmv_rows_kernel(int64_t nr, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+                 const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t row = warp0; row < nr; row += nwarps) {
+    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    double s = 0.0;
+    for (int64_t p = lo + lane; p < hi; p += 32) s = fma(nzval[p], __ldg(x + colval[p]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+int spmv_with_halo(mhd_operator* op, int64_t nr, double* d_x, double* d_y) {
+  if (nr <= 0) return 0;
+  Halo& h = op->halo;
+  if (g_nranks > 1 && h.fused && h.nneigh > 0) {
+    int npush = 0;  // CTAs that push interface values (the same enumeration as in mhd_operator_halo_ipc_connect)
+    for (int k = 0; k < h.nneigh; k++) npush += (int)((h.send_ptr[k + 1] - h.send_ptr[k] + HALO_CHUNK - 1) / HALO_CHUNK);
+    int64_t blocks = (nr + SPMV_WARPS - 1) / SPMV_WARPS;
+    const int64_t cap = (int64_t)sms() * 32 * 4;
+    if (blocks > cap) blocks = cap;
+    const int parity = (int)(h.epoch & 1u);
+    const unsigned round = h.epoch / 2u + 1u;
+    h.epoch++;
+    prof_begin(PROF_SPMV);
+    spmv_fused_halo<<<(unsigned)(blocks + npush), SPMV_WARPS * 32, 0, g_stream>>>(nr, op->nrows, op->d_rowptr, op->d_colval,
+                                                                                  op->d_nzval, d_x, d_y, h.d_dev, parity, round,
+                                                                                  getenv("MHD_FUSED_NOWAIT") ? 1 : 0);
+    prof_end(PROF_SPMV);
+    MHD_LAUNCH_CHECK();
+    return 0;
+  }
+  if (g_nranks > 1) MHD_TRY(halo_exchange(op, d_x));
+  if (nr == op->nrows) return launch_spmv(op, d_x, d_y);
+  int64_t blocks = (nr + 7) / 8;
+  if (blocks > (int64_t)sms() * 32) blocks = (int64_t)sms() * 32;
+  spmv_rows_kernel<<<(unsigned)blocks, 256, 0, g_stream>>>(nr, op->d_rowptr, op->d_colval, op->d_nzval, d_x, d_y);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------- reductions (deterministic two-stage)
 constexpr int RED_T = 256;
 constexpr int RED_MAXB = 1024;

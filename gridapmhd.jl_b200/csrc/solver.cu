@@ -386,32 +386,6 @@ k_apply_mass_inverses(int64_t ncells, int64_t nrows, const int32_t* __restrict__
   }
 }
 
-// SpMV over the first nr rows only (block row of the block-ordered matrix)
-__global__ void __launch_bounds__(256)
-k_spmv_rows(int64_t nr, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
-            const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * 8;
-  for (int64_t row = warp0; row < nr; row += nwarps) {
-    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
-    double s = 0.0;
-    for (int64_t p = lo + lane; p < hi; p += 32) s = fma(nzval[p], __ldg(x + colval[p]), s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[row] = s;
-  }
-}
-
-static int spmv_rows(mhd_operator* op, int64_t nr, const double* x, double* y) {
-  if (nr == 0) return 0;
-  int64_t blocks = (nr + 7) / 8;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  k_spmv_rows<<<(unsigned)blocks, 256, 0, g_stream>>>(nr, op->d_rowptr, op->d_colval, op->d_nzval, x, y);
-  MHD_LAUNCH_CHECK();
-  return 0;
-}
-
 }  // namespace mhd
 
 extern "C" {
@@ -558,14 +532,12 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
   MHD_CUDA(cudaMemcpyAsync(s->d_x, x, n * 8, xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
 
   VecOp matvec = [op](const double* v, double* y) -> int {
-    MHD_TRY(halo_exchange(op, const_cast<double*>(v)));
-    return launch_spmv(op, v, y);
+    return spmv_with_halo(op, op->nrows, const_cast<double*>(v), y);
   };
   // (u,j)-block operator: rows [0,n_uj), p/phi entries of the input are kept at zero by construction
   const int64_t nuj = s->n_uj;
   VecOp matvec_uj = [op, nuj](const double* v, double* y) -> int {
-    MHD_TRY(halo_exchange(op, const_cast<double*>(v)));
-    return spmv_rows(op, nuj, v, y);
+    return spmv_with_halo(op, nuj, const_cast<double*>(v), y);
   };
   double* dinv = s->d_dinv;
   VecOp jacobi_uj = [dinv, nuj](const double* v, double* z) -> int {
@@ -594,8 +566,7 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
           op->ncells, n, op->d_gids, s->d_minv_p, s->d_minv_f, 1.0 / oo.alpha_p, 1.0 / oo.alpha_phi, v, z);
       MHD_LAUNCH_CHECK();
       // t1 = A [0; z_p; z_phi] restricted to the (u,j) rows ; rhs = v_uj - t1
-      MHD_TRY(halo_exchange(op, z));
-      MHD_TRY(spmv_rows(op, nuj, z, s->d_t1));
+      MHD_TRY(spmv_with_halo(op, nuj, z, s->d_t1));
       k_sub<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, v, s->d_t1, s->d_t2);
       MHD_LAUNCH_CHECK();
       if (oo.uj_solver == MHD_UJ_DENSE_LU) {

@@ -181,7 +181,7 @@ def hunt_cell_partition(mesh: HexMesh, np_xy) -> np.ndarray:
     return cartesian_partition(mesh.grid_shape, (np_xy[0], np_xy[1], 1))
 
 
-def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: int, dist=None):
+def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: int, dist=None, use_peer_memory=True):
     """Create this rank's `B200FEOperator` (owned rows, ghost-cell redundant integration), install the halo plan and
     bring up the NCCL communicator of the library (the unique id travels through torch.distributed / MPI)."""
     import ctypes as C
@@ -208,4 +208,28 @@ def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: i
     op = B200FEOperator(ps.fes, params["fluid"], nowned=ps.nowned)
     L.check(lib.mhd_operator_set_halo(op.handle, len(ps.neigh), L.ptr(ps.neigh), L.ptr(ps.send_ptr), L.ptr(ps.send_idx),
                                       L.ptr(ps.recv_ptr), L.ptr(ps.recv_idx)))
+    if world > 1 and len(ps.neigh) > 0 and use_peer_memory:
+        op.allocate_jacobian()  # the fused kernel needs the pattern (rows with ghost columns)
+        # fused SpMV + halo over NVLink peer memory: exchange the CUDA IPC handles of the inboxes through the host
+        raw = (C.c_ubyte * 64)()
+        L.check(lib.mhd_operator_halo_ipc_export(op.handle, raw))
+        mine = {"handle": bytes(raw), "neigh": ps.neigh.tolist(), "recv_ptr": ps.recv_ptr.tolist(),
+                "recv_idx": ps.recv_idx.tolist(), "nrows": ps.nrows, "ncols": ps.ncols}
+        allinfo = [None] * world
+        dist.all_gather_object(allinfo, mine)
+        handles = b"".join(allinfo[s]["handle"] for s in ps.neigh)
+        slot = np.array([allinfo[s]["neigh"].index(rank) for s in ps.neigh], dtype=np.int32)
+        nghost = np.array([allinfo[s]["ncols"] - allinfo[s]["nrows"] for s in ps.neigh], dtype=np.int64)
+        # ghost slot on the neighbour of every value this rank sends (both lists are ordered identically)
+        dst = []
+        for k, s_ in enumerate(ps.neigh):
+            info = allinfo[s_]
+            kk = info["neigh"].index(rank)
+            seg = np.array(info["recv_idx"][info["recv_ptr"][kk] : info["recv_ptr"][kk + 1]], dtype=np.int64) - info["nrows"]
+            assert len(seg) == ps.send_ptr[k + 1] - ps.send_ptr[k]
+            dst.append(seg)
+        send_dst = np.concatenate(dst).astype(np.int32) if dst else np.zeros(0, np.int32)
+        hbuf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        L.check(lib.mhd_operator_halo_ipc_connect(op.handle, hbuf, L.ptr(send_dst), L.ptr(slot), L.ptr(nghost)))
+        dist.barrier()
     return op, ps

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mhd_operator_destroy": (C.c_int, [_P]),
     "mhd_operator_set_params": (C.c_int, [_P, C.POINTER(mhd_params_t)]),
     "mhd_operator_set_halo": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    "mhd_operator_halo_ipc_export": (C.c_int, [_P, _P]),
+    "mhd_operator_halo_ipc_connect": (C.c_int, [_P, _P, _P, _P, _P]),
+    "mhd_operator_halo_status": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mhd_operator_symbolic": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mhd_operator_get_csr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int]),
     "mhd_operator_get_scatter_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

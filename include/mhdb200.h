@@ -134,6 +134,17 @@ int mhd_operator_set_params(mhd_operator_t*, const mhd_params_t*); /* continuati
 int mhd_operator_set_halo(mhd_operator_t*, int32_t nneigh, const int32_t* neigh_ranks, const int64_t* send_ptr,
                           const int32_t* send_idx, const int64_t* recv_ptr, const int32_t* recv_idx);
 
+/* Fused SpMV + ghost exchange over NVLink peer memory (CUDA IPC; same-node ranks): every rank exports the handle of its
+ * inbox, the host exchanges the 64-byte handles (MPI / torch.distributed) and hands each rank its neighbours' handles
+ * plus: for every entry of the send list the ghost slot it fills on its neighbour (the neighbour's recv_idx entry minus
+ * the neighbour's row count), and per neighbour k this rank's position in k's neighbour list and k's ghost count.  Afterwards mhd_spmv / mhd_solve use ONE kernel per
+ * product that pushes interface values into the neighbours' inboxes and multiplies (interior rows never wait).
+ * Without it the exchange runs as pack -> ncclSend/ncclRecv -> unpack. */
+int mhd_operator_halo_ipc_export(mhd_operator_t*, void* handle64 /* 64 bytes out */);
+int mhd_operator_halo_ipc_connect(mhd_operator_t*, const void* handles /* nneigh x 64 B */, const int32_t* send_dst /* [nsend] */,
+                                  const int32_t* peer_slot, const int64_t* peer_nghost);
+int mhd_operator_halo_status(mhd_operator_t*, int32_t* fused, int32_t* timed_out);
+
 /* symbolic phase: symbolic_loop_matrix! + nz_allocation of Gridap's assembler (called through
  * allocate_jacobian; src/main.jl:222,163).  Builds rowptr/colval and the cell-entry -> nnz scatter map. */
 int mhd_operator_symbolic(mhd_operator_t*, int64_t* nrows, int64_t* ncols, int64_t* nnz);

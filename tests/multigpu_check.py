@@ -60,7 +60,21 @@ def main():
     y = op.spmv(vl)
     yref = (Ag @ v)[gl[: op.nrows]]
     err_y = np.abs(y.cpu().numpy() - yref).max() / np.abs(Ag @ v).max()
-    ok &= err_y < 1e-12 and bool(torch.isfinite(vl).all())
+    import ctypes as C
+
+    fused, tmo = C.c_int32(), C.c_int32()
+    L.check(L.load().mhd_operator_halo_status(op.handle, C.byref(fused), C.byref(tmo)))
+    want_fused = os.environ.get("MHD_HALO_NCCL") is None and world > 1
+    ok &= err_y < 1e-12 and tmo.value == 0 and (fused.value == 1) == want_fused
+    if not fused.value:
+        ok &= bool(torch.isfinite(vl).all())  # NCCL path: the exchange fills the ghost section of x
+    # repeated products (double-buffered inboxes, monotone arrival counters)
+    for rep in range(7):
+        vr = torch.from_numpy((v * (rep + 2))[gl[: op.nrows]]).cuda()
+        vfull = torch.zeros(op.ncols, dtype=torch.float64, device="cuda")
+        vfull[: op.nrows] = vr
+        yr = op.spmv(vfull)
+        ok &= np.abs(yr.cpu().numpy() - (rep + 2) * yref).max() / np.abs(Ag @ v).max() < 1e-11
     d = op.dot(vl, vl)  # all-reduced over ranks (owned entries only)
     err_d = abs(d - v @ v) / (v @ v)
     ok &= err_d < 1e-13
@@ -82,7 +96,7 @@ def main():
     true_res = np.linalg.norm(Ag @ t.cpu().numpy() + rg)
     ok &= abs(true_res - ns.resnorm) < 1e-6 * ns.history[0]
     print(f"[rank {rank}] rows {op.nrows} cols {op.ncols} nnz {op.nnz} errA {err_a:.1e} errR {err_r:.1e} errY {err_y:.1e} "
-          f"errDot {err_d:.1e} fgmres {ns.history[0]:.3e}->{ns.history[-1]:.3e} true {true_res:.3e} ok={ok}", flush=True)
+          f"errDot {err_d:.1e} fused={fused.value} fgmres {ns.history[0]:.3e}->{ns.history[-1]:.3e} true {true_res:.3e} ok={ok}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ns.destroy()
