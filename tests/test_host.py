@@ -50,13 +50,20 @@ def test_no_cpu_fallback_fails_loudly():
         L.init(0)
 
 
-def test_c_struct_layouts_match_header_sizes():
+def test_c_struct_layouts_match_header_sizes(tmp_path):
+    """ctypes mirrors of the ABI structs have the sizes the C compiler gives the header's structs."""
+    import subprocess
+
     from gridapmhd_jl_b200 import lib as L
 
-    assert ctypes.sizeof(L.mhd_params_t) == 6 * 8 + 9 * 8 + 8  # 15 doubles + int32 (+ padding)
-    assert ctypes.sizeof(L.mhd_solver_opts_t) == 64
-    assert ctypes.sizeof(L.mhd_mesh_t) == 40
-    assert ctypes.sizeof(L.mhd_layout_t) == 4 * 8 + 8 + 3 * 32 + 32 + 16
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "mhdb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(mhd_mesh_t),'
+                   " sizeof(mhd_tables_t), sizeof(mhd_layout_t), sizeof(mhd_params_t), sizeof(mhd_solver_opts_t)); return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    mine = [ctypes.sizeof(t) for t in (L.mhd_mesh_t, L.mhd_tables_t, L.mhd_layout_t, L.mhd_params_t, L.mhd_solver_opts_t)]
+    assert mine == sizes, (mine, sizes)
 
 
 # ---- reference elements --------------------------------------------------------------------------
@@ -193,3 +200,35 @@ def test_cartesian_and_rcb_partitions():
     c = np.random.default_rng(0).random((1000, 3))
     p = M.rcb_partition(c, 8)
     assert np.bincount(p).min() >= 120 and np.bincount(p).max() <= 130
+
+
+REF_MESH = "/root/reference/meshes/Expansion_710.msh"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MESH), reason="reference checkout not present (GPU box)")
+def test_gmsh_reader_on_the_reference_expansion_mesh():
+    """The reference's own fixture (402 nodes / 240 hexes, graded cells, physical names
+    inlet/outlet/wall/fluid): read it, build the Expansion spaces on it and check the oracle Jacobian against its FD."""
+    from gridapmhd_jl_b200.applications import expansion_params, setup_spaces
+    from oracle import mhd_oracle as O
+
+    m = M.read_gmsh41(REF_MESH)
+    assert m.ncells == 240 and m.coords.shape[0] == 402
+    for tag in ("inlet", "outlet", "wall"):
+        assert m.face_tags[tag].sum() > 0
+    assert (m.face_tags["inlet"] | m.face_tags["outlet"] | m.face_tags["wall"]).sum() == (m.face_ncells == 1).sum()
+    assert m.cell_tags["fluid"].all()
+    X = m.cell_coords()
+    assert abs(X[..., 0].min() + 8) < 1e-9 and abs(X[..., 0].max() - 8) < 1e-9  # x in [-8, 8]
+    params = expansion_params(Ha=10.0, N=5.0, mesh=m)
+    fes = setup_spaces(params)
+    _, det, _ = O.cell_geometry(fes.tables, X)
+    assert det.min() > 0  # positively oriented after the Gmsh -> lexicographic vertex permutation
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    rng = np.random.default_rng(0)
+    x, d = rng.random(fes.ndofs), rng.standard_normal(fes.ndofs)
+    A = O.jacobian(fes, x, prm)
+    eps = 1e-6
+    fd = (O.residual(fes, x + eps * d, prm) - O.residual(fes, x - eps * d, prm)) / (2 * eps)
+    assert np.abs(fd - A @ d).max() / np.abs(A @ d).max() < 1e-6
