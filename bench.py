@@ -24,8 +24,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the single JSON line only (NCCL's banner goes to stderr)
 
 import numpy as np  # noqa: E402
 
