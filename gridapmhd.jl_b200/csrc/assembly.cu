@@ -271,6 +271,43 @@ __device__ __forceinline__ void warp_mma_product(const double* __restrict__ A, i
       }
 }
 
+// Velocity gradient at the 27 Gauss points through the tensor cores:
+//   Gq[q][d*3+c] = sum_b G'[(q,d)][b] u_c,b   (= sqrt(w) d_d u_c),   T[q][d*3+c] = Gq / sqrt(w)
+// an 81 x 3 x 27 product: A = G' read row-major ((q,d) rows, b contiguous: conflict-free fragment loads since
+// LDN = 12 mod 16), B = the local velocity dofs.  11 row tiles dealt to the 8 warps.  Computed ONCE per cell and
+// shared by the residual and the Newton block of the fused kernel.
+__device__ __forceinline__ void velocity_gradient_mma(const double* __restrict__ G, const double* __restrict__ U,
+                                                      const double* __restrict__ sw, double* __restrict__ Gq,
+                                                      double* __restrict__ T, int ldt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+  for (int mt = warp; mt < 11; mt += NT / 32) {
+    double c0 = 0.0, c1 = 0.0;
+    const double* ap = G + (8 * mt + lr) * LDN;  // row (q,d) = 8 mt + lr (rows >= 81 read the next panel: discarded)
+    const double* bp = U + lr * 27;              // column c = lr (columns >= 3 discarded)
+#pragma unroll
+    for (int k0 = 0; k0 < 28; k0 += 4) {
+      const int kk = k0 + lk;
+      const bool valid = kk < 27;
+      const double a = valid ? ap[kk] : 0.0;
+      const double b = (valid && lr < 3) ? bp[kk] : 0.0;
+      dmma884(c0, c1, a, b);
+    }
+    const int m = 8 * mt + lr;  // accumulator row; columns 2 lk, 2 lk + 1
+    if (m < 81) {
+      const int q = m / 3, d = m - q * 3;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int c = 2 * lk + r;
+        if (c < 3) {
+          const double v = r ? c1 : c0;
+          if (Gq) Gq[q * 9 + d * 3 + c] = v;
+          if (T) T[q * ldt + d * 3 + c] = v / sw[q];
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 struct CellCtx {
   double* sm;
@@ -390,6 +427,7 @@ __device__ __forceinline__ void scatter_entry(double* __restrict__ nz, long long
 template <int CONV, bool ZU>
 __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, int64_t nrows, double* __restrict__ r,
                                               const KParams& P);
+constexpr int RES_GQ = 81 + 243 + 81 + 27 * 4;  // offset of the velocity-gradient table inside the residual scratch
 
 // =============================================================================================
 // Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0.
@@ -417,7 +455,13 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       const int32_t g = cx.gid[i];
       cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
     }
+    if (RES || CONV == 2) {
+      // velocity gradient once per cell: Gq for the residual (its scratch area), T for the Newton block
+      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr,
+                            CONV == 2 ? sm + S_T : nullptr, LDT);
+    }
     if (RES) {
+      __syncthreads();
       cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, cell, nrows, rvec, P);
       __syncthreads();  // the residual's scratch lives in the staging area that phase 0 overwrites
     }
@@ -429,14 +473,6 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
 #pragma unroll
         for (int i = 0; i < 3; i++) s = fma(sm[S_UQ + q * 3 + i], sm[S_G + (q * 3 + i) * LDN + b], s);
         sm[S_UG + q * LDN + b] = s;
-      }
-      if (CONV == 2) {
-        for (int idx = tid; idx < NQ * 9; idx += NT) {
-          const int q = idx / 9, dc = idx - q * 9, d = dc / 3, c = dc - d * 3;
-          double s = 0.0;
-          for (int b = 0; b < 27; b++) s = fma(sm[S_G + (q * 3 + d) * LDN + b], sm[S_U + c * 27 + b], s);
-          sm[S_T + q * LDT + dc] = s / sm[S_SW + q];
-        }
       }
     }
     if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
@@ -776,13 +812,7 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, i
   double* Rh = Pr + 27;           // [4] rhs / coefficients of the projection
   {
     const double* U = sm + S_U;
-    // gradients of u, div u, p at q
-    for (int idx = tid; idx < NQ * 9; idx += NT) {
-      const int q = idx / 9, dc = idx - q * 9, d = dc / 3, c = dc - d * 3;
-      double s = 0.0;
-      for (int b = 0; b < 27; b++) s = fma(sm[S_G + (q * 3 + d) * LDN + b], U[c * 27 + b], s);
-      Gq[idx] = s;
-    }
+    // Gq (velocity gradient at q) has been filled by velocity_gradient_mma; div u, p at q
     if (tid < NQ) {
       const int q = tid;
       double s = 0.0;
@@ -927,6 +957,8 @@ residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();
     cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    velocity_gradient_mma(cx.sm + S_G, cx.sm + S_U, cx.sm + S_SW, cx.sm + S_ST + RES_GQ, nullptr, 0);
+    __syncthreads();
     cell_residual<CONV, ZU>(cx, cell, nrows, r, P);
   }
 }
