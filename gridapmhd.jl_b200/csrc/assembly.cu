@@ -450,6 +450,18 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();  // previous cell's scatter done before its tables are overwritten
+    {
+      // pull the NEXT cell's scatter map (30 KB), dof ids and vertex ids into L2 while this cell is being processed:
+      // every later load of them then pays L2 latency instead of DRAM latency inside the barrier-separated phases
+      const int64_t nxt = cell + gridDim.x;
+      if (nxt < ncells) {
+        const char* m0 = reinterpret_cast<const char*>(map + nxt * NENT_PAD);
+        if (tid * 128 < NENT_PAD * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + tid * 128));
+        if (tid < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gids + nxt * NLOC) + tid * 128));
+        if (tid == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_nodes + nxt * 8));
+        if (tid == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(jsign + nxt * NJ));
+      }
+    }
     cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
     for (int i = tid; i < NLOC; i += NT) {
       const int32_t g = cx.gid[i];
@@ -596,45 +608,75 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       // no u block on solid cells
     } else if (CONV == 2 && USE_MMA) {
       // Newton: K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term].
-      // 18 warp jobs = 9 component pairs x 2 column halves of the product N'^T diag(T_dc) N'; the accumulators are
-      // scattered straight from registers (16 map codes loaded first), S and C come from the staging buffer.
+      // Perfectly balanced over the 8 warps: warp w owns row tile w/2 and the column-tile pair w%2 of EVERY component
+      // pair (c,d).  Its operand fragments of N' are loaded once (7 k-steps: 7 + 14 words per lane) and reused for
+      // the 9 products N'^T diag(T_dc) N'; accumulators are scattered straight from registers (the 4 map codes of
+      // a product are fetched before its MMAs), S and C come from the staging buffer.
       const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
-      for (int job = warp; job < 18; job += 8) {
-        const int dc = job >> 1, half = job & 1, d = dc / 3, c = dc - d * 3;
-        double acc[4][2][2];
-        uint16_t code[4][2][2];
+      const int mt = warp >> 1, np = warp & 1;
+      double fa[7], fb[7][2];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+      for (int ks = 0; ks < 7; ks++) {
+        const int kk = 4 * ks + lk;
+        const bool valid = kk < NQ;
+        const int kc = valid ? kk : 0;
+        const double va = sm[S_N + kc * LDN + 8 * mt + lr];
+        const double vb0 = sm[S_N + kc * LDN + 16 * np + lr], vb1 = sm[S_N + kc * LDN + 16 * np + 8 + lr];
+        fa[ks] = valid ? va : 0.0;
+        fb[ks][0] = valid ? vb0 : 0.0;
+        fb[ks][1] = valid ? vb1 : 0.0;
+      }
+      const int a = 8 * mt + lr;
+      // map codes are fetched one product ahead (their DRAM latency is longer than the 14 MMAs of a product)
+      auto load_uu_codes = [&](int dc, uint16_t (&code)[2][2]) {
+        const int d = dc / 3, c = dc - d * 3;
 #pragma unroll
-          for (int j = 0; j < 2; j++)
+        for (int j = 0; j < 2; j++)
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-              const int a = 8 * i + lr, b = 16 * half + 8 * j + 2 * lk + r;
-              code[i][j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
+          for (int r = 0; r < 2; r++) {
+            const int b = 16 * np + 8 * j + 2 * lk + r;
+            code[j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
+          }
+      };
+      uint16_t code_next[2][2];
+      load_uu_codes(0, code_next);
+#pragma unroll 1
+      for (int dc = 0; dc < 9; dc++) {
+        const int d = dc / 3, c = dc - d * 3;
+        uint16_t code[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) code[j][r] = code_next[j][r];
+        if (dc < 8) load_uu_codes(dc + 1, code_next);
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int ks = 0; ks < 7; ks++) {
+          const int kk = 4 * ks + lk;
+          const double t = sm[S_T + (kk < NQ ? kk : 0) * LDT + dc];
+          dmma884(acc[0][0], acc[0][1], fa[ks], fb[ks][0] * t);
+          dmma884(acc[1][0], acc[1][1], fa[ks], fb[ks][1] * t);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const uint16_t cd = code[j][r];
+            if (cd == MAP_SKIP) continue;
+            const int b = 16 * np + 8 * j + 2 * lk + r;
+            const int li = c * 27 + a, lj = d * 27 + b;
+            double v = P.alpha * acc[j][r];
+            if (c == d) v += P.beta * St[ST_S + a * 27 + b] + P.alpha * St[ST_C + a * 27 + b];
+            if (ZU) {
+              double z = 0.0;
+#pragma unroll
+              for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
+              v = fma(P.zeta_u, z, v);
             }
-        warp_mma_acc<4, 2, true>(sm + S_N, LDN, sm + S_N, LDN, NQ, sm + S_T + dc, LDT, 0, 16 * half, acc);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-              const uint16_t cd = code[i][j][r];
-              if (cd == MAP_SKIP) continue;
-              const int a = 8 * i + lr, b = 16 * half + 8 * j + 2 * lk + r;
-              const int li = c * 27 + a, lj = d * 27 + b;
-              double v = P.alpha * acc[i][j][r];
-              if (c == d) v += P.beta * St[ST_S + a * 27 + b] + P.alpha * St[ST_C + a * 27 + b];
-              if (ZU) {
-                double z = 0.0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
-                v = fma(P.zeta_u, z, v);
-              }
-              double* pz = nz + row[li] + (cd & 0x7FFF);
-              if (cd & MAP_EXCL) *pz = v;
-              else atomicAdd(pz, v);
-            }
+            double* pz = nz + row[li] + (cd & 0x7FFF);
+            if (cd & MAP_EXCL) *pz = v;
+            else atomicAdd(pz, v);
+          }
       }
     } else     if (CONV == 2) {
       // Newton: a thread owns the 2x2 (a,b) node tile of all 9 component blocks:
