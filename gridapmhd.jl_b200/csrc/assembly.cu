@@ -11,6 +11,8 @@
 //   blocks : register-tiled FP64 panel products (4x4 per thread) into a shared staging buffer;
 //   scatter: row-major sweep of each block section of the 16-bit scatter map (coalesced map reads, runs of
 //            consecutive nnz), plain stores for single-contribution nnz, RED.ADD.F64 otherwise.
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace mhd {
@@ -1005,6 +1007,318 @@ residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
   }
 }
 
+// =============================================================================================
+// Jacobian kernel, single-phase variant ("v4").  After the cell preparation there is ONE barrier-free phase: every
+// warp runs a fixed list of tensor-core jobs and scatters each job's accumulators straight from registers (map
+// codes are fetched before the job's MMAs).  No staging buffer, no barrier between products and scatter:
+//   * uu job (every warp): warp w owns row tile w/2 and the column-tile pair w%2 of the 27x27 node space for ALL
+//     9 component pairs: S = G'^T G' and C = N'^T UG' of that tile stay in registers and are added on the three
+//     diagonal pairs; the Newton products N'^T diag(T_dc) N' reuse one set of N' fragments;
+//   * pooled jobs: jj (5 column strips), uj/ju (7 column pairs, psi x B formed on the fly from the Psi panel),
+//     j-phi/phi-j, up/pu (3 components), dealt statically: w0..w2: jj+D, w3: jj+JF, w4: jj+uj, w5..w7: 2 uj.
+// The barrier-heavy staged kernel above remains for zeta_u != 0 (its rank-4 update needs D and M_p^-1 D first).
+__device__ __forceinline__ void scatter_reg(double* __restrict__ nz, long long rowstart, uint16_t cd, double v) {
+  if (cd == MAP_SKIP) return;
+  double* p = nz + rowstart + (cd & 0x7FFF);
+  if (cd & MAP_EXCL) *p = v;
+  else atomicAdd(p, v);
+}
+
+template <int CONV, bool RES>
+__global__ void __launch_bounds__(NT, 2)
+jacobian_kernel_v4(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
+                   const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
+                   const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
+                   const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ map, double* __restrict__ nz,
+                   double* __restrict__ rvec, KParams P) {
+  extern __shared__ __align__(16) double smem[];
+  CellCtx cx;
+  cx.sm = smem;
+  cx.row = (long long*)(smem + S_END);
+  cx.gid = (int32_t*)(cx.row + NLOC);
+  double* sm = smem;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+
+  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
+    __syncthreads();  // every warp is done with the previous cell's panels
+    {
+      const int64_t nxt = cell + gridDim.x;  // next cell's map / ids into L2 (see jacobian_kernel)
+      if (nxt < ncells) {
+        const char* m0 = reinterpret_cast<const char*>(map + nxt * NENT_PAD);
+        if (tid * 128 < NENT_PAD * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + tid * 128));
+        if (tid < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gids + nxt * NLOC) + tid * 128));
+        if (tid == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_nodes + nxt * 8));
+        if (tid == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(jsign + nxt * NJ));
+      }
+    }
+    cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    for (int i = tid; i < NLOC; i += NT) {
+      const int32_t g = cx.gid[i];
+      cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
+    }
+    if (RES || CONV == 2)
+      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr, CONV == 2 ? sm + S_T : nullptr, LDT);
+    if (CONV > 0) {
+      // UG[q][b] = sqrt(w) u_q . grad N_b
+      for (int idx = tid; idx < NQ * 27; idx += NT) {
+        const int q = idx / 27, b = idx - q * 27;
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) s = fma(sm[S_UQ + q * 3 + i], sm[S_G + (q * 3 + i) * LDN + b], s);
+        sm[S_UG + q * LDN + b] = s;
+      }
+    }
+    if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
+    if (RES) {
+      __syncthreads();
+      cell_residual<(CONV > 0 ? 1 : 0), false>(cx, cell, nrows, rvec, P);  // touches only its scratch area
+    }
+    __syncthreads();
+
+    const uint16_t* cmap = map + cell * NENT_PAD;
+    const long long* row = cx.row;
+    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+    const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
+    const double fj_sign = solid ? 1.0 : -1.0;
+
+    // ------------------------------------------------------------------ uu job (all warps; none on solid cells)
+    if (!solid) {
+      const int mt = warp >> 1, np = warp & 1;
+      const int a = 8 * mt + lr;
+      double base[1][2][2];
+      warp_mma_acc<1, 2, false>(sm + S_G, LDN, sm + S_G, LDN, 81, nullptr, 0, 8 * mt, 16 * np, base);
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) base[0][j][r] *= P.beta;
+      if (CONV > 0) {
+        double cc[1][2][2];
+        warp_mma_acc<1, 2, false>(sm + S_N, LDN, sm + S_UG, LDN, NQ, nullptr, 0, 8 * mt, 16 * np, cc);
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) base[0][j][r] = fma(P.alpha, cc[0][j][r], base[0][j][r]);
+      }
+      auto load_uu_codes = [&](int c, int d, uint16_t (&code)[2][2]) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const int b = 16 * np + 8 * j + 2 * lk + r;
+            code[j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
+          }
+      };
+      if (CONV == 2) {
+        double fa[7], fb[7][2];
+#pragma unroll
+        for (int ks = 0; ks < 7; ks++) {
+          const int kk = 4 * ks + lk;
+          const bool valid = kk < NQ;
+          const int kc = valid ? kk : 0;
+          const double va = sm[S_N + kc * LDN + 8 * mt + lr];
+          const double vb0 = sm[S_N + kc * LDN + 16 * np + lr], vb1 = sm[S_N + kc * LDN + 16 * np + 8 + lr];
+          fa[ks] = valid ? va : 0.0;
+          fb[ks][0] = valid ? vb0 : 0.0;
+          fb[ks][1] = valid ? vb1 : 0.0;
+        }
+        uint16_t code_next[2][2];
+        load_uu_codes(0, 0, code_next);
+#pragma unroll 1
+        for (int dc = 0; dc < 9; dc++) {
+          const int d = dc / 3, c = dc - d * 3;
+          uint16_t code[2][2];
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) code[j][r] = code_next[j][r];
+          if (dc < 8) load_uu_codes((dc + 1) % 3, (dc + 1) / 3, code_next);
+          double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int ks = 0; ks < 7; ks++) {
+            const int kk = 4 * ks + lk;
+            const double t = sm[S_T + (kk < NQ ? kk : 0) * LDT + dc];
+            dmma884(acc[0][0], acc[0][1], fa[ks], fb[ks][0] * t);
+            dmma884(acc[1][0], acc[1][1], fa[ks], fb[ks][1] * t);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+              double v = P.alpha * acc[j][r];
+              if (c == d) v += base[0][j][r];
+              if (a < 27) scatter_reg(nz, row[c * 27 + a], code[j][r], v);
+            }
+        }
+      } else {
+        // none / picard: only the three diagonal component blocks carry values
+#pragma unroll 1
+        for (int c = 0; c < 3; c++) {
+          uint16_t code[2][2];
+          load_uu_codes(c, c, code);
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+              if (a < 27) scatter_reg(nz, row[c * 27 + a], code[j][r], base[0][j][r]);
+        }
+      }
+    }
+
+    // ------------------------------------------------------------------ pooled jobs
+    // jj strip s: columns 8s..8s+7
+    auto job_jj = [&](int s_) {
+      double acc[5][1][2];
+      uint16_t code[5][2];
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int m = 8 * i + lr, n = 8 * s_ + 2 * lk + r;
+          code[i][r] = (m < NJ && n < NJ) ? __ldg(cmap + SEC_JJ + m * NJ + n) : MAP_SKIP;
+        }
+      if (P.zeta_j != 0.0) warp_mma_acc<5, 1, true>(sm + S_PSI, NJ, sm + S_PSI, NJ, 108, sm + S_SC, 1, 0, 8 * s_, acc);
+      else warp_mma_acc<5, 1, false>(sm + S_PSI, NJ, sm + S_PSI, NJ, 81, nullptr, 0, 0, 8 * s_, acc);
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int m = 8 * i + lr;
+          if (m < NJ) scatter_reg(nz, row[OFF_J + m], code[i][r], acc[i][0][r]);
+        }
+    };
+    // j-phi / phi-j
+    auto job_jf = [&]() {
+      double acc[5][1][2];
+      uint16_t cjf[5][2], cfj[5][2];
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int m = 8 * i + lr, l = 2 * lk + r;
+          const bool ok = m < NJ;
+          cjf[i][r] = ok ? __ldg(cmap + SEC_JF + m * NF + l) : MAP_SKIP;
+          cfj[i][r] = ok ? __ldg(cmap + SEC_FJ + l * NJ + m) : MAP_SKIP;
+        }
+      warp_mma_acc<5, 1, false>(sm + S_DIV, NJ, sm + S_CHI, 8, NQ, nullptr, 0, 0, 0, acc);
+#pragma unroll
+      for (int i = 0; i < 5; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int m = 8 * i + lr, l = 2 * lk + r;
+          if (m < NJ) {
+            scatter_reg(nz, row[OFF_J + m], cjf[i][r], -sig_c * acc[i][0][r]);
+            scatter_reg(nz, row[OFF_F + l], cfj[i][r], fj_sign * acc[i][0][r]);
+          }
+        }
+    };
+    // up / pu, component c
+    auto job_d = [&](int c) {
+      double acc[4][1][2];
+      uint16_t cup[4][2], cpu[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int a = 8 * i + lr, k = 2 * lk + r;
+          const bool ok = a < 27 && k < NP;
+          cup[i][r] = ok ? __ldg(cmap + SEC_UP + (c * 27 + a) * NP + k) : MAP_SKIP;
+          cpu[i][r] = ok ? __ldg(cmap + SEC_PU + k * NU + c * 27 + a) : MAP_SKIP;
+        }
+      warp_mma_acc<4, 1, false>(sm + S_G + c * LDN, 3 * LDN, sm + S_PP, 4, NQ, nullptr, 0, 0, 0, acc);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int a = 8 * i + lr, k = 2 * lk + r;
+          if (a < 27 && k < NP) {
+            scatter_reg(nz, row[c * 27 + a], cup[i][r], -acc[i][0][r]);
+            scatter_reg(nz, row[OFF_P + k], cpu[i][r], -acc[i][0][r]);
+          }
+        }
+    };
+    // uj / ju, columns n = 16u .. 16u+15 of the 108 (c,m) columns; B fragment = sqrt(w) (psi_m x B)_c formed on the fly
+    auto job_uj = [&](int u) {
+      double acc[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      // this lane's B-fragment columns (one per column tile)
+      int pb1[2], pb2[2];
+      double w1[2], w2[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int nb = 16 * u + 8 * j + lr;
+        const int cb = nb < 108 ? nb / NJ : 0, mb = nb < 108 ? nb - cb * NJ : 0;
+        const int c1 = (cb + 1) % 3, c2 = (cb + 2) % 3;
+        pb1[j] = c1 * NJ + mb;
+        pb2[j] = c2 * NJ + mb;
+        w1[j] = nb < 108 ? P.B[c2] : 0.0;   // (psi x B)_c = psi_{c+1} B_{c+2} - psi_{c+2} B_{c+1}
+        w2[j] = nb < 108 ? -P.B[c1] : 0.0;
+      }
+#pragma unroll 2
+      for (int k0 = 0; k0 < 28; k0 += 4) {
+        const int kk = k0 + lk;
+        const bool valid = kk < NQ;
+        const int kc = valid ? kk : 0;
+        double av[4], bv[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const double v = sm[S_N + kc * LDN + 8 * i + lr];
+          av[i] = valid ? v : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const double v = sm[S_PSI + kc * 3 * NJ + pb1[j]] * w1[j] + sm[S_PSI + kc * 3 * NJ + pb2[j]] * w2[j];
+          bv[j] = valid ? v : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+      }
+      // scatter: K_uj[(c,a)][m] = -gamma R ; K_ju[m][(c,a)] = +sigma R
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int n = 16 * u + 8 * j + 2 * lk + r;
+          if (n >= 108) continue;
+          const int c = n / NJ, m = n - c * NJ;
+          uint16_t cuj[4], cju[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int a = 8 * i + lr;
+            cuj[i] = a < 27 ? __ldg(cmap + SEC_UJ + (c * 27 + a) * NJ + m) : MAP_SKIP;
+            cju[i] = a < 27 ? __ldg(cmap + SEC_JU + m * NU + c * 27 + a) : MAP_SKIP;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int a = 8 * i + lr;
+            if (a < 27) {
+              scatter_reg(nz, row[c * 27 + a], cuj[i], -P.gamma * acc[i][j][r]);
+              scatter_reg(nz, row[OFF_J + m], cju[i], sig_c * acc[i][j][r]);
+            }
+          }
+        }
+    };
+    // static deal (costs in MMAs: jj 105(140), uj 56, JF 35, D 28)
+    if (warp < 5) job_jj(warp);
+    if (solid) {
+      if (warp == 5) job_jf();
+    } else {
+      if (warp < 3) job_d(warp);
+      else if (warp == 3) job_jf();
+      else if (warp == 4) job_uj(0);
+      else {
+        job_uj(2 * warp - 9);   // w5: 1,2  w6: 3,4  w7: 5,6
+        job_uj(2 * warp - 8);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 static KParams make_kparams(const mhd_params_t& p) {
   KParams k;
@@ -1045,13 +1359,28 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
         op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, d_r, P); \
   } while (0)
 #define JKR(C, Z) do { if (d_r) JK(C, Z, true); else JK(C, Z, false); } while (0)
+  static int staged = -1;
+  if (staged < 0) staged = getenv("MHD_JAC_STAGED") ? 1 : 0;
+#define JK4(C, R)                                                                                            \
+  do {                                                                                                       \
+    MHD_TRY(set_smem(jacobian_kernel_v4<C, R>));                                                             \
+    jacobian_kernel_v4<C, R><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
+        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, d_r, P); \
+  } while (0)
+#define JK4R(C) do { if (d_r) JK4(C, true); else JK4(C, false); } while (0)
   prof_begin(PROF_JAC);
-  if (conv == 0 && !zu) JKR(0, false);
+  if (!zu && !staged) {
+    if (conv == 0) JK4R(0);
+    else if (conv == 1) JK4R(1);
+    else JK4R(2);
+  } else if (conv == 0 && !zu) JKR(0, false);
   else if (conv == 0 && zu) JKR(0, true);
   else if (conv == 1 && !zu) JKR(1, false);
   else if (conv == 1 && zu) JKR(1, true);
   else if (conv == 2 && !zu) JKR(2, false);
   else JKR(2, true);
+#undef JK4R
+#undef JK4
 #undef JKR
 #undef JK
   prof_end(PROF_JAC);
