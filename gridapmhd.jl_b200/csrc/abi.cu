@@ -78,6 +78,33 @@ static void prof_collect() {
 
 using namespace mhd;
 
+// ---- FP64 peak microbenchmark (roofline denominator for the assembly kernels)
+namespace mhd {
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double* out) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = threadIdx.x * 1e-3 + i;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * blockIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (KIND == 0)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[2 * i]), "+d"(acc[2 * i + 1]) : "d"(a), "d"(b));
+      else {
+        acc[2 * i] = fma(acc[2 * i], a, b);
+        acc[2 * i + 1] = fma(acc[2 * i + 1], a, b);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += acc[i];
+  if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+}  // namespace mhd
+
 extern "C" {
 
 const char* mhd_last_error_string(void) { return g_err; }
@@ -134,6 +161,39 @@ int mhd_set_stream(void* s) {
   return MHD_OK;
 }
 
+int mhd_fp64_peak(int32_t kind, double* tflops) {
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(tflops && (kind == 0 || kind == 1), MHD_E_INVALID, "mhd_fp64_peak: invalid argument");
+  MHD_CUDA(cudaSetDevice(g_device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
+  double* d_out = nullptr;
+  MHD_CUDA(cudaMalloc((void**)&d_out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  MHD_CUDA(cudaEventCreate(&e0));
+  MHD_CUDA(cudaEventCreate(&e1));
+  const int iters = 20000, grid = sms * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {  // first repetition = warm-up
+    MHD_CUDA(cudaEventRecord(e0, g_stream));
+    if (kind == 0) mhd::fp64_peak_kernel<0><<<grid, 256, 0, g_stream>>>(iters, d_out);
+    else mhd::fp64_peak_kernel<1><<<grid, 256, 0, g_stream>>>(iters, d_out);
+    MHD_CUDA(cudaEventRecord(e1, g_stream));
+    MHD_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MHD_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+    g_launches++;
+  }
+  // per warp and iteration: 8 MMAs of 8x8x4 = 256 FMA each, or 16 DFMA x 32 lanes
+  const double fma_per_warp_iter = kind == 0 ? 8.0 * 256.0 : 16.0 * 32.0;
+  *tflops = 2.0 * fma_per_warp_iter * iters * (double)grid * 8.0 / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return MHD_OK;
+}
+
 int mhd_device_synchronize(void) {
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CUDA(cudaSetDevice(g_device));
@@ -183,8 +243,8 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
     op->ndir[i] = lay->ndir[i];
     op->field_order[i] = lay->field_order[i];
     if (op->nowned[i] > op->nfree[i] || op->nfree[i] < 0 || op->ndir[i] < 0) {
-      delete op;
       set_error("inconsistent nfree/nowned/ndir for field %d", i);
+      delete op;
       return MHD_E_INVALID;
     }
   }
@@ -206,8 +266,8 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
   op->ncols = own + gh;
   op->ndir_total = dir;
   if (op->ncols >= (int64_t)INT32_MAX) {
-    delete op;
     set_error("local vector length %lld exceeds int32 column indices", (long long)op->ncols);
+    delete op;
     return MHD_E_CAPACITY;
   }
 
@@ -218,8 +278,8 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
   for (int f = 0; f < 4; f++) {
     const int32_t* cd = lay->cell_dofs[f];
     if (!cd) {
-      delete op;
       set_error("cell_dofs[%d] is null", f);
+      delete op;
       return MHD_E_INVALID;
     }
     for (int64_t c = 0; c < op->ncells; c++) {
@@ -228,16 +288,16 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
         int32_t g;
         if (id > 0) {
           if (id > op->nfree[f]) {
-            delete op;
             set_error("cell %lld field %d: dof id %d > nfree %lld", (long long)c, f, id, (long long)op->nfree[f]);
+            delete op;
             return MHD_E_INVALID;
           }
           g = id <= op->nowned[f] ? (int32_t)(op->own_off[f] + id - 1)
                                   : (int32_t)(op->ghost_off[f] + (id - 1 - op->nowned[f]));
         } else if (id < 0) {
           if (-id > op->ndir[f]) {
-            delete op;
             set_error("cell %lld field %d: Dirichlet id %d beyond ndir %lld", (long long)c, f, id, (long long)op->ndir[f]);
+            delete op;
             return MHD_E_INVALID;
           }
           g = -(int32_t)(op->dir_off[f] + (-id - 1)) - 1;
@@ -245,8 +305,8 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
           // id 0: the dof does not exist on this cell (u, p on solid cells).  Treated as a Dirichlet dof with value 0:
           // one extra zero is appended to the Dirichlet-value array.
           if (!(mesh->cell_solid && mesh->cell_solid[c] && (f == MHD_FIELD_U || f == MHD_FIELD_P))) {
-            delete op;
             set_error("cell %lld field %d: dof id 0 is only valid for u/p on solid cells", (long long)c, f);
+            delete op;
             return MHD_E_INVALID;
           }
           g = -(int32_t)dir - 1;
@@ -259,8 +319,8 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
   for (size_t i = 0; i < cn.size(); i++) {
     int32_t v = mesh->cell_nodes[i] - mesh->index_base;
     if (v < 0 || v >= mesh->nnodes) {
-      delete op;
       set_error("cell_nodes[%zu]=%d out of range", i, mesh->cell_nodes[i]);
+      delete op;
       return MHD_E_INVALID;
     }
     cn[i] = v;
@@ -291,6 +351,7 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
     CR(h2d(op->d_cell_sigma, mesh->cell_sigma, op->ncells));
   }
   CR(pack_tables(op, tab));
+  CR(build_permutation(op));
   CR(ensure_red(op, 4096 + 65 * 1024));
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
 #undef CR
@@ -318,6 +379,11 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_colval);
   cudaFree(op->d_nzval);
   cudaFree(op->d_map);
+  cudaFree(op->d_ptab);
+  cudaFree(op->d_rowstart);
+  cudaFree(op->d_pgids);
+  cudaFree(op->d_perm);
+  cudaFree(op->d_order);
   cudaFree(op->d_x);
   cudaFree(op->d_y);
   cudaFree(op->d_red);

@@ -2,15 +2,22 @@
 // H1-HDiv weak form, scattered into CSR / the residual vector through the precomputed map.
 //
 // Integrands: jac_fluid_h1_hdiv (src/weakforms.jl:283-312), res_fluid_h1_hdiv (src/weakforms.jl:255-281),
-// conv (weakforms.jl:670), local projection (weakforms.jl:672-681).  Notation of SURVEY.md Appendix A.
+// solid cells jac/res_solid_h1_hdiv (:314-338), conv (weakforms.jl:670), local projection (weakforms.jl:672-681).
+// Notation of SURVEY.md Appendix A.
 //
-// Design (one persistent CTA per SM slot, one cell at a time):
-//   prep   : geometry Jacobians at the 27 Gauss points (registers -> smem), physical gradients of the Q2 basis,
-//            Piola-mapped RT basis, all pre-scaled by sqrt(w_q |det J_q|) so every block is a plain product
-//            sum_k A[k][m] B[k][n] of two shared-memory panels;
-//   blocks : register-tiled FP64 panel products (4x4 per thread) into a shared staging buffer;
-//   scatter: row-major sweep of each block section of the 16-bit scatter map (coalesced map reads, runs of
-//            consecutive nnz), plain stores for single-contribution nnz, RED.ADD.F64 otherwise.
+// Design (persistent CTAs, 2 per SM, 8 warps, one cell at a time):
+//   prep   : geometry Jacobians at the 27 Gauss points, physical gradients of the Q2 basis, Piola-mapped RT basis, all
+//            pre-scaled by sqrt(w_q |det J_q|) so that every block is a plain product sum_k A[k][m] B[k][n] of two
+//            shared-memory panels.  The reference tables arrive in panel layout with ONE bulk copy (cp.async.bulk +
+//            mbarrier) per cell, issued before the id / state loads, and are transformed in place.  Panels stay in
+//            reference order; the tensor-core jobs address their operand columns through the cell's permutation
+//            (each field sorted by global id, symbolic.cu) so that consecutive columns of a product are consecutive
+//            nnz of a CSR row.
+//   main   : one barrier-free phase.  Every warp runs tensor-core jobs (FP64 mma.sync m8n8k4): its tile of the uu block
+//            (all 9 component pairs) and then jobs drawn from a shared counter (jj strips, uj/ju, up/pu, j-phi/phi-j).
+//            A job's accumulators are transposed through a warp-private staging tile into destination order
+//            (row-major, velocity components fastest) and swept out with 32 consecutive entries per store / RED
+//            instruction; the 16-bit map codes of a job are fetched before its MMAs.
 #include <stdlib.h>
 
 #include "common.h"
@@ -29,10 +36,61 @@ int pack_tables(mhd_operator* op, const mhd_tables_t* t) {
   memcpy(&h[T_PSI], t->j_val, NQ * 108 * sizeof(double));
   memcpy(&h[T_DPSI], t->j_div, NQ * 36 * sizeof(double));
   memcpy(&h[T_CHI], t->phi_val, NQ * 8 * sizeof(double));
+  std::vector<double> pt(PT_TOTAL, 0.0);
+  for (int q = 0; q < NQ; q++) {
+    for (int v = 0; v < 8; v++)
+      for (int k = 0; k < 3; k++) h[T_GGT + (v * 3 + k) * 27 + q] = t->geo_grad[(q * 8 + v) * 3 + k];
+    for (int a = 0; a < 27; a++) {
+      pt[PT_N + q * 28 + a] = t->u_val[q * 27 + a];
+      for (int k = 0; k < 3; k++) pt[PT_G + (q * 3 + k) * 28 + a] = t->u_grad[(q * 27 + a) * 3 + k];
+    }
+    for (int m = 0; m < 36; m++) {
+      pt[PT_DIV + q * 36 + m] = t->j_div[q * 36 + m];
+      for (int k = 0; k < 3; k++) pt[PT_PSI + (q * 3 + k) * 36 + m] = t->j_val[(q * 36 + m) * 3 + k];
+    }
+    for (int k = 0; k < 4; k++) pt[PT_PP + q * 4 + k] = t->p_val[q * 4 + k];
+    for (int l = 0; l < 8; l++) pt[PT_CHI + q * 8 + l] = t->phi_val[q * 8 + l];
+  }
+  MHD_TRY(dev_alloc(&op->d_ptab, PT_TOTAL));
+  MHD_TRY(h2d(op->d_ptab, pt.data(), PT_TOTAL));
   MHD_TRY(dev_alloc(&op->d_tables, T_TOTAL));
   MHD_TRY(h2d(op->d_tables, h.data(), T_TOTAL));
   MHD_CUDA(cudaStreamSynchronize(g_stream));
   return 0;
+}
+
+// The order in which the Jacobian kernel consumes the scatter map (layout in common.h); slots are indices of the
+// permuted local numbering.  symbolic.cu resolves every (row slot, col slot) to its nnz.
+void entry_order(std::vector<uint16_t>& ord) {
+  ord.assign(NENT, ORDER_PAD);
+  auto put = [&](int e, int ri, int ci) { ord[e] = (uint16_t)((ri << 8) | ci); };
+  for (int w = 0; w < 8; w++) {
+    const int mt = w >> 1, np = w & 1, nrow = uu_nrow(mt), ncol = uu_ncol(np);
+    for (int c = 0; c < 3; c++)
+      for (int r = 0; r < nrow; r++)
+        for (int col = 0; col < ncol; col++)
+          put(uu_base(w, c) + r * ncol + col, c * 27 + 8 * mt + r, (col % 3) * 27 + 16 * np + col / 3);
+  }
+  for (int m = 0; m < NJ; m++)
+    for (int n = 0; n < NJ; n++) put(jj_base(m / 8) + (m % 8) * NJ + n, OFF_J + m, OFF_J + n);
+  for (int s = 0; s < 5; s++)
+    for (int h = 0; h < 2; h++) {
+      const int nm = uj_nm(s), na = uj_na(h), b0 = uj_base(s, h);
+      for (int c = 0; c < 3; c++)
+        for (int al = 0; al < na; al++)
+          for (int ml = 0; ml < nm; ml++) put(b0 + (c * na + al) * nm + ml, c * 27 + 16 * h + al, OFF_J + 8 * s + ml);
+      const int b1 = b0 + uj_part(s, h);
+      for (int ml = 0; ml < nm; ml++)
+        for (int col = 0; col < 3 * na; col++) put(b1 + ml * 3 * na + col, OFF_J + 8 * s + ml, (col % 3) * 27 + 16 * h + col / 3);
+    }
+  for (int i = 0; i < NU; i++)
+    for (int k = 0; k < NP; k++) put(SEC_UP + i * NP + k, i, OFF_P + k);
+  for (int k = 0; k < NP; k++)
+    for (int col = 0; col < NU; col++) put(SEC_PU + k * NU + col, OFF_P + k, (col % 3) * 27 + col / 3);
+  for (int m = 0; m < NJ; m++)
+    for (int l = 0; l < NF; l++) put(SEC_JF + m * NF + l, OFF_J + m, OFF_F + l);
+  for (int l = 0; l < NF; l++)
+    for (int m = 0; m < NJ; m++) put(SEC_FJ + l * NJ + m, OFF_F + l, OFF_J + m);
 }
 
 struct KParams {
@@ -40,177 +98,49 @@ struct KParams {
   double B[3], f[3], g[3];
   const uint8_t* cell_solid;  // null: no solid sub-domain
   const double* cell_sigma;
+  int dbg;  // MHD_JAC_DEBUG bit mask (timing experiments only): 1 no stores, 2 no main phase, 4 preparation only once,
+            // 16 phase clocks of thread 0 (summed over CTAs into clk_out, printed by the launcher)
+  unsigned long long* clk_out;
 };
 
 constexpr int NT = 256;  // threads per CTA
 
 // ---- shared-memory plan (doubles)
 constexpr int LDN = 28;                       // padded leading dimension of 27-wide panels
-constexpr int S_G = 0;                        // [81][28]  sqrt(w) dN_a/dx_i, row = q*3+i
-constexpr int S_UG = S_G + 81 * LDN;          // [27][28]  sqrt(w) (u_q . grad N_b)
-constexpr int S_XB = S_G;                     // [27][108] sqrt(w) (psi_m x B)_c, row q, col c*36+m (aliases G,UG)
-constexpr int S_N = S_UG + 27 * LDN;          // [27][28]  sqrt(w) N_a
-constexpr int S_PSI = S_N + 27 * LDN;         // [81][36]  sqrt(w) Piola(psi_m)_i, row = q*3+i
-constexpr int S_DIV = S_PSI + 81 * 36;        // [27][36]  sqrt(w) div psi_m   (contiguous after PSI)
-constexpr int S_PP = S_DIV + 27 * 36;         // [27][4]
-constexpr int S_CHI = S_PP + 27 * 4;          // [27][8]
-constexpr int S_T = S_CHI + 27 * 8;           // [27][9]   (d_d u_c)(q), index d*3+c
+// the first PT_TOTAL doubles mirror the panel-layout tables (PT_*): destination of the per-cell bulk copy
+constexpr int S_G = PT_G;                     // [81][28]  sqrt(w) dN_a/dx_i, row = q*3+i
+constexpr int S_N = PT_N;                     // [27][28]  sqrt(w) N_a
+constexpr int S_PSI = PT_PSI;                 // [81][36]  sqrt(w) Piola(psi_m)_i, row = q*3+i
+constexpr int S_DIV = PT_DIV;                 // [27][36]  sqrt(w) div psi_m   (contiguous after PSI)
+constexpr int S_PP = PT_PP;                   // [27][4]
+constexpr int S_CHI = PT_CHI;                 // [27][8]
+constexpr int S_UG = PT_TOTAL;                // [27][28]  sqrt(w) (u_q . grad N_b)
+constexpr int S_T = S_UG + 27 * LDN;           // [27][9]   (d_d u_c)(q), index d*3+c
 constexpr int LDT = 10;                       // padded row of the velocity-gradient table
-constexpr int S_ST = S_T + 27 * LDT + 2;      // staging
-constexpr int ST_SIZE = 2070 + 1296;
-constexpr int S_J = S_ST + ST_SIZE;           // [27][9]
-constexpr int S_INV = S_J + 243;              // [27][9]
-constexpr int S_DET = S_INV + 243;            // [27]
+constexpr int SWN = 400;                      // warp-private staging tile (doubles)
+constexpr int S_ST = S_T + 27 * LDT + 2;      // staging: 8 warps x SWN (the residual's scratch during the preparation)
+constexpr int ST_SIZE = 8 * SWN;
+constexpr int S_J = S_ST + ST_SIZE;           // [27][9] J sqrt(w |det|) / det
+constexpr int S_INV = S_J + 243;              // [27][9] J^-1 sqrt(w |det|)
+constexpr int S_DET = S_INV + 243;            // [27] sqrt(w |det J|) / det J
 constexpr int S_SW = S_DET + 27;              // [27]
 constexpr int S_X = S_SW + 27;                // [8][3]
 constexpr int S_U = S_X + 24;                 // [129] local state
 constexpr int S_SG = S_U + 130;               // [36] sign
-constexpr int S_E = S_SG + 36;                // [4][81]
-constexpr int S_MI = S_E + 324;               // [16]
+constexpr int S_E = S_SG + 36;                // [4][81]  zeta_u M_p^-1 D, column = d*27+b
+constexpr int S_D = S_E + 324;                // [81][4]  D[(c,a)][k] = sum_q w pi_k d_c N_a
+constexpr int S_MI = S_D + 324;               // [16]
 constexpr int S_UQ = S_MI + 16;               // [27][3] u at q (unweighted)
 constexpr int S_SC = S_UQ + 82;               // [108] scale vector for the jj product
-constexpr int S_END = S_SC + 108;
-constexpr int SMEM_BYTES = S_END * 8 + NLOC * 8 /*row starts*/ + 132 * 4 /*gids*/;
-
-// staging sub-buffers of phase 1
-constexpr int ST_D = 0;      // [81][4]  D[(c,a)][k] = sum_q w pi_k d_c N_a
-constexpr int ST_S = 324;    // [27][27]
-constexpr int ST_C = 1053;   // [27][27]
-constexpr int ST_JF = 1782;  // [36][8]
-constexpr int ST_JJ = 2070;  // [36][36]   (uj/ju results reuse [0,2916) after phase 0 is scattered)
-
-// ---------------------------------------------------------------------------------------------
-// register-tiled panel product:  C[batch][m][n] = sum_k A[k*lda + m] * (sc ? sc[k*scs] : 1) * B[k*ldb + n]
-// A thread owns TM x TN outputs arranged as PAIRS of adjacent rows/columns: rows {2(tm + MT*p), +1}, p < TM/2 and
-// columns {2(tn + NTL*p), +1}, p < TN/2.  Adjacent lanes therefore read adjacent 16-byte words of a panel row
-// (LDS.128, bank-conflict free) while lanes that share tm read the same A word (broadcast).  Panels need
-// lda >= TM*MT, ldb >= TN*NTL (even) and 16-byte aligned rows.  tile t -> thread (t + toff) % NT.
-// store(batch, m, n, value) is called for in-range entries.
-template <int M, int N, int TM, int TN, bool SCALE, class Store>
-__device__ __forceinline__ void panel_product(int nbatch, const double* __restrict__ A, int lda, int a_bs,
-                                              const double* __restrict__ B, int ldb, int b_bs, int K,
-                                              const double* __restrict__ sc, int scs, int sc_bs, int toff,
-                                              Store store) {
-  static_assert(TM % 2 == 0 && TN % 2 == 0, "tiles are built from pairs");
-  constexpr int MT = (M + TM - 1) / TM, NTL = (N + TN - 1) / TN;
-  constexpr int PM = TM / 2, PN = TN / 2;
-  const int ntiles = nbatch * MT * NTL;
-  int t0 = (int)threadIdx.x - toff;
-  t0 %= NT;
-  if (t0 < 0) t0 += NT;
-  for (int t = t0; t < ntiles; t += NT) {
-    const int batch = t / (MT * NTL);
-    const int r = t - batch * (MT * NTL);
-    const int tm = r / NTL, tn = r - tm * NTL;
-    const double* a = A + batch * a_bs + 2 * tm;
-    const double* b = B + batch * b_bs + 2 * tn;
-    const double* s = SCALE ? sc + batch * sc_bs : nullptr;
-    double acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-      for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
-#pragma unroll 3
-    for (int k = 0; k < K; k++) {
-      double av[TM], bv[TN];
-#pragma unroll
-      for (int p = 0; p < PM; p++) {
-        const double2 v = *reinterpret_cast<const double2*>(a + k * lda + 2 * MT * p);
-        av[2 * p] = v.x;
-        av[2 * p + 1] = v.y;
-      }
-#pragma unroll
-      for (int p = 0; p < PN; p++) {
-        const double2 v = *reinterpret_cast<const double2*>(b + k * ldb + 2 * NTL * p);
-        bv[2 * p] = v.x;
-        bv[2 * p + 1] = v.y;
-      }
-      if (SCALE) {
-        const double sk = s[k * scs];
-#pragma unroll
-        for (int i = 0; i < TM; i++) av[i] *= sk;
-      }
-#pragma unroll
-      for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < TN; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-      for (int j = 0; j < TN; j++) {
-        const int m = 2 * (tm + MT * (i / 2)) + (i & 1), n = 2 * (tn + NTL * (j / 2)) + (j & 1);
-        if (m < M && n < N) store(batch, m, n, acc[i][j]);
-      }
-  }
-}
-
-// Unrolled scatter sweep: U map codes are loaded before any of them is used (memory-level parallelism; the sweep
-// is otherwise bound by the latency of the 2-byte map loads).  getcode(e) reads the map code of sweep entry e,
-// f(e, rowstart&, value&) supplies the nnz row offset and the value.
-template <int U, class G, class F>
-__device__ __forceinline__ void scatter_generic(double* __restrict__ nz, int count, G getcode, F f) {
-  for (int base = 0; base < count; base += NT * U) {
-    uint16_t c[U];
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      const int e = base + k * NT + (int)threadIdx.x;
-      c[k] = e < count ? getcode(e) : MAP_SKIP;
-    }
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      if (c[k] == MAP_SKIP) continue;
-      const int e = base + k * NT + (int)threadIdx.x;
-      long long rowstart;
-      double v;
-      f(e, rowstart, v);
-      double* p = nz + rowstart + (c[k] & 0x7FFF);
-      if (c[k] & MAP_EXCL) *p = v;
-      else atomicAdd(p, v);
-    }
-  }
-}
-
-// Split form of the sweep for single-pass sections (count <= U * NT): the map codes are fetched into registers
-// BEFORE the panel products that produce the values, so their global-load latency is hidden by the math.
-template <int U>
-struct Codes {
-  uint16_t c[U];
-};
-template <int U>
-__device__ __forceinline__ void load_codes(Codes<U>& cd, const uint16_t* __restrict__ codes, int count) {
-#pragma unroll
-  for (int k = 0; k < U; k++) {
-    const int e = k * NT + (int)threadIdx.x;
-    cd.c[k] = e < count ? __ldg(codes + e) : MAP_SKIP;
-  }
-}
-template <int U, class F>
-__device__ __forceinline__ void scatter_loaded(double* __restrict__ nz, const Codes<U>& cd, F f) {
-#pragma unroll
-  for (int k = 0; k < U; k++) {
-    const uint16_t c = cd.c[k];
-    if (c == MAP_SKIP) continue;
-    const int e = k * NT + (int)threadIdx.x;
-    long long rowstart;
-    double v;
-    f(e, rowstart, v);
-    double* p = nz + rowstart + (c & 0x7FFF);
-    if (c & MAP_EXCL) *p = v;
-    else atomicAdd(p, v);
-  }
-}
+constexpr int S_GGT = S_SC + 108;             // [8][3][27] geometry-map gradients (persistent: loaded once per CTA)
+constexpr int S_W = S_GGT + 648;              // [27] quadrature weights (persistent)
+constexpr int S_END = S_W + 28;
+constexpr int SMEM_BYTES = S_END * 8 + NLOC * 8 /*row starts*/ + 132 * 4 /*gids*/ + PERM_STRIDE + 16 /*job counter*/ +
+                           128 /*phase clocks*/ + 16 /*mbarrier*/ + 132 * 4 /*next gids*/;
 
 // ---------------------------------------------------------------------------------------------
 // FP64 tensor-core path: mma.sync.m8n8k4 (DMMA).  Same peak rate as the FP64 FMA pipe on B200, but an 8x8x4 product
-// costs one operand word per lane and operand fragments are shared by all tiles of a warp's output block, which
-// halves the shared-memory wavefronts of the panel products (the kernel is L1TEX-bound, not FP64- or HBM-bound).
-#ifndef MHD_NO_MMA
-constexpr bool USE_MMA = true;
-#else
-constexpr bool USE_MMA = false;
-#endif
-
+// costs one operand word per lane and operand fragments are shared by all tiles of a warp's output block.
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
@@ -255,22 +185,64 @@ __device__ __forceinline__ void warp_mma_acc(const double* __restrict__ A, int l
   }
 }
 
-template <int MT, int NTL, bool SCALE, class Store>
-__device__ __forceinline__ void warp_mma_product(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                                                 int K, const double* __restrict__ sc, int scs, int m0, int n0, int M, int N,
-                                                 Store store) {
-  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
-  double acc[MT][NTL][2];
-  warp_mma_acc<MT, NTL, SCALE>(A, lda, B, ldb, K, sc, scs, m0, n0, acc);
+// Same product with GATHERED operand columns: this lane's column of row tile i is A[.][acol[i]], of column tile j
+// B[.][bcol[j]] (the caller resolves slots of the permuted numbering to panel columns once per job).
+template <int MT, int NTL, bool SCALE>
+__device__ __forceinline__ void warp_mma_cols(const double* __restrict__ A, int lda, const int (&acol)[MT],
+                                              const double* __restrict__ B, int ldb, const int (&bcol)[NTL], int K,
+                                              const double* __restrict__ sc, int scs, double (&acc)[MT][NTL][2]) {
+  const int lk = threadIdx.x & 3;
 #pragma unroll
   for (int i = 0; i < MT; i++)
 #pragma unroll
-    for (int j = 0; j < NTL; j++)
+    for (int j = 0; j < NTL; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const int kk = k0 + lk;
+    const bool valid = kk < K;
+    const int kc = valid ? kk : 0;
+    double a[MT], b[NTL];
+    const double s = SCALE ? sc[kc * scs] : 1.0;
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const int m = m0 + 8 * i + lr, n = n0 + 8 * j + 2 * lk + r;
-        if (m < M && n < N) store(m, n, acc[i][j][r]);
-      }
+    for (int i = 0; i < MT; i++) {
+      const double v = A[kc * lda + acol[i]];
+      a[i] = valid ? v : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NTL; j++) {
+      const double v = B[kc * ldb + bcol[j]];
+      b[j] = valid ? (SCALE ? v * s : v) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++)
+#pragma unroll
+      for (int j = 0; j < NTL; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// ---- bulk asynchronous copy (TMA engine, no tensor map) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 
 // Velocity gradient at the 27 Gauss points through the tensor cores:
@@ -280,7 +252,7 @@ __device__ __forceinline__ void warp_mma_product(const double* __restrict__ A, i
 // shared by the residual and the Newton block of the fused kernel.
 __device__ __forceinline__ void velocity_gradient_mma(const double* __restrict__ G, const double* __restrict__ U,
                                                       const double* __restrict__ sw, double* __restrict__ Gq,
-                                                      double* __restrict__ T, int ldt) {
+                                                      double* __restrict__ T, int ldt, double tscale = 1.0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
   for (int mt = warp; mt < 11; mt += NT / 32) {
     double c0 = 0.0, c1 = 0.0;
@@ -303,7 +275,7 @@ __device__ __forceinline__ void velocity_gradient_mma(const double* __restrict__
         if (c < 3) {
           const double v = r ? c1 : c0;
           if (Gq) Gq[q * 9 + d * 3 + c] = v;
-          if (T) T[q * ldt + d * 3 + c] = v / sw[q];
+          if (T) T[q * ldt + d * 3 + c] = tscale * v / sw[q];
         }
       }
     }
@@ -313,26 +285,90 @@ __device__ __forceinline__ void velocity_gradient_mma(const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 struct CellCtx {
   double* sm;
-  long long* row;  // [129] nnz offset of each local row (-1: dropped)
-  int32_t* gid;    // [129]
+  long long* row;  // [129] byte address of the first nnz of each local row, PERMUTED numbering (0: dropped)
+  int32_t* gid;    // [129] permuted local numbering (state, residual, row starts)
+  uint8_t* perm;   // [PERM_STRIDE] slot -> reference basis index
+  int32_t* gidn;   // [129] dof ids of the CTA's next cell (fetched while the geometry is computed)
+  bool have_next;  // gidn is valid for the cell being prepared
+  uint64_t* mbar;  // completion of the table bulk copy
+  uint32_t parity;
+  long long* clk;  // [16] phase clock accumulators (MHD_JAC_DEBUG & 16), thread 0 only
+  bool clk_on;
 };
 
-// loads + geometry + mapped bases.  NEED_STATE: 0 none, 1 u only, 2 all fields
+// phase timing (timing experiments only): thread 0 accumulates the cycles since the previous mark into slot i
+#define MHD_MARK(cx, i)                                   \
+  do {                                                    \
+    if ((cx).clk_on && threadIdx.x == 0) {                \
+      const long long _t = clock64();                     \
+      (cx).clk[i] += _t - (cx).clk[15];                   \
+      (cx).clk[15] = _t;                                  \
+    }                                                     \
+  } while (0)
+
+__device__ __forceinline__ CellCtx make_ctx(double* smem) {
+  CellCtx cx;
+  cx.sm = smem;
+  cx.row = (long long*)(smem + S_END);
+  cx.gid = (int32_t*)(cx.row + NLOC);
+  cx.perm = (uint8_t*)(cx.gid + 132);
+  cx.clk = (long long*)(cx.perm + PERM_STRIDE + 16);
+  cx.mbar = (uint64_t*)(cx.clk + 16);
+  cx.gidn = (int32_t*)(cx.mbar + 2);
+  cx.have_next = false;
+  cx.parity = 0;
+  cx.clk_on = false;
+  return cx;
+}
+
+struct CellArgs {
+  const double* tab;         // d_tables (T_*)
+  const double* ptab;        // d_ptab (PT_*)
+  const double* coords;
+  const int32_t* cell_nodes;
+  const int32_t* gids;       // permuted numbering (d_pgids): local dofs of each field sorted by global id
+  const int64_t* rowstart;   // [ncells][129] first nnz of each local row (permuted numbering), -1: dropped
+  const uint8_t* perm;
+  const int8_t* jsign;
+  const double* dirv;
+};
+
+// once per CTA: mbarrier, persistent geometry tables
+__device__ __forceinline__ void prep_init(const CellCtx& cx, const CellArgs& A) {
+  if (threadIdx.x == 0) mbar_init(cx.mbar, 1);
+  for (int i = threadIdx.x; i < 648; i += NT) cx.sm[S_GGT + i] = A.tab[T_GGT + i];
+  if (threadIdx.x < NQ) cx.sm[S_W + threadIdx.x] = A.tab[T_W + threadIdx.x];
+  __syncthreads();
+}
+
+// loads + geometry + mapped bases.  NEED_STATE: 0 none, 1 u only, 2 all fields.  rowptr != null: also the nnz row starts
+// (permuted numbering).  Must be entered right after a CTA barrier that retires every use of the previous panels.
 template <int NEED_STATE>
-__device__ __forceinline__ void cell_prep(const CellCtx& cx, int64_t cell, const double* __restrict__ tab,
-                                          const double* __restrict__ coords, const int32_t* __restrict__ cell_nodes,
-                                          const int32_t* __restrict__ gids, const int8_t* __restrict__ jsign,
-                                          const double* __restrict__ dirv, const double* __restrict__ x) {
+__device__ __forceinline__ void cell_prep(CellCtx& cx, int64_t cell, int64_t next_cell /* -1: none */, const CellArgs& A,
+                                          const double* __restrict__ x, const double* __restrict__ nz /* null: no row starts */) {
   double* sm = cx.sm;
   const int tid = threadIdx.x;
-  for (int i = tid; i < NLOC; i += NT) {
-    const int32_t g = gids[cell * NLOC + i];
+  if (tid == NT - 1) bulk_load(sm, A.ptab, PT_TOTAL * 8, cx.mbar);  // reference tables -> panel buffers (async)
+  MHD_MARK(cx, 10);
+  if (tid < NLOC) {
+    const int i = tid;
+    const int32_t g = cx.have_next ? cx.gidn[i] : A.gids[cell * NLOC + i];
     cx.gid[i] = g;
-    if (NEED_STATE == 2 || (NEED_STATE == 1 && i < NU)) sm[S_U + i] = g >= 0 ? x[g] : dirv[-g - 1];
+    if (NEED_STATE == 2 || (NEED_STATE == 1 && i < NU)) sm[S_U + i] = g >= 0 ? x[g] : A.dirv[-g - 1];
+    if (nz) {
+      const int64_t rs = A.rowstart[cell * NLOC + i];
+      cx.row[i] = rs >= 0 ? (long long)(nz + rs) : 0;
+    }
+  } else if (tid < NLOC + 24) {
+    const int t = tid - NLOC;
+    sm[S_X + t] = A.coords[(int64_t)A.cell_nodes[cell * 8 + t / 3] * 3 + t % 3];
+  } else if (tid < NLOC + 24 + PERM_STRIDE / 4) {
+    const int t = tid - NLOC - 24;
+    reinterpret_cast<uint32_t*>(cx.perm)[t] = reinterpret_cast<const uint32_t*>(A.perm + cell * PERM_STRIDE)[t];
   }
-  if (tid < 24) sm[S_X + tid] = coords[(int64_t)cell_nodes[cell * 8 + tid / 3] * 3 + tid % 3];
-  if (tid >= 32 && tid < 32 + NJ) sm[S_SG + tid - 32] = (double)jsign[cell * NJ + tid - 32];
+  MHD_MARK(cx, 11);
   __syncthreads();
+  MHD_MARK(cx, 1);
   if (tid < NQ) {
     const int q = tid;
     double J[3][3];
@@ -340,12 +376,16 @@ __device__ __forceinline__ void cell_prep(const CellCtx& cx, int64_t cell, const
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int k = 0; k < 3; k++) J[i][k] = 0.0;
+#pragma unroll
     for (int v = 0; v < 8; v++) {
+      double gk[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) gk[k] = sm[S_GGT + (v * 3 + k) * 27 + q];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         const double xv = sm[S_X + v * 3 + i];
 #pragma unroll
-        for (int k = 0; k < 3; k++) J[i][k] = fma(xv, tab[T_GG + (q * 8 + v) * 3 + k], J[i][k]);
+        for (int k = 0; k < 3; k++) J[i][k] = fma(xv, gk[k], J[i][k]);
       }
     }
     const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
@@ -364,66 +404,85 @@ __device__ __forceinline__ void cell_prep(const CellCtx& cx, int64_t cell, const
     inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
     inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
     inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    const double sw = sqrt(sm[S_W + q] * fabs(det));
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        sm[S_J + q * 9 + i * 3 + k] = J[i][k];
-        sm[S_INV + q * 9 + k * 3 + i] = inv[k][i];
+        sm[S_J + q * 9 + i * 3 + k] = J[i][k] * (sw * id);   // Piola factor sqrt(w|det|)/det folded in
+        sm[S_INV + q * 9 + k * 3 + i] = inv[k][i] * sw;
       }
-    sm[S_DET + q] = det;
-    sm[S_SW + q] = sqrt(tab[T_W + q] * fabs(det));
+    sm[S_SW + q] = sw;
+    sm[S_DET + q] = sw * id;  // sqrt(w |det|) / det
+    MHD_MARK(cx, 9);
+  } else if (NEED_STATE >= 1 && tid >= 32 && tid < 32 + 81) {
+    // u at the quadrature points (unweighted) from the still untransformed N table, by warps without geometry work
+    mbar_wait(cx.mbar, cx.parity);
+    const int t = tid - 32, q = t / 3, i = t - q * 3;
+    double s = 0.0;
+#pragma unroll 9
+    for (int a = 0; a < 27; a++) s = fma(sm[S_N + q * LDN + cx.perm[a]], sm[S_U + i * 27 + a], s);
+    sm[S_UQ + t] = s;
+  }
+  // threads without geometry work: ids of the CTA's next cell -> shared memory, and its state / vertex lines -> L2
+  cx.have_next = next_cell >= 0;
+  if (next_cell >= 0) {
+    if (tid >= 113 && tid < 113 + NLOC) {
+      const int32_t gn = A.gids[next_cell * NLOC + tid - 113];
+      cx.gidn[tid - 113] = gn;
+      if (NEED_STATE >= 1 && gn >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + gn));
+    } else if (tid >= 113 + NLOC && tid < 113 + NLOC + 8) {
+      const int32_t nd = A.cell_nodes[next_cell * 8 + tid - 113 - NLOC];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(A.coords + (int64_t)nd * 3));
+    }
   }
   __syncthreads();
-  // Q2 panels
-  for (int idx = tid; idx < NQ * LDN; idx += NT) {
-    const int q = idx / LDN, a = idx - q * LDN;
-    if (a < 27) {
-      const double sw = sm[S_SW + q];
-      const double d0 = tab[T_DNU + (q * 27 + a) * 3 + 0], d1 = tab[T_DNU + (q * 27 + a) * 3 + 1],
-                   d2 = tab[T_DNU + (q * 27 + a) * 3 + 2];
+  MHD_MARK(cx, 2);
+  mbar_wait(cx.mbar, cx.parity);  // (complete long ago) makes the bulk copy visible to this thread
+  cx.parity ^= 1;
+  // In-place transforms WITH the column permutation (slot -> reference basis function): one warp owns the rows of one
+  // quadrature point; every lane gathers its (reference) column entries, the warp synchronises, then the transformed
+  // values are written to the slot column.  Panels end up in the permuted numbering: fragment loads are plain strided.
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ar = lane < 27 ? cx.perm[lane] : 27;                      // Q2 column of this lane (27 = zero pad column)
+    const int m1 = lane + 32;                                           // second RT column (lanes 0..3)
+    const int pm0 = cx.perm[27 + lane], pm1 = lane < 4 ? cx.perm[27 + m1] : 0;
+    const double sg0 = (pm0 & 0x80) ? -1.0 : 1.0, sg1 = (pm1 & 0x80) ? -1.0 : 1.0;
+    const int mr0 = pm0 & 0x7F, mr1 = pm1 & 0x7F;
+    for (int q = warp; q < NQ; q += NT / 32) {
+      const double d0 = sm[S_G + (q * 3 + 0) * LDN + ar], d1 = sm[S_G + (q * 3 + 1) * LDN + ar], d2 = sm[S_G + (q * 3 + 2) * LDN + ar];
+      const double nn = sm[S_N + q * LDN + ar];
+      const double p0 = sm[S_PSI + (q * 3 + 0) * NJ + mr0], p1 = sm[S_PSI + (q * 3 + 1) * NJ + mr0], p2 = sm[S_PSI + (q * 3 + 2) * NJ + mr0];
+      const double dv0 = sm[S_DIV + q * NJ + mr0];
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0, dv1 = 0.0;
+      if (lane < 4) {
+        r0 = sm[S_PSI + (q * 3 + 0) * NJ + mr1]; r1 = sm[S_PSI + (q * 3 + 1) * NJ + mr1]; r2 = sm[S_PSI + (q * 3 + 2) * NJ + mr1];
+        dv1 = sm[S_DIV + q * NJ + mr1];
+      }
       const double* inv = sm + S_INV + q * 9;
+      const double* J = sm + S_J + q * 9;
+      const double sw = sm[S_SW + q], pdet = sm[S_DET + q];
+      __syncwarp();
+      if (lane < LDN) {
 #pragma unroll
-      for (int i = 0; i < 3; i++)
-        sm[S_G + (q * 3 + i) * LDN + a] = sw * (d0 * inv[0 * 3 + i] + d1 * inv[1 * 3 + i] + d2 * inv[2 * 3 + i]);
-      sm[S_N + q * LDN + a] = sw * tab[T_NU + q * 27 + a];
-    } else {
+        for (int i = 0; i < 3; i++) sm[S_G + (q * 3 + i) * LDN + lane] = d0 * inv[0 * 3 + i] + d1 * inv[1 * 3 + i] + d2 * inv[2 * 3 + i];
+        sm[S_N + q * LDN + lane] = nn * sw;
+        if (lane == 27) sm[S_UG + q * LDN + lane] = 0.0;
+      }
 #pragma unroll
-      for (int i = 0; i < 3; i++) sm[S_G + (q * 3 + i) * LDN + a] = 0.0;
-      sm[S_N + q * LDN + a] = 0.0;
-      sm[S_UG + q * LDN + a] = 0.0;
+      for (int i = 0; i < 3; i++) sm[S_PSI + (q * 3 + i) * NJ + lane] = sg0 * (J[i * 3 + 0] * p0 + J[i * 3 + 1] * p1 + J[i * 3 + 2] * p2);
+      sm[S_DIV + q * NJ + lane] = dv0 * sg0 * pdet;
+      if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) sm[S_PSI + (q * 3 + i) * NJ + m1] = sg1 * (J[i * 3 + 0] * r0 + J[i * 3 + 1] * r1 + J[i * 3 + 2] * r2);
+        sm[S_DIV + q * NJ + m1] = dv1 * sg1 * pdet;
+      }
     }
   }
-  // RT panels (contravariant Piola + sign flip)
-  for (int idx = tid; idx < NQ * NJ; idx += NT) {
-    const int q = idx / NJ, m = idx - q * NJ;
-    const double s = sm[S_SG + m] * sm[S_SW + q] / sm[S_DET + q];
-    const double p0 = tab[T_PSI + (q * 36 + m) * 3 + 0], p1 = tab[T_PSI + (q * 36 + m) * 3 + 1],
-                 p2 = tab[T_PSI + (q * 36 + m) * 3 + 2];
-    const double* J = sm + S_J + q * 9;
-#pragma unroll
-    for (int i = 0; i < 3; i++) sm[S_PSI + (q * 3 + i) * NJ + m] = s * (J[i * 3 + 0] * p0 + J[i * 3 + 1] * p1 + J[i * 3 + 2] * p2);
-    sm[S_DIV + q * NJ + m] = s * tab[T_DPSI + q * 36 + m];
-  }
-  for (int idx = tid; idx < NQ * 4; idx += NT) sm[S_PP + idx] = sm[S_SW + idx / 4] * tab[T_PP + idx];
-  for (int idx = tid; idx < NQ * 8; idx += NT) sm[S_CHI + idx] = sm[S_SW + idx / 8] * tab[T_CHI + idx];
-  if (NEED_STATE >= 1) {
-    // u at the quadrature points (unweighted)
-    if (tid < 81) {
-      const int q = tid / 3, i = tid - q * 3;
-      double s = 0.0;
-      for (int a = 0; a < 27; a++) s = fma(tab[T_NU + q * 27 + a], sm[S_U + i * 27 + a], s);
-      sm[S_UQ + tid] = s;
-    }
-  }
+  for (int idx = tid; idx < NQ * 12; idx += NT) sm[S_PP + idx] *= sm[S_SW + (idx < 108 ? idx / 4 : (idx - 108) / 8)];
   __syncthreads();
-}
-
-__device__ __forceinline__ void scatter_entry(double* __restrict__ nz, long long rowstart, uint16_t code, double v) {
-  if (code == MAP_SKIP) return;
-  double* p = nz + rowstart + (code & 0x7FFF);
-  if (code & MAP_EXCL) *p = v;
-  else atomicAdd(p, v);
+  MHD_MARK(cx, 3);
 }
 
 template <int CONV, bool ZU>
@@ -431,56 +490,104 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, i
                                               const KParams& P);
 constexpr int RES_GQ = 81 + 243 + 81 + 27 * 4;  // offset of the velocity-gradient table inside the residual scratch
 
+// ---------------------------------------------------------------------------------------------
+// Sweep of a staged tile: entry e = k*32 + lane of the job's map range <-> staged value Sw[(e / NCOL) * LD + e % NCOL],
+// local row rowof(e / NCOL).  A warp instruction therefore covers 32 consecutive entries of a destination-ordered
+// (row-major, sorted columns) range: full-sector stores / REDs wherever the nnz are contiguous.
+// Map codes as signed 16-bit values: >= 0: RED.ADD at that row-relative position; < -1: bit 15 = exclusive nnz, plain
+// store at position (code & 0x7FFF); -1 (MAP_SKIP): dropped.
+template <int KMAX>
+__device__ __forceinline__ void load_codes(int (&code)[KMAX], const uint16_t* __restrict__ cmap, int n) {
+  const short* p = reinterpret_cast<const short*>(cmap) + (threadIdx.x & 31);
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) code[k] = k * 32 < n ? (int)__ldg(p + k * 32) : -1;  // ranges are padded to 32
+}
+
+__device__ __forceinline__ void scatter_pred(double* p, double v, int code) {
+  asm volatile(
+      "{\n\t.reg .pred pr, ps;\n\t"
+      "setp.ge.s32 pr, %2, 0;\n\t"
+      "setp.lt.s32 ps, %2, -1;\n\t"
+      "@ps st.global.f64 [%0], %1;\n\t"
+      "@pr red.global.add.f64 [%0], %1;\n\t}"
+      ::"l"(p), "d"(v), "r"(code)
+      : "memory");
+}
+
+// row[] holds the byte address of the first nnz of each local row (0 for dropped rows: their codes are all SKIP)
+template <int NCOL, int LD, int KMAX, class RowOf>
+__device__ __forceinline__ void sweep(const int (&code)[KMAX], int n, const double* __restrict__ Sw,
+                                      const long long* __restrict__ row, RowOf rowof, bool nostore = false) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    if (k * 32 >= n) break;
+    int r, col;
+    if (NCOL >= 32) {
+      r = (k * 32) / NCOL;
+      col = (k * 32) % NCOL + lane;
+      if (col >= NCOL) { col -= NCOL; r++; }
+    } else {
+      const int e = k * 32 + lane;
+      r = e / NCOL;      // NCOL is 4 or 8
+      col = e % NCOL;
+    }
+    const double v = Sw[r * LD + col];
+    double* p = reinterpret_cast<double*>(row[rowof(r)]) + (code[k] & 0x7FFF);
+    if (!nostore) scatter_pred(p, v, code[k]);
+  }
+}
+
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
 // =============================================================================================
-// Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0.
-// RES: also assemble the residual at the same state (residual_and_jacobian!), sharing the cell preparation.
+// Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0 (rank-4 update zeta_u D^T M_p^-1 D of the uu
+// block, folded into the tensor-core products as one extra k-step).  RES: also assemble the residual at the same state
+// (residual_and_jacobian!), sharing the cell preparation.
+constexpr int NJOBS = 17;
+
 template <int CONV, bool ZU, bool RES>
 __global__ void __launch_bounds__(NT, 2)
-jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
-                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
-                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
-                const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ map, double* __restrict__ nz,
+jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restrict__ x,
+                const uint16_t* __restrict__ map, double* __restrict__ nz,
                 double* __restrict__ rvec, KParams P) {
   extern __shared__ __align__(16) double smem[];
-  CellCtx cx;
-  cx.sm = smem;
-  cx.row = (long long*)(smem + S_END);
-  cx.gid = (int32_t*)(cx.row + NLOC);
+  CellCtx cx = make_ctx(smem);
+  cx.clk_on = (P.dbg & 16) != 0;
+  if (cx.clk_on && threadIdx.x == 0) {
+    for (int i = 0; i < 15; i++) cx.clk[i] = 0;
+    cx.clk[15] = clock64();
+  }
   double* sm = smem;
+  int* jobctr = reinterpret_cast<int*>(cx.perm + PERM_STRIDE);
   const int tid = threadIdx.x;
-  double* St = sm + S_ST;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+  double* Sw = sm + S_ST + warp * SWN;
+  prep_init(cx, A);
 
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
-    __syncthreads();  // previous cell's scatter done before its tables are overwritten
+    __syncthreads();  // every warp is done with the previous cell's panels
+    MHD_MARK(cx, 0);
     {
-      // pull the NEXT cell's scatter map (30 KB), dof ids and vertex ids into L2 while this cell is being processed:
-      // every later load of them then pays L2 latency instead of DRAM latency inside the barrier-separated phases
+      // pull the NEXT cell's scatter map (30 KB), dof ids and vertex ids into L2 while this cell is being processed
       const int64_t nxt = cell + gridDim.x;
-      if (nxt < ncells) {
+      if (nxt < ncells && !(P.dbg & 32)) {
         const char* m0 = reinterpret_cast<const char*>(map + nxt * NENT_PAD);
         if (tid * 128 < NENT_PAD * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + tid * 128));
-        if (tid < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gids + nxt * NLOC) + tid * 128));
-        if (tid == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_nodes + nxt * 8));
-        if (tid == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(jsign + nxt * NJ));
+        if (tid >= 16 && tid < 25) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(A.rowstart + nxt * NLOC) + (tid - 16) * 128));
+        if (tid >= 8 && tid < 13) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(A.gids + nxt * NLOC) + (tid - 8) * 128));
+        if (tid == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cell_nodes + nxt * 8));
+        if (tid == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.perm + nxt * PERM_STRIDE));
       }
     }
-    cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
-    for (int i = tid; i < NLOC; i += NT) {
-      const int32_t g = cx.gid[i];
-      cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
-    }
-    if (RES || CONV == 2) {
-      // velocity gradient once per cell: Gq for the residual (its scratch area), T for the Newton block
-      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr,
-                            CONV == 2 ? sm + S_T : nullptr, LDT);
-    }
-    if (RES) {
-      __syncthreads();
-      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, cell, nrows, rvec, P);
-      __syncthreads();  // the residual's scratch lives in the staging area that phase 0 overwrites
-    }
+    const int64_t nxt_cell = cell + gridDim.x < ncells ? cell + gridDim.x : -1;
+    if (!(P.dbg & 4) || cell == blockIdx.x)
+    cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, nxt_cell, A, x, nz);
+    if (RES || CONV == 2)
+      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr, CONV == 2 ? sm + S_T : nullptr, LDT,
+                            P.alpha);  // T = alpha d_d u_c
     if (CONV > 0) {
-      // UG[q][b] = sqrt(w) u_q . grad N_b ;  T[q][d*3+c] = d_d u_c (unweighted)
+      // UG[q][b] = sqrt(w) u_q . grad N_b
       for (int idx = tid; idx < NQ * 27; idx += NT) {
         const int q = idx / 27, b = idx - q * 27;
         double s = 0.0;
@@ -490,90 +597,28 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
       }
     }
     if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
-    __syncthreads();
-
-    const uint16_t* cmap = map + cell * NENT_PAD;
-    const long long* row = cx.row;
-    // solid cells (jac_solid_h1_hdiv, weakforms.jl:327-338): own conductivity, +phi div j instead of -div j phi; their
-    // u/p dofs are absent (map codes SKIP), so the u-related products are skipped
-    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
-    const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
-    const double fj_sign = solid ? 1.0 : -1.0;
-    // map codes of the sections scattered right after phase 0, fetched now (latency hidden by the panel products)
-    Codes<2> c_up, c_pu, c_jf, c_fj;
-    Codes<6> c_jj;
-    load_codes(c_up, cmap + SEC_UP, NU * NP);
-    load_codes(c_pu, cmap + SEC_PU, NP * NU);
-    load_codes(c_jf, cmap + SEC_JF, NJ * NF);
-    load_codes(c_fj, cmap + SEC_FJ, NF * NJ);
-    load_codes(c_jj, cmap + SEC_JJ, NJ * NJ);
-
-    // ---------------- phase 0: D (up), j-phi, jj, S, C (+ pressure mass matrix), all independent panel products
-    if (USE_MMA) {
-      // 12 warp jobs, heaviest first, dealt round-robin to the 8 warps
-      const int warp = tid >> 5;
-      const bool zj = P.zeta_j != 0.0;
-      for (int job = warp; job < 12; job += 8) {
-        if (job < 2) {
-          // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b], two column halves
-          warp_mma_product<4, 2, false>(sm + S_G, LDN, sm + S_G, LDN, 81, nullptr, 0, 0, 16 * job, 27, 27,
-                                        [&](int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
-        } else if (job < 7) {
-          // jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous), one 8-column strip each
-          const int n0 = 8 * (job - 2);
-          if (zj)
-            warp_mma_product<5, 1, true>(sm + S_PSI, NJ, sm + S_PSI, NJ, 108, sm + S_SC, 1, 0, n0, NJ, NJ,
-                                         [&](int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
-          else
-            warp_mma_product<5, 1, false>(sm + S_PSI, NJ, sm + S_PSI, NJ, 81, nullptr, 0, 0, n0, NJ, NJ,
-                                          [&](int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
-        } else if (job == 7) {
-          // C[a][b] = sum_q N[q][a] UG[q][b]
-          if (CONV > 0)
-            warp_mma_product<4, 4, false>(sm + S_N, LDN, sm + S_UG, LDN, NQ, nullptr, 0, 0, 0, 27, 27,
-                                          [&](int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
-        } else if (job == 8) {
-          // JF[m][l] = sum_q Div[q][m] Chi[q][l]
-          warp_mma_product<5, 1, false>(sm + S_DIV, NJ, sm + S_CHI, 8, NQ, nullptr, 0, 0, 0, NJ, NF,
-                                        [&](int m, int l, double v) { St[ST_JF + m * 8 + l] = v; });
-        } else {
-          // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]
-          const int c = job - 9;
-          warp_mma_product<4, 1, false>(sm + S_G + c * LDN, 3 * LDN, sm + S_PP, 4, NQ, nullptr, 0, 0, 0, 27, NP,
-                                        [&](int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
-        }
-      }
-    } else {
-    // D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]   (batch = c)
-    panel_product<27, 4, 4, 4, false>(3, sm + S_G, 3 * LDN, LDN, sm + S_PP, 4, 0, NQ, nullptr, 0, 0, 0,
-                                      [&](int c, int a, int k, double v) { St[ST_D + (c * 27 + a) * 4 + k] = v; });
-    // JF[m][l] = sum_q Div[q][m] Chi[q][l]
-    panel_product<36, 8, 4, 4, false>(1, sm + S_DIV, NJ, 0, sm + S_CHI, 8, 0, NQ, nullptr, 0, 0, 21,
-                                      [&](int, int m, int l, double v) { St[ST_JF + m * 8 + l] = v; });
-    // jj = sum_{q,i} Psi Psi + zeta_j sum_q Div Div  (K = 81 or 108: Psi and Div panels are contiguous)
-    if (P.zeta_j != 0.0)
-      panel_product<36, 36, 2, 4, true>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 108, sm + S_SC, 1, 0, 39,
-                                        [&](int, int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
-    else
-      panel_product<36, 36, 2, 4, false>(1, sm + S_PSI, NJ, 0, sm + S_PSI, NJ, 0, 81, nullptr, 0, 0, 39,
-                                         [&](int, int m, int n, double v) { St[ST_JJ + m * NJ + n] = v; });
-    {
-      // S[a][b] = sum_{q,i} G[(q,i)][a] G[(q,i)][b] ; C[a][b] = sum_q N[q][a] UG[q][b]
-      panel_product<27, 27, 2, 4, false>(1, sm + S_G, LDN, 0, sm + S_G, LDN, 0, 81, nullptr, 0, 0, 39 + 162,
-                                         [&](int, int a, int b, double v) { St[ST_S + a * 27 + b] = v; });
-      if (CONV > 0)
-        panel_product<27, 27, 4, 4, false>(1, sm + S_N, LDN, 0, sm + S_UG, LDN, 0, NQ, nullptr, 0, 0, 39 + 162 + 98,
-                                           [&](int, int a, int b, double v) { St[ST_C + a * 27 + b] = v; });
-    }
-    }
-    if (ZU && tid >= NT - 16) {
-      const int kl = tid - (NT - 16), k = kl >> 2, l = kl & 3;
-      double s = 0.0;
-      for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
-      sm[S_MI + kl] = s;
-    }
-    __syncthreads();
+    if (tid == 0) *jobctr = 0;
     if (ZU) {
+      // D[(c,a)][k] (3 warps), pressure mass matrix (16 threads of another warp), then E = zeta_u M_p^-1 D
+      if (warp < 3) {
+        double acc[4][1][2];
+        int ca[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ca[i] = 8 * i + lr;
+        const int cb[1] = {lr};
+        warp_mma_cols<4, 1, false>(sm + S_G + warp * LDN, 3 * LDN, ca, sm + S_PP, 4, cb, NQ, nullptr, 0, acc);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int a = 8 * i + lr;
+          if (a < 27 && lk < 2) st2(sm + S_D + (warp * 27 + a) * 4 + 2 * lk, acc[i][0][0], acc[i][0][1]);
+        }
+      } else if (warp == 3 && lane < 16) {
+        const int k = lane >> 2, l = lane & 3;
+        double s = 0.0;
+        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
+        sm[S_MI + lane] = s;
+      }
+      __syncthreads();
       if (tid == 0) {
         // in-place inverse of the SPD 4x4 mass matrix (Gauss-Jordan, no pivoting)
         double a[4][8];
@@ -599,236 +644,305 @@ jacobian_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, c
         const int k = idx / 81, i = idx - k * 81;
         double s = 0.0;
 #pragma unroll
-        for (int l = 0; l < 4; l++) s = fma(sm[S_MI + k * 4 + l], St[ST_D + i * 4 + l], s);
-        sm[S_E + k * 81 + i] = s;
+        for (int l = 0; l < 4; l++) s = fma(sm[S_MI + k * 4 + l], sm[S_D + i * 4 + l], s);
+        sm[S_E + k * 81 + i] = P.zeta_u * s;
       }
-      __syncthreads();
     }
+    if (RES) {
+      __syncthreads();
+      MHD_MARK(cx, 4);
+      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, cell, nrows, rvec, P);  // scratch = the (still unused) staging tiles
+    }
+    __syncthreads();
+    MHD_MARK(cx, 5);
 
-    // ---------------- uu
-    if (solid) {
-      // no u block on solid cells
-    } else if (CONV == 2 && USE_MMA) {
-      // Newton: K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term].
-      // Perfectly balanced over the 8 warps: warp w owns row tile w/2 and the column-tile pair w%2 of EVERY component
-      // pair (c,d).  Its operand fragments of N' are loaded once (7 k-steps: 7 + 14 words per lane) and reused for
-      // the 9 products N'^T diag(T_dc) N'; accumulators are scattered straight from registers (the 4 map codes of
-      // a product are fetched before its MMAs), S and C come from the staging buffer.
-      const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+    if (P.dbg & 2) continue;
+    const bool nostore = P.dbg & 1;
+    const uint16_t* cmap = map + cell * NENT_PAD;
+    const long long* row = cx.row;
+    // solid cells (jac_solid_h1_hdiv, weakforms.jl:327-338): own conductivity, +phi div j instead of -div j phi; their
+    // u/p dofs are absent, so only the jj and j-phi jobs run
+    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+    const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
+    const double fj_sign = solid ? 1.0 : -1.0;
+
+    // ------------------------------------------------------------------ uu job (every warp; none on solid cells)
+    // warp w owns the node-slot tile (rows 8 mt .. 8 mt + 7) x (columns 16 np .. 16 np + 15) for all 9 component pairs:
+    //   K[(c,a),(d,b)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q) + zeta_u (D^T M^-1 D)
+    if (!solid) {
       const int mt = warp >> 1, np = warp & 1;
-      double fa[7], fb[7][2];
+      const int nrow = uu_nrow(mt), ncol = uu_ncol(np);
+      // operand columns of this lane: node slots resolved through the permutation (slots >= 27: the zero pad column)
+      const int ca[1] = {8 * mt + lr};
+      const int cb[2] = {16 * np + lr, 16 * np + 8 + lr};
+      double base[1][2][2];
+      warp_mma_cols<1, 2, false>(sm + S_G, LDN, ca, sm + S_G, LDN, cb, 81, nullptr, 0, base);
 #pragma unroll
-      for (int ks = 0; ks < 7; ks++) {
-        const int kk = 4 * ks + lk;
-        const bool valid = kk < NQ;
-        const int kc = valid ? kk : 0;
-        const double va = sm[S_N + kc * LDN + 8 * mt + lr];
-        const double vb0 = sm[S_N + kc * LDN + 16 * np + lr], vb1 = sm[S_N + kc * LDN + 16 * np + 8 + lr];
-        fa[ks] = valid ? va : 0.0;
-        fb[ks][0] = valid ? vb0 : 0.0;
-        fb[ks][1] = valid ? vb1 : 0.0;
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) base[0][j][r] *= P.beta;
+      if (CONV > 0) {
+        double cc[1][2][2];
+        warp_mma_cols<1, 2, false>(sm + S_N, LDN, ca, sm + S_UG, LDN, cb, NQ, nullptr, 0, cc);
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) base[0][j][r] = fma(P.alpha, cc[0][j][r], base[0][j][r]);
       }
-      const int a = 8 * mt + lr;
-      // map codes are fetched one product ahead (their DRAM latency is longer than the 14 MMAs of a product)
-      auto load_uu_codes = [&](int dc, uint16_t (&code)[2][2]) {
-        const int d = dc / 3, c = dc - d * 3;
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int r = 0; r < 2; r++) {
-            const int b = 16 * np + 8 * j + 2 * lk + r;
-            code[j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
-          }
-      };
-      uint16_t code_next[2][2];
-      load_uu_codes(0, code_next);
-#pragma unroll 1
-      for (int dc = 0; dc < 9; dc++) {
-        const int d = dc / 3, c = dc - d * 3;
-        uint16_t code[2][2];
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int r = 0; r < 2; r++) code[j][r] = code_next[j][r];
-        if (dc < 8) load_uu_codes(dc + 1, code_next);
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      double fa[7], fb[7][2];
+      if (CONV == 2) {
 #pragma unroll
         for (int ks = 0; ks < 7; ks++) {
           const int kk = 4 * ks + lk;
-          const double t = sm[S_T + (kk < NQ ? kk : 0) * LDT + dc];
-          dmma884(acc[0][0], acc[0][1], fa[ks], fb[ks][0] * t);
-          dmma884(acc[1][0], acc[1][1], fa[ks], fb[ks][1] * t);
+          const bool valid = kk < NQ;
+          const int kc = valid ? kk : 0;
+          const double va = sm[S_N + kc * LDN + ca[0]];
+          const double vb0 = sm[S_N + kc * LDN + cb[0]], vb1 = sm[S_N + kc * LDN + cb[1]];
+          fa[ks] = valid ? va : 0.0;
+          fb[ks][0] = valid ? vb0 : 0.0;
+          fb[ks][1] = valid ? vb1 : 0.0;
         }
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int r = 0; r < 2; r++) {
-            const uint16_t cd = code[j][r];
-            if (cd == MAP_SKIP) continue;
-            const int b = 16 * np + 8 * j + 2 * lk + r;
-            const int li = c * 27 + a, lj = d * 27 + b;
-            double v = P.alpha * acc[j][r];
-            if (c == d) v += P.beta * St[ST_S + a * 27 + b] + P.alpha * St[ST_C + a * 27 + b];
-            if (ZU) {
-              double z = 0.0;
-#pragma unroll
-              for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
-              v = fma(P.zeta_u, z, v);
-            }
-            double* pz = nz + row[li] + (cd & 0x7FFF);
-            if (cd & MAP_EXCL) *pz = v;
-            else atomicAdd(pz, v);
-          }
       }
-    } else     if (CONV == 2) {
-      // Newton: a thread owns the 2x2 (a,b) node tile of all 9 component blocks:
-      //   K[(a,c),(b,d)] = delta_cd (beta S_ab + alpha C_ab) + alpha sum_q N_a N_b (d_d u_c)(q)  [+ zeta_u term]
-      // accumulated in registers and scattered straight from them (no staging, no extra barrier).
-      if (tid < 196) {
-        const int ta = tid / 14, tb = tid - ta * 14;
-        const double* Ga = sm + S_G + 2 * ta;
-        const double* Gb = sm + S_G + 2 * tb;
-        const double* Na = sm + S_N + 2 * ta;
-        const double* Nb = sm + S_N + 2 * tb;
-        const double* Ub = sm + S_UG + 2 * tb;
-        double sS[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, sC[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        double nw[9][2][2];
-#pragma unroll
-        for (int dc = 0; dc < 9; dc++) nw[dc][0][0] = nw[dc][0][1] = nw[dc][1][0] = nw[dc][1][1] = 0.0;
 #pragma unroll 1
-        for (int q = 0; q < NQ; q++) {
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const double2 ga = *reinterpret_cast<const double2*>(Ga + (q * 3 + i) * LDN);
-            const double2 gb = *reinterpret_cast<const double2*>(Gb + (q * 3 + i) * LDN);
-            sS[0][0] = fma(ga.x, gb.x, sS[0][0]);
-            sS[0][1] = fma(ga.x, gb.y, sS[0][1]);
-            sS[1][0] = fma(ga.y, gb.x, sS[1][0]);
-            sS[1][1] = fma(ga.y, gb.y, sS[1][1]);
-          }
-          const double2 na = *reinterpret_cast<const double2*>(Na + q * LDN);
-          const double2 nb = *reinterpret_cast<const double2*>(Nb + q * LDN);
-          const double2 ub = *reinterpret_cast<const double2*>(Ub + q * LDN);
-          sC[0][0] = fma(na.x, ub.x, sC[0][0]);
-          sC[0][1] = fma(na.x, ub.y, sC[0][1]);
-          sC[1][0] = fma(na.y, ub.x, sC[1][0]);
-          sC[1][1] = fma(na.y, ub.y, sC[1][1]);
-          const double p00 = na.x * nb.x, p01 = na.x * nb.y, p10 = na.y * nb.x, p11 = na.y * nb.y;
-          const double* Tq = sm + S_T + q * LDT;
-#pragma unroll
-          for (int dc = 0; dc < 9; dc++) {
-            const double t = Tq[dc];
-            nw[dc][0][0] = fma(t, p00, nw[dc][0][0]);
-            nw[dc][0][1] = fma(t, p01, nw[dc][0][1]);
-            nw[dc][1][0] = fma(t, p10, nw[dc][1][0]);
-            nw[dc][1][1] = fma(t, p11, nw[dc][1][1]);
-          }
-        }
-        // 36 entries per thread, swept one column component d at a time: 12 map codes are loaded first, then
-        // the 12 values are scattered
+      for (int c = 0; c < 3; c++) {
+        int code[12];
+        const int nuu = nrow * ncol;
+        load_codes(code, cmap + uu_base(warp, c), nuu);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-          uint16_t code[3][2][2];
+          double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+          if (CONV == 2) {
+            const int dc = d * 3 + c;
 #pragma unroll
-          for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const int a = 2 * ta + i, b = 2 * tb + j;
-                code[c][i][j] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
-              }
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const uint16_t cd = code[c][i][j];
-                if (cd == MAP_SKIP) continue;
-                const int li = c * 27 + 2 * ta + i, lj = d * 27 + 2 * tb + j;
-                double v = P.alpha * nw[d * 3 + c][i][j];
-                if (c == d) v += P.beta * sS[i][j] + P.alpha * sC[i][j];
-                if (ZU) {
-                  double z = 0.0;
-#pragma unroll
-                  for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
-                  v = fma(P.zeta_u, z, v);
-                }
-                double* pz = nz + row[li] + (cd & 0x7FFF);
-                if (cd & MAP_EXCL) *pz = v;
-                else atomicAdd(pz, v);
-              }
-        }
-      }
-    } else if (!ZU) {
-      // only the three diagonal component blocks carry values: beta S + alpha C
-      scatter_generic<8>(nz, 3 * 729,
-          [&](int idx) { const int c = idx / 729, ab = idx - c * 729, a = ab / 27, b = ab - a * 27;
-                         return cmap[SEC_UU + (c * 27 + a) * NU + c * 27 + b]; },
-          [&](int idx, long long& rs, double& v) {
-            const int c = idx / 729, ab = idx - c * 729, a = ab / 27;
-            rs = row[c * 27 + a];
-            v = P.beta * St[ST_S + ab];
-            if (CONV > 0) v = fma(P.alpha, St[ST_C + ab], v);
-          });
-    } else {
-      scatter_generic<8>(nz, NU * NU, [&](int e) { return cmap[SEC_UU + e]; },
-          [&](int e, long long& rs, double& v) {
-            const int li = e / NU, lj = e - li * NU;
-            const int c = li / 27, a = li - c * 27, d = lj / 27, b = lj - d * 27;
-            double z = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) z = fma(St[ST_D + li * 4 + k], sm[S_E + k * 81 + lj], z);
-            z *= P.zeta_u;
-            if (c == d) {
-              z = fma(P.beta, St[ST_S + a * 27 + b], z);
-              if (CONV > 0) z = fma(P.alpha, St[ST_C + a * 27 + b], z);
+            for (int ks = 0; ks < 7; ks++) {
+              const int kk = 4 * ks + lk;
+              const double at = fa[ks] * sm[S_T + (kk < NQ ? kk : 0) * LDT + dc];
+              dmma884(acc[0][0], acc[0][1], at, fb[ks][0]);
+              dmma884(acc[1][0], acc[1][1], at, fb[ks][1]);
             }
-            rs = row[li];
-            v = z;
-          });
+          }
+          if (ZU) {
+            const int am = 8 * mt + lr;
+            const double da = am < 27 ? sm[S_D + (c * 27 + am) * 4 + lk] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int bn = 16 * np + 8 * j + lr;
+              const double eb = bn < 27 ? sm[S_E + lk * 81 + d * 27 + bn] : 0.0;
+              dmma884(acc[j][0], acc[j][1], da, eb);
+            }
+          }
+          if (CONV == 2 || ZU || d == c) {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+              for (int r = 0; r < 2; r++) {
+                double v = acc[j][r];
+                if (d == c) v += base[0][j][r];
+                Sw[lr * 49 + 3 * (8 * j + 2 * lk + r) + d] = v;
+              }
+          }
+        }
+        __syncwarp();
+        if (CONV == 2 || ZU) {
+          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+        } else {
+          // none / picard: only the diagonal component pairs carry values (the others stay at the memset zero)
+#pragma unroll
+          for (int k = 0; k < 12; k++) {
+            const int e = k * 32 + lane;
+            const int col = np == 0 ? e % 48 : e % 33;
+            if (col % 3 != c) code[k] = -1;
+          }
+          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+        }
+        __syncwarp();
+      }
     }
-    // ---------------- up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(d,b)] = -D
-    scatter_loaded(nz, c_up, [&](int e, long long& rs, double& v) { rs = row[e >> 2]; v = -St[ST_D + e]; });
-    scatter_loaded(nz, c_pu, [&](int e, long long& rs, double& v) { const int k = e / NU, i = e - k * NU; rs = row[OFF_P + k]; v = -St[ST_D + i * 4 + k]; });
-    // ---------------- j-phi: -sigma JF[m][l] ; phi-j: -JF[m][l]
-    scatter_loaded(nz, c_jf, [&](int e, long long& rs, double& v) { rs = row[OFF_J + (e >> 3)]; v = -sig_c * St[ST_JF + e]; });
-    scatter_loaded(nz, c_fj, [&](int e, long long& rs, double& v) { const int l = e / NJ, m = e - l * NJ; rs = row[OFF_F + l]; v = fj_sign * St[ST_JF + m * 8 + l]; });
-    // ---------------- jj
-    scatter_loaded(nz, c_jj, [&](int e, long long& rs, double& v) { rs = row[OFF_J + e / NJ]; v = St[ST_JJ + e]; });
-    // map codes of the uj / ju sections, fetched before the XB fill and the uj product
-    if (solid) continue;  // CTA-uniform: no uj / ju blocks on solid cells (the loop-top barrier follows)
-    Codes<12> c_uj, c_ju;
-    load_codes(c_uj, cmap + SEC_UJ, NU * NJ);
-    load_codes(c_ju, cmap + SEC_JU, NJ * NU);
-    __syncthreads();
 
-    // ---------------- uj / ju.  XB[q][c*36+m] = sqrt(w) (psi_m x B)_c (overwrites G, UG)
-    for (int idx = tid; idx < NQ * NJ; idx += NT) {
-      const int q = idx / NJ, m = idx - q * NJ;
-      const double p0 = sm[S_PSI + (q * 3 + 0) * NJ + m], p1 = sm[S_PSI + (q * 3 + 1) * NJ + m],
-                   p2 = sm[S_PSI + (q * 3 + 2) * NJ + m];
-      sm[S_XB + q * 108 + 0 * 36 + m] = p1 * P.B[2] - p2 * P.B[1];
-      sm[S_XB + q * 108 + 1 * 36 + m] = p2 * P.B[0] - p0 * P.B[2];
-      sm[S_XB + q * 108 + 2 * 36 + m] = p0 * P.B[1] - p1 * P.B[0];
+    MHD_MARK(cx, 6);
+    // ------------------------------------------------------------------ pooled jobs, drawn from a shared counter
+    // order = decreasing cost: 0 up/pu | 1..5 jj strips | 6..9 uj(s,0) | 10..13 uj(s,1) | 14 j-phi | 15,16 uj(4,h)
+    for (;;) {
+      int job = 0;
+      if (lane == 0) job = atomicAdd(jobctr, 1);
+      job = __shfl_sync(0xffffffffu, job, 0);
+      if (job >= NJOBS) break;
+      if (job >= 1 && job <= 5) {
+        // ---- jj rows 8 s .. 8 s + 7: sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous)
+        const int s_ = job - 1;
+        const int nrow = s_ < 4 ? 8 : 4;
+        int code[9];
+        load_codes(code, cmap + jj_base(s_), nrow * NJ);
+        double acc[1][5][2];
+        const int ca[1] = {8 * s_ + lr};
+        int cb[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) cb[j] = 8 * j + lr;
+        if (P.zeta_j != 0.0) warp_mma_cols<1, 5, true>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
+        else warp_mma_cols<1, 5, false>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+#pragma unroll
+        for (int j = 0; j < 5; j++) st2(Sw + lr * 40 + 8 * j + 2 * lk, acc[0][j][0], acc[0][j][1]);
+        __syncwarp();
+        sweep<NJ, 40, 9>(code, nrow * NJ, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
+        __syncwarp();
+      } else if (job == 14) {
+        // ---- j-phi: -sigma JF[m][l] ; phi-j: -/+ JF[m][l],  JF = sum_q Div[q][m] Chi[q][l]
+        int cjf[9], cfj[9];
+        load_codes(cjf, cmap + SEC_JF, NJ * NF);
+        load_codes(cfj, cmap + SEC_FJ, NF * NJ);
+        double acc[5][1][2];
+        int ca[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) ca[i] = 8 * i + lr;
+        const int cb[1] = {lr};
+        warp_mma_cols<5, 1, false>(sm + S_DIV, NJ, ca, sm + S_CHI, 8, cb, NQ, nullptr, 0, acc);
+#pragma unroll
+        for (int i = 0; i < 5; i++) st2(Sw + (8 * i + lr) * 8 + 2 * lk, -sig_c * acc[i][0][0], -sig_c * acc[i][0][1]);
+        __syncwarp();
+        sweep<NF, NF, 9>(cjf, NJ * NF, Sw, row, [&](int r) { return OFF_J + r; }, nostore);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+          const int m = 8 * i + lr;
+          if (m < NJ) {
+            Sw[(2 * lk) * 38 + m] = fj_sign * acc[i][0][0];
+            Sw[(2 * lk + 1) * 38 + m] = fj_sign * acc[i][0][1];
+          }
+        }
+        __syncwarp();
+        sweep<NJ, 38, 9>(cfj, NF * NJ, Sw, row, [&](int r) { return OFF_F + r; }, nostore);
+        __syncwarp();
+      } else if (solid) {
+        continue;
+      } else if (job == 0) {
+        // ---- up: K_up[(c,a)][k] = -D ; pu: K_pu[k][(b,d)] = -D,  D[(c,a)][k] = sum_q G[(q,c)][a] Pp[q][k]
+        int cup[11], cpu[11];
+        load_codes(cup, cmap + SEC_UP, NU * NP);
+        load_codes(cpu, cmap + SEC_PU, NP * NU);
+        double acc[3][4][1][2];
+        int ca[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) ca[i] = 8 * i + lr;
+        const int cb[1] = {lr};
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+          warp_mma_cols<4, 1, false>(sm + S_G + c * LDN, 3 * LDN, ca, sm + S_PP, 4, cb, NQ, nullptr, 0, acc[c]);
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int a = 8 * i + lr;
+            if (a < 27 && lk < 2) st2(Sw + (c * 27 + a) * 4 + 2 * lk, -acc[c][i][0][0], -acc[c][i][0][1]);
+          }
+        __syncwarp();
+        sweep<NP, NP, 11>(cup, NU * NP, Sw, row, [&](int r) { return r; }, nostore);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int a = 8 * i + lr;
+            if (a < 27 && lk < 2) {
+              Sw[(2 * lk) * 82 + 3 * a + c] = -acc[c][i][0][0];
+              Sw[(2 * lk + 1) * 82 + 3 * a + c] = -acc[c][i][0][1];
+            }
+          }
+        __syncwarp();
+        sweep<NU, 82, 11>(cpu, NP * NU, Sw, row, [&](int r) { return OFF_P + r; }, nostore);
+        __syncwarp();
+      } else {
+        // ---- uj / ju job (s, h): j slots 8 s .. (8 | 4 of them), node slots 16 h .. (16 | 11 of them).
+        //   Q_i[a][m] = sum_q N'[q][a] Psi'[(q,i)][m] for i = 0..2 (tensor cores), then in registers
+        //   R_c = (psi x B)_c-weighted = B_{c+2} Q_{c+1} - B_{c+1} Q_{c+2};  K_uj[(c,a)][m] = -gamma R_c[a][m],
+        //   K_ju[m][(b,d)] = +sigma R_d[b][m]
+        const int s_ = job < 10 ? job - 6 : (job < 14 ? job - 10 : 4);
+        const int h = job < 10 ? 0 : (job < 14 ? 1 : job - 15);
+        const int nm = uj_nm(s_), na = uj_na(h);
+        const uint16_t* cbase = cmap + uj_base(s_, h);
+        int cuj[12], cju[12];
+        const int nuj = 3 * na * nm;
+        load_codes(cuj, cbase, nuj);
+        load_codes(cju, cbase + uj_part(s_, h), nuj);
+        double q[2][3][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) q[i][c][0] = q[i][c][1] = 0.0;
+        {
+          const int ca0 = 16 * h + lr, ca1 = 16 * h + 8 + lr;
+          const double* ap = sm + S_N;
+          const double* bp = sm + S_PSI + 8 * s_ + lr;
+#pragma unroll 2
+          for (int k0 = 0; k0 < 28; k0 += 4) {
+            const int kk = k0 + lk;
+            const bool valid = kk < NQ;
+            const int kc = valid ? kk : 0;
+            double av[2], bv[3];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const double v = ap[kc * LDN + (i ? ca1 : ca0)];
+              av[i] = valid ? v : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              const double v = bp[(kc * 3 + c) * NJ];
+              bv[c] = valid ? v : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+              for (int c = 0; c < 3; c++) dmma884(q[i][c][0], q[i][c][1], av[i], bv[c]);
+          }
+        }
+        double R[2][3][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+#pragma unroll
+            for (int r = 0; r < 2; r++) R[i][c][r] = P.B[c2] * q[i][c1][r] - P.B[c1] * q[i][c2][r];
+          }
+        // uj part: Sw[(c * na + al) * 8 + ml]
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const int al = 8 * i + lr;
+            if (al < na) st2(Sw + (c * na + al) * 8 + 2 * lk, -P.gamma * R[i][c][0], -P.gamma * R[i][c][1]);
+          }
+        __syncwarp();
+        if (h == 0) {
+          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); }, nostore);
+          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); }, nostore);
+        } else {
+          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; }, nostore);
+          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; }, nostore);
+        }
+        __syncwarp();
+        // ju part: Sw[ml * 50 + 3 * al + d]
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const int al = 8 * i + lr;
+            if (al < na) {
+              Sw[(2 * lk) * 50 + 3 * al + c] = sig_c * R[i][c][0];
+              Sw[(2 * lk + 1) * 50 + 3 * al + c] = sig_c * R[i][c][1];
+            }
+          }
+        __syncwarp();
+        if (h == 0) sweep<48, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
+        else sweep<33, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
+        __syncwarp();
+      }
     }
-    __syncthreads();
-    // R[c][a][m] = sum_q N[q][a] XB[q][c*36+m]
-    if (USE_MMA) {
-      const int warp = tid >> 5;
-      if (warp < 7)
-        warp_mma_product<4, 2, false>(sm + S_N, LDN, sm + S_XB, 108, NQ, nullptr, 0, 0, 16 * warp, 27, 108,
-                                      [&](int a, int n, double v) { const int c = n / NJ; St[(c * 27 + a) * NJ + (n - c * NJ)] = v; });
-    } else {
-      panel_product<27, 36, 4, 4, false>(3, sm + S_N, LDN, 0, sm + S_XB, 108, 36, NQ, nullptr, 0, 0, 0,
-                                         [&](int c, int a, int m, double v) { St[(c * 27 + a) * NJ + m] = v; });
-    }
-    __syncthreads();
-    // K_uj[(c,a)][m] = -gamma R ; K_ju[m][(d,b)] = +sigma R[d][b][m]
-    scatter_loaded(nz, c_uj, [&](int e, long long& rs, double& v) { rs = row[e / NJ]; v = -P.gamma * St[e]; });
-    scatter_loaded(nz, c_ju, [&](int e, long long& rs, double& v) { const int m = e / NU, i = e - m * NU; rs = row[OFF_J + m]; v = sig_c * St[i * NJ + m]; });
+    MHD_MARK(cx, 7);
   }
+  if (cx.clk_on && threadIdx.x == 0 && P.clk_out)
+    for (int i = 0; i < 12; i++) atomicAdd(P.clk_out + i, (unsigned long long)cx.clk[i]);
 }
 
 // =============================================================================================
@@ -989,333 +1103,16 @@ __device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, i
 
 template <int CONV, bool ZU>
 __global__ void __launch_bounds__(NT, 2)
-residual_kernel(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
-                const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
-                const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
-                double* __restrict__ r, KParams P) {
+residual_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restrict__ x, double* __restrict__ r, KParams P) {
   extern __shared__ __align__(16) double smem[];
-  CellCtx cx;
-  cx.sm = smem;
-  cx.row = (long long*)(smem + S_END);
-  cx.gid = (int32_t*)(cx.row + NLOC);
+  CellCtx cx = make_ctx(smem);
+  prep_init(cx, A);
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();
-    cell_prep<2>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
+    cell_prep<2>(cx, cell, cell + gridDim.x < ncells ? cell + gridDim.x : -1, A, x, nullptr);
     velocity_gradient_mma(cx.sm + S_G, cx.sm + S_U, cx.sm + S_SW, cx.sm + S_ST + RES_GQ, nullptr, 0);
     __syncthreads();
     cell_residual<CONV, ZU>(cx, cell, nrows, r, P);
-  }
-}
-
-// =============================================================================================
-// Jacobian kernel, single-phase variant ("v4").  After the cell preparation there is ONE barrier-free phase: every
-// warp runs a fixed list of tensor-core jobs and scatters each job's accumulators straight from registers (map
-// codes are fetched before the job's MMAs).  No staging buffer, no barrier between products and scatter:
-//   * uu job (every warp): warp w owns row tile w/2 and the column-tile pair w%2 of the 27x27 node space for ALL
-//     9 component pairs: S = G'^T G' and C = N'^T UG' of that tile stay in registers and are added on the three
-//     diagonal pairs; the Newton products N'^T diag(T_dc) N' reuse one set of N' fragments;
-//   * pooled jobs: jj (5 column strips), uj/ju (7 column pairs, psi x B formed on the fly from the Psi panel),
-//     j-phi/phi-j, up/pu (3 components), dealt statically: w0..w2: jj+D, w3: jj+JF, w4: jj+uj, w5..w7: 2 uj.
-// The barrier-heavy staged kernel above remains for zeta_u != 0 (its rank-4 update needs D and M_p^-1 D first).
-__device__ __forceinline__ void scatter_reg(double* __restrict__ nz, long long rowstart, uint16_t cd, double v) {
-  if (cd == MAP_SKIP) return;
-  double* p = nz + rowstart + (cd & 0x7FFF);
-  if (cd & MAP_EXCL) *p = v;
-  else atomicAdd(p, v);
-}
-
-template <int CONV, bool RES>
-__global__ void __launch_bounds__(NT, 2)
-jacobian_kernel_v4(int64_t ncells, int64_t nrows, const double* __restrict__ tab, const double* __restrict__ coords,
-                   const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ gids,
-                   const int8_t* __restrict__ jsign, const double* __restrict__ dirv, const double* __restrict__ x,
-                   const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ map, double* __restrict__ nz,
-                   double* __restrict__ rvec, KParams P) {
-  extern __shared__ __align__(16) double smem[];
-  CellCtx cx;
-  cx.sm = smem;
-  cx.row = (long long*)(smem + S_END);
-  cx.gid = (int32_t*)(cx.row + NLOC);
-  double* sm = smem;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
-
-  for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
-    __syncthreads();  // every warp is done with the previous cell's panels
-    {
-      const int64_t nxt = cell + gridDim.x;  // next cell's map / ids into L2 (see jacobian_kernel)
-      if (nxt < ncells) {
-        const char* m0 = reinterpret_cast<const char*>(map + nxt * NENT_PAD);
-        if (tid * 128 < NENT_PAD * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(m0 + tid * 128));
-        if (tid < 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(gids + nxt * NLOC) + tid * 128));
-        if (tid == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(cell_nodes + nxt * 8));
-        if (tid == 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(jsign + nxt * NJ));
-      }
-    }
-    cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, tab, coords, cell_nodes, gids, jsign, dirv, x);
-    for (int i = tid; i < NLOC; i += NT) {
-      const int32_t g = cx.gid[i];
-      cx.row[i] = (g >= 0 && g < nrows) ? (long long)rowptr[g] : -1;
-    }
-    if (RES || CONV == 2)
-      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr, CONV == 2 ? sm + S_T : nullptr, LDT);
-    if (CONV > 0) {
-      // UG[q][b] = sqrt(w) u_q . grad N_b
-      for (int idx = tid; idx < NQ * 27; idx += NT) {
-        const int q = idx / 27, b = idx - q * 27;
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; i++) s = fma(sm[S_UQ + q * 3 + i], sm[S_G + (q * 3 + i) * LDN + b], s);
-        sm[S_UG + q * LDN + b] = s;
-      }
-    }
-    if (tid < 108) sm[S_SC + tid] = tid < 81 ? 1.0 : P.zeta_j;
-    if (RES) {
-      __syncthreads();
-      cell_residual<(CONV > 0 ? 1 : 0), false>(cx, cell, nrows, rvec, P);  // touches only its scratch area
-    }
-    __syncthreads();
-
-    const uint16_t* cmap = map + cell * NENT_PAD;
-    const long long* row = cx.row;
-    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
-    const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
-    const double fj_sign = solid ? 1.0 : -1.0;
-
-    // ------------------------------------------------------------------ uu job (all warps; none on solid cells)
-    if (!solid) {
-      const int mt = warp >> 1, np = warp & 1;
-      const int a = 8 * mt + lr;
-      double base[1][2][2];
-      warp_mma_acc<1, 2, false>(sm + S_G, LDN, sm + S_G, LDN, 81, nullptr, 0, 8 * mt, 16 * np, base);
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) base[0][j][r] *= P.beta;
-      if (CONV > 0) {
-        double cc[1][2][2];
-        warp_mma_acc<1, 2, false>(sm + S_N, LDN, sm + S_UG, LDN, NQ, nullptr, 0, 8 * mt, 16 * np, cc);
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int r = 0; r < 2; r++) base[0][j][r] = fma(P.alpha, cc[0][j][r], base[0][j][r]);
-      }
-      auto load_uu_codes = [&](int c, int d, uint16_t (&code)[2][2]) {
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-          for (int r = 0; r < 2; r++) {
-            const int b = 16 * np + 8 * j + 2 * lk + r;
-            code[j][r] = (a < 27 && b < 27) ? __ldg(cmap + SEC_UU + (c * 27 + a) * NU + d * 27 + b) : MAP_SKIP;
-          }
-      };
-      if (CONV == 2) {
-        double fa[7], fb[7][2];
-#pragma unroll
-        for (int ks = 0; ks < 7; ks++) {
-          const int kk = 4 * ks + lk;
-          const bool valid = kk < NQ;
-          const int kc = valid ? kk : 0;
-          const double va = sm[S_N + kc * LDN + 8 * mt + lr];
-          const double vb0 = sm[S_N + kc * LDN + 16 * np + lr], vb1 = sm[S_N + kc * LDN + 16 * np + 8 + lr];
-          fa[ks] = valid ? va : 0.0;
-          fb[ks][0] = valid ? vb0 : 0.0;
-          fb[ks][1] = valid ? vb1 : 0.0;
-        }
-        uint16_t code_next[2][2];
-        load_uu_codes(0, 0, code_next);
-#pragma unroll 1
-        for (int dc = 0; dc < 9; dc++) {
-          const int d = dc / 3, c = dc - d * 3;
-          uint16_t code[2][2];
-#pragma unroll
-          for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) code[j][r] = code_next[j][r];
-          if (dc < 8) load_uu_codes((dc + 1) % 3, (dc + 1) / 3, code_next);
-          double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-          for (int ks = 0; ks < 7; ks++) {
-            const int kk = 4 * ks + lk;
-            const double t = sm[S_T + (kk < NQ ? kk : 0) * LDT + dc];
-            dmma884(acc[0][0], acc[0][1], fa[ks], fb[ks][0] * t);
-            dmma884(acc[1][0], acc[1][1], fa[ks], fb[ks][1] * t);
-          }
-#pragma unroll
-          for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-              double v = P.alpha * acc[j][r];
-              if (c == d) v += base[0][j][r];
-              if (a < 27) scatter_reg(nz, row[c * 27 + a], code[j][r], v);
-            }
-        }
-      } else {
-        // none / picard: only the three diagonal component blocks carry values
-#pragma unroll 1
-        for (int c = 0; c < 3; c++) {
-          uint16_t code[2][2];
-          load_uu_codes(c, c, code);
-#pragma unroll
-          for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-              if (a < 27) scatter_reg(nz, row[c * 27 + a], code[j][r], base[0][j][r]);
-        }
-      }
-    }
-
-    // ------------------------------------------------------------------ pooled jobs
-    // jj strip s: columns 8s..8s+7
-    auto job_jj = [&](int s_) {
-      double acc[5][1][2];
-      uint16_t code[5][2];
-#pragma unroll
-      for (int i = 0; i < 5; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int m = 8 * i + lr, n = 8 * s_ + 2 * lk + r;
-          code[i][r] = (m < NJ && n < NJ) ? __ldg(cmap + SEC_JJ + m * NJ + n) : MAP_SKIP;
-        }
-      if (P.zeta_j != 0.0) warp_mma_acc<5, 1, true>(sm + S_PSI, NJ, sm + S_PSI, NJ, 108, sm + S_SC, 1, 0, 8 * s_, acc);
-      else warp_mma_acc<5, 1, false>(sm + S_PSI, NJ, sm + S_PSI, NJ, 81, nullptr, 0, 0, 8 * s_, acc);
-#pragma unroll
-      for (int i = 0; i < 5; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int m = 8 * i + lr;
-          if (m < NJ) scatter_reg(nz, row[OFF_J + m], code[i][r], acc[i][0][r]);
-        }
-    };
-    // j-phi / phi-j
-    auto job_jf = [&]() {
-      double acc[5][1][2];
-      uint16_t cjf[5][2], cfj[5][2];
-#pragma unroll
-      for (int i = 0; i < 5; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int m = 8 * i + lr, l = 2 * lk + r;
-          const bool ok = m < NJ;
-          cjf[i][r] = ok ? __ldg(cmap + SEC_JF + m * NF + l) : MAP_SKIP;
-          cfj[i][r] = ok ? __ldg(cmap + SEC_FJ + l * NJ + m) : MAP_SKIP;
-        }
-      warp_mma_acc<5, 1, false>(sm + S_DIV, NJ, sm + S_CHI, 8, NQ, nullptr, 0, 0, 0, acc);
-#pragma unroll
-      for (int i = 0; i < 5; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int m = 8 * i + lr, l = 2 * lk + r;
-          if (m < NJ) {
-            scatter_reg(nz, row[OFF_J + m], cjf[i][r], -sig_c * acc[i][0][r]);
-            scatter_reg(nz, row[OFF_F + l], cfj[i][r], fj_sign * acc[i][0][r]);
-          }
-        }
-    };
-    // up / pu, component c
-    auto job_d = [&](int c) {
-      double acc[4][1][2];
-      uint16_t cup[4][2], cpu[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int a = 8 * i + lr, k = 2 * lk + r;
-          const bool ok = a < 27 && k < NP;
-          cup[i][r] = ok ? __ldg(cmap + SEC_UP + (c * 27 + a) * NP + k) : MAP_SKIP;
-          cpu[i][r] = ok ? __ldg(cmap + SEC_PU + k * NU + c * 27 + a) : MAP_SKIP;
-        }
-      warp_mma_acc<4, 1, false>(sm + S_G + c * LDN, 3 * LDN, sm + S_PP, 4, NQ, nullptr, 0, 0, 0, acc);
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int a = 8 * i + lr, k = 2 * lk + r;
-          if (a < 27 && k < NP) {
-            scatter_reg(nz, row[c * 27 + a], cup[i][r], -acc[i][0][r]);
-            scatter_reg(nz, row[OFF_P + k], cpu[i][r], -acc[i][0][r]);
-          }
-        }
-    };
-    // uj / ju, columns n = 16u .. 16u+15 of the 108 (c,m) columns; B fragment = sqrt(w) (psi_m x B)_c formed on the fly
-    auto job_uj = [&](int u) {
-      double acc[4][2][2];
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-      // this lane's B-fragment columns (one per column tile)
-      int pb1[2], pb2[2];
-      double w1[2], w2[2];
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int nb = 16 * u + 8 * j + lr;
-        const int cb = nb < 108 ? nb / NJ : 0, mb = nb < 108 ? nb - cb * NJ : 0;
-        const int c1 = (cb + 1) % 3, c2 = (cb + 2) % 3;
-        pb1[j] = c1 * NJ + mb;
-        pb2[j] = c2 * NJ + mb;
-        w1[j] = nb < 108 ? P.B[c2] : 0.0;   // (psi x B)_c = psi_{c+1} B_{c+2} - psi_{c+2} B_{c+1}
-        w2[j] = nb < 108 ? -P.B[c1] : 0.0;
-      }
-#pragma unroll 2
-      for (int k0 = 0; k0 < 28; k0 += 4) {
-        const int kk = k0 + lk;
-        const bool valid = kk < NQ;
-        const int kc = valid ? kk : 0;
-        double av[4], bv[2];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const double v = sm[S_N + kc * LDN + 8 * i + lr];
-          av[i] = valid ? v : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const double v = sm[S_PSI + kc * 3 * NJ + pb1[j]] * w1[j] + sm[S_PSI + kc * 3 * NJ + pb2[j]] * w2[j];
-          bv[j] = valid ? v : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
-      }
-      // scatter: K_uj[(c,a)][m] = -gamma R ; K_ju[m][(c,a)] = +sigma R
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const int n = 16 * u + 8 * j + 2 * lk + r;
-          if (n >= 108) continue;
-          const int c = n / NJ, m = n - c * NJ;
-          uint16_t cuj[4], cju[4];
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int a = 8 * i + lr;
-            cuj[i] = a < 27 ? __ldg(cmap + SEC_UJ + (c * 27 + a) * NJ + m) : MAP_SKIP;
-            cju[i] = a < 27 ? __ldg(cmap + SEC_JU + m * NU + c * 27 + a) : MAP_SKIP;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int a = 8 * i + lr;
-            if (a < 27) {
-              scatter_reg(nz, row[c * 27 + a], cuj[i], -P.gamma * acc[i][j][r]);
-              scatter_reg(nz, row[OFF_J + m], cju[i], sig_c * acc[i][j][r]);
-            }
-          }
-        }
-    };
-    // static deal (costs in MMAs: jj 105(140), uj 56, JF 35, D 28)
-    if (warp < 5) job_jj(warp);
-    if (solid) {
-      if (warp == 5) job_jf();
-    } else {
-      if (warp < 3) job_d(warp);
-      else if (warp == 3) job_jf();
-      else if (warp == 4) job_uj(0);
-      else {
-        job_uj(2 * warp - 9);   // w5: 1,2  w6: 3,4  w7: 5,6
-        job_uj(2 * warp - 8);
-      }
-    }
   }
 }
 
@@ -1326,7 +1123,16 @@ static KParams make_kparams(const mhd_params_t& p) {
   for (int i = 0; i < 3; i++) { k.B[i] = p.B[i]; k.f[i] = p.f[i]; k.g[i] = p.g[i]; }
   k.cell_solid = nullptr;
   k.cell_sigma = nullptr;
+  k.dbg = 0;
+  k.clk_out = nullptr;
   return k;
+}
+
+static CellArgs make_cell_args(const mhd_operator* op) {
+  CellArgs a;
+  a.tab = op->d_tables; a.ptab = op->d_ptab; a.coords = op->d_coords; a.cell_nodes = op->d_cell_nodes;
+  a.gids = op->d_pgids; a.rowstart = op->d_rowstart; a.perm = op->d_perm; a.jsign = op->d_jsign; a.dirv = op->d_dir;
+  return a;
 }
 
 static int g_sm_count = 0;
@@ -1355,36 +1161,39 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
 #define JK(C, Z, R)                                                                                          \
   do {                                                                                                       \
     MHD_TRY(set_smem(jacobian_kernel<C, Z, R>));                                                             \
-    jacobian_kernel<C, Z, R><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
-        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, d_r, P); \
+    jacobian_kernel<C, Z, R><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, make_cell_args(op), d_x,    \
+        op->d_map, op->d_nzval, d_r, P);                                                                      \
   } while (0)
 #define JKR(C, Z) do { if (d_r) JK(C, Z, true); else JK(C, Z, false); } while (0)
-  static int staged = -1;
-  if (staged < 0) staged = getenv("MHD_JAC_STAGED") ? 1 : 0;
-#define JK4(C, R)                                                                                            \
-  do {                                                                                                       \
-    MHD_TRY(set_smem(jacobian_kernel_v4<C, R>));                                                             \
-    jacobian_kernel_v4<C, R><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
-        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, op->d_rowptr, op->d_map, op->d_nzval, d_r, P); \
-  } while (0)
-#define JK4R(C) do { if (d_r) JK4(C, true); else JK4(C, false); } while (0)
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("MHD_JAC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  P.dbg = dbg;
+  static unsigned long long* d_clk = nullptr;
+  if ((dbg & 16) && !d_clk) MHD_CUDA(cudaMalloc((void**)&d_clk, 16 * sizeof(unsigned long long)));
+  if (dbg & 16) MHD_CUDA(cudaMemsetAsync(d_clk, 0, 16 * sizeof(unsigned long long), g_stream));
+  P.clk_out = d_clk;
   prof_begin(PROF_JAC);
-  if (!zu && !staged) {
-    if (conv == 0) JK4R(0);
-    else if (conv == 1) JK4R(1);
-    else JK4R(2);
-  } else if (conv == 0 && !zu) JKR(0, false);
+  if (conv == 0 && !zu) JKR(0, false);
   else if (conv == 0 && zu) JKR(0, true);
   else if (conv == 1 && !zu) JKR(1, false);
   else if (conv == 1 && zu) JKR(1, true);
   else if (conv == 2 && !zu) JKR(2, false);
   else JKR(2, true);
-#undef JK4R
-#undef JK4
 #undef JKR
 #undef JK
   prof_end(PROF_JAC);
   MHD_LAUNCH_CHECK();
+  if (dbg & 16) {
+    unsigned long long h[16];
+    MHD_CUDA(cudaMemcpyAsync(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    const double per = 1.0 / (double)op->ncells;
+    fprintf(stderr, "[mhd phase clocks / cell] top %.0f  loads(bulk issue %.0f, own %.0f, wait %.0f)  geometry(math %.0f, wait %.0f)  panels %.0f  velgrad+UG %.0f  residual %.0f  uu %.0f  pool+tail %.0f\n",
+            h[0] * per, h[10] * per, h[11] * per, h[1] * per, h[9] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per, h[7] * per);
+  }
   return 0;
 }
 
@@ -1400,8 +1209,7 @@ int launch_residual(mhd_operator* op, const double* d_x, double* d_r) {
 #define RK(C, Z)                                                                                             \
   do {                                                                                                       \
     MHD_TRY(set_smem(residual_kernel<C, Z>));                                                                \
-    residual_kernel<C, Z><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, op->d_tables, op->d_coords, \
-        op->d_cell_nodes, op->d_gids, op->d_jsign, op->d_dir, d_x, d_r, P);                                   \
+    residual_kernel<C, Z><<<grid, NT, SMEM_BYTES, g_stream>>>(op->ncells, op->nrows, make_cell_args(op), d_x, d_r, P); \
   } while (0)
   prof_begin(PROF_RES);
   if (conv == 0 && !zu) RK(0, false);

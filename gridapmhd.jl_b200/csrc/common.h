@@ -18,17 +18,41 @@ constexpr int NU = 81, NP = 4, NJ = 36, NF = 8;
 constexpr int OFF_U = 0, OFF_P = 81, OFF_J = 85, OFF_F = 121;
 constexpr int NLOC = 129;
 
-// canonical enumeration of the touched cell entries (row-major inside each block section)
-constexpr int SEC_UU = 0;                       // [81][81]
-constexpr int SEC_UP = SEC_UU + NU * NU;        // [81][4]
-constexpr int SEC_PU = SEC_UP + NU * NP;        // [4][81]
-constexpr int SEC_UJ = SEC_PU + NP * NU;        // [81][36]
-constexpr int SEC_JU = SEC_UJ + NU * NJ;        // [36][81]
-constexpr int SEC_JJ = SEC_JU + NJ * NU;        // [36][36]
-constexpr int SEC_JF = SEC_JJ + NJ * NJ;        // [36][8]
-constexpr int SEC_FJ = SEC_JF + NJ * NF;        // [8][36]
-constexpr int NENT = SEC_FJ + NF * NJ;          // 14913
-constexpr int NENT_PAD = (NENT + 7) / 8 * 8;    // per-cell stride of the u16 scatter map (16 B aligned)
+// Enumeration of the touched cell entries = the order in which the Jacobian kernel consumes the scatter map
+// (assembly.cu).  Entries are addressed in the PERMUTED local numbering of a cell: inside each field the local dofs are
+// sorted by global id (u: the 27 nodes sorted, slot index c*27+s; j: the 36 dofs sorted), so that a sweep over
+// consecutive slots of a row walks consecutive nnz of the CSR row.  The range of every warp job is padded to a multiple
+// of 32 entries (pad codes = MAP_SKIP) so that a job's codes are fetched with one address and immediate offsets.
+//   uu : warp w = 0..7 (row tile mt = w/2 of 8 node slots, column half np = w%2 of 16|11 node slots), component c:
+//        [nrow][ncol] with columns (node slot, component d) component-fastest
+//   jj : job s = 0..4: rows 8 s .. (8 | 4 of them) x 36 columns
+//   uj : job (s = 0..4: 8|4 j slots, h = 0..1: 16|11 node slots): [c][node][j] then the ju part [j][(node, d)]
+//   up : [81][4] ; pu : [4][(node, d)] ; j-phi : [36][8] ; phi-j : [8][36]
+__host__ __device__ constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
+__host__ __device__ constexpr int uu_nrow(int mt) { return mt < 3 ? 8 : 3; }
+__host__ __device__ constexpr int uu_ncol(int np) { return np ? 33 : 48; }
+__host__ __device__ constexpr int uj_nm(int s) { return s < 4 ? 8 : 4; }
+__host__ __device__ constexpr int uj_na(int h) { return h ? 11 : 16; }
+constexpr int SEC_UU = 0;
+__host__ __device__ constexpr int uu_base(int w, int c) {
+  return SEC_UU + 3 * (pad32(8 * 48) + pad32(8 * 33)) * (w >> 1) + (w & 1) * 3 * pad32(uu_nrow(w >> 1) * 48) +
+         c * pad32(uu_nrow(w >> 1) * uu_ncol(w & 1));
+}
+constexpr int SEC_JJ = uu_base(6, 0) + 3 * (pad32(3 * 48) + pad32(3 * 33));
+__host__ __device__ constexpr int jj_base(int s) { return SEC_JJ + pad32(8 * NJ) * s; }
+constexpr int SEC_UJ = jj_base(4) + pad32(4 * NJ);
+__host__ __device__ constexpr int uj_part(int s, int h) { return pad32(3 * uj_na(h) * uj_nm(s)); }
+__host__ __device__ constexpr int uj_base(int s, int h) {
+  return SEC_UJ + 2 * (uj_part(0, 0) + uj_part(0, 1)) * (s < 4 ? s : 4) + h * 2 * uj_part(s, 0);
+}
+constexpr int SEC_UP = uj_base(4, 1) + 2 * uj_part(4, 1);
+constexpr int SEC_PU = SEC_UP + pad32(NU * NP);
+constexpr int SEC_JF = SEC_PU + pad32(NP * NU);
+constexpr int SEC_FJ = SEC_JF + pad32(NJ * NF);
+constexpr int NENT = SEC_FJ + pad32(NF * NJ);   // 15584 map codes per cell, 14913 of them real entries
+constexpr int NENT_PAD = NENT;                  // per-cell stride of the u16 scatter map (multiple of 32)
+constexpr uint16_t ORDER_PAD = 0xFFFFu;         // entry_order() value of a padding code
+constexpr int PERM_STRIDE = 64;  // bytes per cell: [0,27) node slot -> reference node, [27,63) j slot -> reference dof | 0x80 if sign < 0
 
 constexpr uint16_t MAP_SKIP = 0xFFFFu;  // entry dropped (Dirichlet row/col or non-owned row)
 constexpr uint16_t MAP_EXCL = 0x8000u;  // nnz receives exactly one contribution: plain store, no atomic
@@ -43,7 +67,17 @@ constexpr int T_PP = T_DNU + NQ * 27 * 3;   // [27][4]
 constexpr int T_PSI = T_PP + NQ * 4;        // [27][36][3]
 constexpr int T_DPSI = T_PSI + NQ * 36 * 3; // [27][36]
 constexpr int T_CHI = T_DPSI + NQ * 36;     // [27][8]
-constexpr int T_TOTAL = T_CHI + NQ * 8;
+constexpr int T_GGT = T_CHI + NQ * 8;       // [8][3][27]  geo_grad[q][v][k] at (v*3+k)*27+q (coalesced across q)
+constexpr int T_TOTAL = T_GGT + NQ * 24;
+// Second copy of the basis tables in the PANEL layout of the assembly kernels (reference order, rows k-major, padded
+// leading dimensions): one bulk copy per cell brings it into shared memory, where it is transformed in place.
+constexpr int PT_G = 0;                     // [27 q][3 k][28]  d N_a / d xi_k   (column 27 = 0)
+constexpr int PT_N = PT_G + 81 * 28;        // [27 q][28]       N_a
+constexpr int PT_PSI = PT_N + 27 * 28;      // [27 q][3 k][36]  psi_m component k
+constexpr int PT_DIV = PT_PSI + 81 * 36;    // [27 q][36]       div psi_m
+constexpr int PT_PP = PT_DIV + 27 * 36;     // [27 q][4]
+constexpr int PT_CHI = PT_PP + 27 * 4;      // [27 q][8]
+constexpr int PT_TOTAL = PT_CHI + 27 * 8;   // 7236 doubles = 57888 B (multiple of 16)
 
 struct Comm;  // comm.cu
 
@@ -107,10 +141,15 @@ struct mhd_operator {
   int32_t* d_cell_nodes = nullptr; // [ncells*8] 0-based
   int32_t* d_gids = nullptr;       // [ncells*129] >=0 local free id (owned first, ghosts after); <0: -(dirichlet index+1)
   int8_t* d_jsign = nullptr;       // [ncells*36]
+  int32_t* d_pgids = nullptr;      // [ncells*129] d_gids in the permuted local numbering (fields sorted by global id)
+  uint8_t* d_perm = nullptr;       // [ncells*PERM_STRIDE] slot -> reference basis index (+ RT sign bit)
+  int64_t* d_rowstart = nullptr;   // [ncells*129] first nnz of each local row in the permuted numbering (-1: dropped row)
+  uint16_t* d_order = nullptr;     // [NENT] (row slot << 8 | col slot) of each map entry, kernel consumption order
   uint8_t* d_cell_solid = nullptr; // [ncells] or null
   double* d_cell_sigma = nullptr;  // [ncells] or null
   double* d_dir = nullptr;         // [ndir_total]
   double* d_tables = nullptr;      // packed reference tables (see assembly.cu)
+  double* d_ptab = nullptr;        // the same tables in panel layout (PT_*)
   int64_t* d_rowptr = nullptr;     // [nrows+1]
   int32_t* d_colval = nullptr;     // [nnz]
   double* d_nzval = nullptr;       // [nnz]
@@ -188,6 +227,9 @@ int d2h(T* h, const T* d, int64_t n) {
 
 // symbolic.cu
 int symbolic_build(mhd_operator* op);
+int build_permutation(mhd_operator* op);  // d_perm, d_pgids (needs d_gids, d_jsign)
+// assembly.cu
+void entry_order(std::vector<uint16_t>& ord);  // [NENT] (row slot << 8 | col slot), mirrors the kernel's sweeps
 // assembly.cu
 int pack_tables(mhd_operator* op, const mhd_tables_t* t);
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);

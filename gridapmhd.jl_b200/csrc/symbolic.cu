@@ -8,7 +8,9 @@
 //   1. row -> (cell,local row) incidence lists (count, scan, fill)
 //   2. one warp per row: gather the candidate columns of its incident cells into shared memory, bitonic sort,
 //      unique -> row length (pass 1) and column values (pass 2)
-//   3. one CTA per cell: binary-search each touched entry in its row -> 16-bit row-relative position;
+//   0. (operator creation) per-cell permutation that sorts the local dofs of each field by global id
+//   3. one CTA per cell: binary-search each touched entry (enumerated in the Jacobian kernel's consumption order,
+//      common.h) in its row -> 16-bit row-relative position;
 //      count contributions per nnz and flag the nnz that receive exactly one (plain store instead of atomic).
 #include "common.h"
 
@@ -24,16 +26,52 @@ __device__ __forceinline__ bool coupled(int li, int lj) {
   return (m >> (fi * 4 + fj)) & 1u;
 }
 
-// canonical entry e -> (li, lj)
-__device__ __forceinline__ void entry_to_lilj(int e, int& li, int& lj) {
-  if (e < SEC_UP) { li = e / NU; lj = e % NU; }
-  else if (e < SEC_PU) { e -= SEC_UP; li = e / NP; lj = OFF_P + e % NP; }
-  else if (e < SEC_UJ) { e -= SEC_PU; li = OFF_P + e / NU; lj = e % NU; }
-  else if (e < SEC_JU) { e -= SEC_UJ; li = e / NJ; lj = OFF_J + e % NJ; }
-  else if (e < SEC_JJ) { e -= SEC_JU; li = OFF_J + e / NU; lj = e % NU; }
-  else if (e < SEC_JF) { e -= SEC_JJ; li = OFF_J + e / NJ; lj = OFF_J + e % NJ; }
-  else if (e < SEC_FJ) { e -= SEC_JF; li = OFF_J + e / NF; lj = OFF_F + e % NF; }
-  else { e -= SEC_FJ; li = OFF_F + e / NJ; lj = OFF_J + e % NJ; }
+// ---------------------------------------------------------------- 0. per-cell permutation (once per operator)
+// Inside each field the local dofs of a cell are sorted by global id (Dirichlet / absent dofs last, ties in reference
+// order).  u: the 27 nodes are sorted by the id of their first component; the three components keep the node order.
+__global__ void __launch_bounds__(64)
+cell_permutation(int64_t ncells, const int32_t* __restrict__ gids, const int8_t* __restrict__ jsign,
+                 uint8_t* __restrict__ perm, int32_t* __restrict__ pgids) {
+  __shared__ int32_t key[64];
+  __shared__ uint8_t pm[64];
+  const int64_t cell = blockIdx.x;
+  const int t = threadIdx.x;
+  const int32_t* g = gids + cell * NLOC;
+  // t < 27: node t (key = id of component 0); 27 <= t < 63: j dof t - 27
+  int32_t k = INT32_MAX;
+  if (t < 27) k = g[t];
+  else if (t < 63) k = g[OFF_J + t - 27];
+  if (k < 0) k = INT32_MAX;
+  key[t] = k;
+  __syncthreads();
+  if (t < 63) {
+    const int lo = t < 27 ? 0 : 27, hi = t < 27 ? 27 : 63;
+    int rank = 0;
+    for (int o = lo; o < hi; o++) rank += (key[o] < k) || (key[o] == k && o < t);
+    uint8_t v = (uint8_t)(t - lo);
+    if (t >= 27 && jsign[cell * NJ + t - 27] < 0) v |= 0x80;
+    pm[lo + rank] = v;
+  }
+  if (t == 63) pm[63] = 0;
+  __syncthreads();
+  perm[cell * PERM_STRIDE + t] = pm[t];
+  int32_t* pg = pgids + cell * NLOC;
+  for (int i = t; i < NLOC; i += 64) {
+    int src = i;
+    if (i < NU) src = (i / 27) * 27 + pm[i % 27];
+    else if (i >= OFF_J && i < OFF_F) src = OFF_J + (pm[27 + i - OFF_J] & 0x7F);
+    pg[i] = g[src];
+  }
+}
+
+int build_permutation(mhd_operator* op) {
+  cudaFree(op->d_perm); op->d_perm = nullptr;
+  cudaFree(op->d_pgids); op->d_pgids = nullptr;
+  MHD_TRY(dev_alloc(&op->d_perm, op->ncells * PERM_STRIDE));
+  MHD_TRY(dev_alloc(&op->d_pgids, op->ncells * NLOC));
+  cell_permutation<<<(unsigned)op->ncells, 64, 0, g_stream>>>(op->ncells, op->d_gids, op->d_jsign, op->d_perm, op->d_pgids);
+  MHD_LAUNCH_CHECK();
+  return 0;
 }
 
 // ---------------------------------------------------------------- exclusive scan (int32 counts -> int64 offsets)
@@ -209,7 +247,8 @@ row_columns(const int32_t* __restrict__ gids, const int64_t* __restrict__ inc_pt
 
 // ---------------------------------------------------------------- 3. scatter map
 __global__ void __launch_bounds__(256)
-build_map(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+build_map(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order,
+          const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
           int64_t nrows, uint16_t* __restrict__ map, uint8_t* __restrict__ contrib) {
   __shared__ int32_t g[NLOC];
   int64_t cell = blockIdx.x;
@@ -219,9 +258,9 @@ build_map(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, 
   for (int e = threadIdx.x; e < NENT_PAD; e += blockDim.x) {
     uint16_t code = MAP_SKIP;
     if (e < NENT) {
-      int li, lj;
-      entry_to_lilj(e, li, lj);
-      int32_t r = g[li], c = g[lj];
+      const int li = order[e] >> 8, lj = order[e] & 0xFF;
+      int32_t r = -1, c = -1;
+      if (order[e] != ORDER_PAD) { r = g[li]; c = g[lj]; }
       if (r >= 0 && r < nrows && c >= 0) {
         int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1, base = lo;
         while (lo < hi) {
@@ -250,7 +289,8 @@ build_map(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, 
 }
 
 __global__ void __launch_bounds__(256)
-flag_exclusive(const int32_t* __restrict__ gids, const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ contrib,
+flag_exclusive(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order,
+               const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ contrib,
                uint16_t* __restrict__ map, unsigned long long* __restrict__ stats) {
   __shared__ int32_t g[NLOC];
   int64_t cell = blockIdx.x;
@@ -261,8 +301,7 @@ flag_exclusive(const int32_t* __restrict__ gids, const int64_t* __restrict__ row
   for (int e = threadIdx.x; e < NENT; e += blockDim.x) {
     uint16_t code = m[e];
     if (code == MAP_SKIP) continue;
-    int li, lj;
-    entry_to_lilj(e, li, lj);
+    const int li = order[e] >> 8;
     int64_t idx = rowptr[g[li]] + code;
     nent++;
     if (contrib[idx] == 1) {
@@ -279,6 +318,14 @@ flag_exclusive(const int32_t* __restrict__ gids, const int64_t* __restrict__ row
     atomicAdd(&stats[0], (unsigned long long)nent);
     atomicAdd(&stats[1], (unsigned long long)nex);
   }
+}
+
+__global__ void cell_row_starts(int64_t n, int64_t nrows, const int32_t* __restrict__ pgids,
+                                const int64_t* __restrict__ rowptr, int64_t* __restrict__ rowstart) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t g = pgids[i];
+  rowstart[i] = (g >= 0 && g < nrows) ? rowptr[g] : -1;
 }
 
 __global__ void max_row_len(const int32_t* row_len, int64_t nrows, int* out) {
@@ -352,6 +399,13 @@ int symbolic_build(mhd_operator* op) {
   SY(dev_alloc(&op->d_colval, nnz));
   SY(dev_alloc(&op->d_nzval, nnz));
   SY(dev_alloc(&op->d_map, op->ncells * NENT_PAD));
+  if (!rc && !op->d_order) {
+    std::vector<uint16_t> ord;
+    entry_order(ord);
+    SY(dev_alloc(&op->d_order, NENT));
+    SY(h2d(op->d_order, ord.data(), NENT));
+    SYC(cudaStreamSynchronize(g_stream));
+  }
   SY(dev_alloc(&d_contrib, (nnz + 3) / 4 * 4 + 4));
   SYC(cudaMemsetAsync(op->d_nzval, 0, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double), g_stream));
   SYC(cudaMemsetAsync(d_contrib, 0, (size_t)((nnz + 3) / 4 * 4 + 4), g_stream));
@@ -359,8 +413,11 @@ int symbolic_build(mhd_operator* op) {
     row_columns<true><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, nullptr, op->d_rowptr, op->d_colval, d_flags);
     SYL();
   }
-  if (!rc) { build_map<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_gids, op->d_rowptr, op->d_colval, nrows, op->d_map, d_contrib); SYL(); }
-  if (!rc) { flag_exclusive<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_gids, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
+  cudaFree(op->d_rowstart); op->d_rowstart = nullptr;
+  SY(dev_alloc(&op->d_rowstart, nent));
+  if (!rc) { cell_row_starts<<<gb, 256, 0, g_stream>>>(nent, nrows, op->d_pgids, op->d_rowptr, op->d_rowstart); SYL(); }
+  if (!rc) { build_map<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_pgids, op->d_order, op->d_rowptr, op->d_colval, nrows, op->d_map, d_contrib); SYL(); }
+  if (!rc) { flag_exclusive<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_pgids, op->d_order, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
   unsigned long long stats[2] = {0, 0};
   SY(d2h(stats, d_stats, 2));
   SYC(cudaStreamSynchronize(g_stream));

@@ -189,6 +189,9 @@ int mhd_kernel_launch_count(int64_t* count); /* kernels launched by the library 
 int mhd_profile_enable(int on);
 int mhd_profile_get(const char* name, double* total_ms, int64_t* launches);
 int mhd_profile_reset(void);
+/* FP64 peak of this device, measured (no FP64 figure in MEASURED_PEAKS.json): register-resident
+ * mma.sync.m8n8k4.f64 chains (kind 0) or DFMA chains (kind 1) on every SM, CUDA-event timed.  Out: TFLOP/s (FMA = 2). */
+int mhd_fp64_peak(int32_t kind, double* tflops);
 
 #ifdef __cplusplus
 }
