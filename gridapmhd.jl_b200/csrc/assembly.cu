@@ -485,10 +485,230 @@ __device__ __forceinline__ void cell_prep(CellCtx& cx, int64_t cell, int64_t nex
   MHD_MARK(cx, 3);
 }
 
+// ---- residual scratch.  Point values (stage 1) live in the staging area (free until the main phase):
+constexpr int RP_GQ = 0;            // [81][3]  sqrt(w) d_d u_c, row (q,d)
+constexpr int RP_JQ = RP_GQ + 243;  // [81]     sqrt(w) j_i(q), row (q,i)
+constexpr int RP_DJ = RP_JQ + 88;   // [27]     sqrt(w) div j   (tiles of 8 rows: 32 slots each)
+constexpr int RP_FQ = RP_DJ + 32;   // [27]     sqrt(w) phi
+constexpr int RP_PQ = RP_FQ + 32;   // [27]     sqrt(w) p
+constexpr int RP_PR = RP_PQ + 32;   // [27]     sqrt(w) Pi_p(div u)   (zeta_u only)
+constexpr int RP_RH = RP_PR + 32;   // [4]
+constexpr int RES_GQ = RP_GQ;
+// coefficient tables (stage 2) live where the geometry factors were (S_J, S_INV, S_DET: dead after the panel transforms)
+// so that the row products (stage 3) can run as jobs of the main phase:
+constexpr int RC_GU = S_J;            // [81][3]  coefficient of G'[(q,d)][a] in r_u[(c,a)], row (q,d), col c
+constexpr int RC_FU = RC_GU + 243;    // [27][3]  coefficient of N'[q][a]        (contiguous after GU: one K = 108 product)
+constexpr int RC_FJ = RC_FU + 81;     // [81]     coefficient of Psi'[(q,i)][m]
+constexpr int RC_DJ = RC_FJ + 81;     // [27]     coefficient of Div'[q][m]     (contiguous after FJ)
+constexpr int RC_DV = RC_DJ + 27;     // [27]     sqrt(w) div u
+constexpr int RC_JD = RC_DV + 27;     // [27]     sqrt(w) div j
+static_assert(RC_JD + 27 <= S_SW, "residual coefficient tables overflow the geometry scratch");
+constexpr int NRESJOBS = 11;          // 4 r_u tiles, 5 r_j tiles, r_p, r_phi
+
+// =============================================================================================
+// Residual of one cell: res_fluid_h1_hdiv (src/weakforms.jl:255-281), res_solid_h1_hdiv (:314-325) on solid cells.
+// Needs cell_prep<2> (all panels + the full local state), three stages:
+//   1. point values at the 27 Gauss points as (panel rows) x (state) products on the tensor cores:
+//      sqrt(w) grad u, j, div j, phi, p                                         [all warps, then a CTA barrier]
+//   2. per-point coefficient tables (81 threads)                                  [then a CTA barrier]
+//   3. rows: r = panel^T x coefficients, again on the tensor cores, as NRESJOBS independent warp jobs that only
+//      read the panels and the tables -> in the fused kernel they are jobs of the barrier-free main phase.
+
+// (8 rows of a row-major panel) x (up to 8 state columns): out[row0 + lr][2 lk + {0,1}]
+template <class BF>
+__device__ __forceinline__ void rows_mma(const double* __restrict__ Pn, int ld, int row0, int K, BF bval, double& c0, double& c1) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+  const double* ap = Pn + (row0 + lr) * ld;
+  double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;  // two accumulator chains (even / odd k-steps)
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    {
+      const int kk = k0 + lk;
+      const bool valid = kk < K;
+      const double a = valid ? ap[kk] : 0.0;
+      const double b = valid ? bval(kk, lr) : 0.0;
+      dmma884(e0, e1, a, b);
+    }
+    if (k0 + 4 < K) {
+      const int kk = k0 + 4 + lk;
+      const bool valid = kk < K;
+      const double a = valid ? ap[kk] : 0.0;
+      const double b = valid ? bval(kk, lr) : 0.0;
+      dmma884(o0, o1, a, b);
+    }
+  }
+  c0 = e0 + o0;
+  c1 = e1 + o1;
+}
+
+// stages 1 and 2.  Enter after the cell_prep barrier; ends WITHOUT a barrier (the caller synchronises before stage 3).
+// T != null: also the table alpha d_d u_c of the Newton block.
 template <int CONV, bool ZU>
-__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, int64_t nrows, double* __restrict__ r,
-                                              const KParams& P);
-constexpr int RES_GQ = 81 + 243 + 81 + 27 * 4;  // offset of the velocity-gradient table inside the residual scratch
+__device__ __forceinline__ void residual_points(const CellCtx& cx, int64_t cell, const KParams& P, double* __restrict__ T) {
+  double* sm = cx.sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+  const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+  const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
+  const double* U = sm + S_U;
+  double* Rp = sm + S_ST;
+  // ---- stage 1: 11 tiles grad u | 11 tiles j | 4 tiles (div j, phi, p)
+  for (int job = warp; job < 26; job += NT / 32) {
+    double c0, c1;
+    if (job < 11) {
+      rows_mma(sm + S_G, LDN, 8 * job, 27, [&](int k, int n) { return n < 3 ? U[n * 27 + k] : 0.0; }, c0, c1);
+      const int m = 8 * job + lr;
+      if (m < 81) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          const int c = 2 * lk + r;
+          if (c < 3) {
+            const double v = r ? c1 : c0;
+            Rp[RP_GQ + m * 3 + c] = v;
+            if (T) T[(m / 3) * LDT + (m % 3) * 3 + c] = P.alpha * v / sm[S_SW + m / 3];
+          }
+        }
+      }
+    } else if (job < 22) {
+      const int t = job - 11;
+      rows_mma(sm + S_PSI, NJ, 8 * t, NJ, [&](int k, int n) { return n == 0 ? U[OFF_J + k] : 0.0; }, c0, c1);
+      if (lk == 0) Rp[RP_JQ + 8 * t + lr] = c0;
+    } else {
+      const int t = job - 22;
+      rows_mma(sm + S_DIV, NJ, 8 * t, NJ, [&](int k, int n) { return n == 0 ? U[OFF_J + k] : 0.0; }, c0, c1);
+      if (lk == 0) Rp[RP_DJ + 8 * t + lr] = c0;
+      rows_mma(sm + S_CHI, NF, 8 * t, NF, [&](int k, int n) { return n == 0 ? U[OFF_F + k] : 0.0; }, c0, c1);
+      if (lk == 0) Rp[RP_FQ + 8 * t + lr] = c0;
+      rows_mma(sm + S_PP, NP, 8 * t, NP, [&](int k, int n) { return n == 0 ? U[OFF_P + k] : 0.0; }, c0, c1);
+      if (lk == 0) Rp[RP_PQ + 8 * t + lr] = c0;
+    }
+  }
+  __syncthreads();
+  if (ZU) {
+    // Pi_p(div u) = pi . M_p^-1 (pi, div u): 4x4 mass matrix, right-hand side, solve, evaluate
+    if (tid < 16) {
+      const int k = tid >> 2, l = tid & 3;
+      double s = 0.0;
+      for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
+      sm[S_MI + tid] = s;
+    }
+    if (tid >= 32 && tid < 36) {
+      const int k = tid - 32;
+      double s = 0.0;
+      for (int q = 0; q < NQ; q++)
+        s = fma(sm[S_PP + q * 4 + k], Rp[RP_GQ + q * 9 + 0] + Rp[RP_GQ + q * 9 + 4] + Rp[RP_GQ + q * 9 + 8], s);
+      Rp[RP_RH + k] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a[4][5];
+      for (int i = 0; i < 4; i++) {
+        for (int j = 0; j < 4; j++) a[i][j] = sm[S_MI + i * 4 + j];
+        a[i][4] = Rp[RP_RH + i];
+      }
+      for (int p = 0; p < 4; p++) {
+        const double ip = 1.0 / a[p][p];
+        for (int j = 0; j < 5; j++) a[p][j] *= ip;
+        for (int i = 0; i < 4; i++)
+          if (i != p) {
+            const double f = a[i][p];
+            for (int j = 0; j < 5; j++) a[i][j] -= f * a[p][j];
+          }
+      }
+      for (int i = 0; i < 4; i++) Rp[RP_RH + i] = a[i][4];
+    }
+    __syncthreads();
+    if (tid < NQ) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) s = fma(sm[S_PP + tid * 4 + k], Rp[RP_RH + k], s);
+      Rp[RP_PR + tid] = s;
+    }
+    __syncthreads();
+  }
+  // ---- stage 2: thread (q, c)
+  if (tid < 81) {
+    const int q = tid / 3, c = tid - q * 3;
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    const double sw = sm[S_SW + q];
+    const double* Gq = Rp + RP_GQ + q * 9;
+    const double* jq = Rp + RP_JQ + q * 3;
+    const double* uq = sm + S_UQ + q * 3;  // unweighted
+    const double jxB = jq[c1] * P.B[c2] - jq[c2] * P.B[c1];
+    const double uxB = sw * (uq[c1] * P.B[c2] - uq[c2] * P.B[c1]);
+    double fu = -P.gamma * jxB - sw * P.f[c];
+    if (CONV > 0) {
+      // sqrt(w) (u . grad) u_c = sum_d u_d (sqrt(w) d_d u_c)
+      double cv = 0.0;
+#pragma unroll
+      for (int d = 0; d < 3; d++) cv = fma(uq[d], Gq[d * 3 + c], cv);
+      fu = fma(P.alpha, cv, fu);
+    }
+    sm[RC_FU + q * 3 + c] = fu;
+    sm[RC_FJ + q * 3 + c] = jq[c] - sig_c * uxB - sw * P.g[c];
+    double diag = -Rp[RP_PQ + q];
+    if (ZU) diag = fma(P.zeta_u, Rp[RP_PR + q], diag);
+#pragma unroll
+    for (int d = 0; d < 3; d++) sm[RC_GU + (q * 3 + d) * 3 + c] = P.beta * Gq[d * 3 + c] + (d == c ? diag : 0.0);
+    if (c == 0) {
+      sm[RC_DV + q] = Gq[0] + Gq[4] + Gq[8];
+      sm[RC_DJ + q] = P.zeta_j * Rp[RP_DJ + q] - sig_c * Rp[RP_FQ + q];
+      sm[RC_JD + q] = Rp[RP_DJ + q];
+    }
+  }
+}
+
+// stage 3, one warp job: job 0..3 r_u node tiles | 4..8 r_j tiles | 9 r_p | 10 r_phi
+__device__ __forceinline__ void residual_rows_job(const CellCtx& cx, int job, bool solid, int64_t nrows, double* __restrict__ r) {
+  const double* sm = cx.sm;
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+  double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+  auto run = [&](const double* Pn, int ld, int col, int K, auto bval) {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      {
+        const int kk = k0 + lk;
+        const bool valid = kk < K;
+        const double a = valid ? Pn[kk * ld + col] : 0.0;
+        const double b = valid ? bval(kk, lr) : 0.0;
+        dmma884(e0, e1, a, b);
+      }
+      if (k0 + 4 < K) {
+        const int kk = k0 + 4 + lk;
+        const bool valid = kk < K;
+        const double a = valid ? Pn[kk * ld + col] : 0.0;
+        const double b = valid ? bval(kk, lr) : 0.0;
+        dmma884(o0, o1, a, b);
+      }
+    }
+  };
+  auto add = [&](int li, double v) {
+    const int32_t g = cx.gid[li];
+    if (g >= 0 && g < nrows) atomicAdd(&r[g], v);
+  };
+  if (job < 4) {
+    if (solid) return;
+    // r_u[(c,a)] = sum_{(q,d)} G'[(q,d)][a] GU[(q,d)][c] + sum_q N'[q][a] FU[q][c]   (G' and N' are contiguous: K = 108)
+    const int a = 8 * job + lr;
+    run(sm + S_G, LDN, a, 108, [&](int k, int n) { return n < 3 ? sm[RC_GU + k * 3 + n] : 0.0; });
+    if (a < 27) {
+      const int c = 2 * lk;
+      if (c < 3) add(c * 27 + a, e0 + o0);
+      if (c + 1 < 3) add((c + 1) * 27 + a, e1 + o1);
+    }
+  } else if (job < 9) {
+    // r_j[m] = sum_{(q,i)} Psi'[(q,i)][m] FJ[(q,i)] + sum_q Div'[q][m] DJ[q]        (Psi' and Div' are contiguous)
+    const int m = 8 * (job - 4) + lr;
+    run(sm + S_PSI, NJ, m, 108, [&](int k, int n) { return n == 0 ? sm[RC_FJ + k] : 0.0; });
+    if (m < NJ && lk == 0) add(OFF_J + m, e0 + o0);
+  } else if (job == 9) {
+    if (solid) return;
+    // r_p[k] = -sum_q pi_k div u
+    run(sm + S_PP, NP, lr & 3, NQ, [&](int k, int n) { return n == 0 ? -sm[RC_DV + k] : 0.0; });
+    if (lr < NP && lk == 0) add(OFF_P + lr, e0 + o0);
+  } else {
+    // r_phi[l] = -/+ sum_q chi_l div j   (res_solid_h1_hdiv has the opposite sign)
+    run(sm + S_CHI, NF, lr, NQ, [&](int k, int n) { return n == 0 ? sm[RC_JD + k] : 0.0; });
+    if (lk == 0) add(OFF_F + lr, (solid ? 1.0 : -1.0) * (e0 + o0));
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Sweep of a staged tile: entry e = k*32 + lane of the job's map range <-> staged value Sw[(e / NCOL) * LD + e % NCOL],
@@ -583,9 +803,8 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
     const int64_t nxt_cell = cell + gridDim.x < ncells ? cell + gridDim.x : -1;
     if (!(P.dbg & 4) || cell == blockIdx.x)
     cell_prep<(RES ? 2 : (CONV > 0 ? 1 : 0))>(cx, cell, nxt_cell, A, x, nz);
-    if (RES || CONV == 2)
-      velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, RES ? sm + S_ST + RES_GQ : nullptr, CONV == 2 ? sm + S_T : nullptr, LDT,
-                            P.alpha);  // T = alpha d_d u_c
+    if (RES) residual_points<(CONV > 0 ? 1 : 0), ZU>(cx, cell, P, CONV == 2 ? sm + S_T : (double*)nullptr);  // also T = alpha d_d u_c
+    else if (CONV == 2) velocity_gradient_mma(sm + S_G, sm + S_U, sm + S_SW, nullptr, sm + S_T, LDT, P.alpha);
     if (CONV > 0) {
       // UG[q][b] = sqrt(w) u_q . grad N_b
       for (int idx = tid; idx < NQ * 27; idx += NT) {
@@ -647,11 +866,6 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
         for (int l = 0; l < 4; l++) s = fma(sm[S_MI + k * 4 + l], sm[S_D + i * 4 + l], s);
         sm[S_E + k * 81 + i] = P.zeta_u * s;
       }
-    }
-    if (RES) {
-      __syncthreads();
-      MHD_MARK(cx, 4);
-      cell_residual<(CONV > 0 ? 1 : 0), ZU>(cx, cell, nrows, rvec, P);  // scratch = the (still unused) staging tiles
     }
     __syncthreads();
     MHD_MARK(cx, 5);
@@ -768,8 +982,10 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
       int job = 0;
       if (lane == 0) job = atomicAdd(jobctr, 1);
       job = __shfl_sync(0xffffffffu, job, 0);
-      if (job >= NJOBS) break;
-      if (job >= 1 && job <= 5) {
+      if (job >= NJOBS + (RES ? NRESJOBS : 0)) break;
+      if (job >= NJOBS) {
+        residual_rows_job(cx, job - NJOBS, solid, nrows, rvec);
+      } else if (job >= 1 && job <= 5) {
         // ---- jj rows 8 s .. 8 s + 7: sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous)
         const int s_ = job - 1;
         const int nrow = s_ < 4 ? 8 : 4;
@@ -945,162 +1161,6 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
     for (int i = 0; i < 12; i++) atomicAdd(P.clk_out + i, (unsigned long long)cx.clk[i]);
 }
 
-// =============================================================================================
-// Residual of one cell: res_fluid_h1_hdiv (src/weakforms.jl:255-281).  Needs cell_prep<2> (all panels + the full
-// local state); uses the first ~820 doubles of the staging area and leaves the panels untouched.
-template <int CONV, bool ZU>
-__device__ __forceinline__ void cell_residual(const CellCtx& cx, int64_t cell, int64_t nrows, double* __restrict__ r,
-                                              const KParams& P) {
-  double* sm = cx.sm;
-  const int tid = threadIdx.x;
-  // res_solid_h1_hdiv (weakforms.jl:314-325) on solid cells: sigma of the cell, +phi-test * div j; u = 0 there
-  const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
-  const double sig_c = solid ? P.cell_sigma[cell] : P.sigma;
-  const double f_sign = solid ? 1.0 : -1.0;
-  // per-q coefficient tables in the staging area
-  double* Fu = sm + S_ST;         // [27][3]  coefficient of N'[q][a] in r_u[(c,a)]
-  double* Gu = Fu + 81;           // [27][9]  coefficient of G'[(q,d)][a], index d*3+c
-  double* Fj = Gu + 243;          // [27][3]  coefficient of Psi'[(q,i)][m]
-  double* Dj = Fj + 81;           // [27]     coefficient of Div'[q][m]
-  double* Dv = Dj + 27;           // [27]     sqrt(w) div u
-  double* Jd = Dv + 27;           // [27]     sqrt(w) div j
-  double* Pq = Jd + 27;           // [27]     sqrt(w) p
-  double* Gq = Pq + 27;           // [27][9]  sqrt(w) d_d u_c
-  double* Pr = Gq + 243;          // [27]     sqrt(w) Pi_p(div u)
-  double* Rh = Pr + 27;           // [4] rhs / coefficients of the projection
-  {
-    const double* U = sm + S_U;
-    // Gq (velocity gradient at q) has been filled by velocity_gradient_mma; div u, p at q
-    if (tid < NQ) {
-      const int q = tid;
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) s = fma(sm[S_PP + q * 4 + k], U[OFF_P + k], s);
-      Pq[q] = s;
-      double dj = 0.0;
-      for (int m = 0; m < NJ; m++) dj = fma(sm[S_DIV + q * NJ + m], U[OFF_J + m], dj);
-      Jd[q] = dj;
-    }
-    __syncthreads();
-    if (tid < NQ) Dv[tid] = Gq[tid * 9 + 0] + Gq[tid * 9 + 4] + Gq[tid * 9 + 8];
-    __syncthreads();
-    if (ZU) {
-      if (tid < 16) {
-        const int k = tid >> 2, l = tid & 3;
-        double s = 0.0;
-        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], sm[S_PP + q * 4 + l], s);
-        sm[S_MI + tid] = s;
-      }
-      if (tid >= 32 && tid < 36) {
-        const int k = tid - 32;
-        double s = 0.0;
-        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], Dv[q], s);
-        Rh[k] = s;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        double a[4][5];
-        for (int i = 0; i < 4; i++) {
-          for (int j = 0; j < 4; j++) a[i][j] = sm[S_MI + i * 4 + j];
-          a[i][4] = Rh[i];
-        }
-        for (int p = 0; p < 4; p++) {
-          const double ip = 1.0 / a[p][p];
-          for (int j = 0; j < 5; j++) a[p][j] *= ip;
-          for (int i = 0; i < 4; i++)
-            if (i != p) {
-              const double f = a[i][p];
-              for (int j = 0; j < 5; j++) a[i][j] -= f * a[p][j];
-            }
-        }
-        for (int i = 0; i < 4; i++) Rh[i] = a[i][4];
-      }
-      __syncthreads();
-      if (tid < NQ) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) s = fma(sm[S_PP + tid * 4 + k], Rh[k], s);
-        Pr[tid] = s;
-      }
-      __syncthreads();
-    }
-    if (tid < NQ) {
-      const int q = tid;
-      const double sw = sm[S_SW + q];
-      // weighted u, j, phi at q
-      double uq[3], jq[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        uq[i] = sm[S_UQ + q * 3 + i] * sw;
-        double s = 0.0;
-        for (int m = 0; m < NJ; m++) s = fma(sm[S_PSI + (q * 3 + i) * NJ + m], U[OFF_J + m], s);
-        jq[i] = s;
-      }
-      double fq = 0.0;
-#pragma unroll
-      for (int l = 0; l < 8; l++) fq = fma(sm[S_CHI + q * 8 + l], U[OFF_F + l], fq);
-      const double jxB[3] = {jq[1] * P.B[2] - jq[2] * P.B[1], jq[2] * P.B[0] - jq[0] * P.B[2], jq[0] * P.B[1] - jq[1] * P.B[0]};
-      const double uxB[3] = {uq[1] * P.B[2] - uq[2] * P.B[1], uq[2] * P.B[0] - uq[0] * P.B[2], uq[0] * P.B[1] - uq[1] * P.B[0]};
-#pragma unroll
-      for (int c = 0; c < 3; c++) {
-        double v = -P.gamma * jxB[c] - sw * P.f[c];
-        if (CONV > 0) {
-          // sqrt(w) (u . grad) u_c = sum_d u_d (sqrt(w) d_d u_c)
-          double cv = 0.0;
-#pragma unroll
-          for (int d = 0; d < 3; d++) cv = fma(sm[S_UQ + q * 3 + d], Gq[q * 9 + d * 3 + c], cv);
-          v = fma(P.alpha, cv, v);
-        }
-        Fu[q * 3 + c] = v;
-        Fj[q * 3 + c] = jq[c] - sig_c * uxB[c] - sw * P.g[c];
-      }
-#pragma unroll
-      for (int d = 0; d < 3; d++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          double v = P.beta * Gq[q * 9 + d * 3 + c];
-          if (d == c) {
-            v -= Pq[q];
-            if (ZU) v = fma(P.zeta_u, Pr[q], v);
-          }
-          Gu[q * 9 + d * 3 + c] = v;
-        }
-      Dj[q] = P.zeta_j * Jd[q] - sig_c * fq;
-    }
-    __syncthreads();
-    // rows
-    if (tid < NLOC) {
-      const int i = tid;
-      double s = 0.0;
-      if (i < NU) {
-        const int c = i / 27, a = i - c * 27;
-        for (int q = 0; q < NQ; q++) {
-          s = fma(sm[S_N + q * LDN + a], Fu[q * 3 + c], s);
-#pragma unroll
-          for (int d = 0; d < 3; d++) s = fma(sm[S_G + (q * 3 + d) * LDN + a], Gu[q * 9 + d * 3 + c], s);
-        }
-      } else if (i < OFF_J) {
-        const int k = i - OFF_P;
-        for (int q = 0; q < NQ; q++) s = fma(sm[S_PP + q * 4 + k], Dv[q], s);
-        s = -s;
-      } else if (i < OFF_F) {
-        const int m = i - OFF_J;
-        for (int q = 0; q < NQ; q++) {
-#pragma unroll
-          for (int d = 0; d < 3; d++) s = fma(sm[S_PSI + (q * 3 + d) * NJ + m], Fj[q * 3 + d], s);
-          s = fma(sm[S_DIV + q * NJ + m], Dj[q], s);
-        }
-      } else {
-        const int l = i - OFF_F;
-        for (int q = 0; q < NQ; q++) s = fma(sm[S_CHI + q * 8 + l], Jd[q], s);
-        s = f_sign * s;
-      }
-      const int32_t g = cx.gid[i];
-      if (g >= 0 && g < nrows) atomicAdd(&r[g], s);
-    }
-  }
-}
-
 template <int CONV, bool ZU>
 __global__ void __launch_bounds__(NT, 2)
 residual_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restrict__ x, double* __restrict__ r, KParams P) {
@@ -1110,9 +1170,10 @@ residual_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
   for (int64_t cell = blockIdx.x; cell < ncells; cell += gridDim.x) {
     __syncthreads();
     cell_prep<2>(cx, cell, cell + gridDim.x < ncells ? cell + gridDim.x : -1, A, x, nullptr);
-    velocity_gradient_mma(cx.sm + S_G, cx.sm + S_U, cx.sm + S_SW, cx.sm + S_ST + RES_GQ, nullptr, 0);
+    residual_points<CONV, ZU>(cx, cell, P, nullptr);
     __syncthreads();
-    cell_residual<CONV, ZU>(cx, cell, nrows, r, P);
+    const bool solid = P.cell_solid != nullptr && P.cell_solid[cell] != 0;
+    for (int job = threadIdx.x >> 5; job < NRESJOBS; job += NT / 32) residual_rows_job(cx, job, solid, nrows, r);
   }
 }
 

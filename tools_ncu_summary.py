@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Summarise ncu reports (raw page) into a small JSON for profiles/.  usage: tools_ncu_summary.py out.json name=report.ncu-rep ..."""
+import csv, io, json, subprocess, sys
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_src_fp64.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__m_l1tex2xbar_write_sectors_mem_lg_op_st.sum", "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum",
+        "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+out = {}
+for arg in sys.argv[2:]:
+    name, rep = arg.split("=", 1)
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {"Kernel Name": vals[hdr.index("Kernel Name")]}
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            d[k] = (vals[i] + " " + units[i]).strip()
+    out[name] = d
+json.dump(out, open(sys.argv[1], "w"), indent=1)
+print(json.dumps(out, indent=1))
