@@ -161,6 +161,17 @@ int mhd_set_stream(void* s) {
   return MHD_OK;
 }
 
+int mhd_map_entry_order(uint16_t* order, int64_t* n) {
+  MHD_CHECK(n != nullptr, MHD_E_INVALID, "mhd_map_entry_order: null argument");
+  *n = NENT;
+  if (order) {
+    std::vector<uint16_t> ord;
+    entry_order(ord);
+    memcpy(order, ord.data(), NENT * sizeof(uint16_t));
+  }
+  return MHD_OK;
+}
+
 int mhd_fp64_peak(int32_t kind, double* tflops) {
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CHECK(tflops && (kind == 0 || kind == 1), MHD_E_INVALID, "mhd_fp64_peak: invalid argument");

@@ -98,7 +98,7 @@ struct KParams {
   double B[3], f[3], g[3];
   const uint8_t* cell_solid;  // null: no solid sub-domain
   const double* cell_sigma;
-  int dbg;  // MHD_JAC_DEBUG bit mask (timing experiments only): 1 no stores, 2 no main phase, 4 preparation only once,
+  int dbg;  // MHD_JAC_DEBUG bit mask (timing experiments only): 2 no main phase, 4 preparation only once, 32 no L2 prefetch,
             // 16 phase clocks of thread 0 (summed over CTAs into clk_out, printed by the launcher)
   unsigned long long* clk_out;
 };
@@ -737,7 +737,7 @@ __device__ __forceinline__ void scatter_pred(double* p, double v, int code) {
 // row[] holds the byte address of the first nnz of each local row (0 for dropped rows: their codes are all SKIP)
 template <int NCOL, int LD, int KMAX, class RowOf>
 __device__ __forceinline__ void sweep(const int (&code)[KMAX], int n, const double* __restrict__ Sw,
-                                      const long long* __restrict__ row, RowOf rowof, bool nostore = false) {
+                                      const long long* __restrict__ row, RowOf rowof) {
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < KMAX; k++) {
@@ -754,7 +754,7 @@ __device__ __forceinline__ void sweep(const int (&code)[KMAX], int n, const doub
     }
     const double v = Sw[r * LD + col];
     double* p = reinterpret_cast<double*>(row[rowof(r)]) + (code[k] & 0x7FFF);
-    if (!nostore) scatter_pred(p, v, code[k]);
+    scatter_pred(p, v, code[k]);
   }
 }
 
@@ -764,7 +764,7 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 // Jacobian kernel.  CONV: 0 none, 1 picard, 2 newton.  ZU: zeta_u != 0 (rank-4 update zeta_u D^T M_p^-1 D of the uu
 // block, folded into the tensor-core products as one extra k-step).  RES: also assemble the residual at the same state
 // (residual_and_jacobian!), sharing the cell preparation.
-constexpr int NJOBS = 17;
+constexpr int NJOBS = 15;
 
 template <int CONV, bool ZU, bool RES>
 __global__ void __launch_bounds__(NT, 2)
@@ -871,7 +871,6 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
     MHD_MARK(cx, 5);
 
     if (P.dbg & 2) continue;
-    const bool nostore = P.dbg & 1;
     const uint16_t* cmap = map + cell * NENT_PAD;
     const long long* row = cx.row;
     // solid cells (jac_solid_h1_hdiv, weakforms.jl:327-338): own conductivity, +phi div j instead of -div j phi; their
@@ -958,8 +957,8 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
         }
         __syncwarp();
         if (CONV == 2 || ZU) {
-          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
-          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
+          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
         } else {
           // none / picard: only the diagonal component pairs carry values (the others stay at the memset zero)
 #pragma unroll
@@ -968,8 +967,8 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
             const int col = np == 0 ? e % 48 : e % 33;
             if (col % 3 != c) code[k] = -1;
           }
-          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
-          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; }, nostore);
+          if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
+          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
         }
         __syncwarp();
       }
@@ -977,33 +976,44 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
 
     MHD_MARK(cx, 6);
     // ------------------------------------------------------------------ pooled jobs, drawn from a shared counter
-    // order = decreasing cost: 0 up/pu | 1..5 jj strips | 6..9 uj(s,0) | 10..13 uj(s,1) | 14 j-phi | 15,16 uj(4,h)
+    // jobs: 0 up/pu | 1..3 jj | 4..7 uj(s,0) | 8..11 uj(s,1) | 12 j-phi | 13,14 uj(4,h) | then the residual row jobs.
+    // The counter hands them out in the order of JOB_ORDER (decreasing cost).
     for (;;) {
       int job = 0;
       if (lane == 0) job = atomicAdd(jobctr, 1);
       job = __shfl_sync(0xffffffffu, job, 0);
       if (job >= NJOBS + (RES ? NRESJOBS : 0)) break;
+      if (job < NJOBS) job = (0x0EDCBA9876540321ull >> (4 * job)) & 15;  // 1 2 3(jj) 0(up/pu) 4..11 (uj) 12 (j-phi) 13 14
       if (job >= NJOBS) {
         residual_rows_job(cx, job - NJOBS, solid, nrows, rvec);
-      } else if (job >= 1 && job <= 5) {
-        // ---- jj rows 8 s .. 8 s + 7: sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous)
-        const int s_ = job - 1;
-        const int nrow = s_ < 4 ? 8 : 4;
-        int code[9];
-        load_codes(code, cmap + jj_base(s_), nrow * NJ);
-        double acc[1][5][2];
-        const int ca[1] = {8 * s_ + lr};
+      } else if (job >= 1 && job <= 3) {
+        // ---- jj: sum_{q,i} Psi Psi + zeta_j sum_q Div Div (Psi and Div panels are contiguous).  Jobs 1, 2: two 8-row
+        //      strips each (a <2,5> register block: 7 operand loads per 10 MMAs), job 3: the last strip (4 rows)
+        const int s0 = 2 * (job - 1);
+        const bool two = job < 3;
+        int code0[9], code1[9];
+        load_codes(code0, cmap + jj_base(s0), (s0 < 4 ? 8 : 4) * NJ);
+        load_codes(code1, cmap + jj_base(s0 + 1), two ? 8 * NJ : 0);
+        double acc[2][5][2];
+        const int ca[2] = {8 * s0 + lr, two ? 8 * s0 + 8 + lr : 8 * s0 + lr};
         int cb[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) cb[j] = 8 * j + lr;
-        if (P.zeta_j != 0.0) warp_mma_cols<1, 5, true>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
-        else warp_mma_cols<1, 5, false>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+        if (P.zeta_j != 0.0) warp_mma_cols<2, 5, true>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
+        else warp_mma_cols<2, 5, false>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
 #pragma unroll
         for (int j = 0; j < 5; j++) st2(Sw + lr * 40 + 8 * j + 2 * lk, acc[0][j][0], acc[0][j][1]);
         __syncwarp();
-        sweep<NJ, 40, 9>(code, nrow * NJ, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
+        sweep<NJ, 40, 9>(code0, (s0 < 4 ? 8 : 4) * NJ, Sw, row, [&](int r) { return OFF_J + 8 * s0 + r; });
         __syncwarp();
-      } else if (job == 14) {
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 5; j++) st2(Sw + lr * 40 + 8 * j + 2 * lk, acc[1][j][0], acc[1][j][1]);
+          __syncwarp();
+          sweep<NJ, 40, 9>(code1, 8 * NJ, Sw, row, [&](int r) { return OFF_J + 8 * s0 + 8 + r; });
+          __syncwarp();
+        }
+      } else if (job == 12) {
         // ---- j-phi: -sigma JF[m][l] ; phi-j: -/+ JF[m][l],  JF = sum_q Div[q][m] Chi[q][l]
         int cjf[9], cfj[9];
         load_codes(cjf, cmap + SEC_JF, NJ * NF);
@@ -1017,7 +1027,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
 #pragma unroll
         for (int i = 0; i < 5; i++) st2(Sw + (8 * i + lr) * 8 + 2 * lk, -sig_c * acc[i][0][0], -sig_c * acc[i][0][1]);
         __syncwarp();
-        sweep<NF, NF, 9>(cjf, NJ * NF, Sw, row, [&](int r) { return OFF_J + r; }, nostore);
+        sweep<NF, NF, 9>(cjf, NJ * NF, Sw, row, [&](int r) { return OFF_J + r; });
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 5; i++) {
@@ -1028,7 +1038,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
           }
         }
         __syncwarp();
-        sweep<NJ, 38, 9>(cfj, NF * NJ, Sw, row, [&](int r) { return OFF_F + r; }, nostore);
+        sweep<NJ, 38, 9>(cfj, NF * NJ, Sw, row, [&](int r) { return OFF_F + r; });
         __syncwarp();
       } else if (solid) {
         continue;
@@ -1053,7 +1063,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
             if (a < 27 && lk < 2) st2(Sw + (c * 27 + a) * 4 + 2 * lk, -acc[c][i][0][0], -acc[c][i][0][1]);
           }
         __syncwarp();
-        sweep<NP, NP, 11>(cup, NU * NP, Sw, row, [&](int r) { return r; }, nostore);
+        sweep<NP, NP, 11>(cup, NU * NP, Sw, row, [&](int r) { return r; });
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -1066,15 +1076,15 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
             }
           }
         __syncwarp();
-        sweep<NU, 82, 11>(cpu, NP * NU, Sw, row, [&](int r) { return OFF_P + r; }, nostore);
+        sweep<NU, 82, 11>(cpu, NP * NU, Sw, row, [&](int r) { return OFF_P + r; });
         __syncwarp();
       } else {
         // ---- uj / ju job (s, h): j slots 8 s .. (8 | 4 of them), node slots 16 h .. (16 | 11 of them).
         //   Q_i[a][m] = sum_q N'[q][a] Psi'[(q,i)][m] for i = 0..2 (tensor cores), then in registers
         //   R_c = (psi x B)_c-weighted = B_{c+2} Q_{c+1} - B_{c+1} Q_{c+2};  K_uj[(c,a)][m] = -gamma R_c[a][m],
         //   K_ju[m][(b,d)] = +sigma R_d[b][m]
-        const int s_ = job < 10 ? job - 6 : (job < 14 ? job - 10 : 4);
-        const int h = job < 10 ? 0 : (job < 14 ? 1 : job - 15);
+        const int s_ = job < 8 ? job - 4 : (job < 12 ? job - 8 : 4);
+        const int h = job < 8 ? 0 : (job < 12 ? 1 : job - 13);
         const int nm = uj_nm(s_), na = uj_na(h);
         const uint16_t* cbase = cmap + uj_base(s_, h);
         int cuj[12], cju[12];
@@ -1131,11 +1141,11 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
           }
         __syncwarp();
         if (h == 0) {
-          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); }, nostore);
-          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); }, nostore);
+          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); });
+          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r >> 4) * 27 + (r & 15); });
         } else {
-          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; }, nostore);
-          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; }, nostore);
+          if (nm == 8) sweep<8, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; });
+          else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; });
         }
         __syncwarp();
         // ju part: Sw[ml * 50 + 3 * al + d]
@@ -1150,8 +1160,8 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
             }
           }
         __syncwarp();
-        if (h == 0) sweep<48, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
-        else sweep<33, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; }, nostore);
+        if (h == 0) sweep<48, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; });
+        else sweep<33, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; });
         __syncwarp();
       }
     }

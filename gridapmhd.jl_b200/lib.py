@@ -93,6 +93,7 @@ SIGNATURES = {
     "mhd_operator_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mhd_kernel_launch_count": (C.c_int, [C.POINTER(C.c_int64)]),
     "mhd_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "mhd_map_entry_order": (C.c_int, [C.POINTER(C.c_uint16), C.POINTER(C.c_int64)]),
     "mhd_profile_enable": (C.c_int, [C.c_int]),
     "mhd_profile_get": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mhd_profile_reset": (C.c_int, []),

@@ -152,6 +152,11 @@ int mhd_operator_symbolic(mhd_operator_t*, int64_t* nrows, int64_t* ncols, int64
  * src/parameters.jl:224,235) */
 int mhd_operator_get_csr(mhd_operator_t*, void* rowptr, void* colval, int index_bytes, int base);
 int mhd_operator_get_scatter_stats(mhd_operator_t*, int64_t* nentries, int64_t* nexclusive);
+/* The enumeration of a cell's touched entries used by the scatter map = the order in which the Jacobian kernel
+ * consumes it: order[e] = (row slot << 8 | col slot) in the permuted local numbering (u: c*27+s, p: 81+k, j: 85+s,
+ * phi: 121+l), 0xFFFF for the codes that pad a warp job to a multiple of 32.  order == NULL: only *n is returned.
+ * Needs no device (used by the CPU tests to pin the symbolic/numeric contract). */
+int mhd_map_entry_order(uint16_t* order, int64_t* n);
 
 /* numeric phase: jacobian!(A,op,x) / residual!(b,op,x) (Gridap NonlinearOperator API used by
  * solve!(xh,solver,op), src/main.jl:275; and jacobian(op,xh)/residual(op,xh), src/main.jl:158,163).

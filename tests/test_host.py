@@ -66,6 +66,29 @@ def test_c_struct_layouts_match_header_sizes(tmp_path):
     assert mine == sizes, (mine, sizes)
 
 
+def test_scatter_map_entry_order_covers_every_touched_pair_once():
+    """The enumeration shared by the symbolic phase (map construction) and the Jacobian kernel (map consumption):
+    every touched (row, col) pair of the 8 blocks of jac_fluid_h1_hdiv (weakforms.jl:311) exactly once, nothing else,
+    job ranges padded with 0xFFFF to multiples of 32."""
+    from gridapmhd_jl_b200 import lib as L
+    from oracle import mhd_oracle as O
+
+    lib = L.load()
+    n = ctypes.c_int64()
+    assert lib.mhd_map_entry_order(None, ctypes.byref(n)) == 0
+    assert n.value % 32 == 0 and 14913 <= n.value <= 16384
+    order = np.zeros(n.value, dtype=np.uint16)
+    assert lib.mhd_map_entry_order(order.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), ctypes.byref(n)) == 0
+    real = order[order != 0xFFFF]
+    assert len(real) == 14913 and len(np.unique(real)) == 14913
+    seen = np.zeros((129, 129), dtype=bool)
+    seen[real >> 8, real & 0xFF] = True
+    assert np.array_equal(seen, O.touched_mask())  # the permutation acts inside each field: same block structure
+    # padding only at the end of 32-aligned job ranges: a pad code is never followed by a real entry inside a 32-block
+    blocks = (order != 0xFFFF).reshape(-1, 32)
+    assert np.all(np.diff(blocks.astype(np.int8), axis=1) <= 0)
+
+
 # ---- reference elements --------------------------------------------------------------------------
 def test_quadrature_degree5_is_27_point_gauss():
     xi, w = reffe.quadrature_for_degree(5)
