@@ -396,3 +396,77 @@ def solution_norms(fes, x, T6, u0=1.0, jscale=1.0):
     gg = np.einsum("cq,cqdi,cqdi->", w, gu, gu)
     jj = np.einsum("cq,cqi,cqi->", w, jq, jq)
     return {"uh_l2": np.sqrt(uu), "uh_h1": np.sqrt(gg + uu), "jh_l2": np.sqrt(jj)}
+
+
+# ----------------------------------------------------------------------------
+# analytical Hunt solution and the error norms of the reference's post-processing
+
+
+def analytical_hunt(xy, a=1.0, b=1.0, mu=1.0, sigma=1.0, grad_pz=-1.0, Ha=50.0, n=500):
+    """`analytical_hunt_u` / `analytical_hunt_j` (src/Applications/hunt.jl:372-457) at points xy [npts,2], the
+    Fourier series truncated after k = 0..n, plus the derivatives of u_z the H1 error norm needs (the reference gets
+    them from ForwardDiff).  Returns u_z, du_z/dx, du_z/dy, j_x, j_y (zero outside the duct, hunt.jl:385-387)."""
+    xy = np.asarray(xy, dtype=float)
+    ll = b / a
+    xi, eta = xy[:, 0] / a, xy[:, 1] / a
+    inside = (np.abs(xi) <= 1.0) & (np.abs(eta) <= 1.0)
+    k = np.arange(n + 1, dtype=float)[None, :]
+    al = (k + 0.5) * np.pi / ll
+    N = np.sqrt(Ha**2 + 4.0 * al**2)
+    r1, r2 = 0.5 * (Ha + N), 0.5 * (-Ha + N)
+    sgn = np.where(np.arange(n + 1) % 2 == 0, 1.0, -1.0)[None, :]
+    X, E = xi[:, None], eta[:, None]
+    e1m, e1p = np.exp(-r1 * (1 - E)), np.exp(-r1 * (1 + E))
+    e2m, e2p = np.exp(-r2 * (1 - E)), np.exp(-r2 * (1 + E))
+    d1, d2 = 1.0 + np.exp(-2.0 * r1), 1.0 + np.exp(-2.0 * r2)
+    V2, V3 = (r2 / N) * (e1m + e1p) / d1, (r1 / N) * (e2m + e2p) / d2
+    V2e, V3e = (r2 / N) * r1 * (e1m - e1p) / d1, (r1 / N) * r2 * (e2m - e2p) / d2
+    ck, sk = np.cos(al * X), np.sin(al * X)
+    cu = 2.0 * sgn / (ll * al**3)
+    scale_u = (a**2 / mu) * (-grad_pz)
+    uz = scale_u * np.sum(cu * ck * (1.0 - V2 - V3), axis=1)
+    uz_x = scale_u / a * np.sum(cu * (-al * sk) * (1.0 - V2 - V3), axis=1)
+    uz_y = scale_u / a * np.sum(cu * ck * (-V2e - V3e), axis=1)
+    H2, H3 = (r2 / N) * (e1m - e1p) / d1, (r1 / N) * (e2m - e2p) / d2
+    H2y, H3y = (r2 / N) * (r1 / a) * (e1m + e1p) / d1, (r1 / N) * (r2 / a) * (e2m + e2p) / d2
+    H_dx = np.sum(-2.0 * sgn * sk / (a * ll * al**2) * (H2 - H3), axis=1)
+    H_dy = np.sum(2.0 * sgn * ck / (ll * al**3) * (H2y - H3y), axis=1)
+    scale_j = a**2 * np.sqrt(sigma) / np.sqrt(mu) * (-grad_pz)
+    jx, jy = scale_j * H_dy, scale_j * (-H_dx)
+    z = np.zeros_like(uz)
+    return tuple(np.where(inside, v, z) for v in (uz, uz_x, uz_y, jx, jy))
+
+
+def hunt_error_norms(fes, x, T6, Ha, nsums, u0=1.0, jscale=1.0, a=1.0, mu=1.0, sigma=1.0, grad_pz=-1.0, chunk=4096):
+    """eu_l2, eu_h1, ej_l2 of the reference's post-processing (hunt.jl:239-256): errors against the analytical Hunt
+    solution with the degree 2*(order+1) quadrature table T6."""
+    X = fes.mesh.cell_coords()
+    st = fes.cell_state(x)
+    nc = X.shape[0]
+    w, gN, psi, _ = mapped_bases(T6, X, fes.j_sign)
+    # physical coordinates of the quadrature points (trilinear map of the 8 vertices)
+    xq = np.einsum("qv,cvi->cqi", T6.geo_val, X)
+    us = st[:, :81].reshape(nc, 3, 27) * u0
+    js = st[:, 85:121] * jscale
+    uq = np.einsum("qa,cia->cqi", T6.nu, us)
+    gu = np.einsum("cqbd,cib->cqdi", gN, us)  # [d,i] = d_d u_i
+    jq = np.einsum("cqmi,cm->cqi", psi, js)
+    pts = xq.reshape(-1, 3)[:, :2]
+    outs = [np.empty(len(pts)) for _ in range(5)]
+    for s in range(0, len(pts), chunk):
+        r = analytical_hunt(pts[s : s + chunk], a=a, b=a, mu=mu, sigma=sigma, grad_pz=grad_pz, Ha=Ha, n=nsums)
+        for o, v in zip(outs, r):
+            o[s : s + chunk] = v
+    uz, uz_x, uz_y, jx, jy = (o.reshape(nc, -1) for o in outs)
+    eu = -uq.copy()
+    eu[:, :, 2] += uz
+    ge = -gu.copy()
+    ge[:, :, 0, 2] += uz_x
+    ge[:, :, 1, 2] += uz_y
+    ej = -jq.copy()
+    ej[:, :, 0] += jx
+    ej[:, :, 1] += jy
+    l2 = np.einsum("cq,cqi,cqi->", w, eu, eu)
+    h1 = np.einsum("cq,cqdi,cqdi->", w, ge, ge)
+    jl2 = np.einsum("cq,cqi,cqi->", w, ej, ej)
+    return {"eu_l2": np.sqrt(l2), "eu_h1": np.sqrt(h1 + l2), "ej_l2": np.sqrt(jl2)}

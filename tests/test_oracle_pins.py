@@ -49,18 +49,39 @@ def test_k1_nnz_counts_cfg1():
 
 
 # K5 ------------------------------------------------------------------------------------------
-def test_k5_hunt_ha50_nc10_published_norms():
-    """analysis/gadi/results/2023_04/eaab9d14.../hconv_ha00050ns500/summary.csv:7 (nc=10, Ha=50): uh_l2, uh_h1, jh_l2.
-    The 2023 runs used the kmap=1 power map, i.e. the unstretched mesh (BL_adapted=False, kmap=1 here)."""
+@pytest.fixture(scope="module")
+def hunt_ha50_nc10_solution():
+    """Discrete solution of the published run ha00050cx010 (nc=10, Ha=50, kmap=1 = unstretched mesh), sparse LU Newton."""
     Ha = 50.0
     fes = hunt_fes(10, Ha, BL_adapted=False)
     prm = O.FluidParams(alpha=1.0, beta=1.0, gamma=Ha**2, sigma=1.0, B=(0, 1, 0), f=(0, 0, 1), convection="newton")
     x, hist = O.newton_lu(fes, prm)
     assert hist[-1] < 1e-10 * hist[0]
+    return fes, x, Ha
+
+
+def test_k5_hunt_ha50_nc10_published_norms(hunt_ha50_nc10_solution):
+    """analysis/gadi/results/2023_04/eaab9d14.../hconv_ha00050ns500/summary.csv:7 (nc=10, Ha=50): uh_l2, uh_h1, jh_l2.
+    The 2023 runs used the kmap=1 power map, i.e. the unstretched mesh (BL_adapted=False, kmap=1 here)."""
+    fes, x, Ha = hunt_ha50_nc10_solution
     nr = O.solution_norms(fes, x, reffe.make_tables(6), u0=1.0, jscale=Ha)  # jh = sigma*u0*B0*jbar (hunt.jl:217)
     pins = dict(uh_l2=0.001125968494949451, uh_h1=0.009386206346670825, jh_l2=0.019669872964491745)
     for k, v in pins.items():
         assert abs(nr[k] - v) / v < 1e-9, (k, nr[k], v)
+
+
+def test_k6_hunt_error_norms_against_the_analytical_solution(hunt_ha50_nc10_solution):
+    """Same published row: the errors against the analytical Hunt series (hunt.jl:239-256,372-457) with nsums = 500
+    (eu_l2, eu_h1, ej_l2) and 2*nsums = 1000 terms (the *_ref columns), degree-6 quadrature.  Reproduced to 1e-9
+    relative (observed 4e-13): pins the mesh, the spaces, the solve, the RT/Piola evaluation and the series at once."""
+    fes, x, Ha = hunt_ha50_nc10_solution
+    T6 = reffe.make_tables(6)
+    pins = {500: dict(eu_l2=6.274034420523594e-5, eu_h1=0.0021489743289400043, ej_l2=0.0011055397108926523),
+            1000: dict(eu_l2=6.273968018318573e-5, eu_h1=0.002148559357584549, ej_l2=0.0011055397108926512)}
+    for nsums, pin in pins.items():
+        e = O.hunt_error_norms(fes, x, T6, Ha, nsums, u0=1.0, jscale=Ha)
+        for k, v in pin.items():
+            assert abs(e[k] - v) / v < 1e-9, (nsums, k, e[k], v)
 
 
 # K2 ------------------------------------------------------------------------------------------
