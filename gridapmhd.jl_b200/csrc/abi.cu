@@ -545,6 +545,14 @@ int mhd_residual(mhd_operator_t* op, const double* x, double* r_out) {
   return MHD_OK;
 }
 
+int mhd_hunt_error_norms(mhd_operator_t* op, const double* x, const mhd_tables_t* tab6, const mhd_hunt_post_t* prm, double* out6) {
+  MHD_TRY(check_ready(op));
+  MHD_CHECK(x && tab6 && prm && out6, MHD_E_INVALID, "mhd_hunt_error_norms: null argument");
+  const double* dx;
+  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+  return hunt_error_norms(op, dx, tab6, prm, out6);
+}
+
 int mhd_spmv(mhd_operator_t* op, const double* x, double* y) {
   MHD_TRY(check_ready(op));
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_spmv: no matrix");

@@ -79,7 +79,9 @@ constexpr int PT_PP = PT_DIV + 27 * 36;     // [27 q][4]
 constexpr int PT_CHI = PT_PP + 27 * 4;      // [27 q][8]
 constexpr int PT_TOTAL = PT_CHI + 27 * 8;   // 7236 doubles = 57888 B (multiple of 16)
 
-struct Comm;  // comm.cu
+struct Comm;  // postprocess.cu
+int hunt_error_norms(mhd_operator* op, const double* d_x, const mhd_tables_t* t, const mhd_hunt_post_t* p, double* out6);
+// comm.cu
 
 struct Halo {
   int nneigh = 0;
@@ -243,6 +245,8 @@ int launch_axpy(int64_t n, double a, const double* d_x, double* d_y);
 int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int64_t ldv, const double* d_w, double* d_h);
 int launch_multi_axpy(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, double sign, double* d_w);
 int ensure_red(mhd_operator* op, int64_t ndoubles);
+// postprocess.cu
+int hunt_error_norms(mhd_operator* op, const double* d_x, const mhd_tables_t* t, const mhd_hunt_post_t* p, double* out6);
 // comm.cu
 int halo_exchange(mhd_operator* op, double* d_x);
 int allreduce_sum(double* d_buf, int n);

@@ -209,6 +209,18 @@ class B200FEOperator:
             b = np.empty(self.nrows)
         return self.residual_b(b, x)
 
+    # -- post-processing (hunt.jl:239-260) ----------------------------------------------------------
+    def hunt_error_norms(self, x, T6, Ha, nsums, u0=1.0, jscale=1.0, a=1.0, mu=1.0, sigma=1.0, grad_pz=-1.0):
+        """eu_l2, eu_h1, ej_l2 against the analytical Hunt series and uh_l2, uh_h1, jh_l2, integrated on the device with
+        the degree 2*(order+1) tables `T6` (`reffe.make_tables(6)`)."""
+        keep = [np.ascontiguousarray(v, dtype=np.float64) for v in (T6.w, T6.geo_grad, T6.nu, T6.dnu, T6.pp, T6.psi, T6.dpsi, T6.chi)]
+        tab = L.mhd_tables_t(T6.nq, *[v.ctypes.data for v in keep])
+        prm = L.mhd_hunt_post_t(a, mu, sigma, grad_pz, Ha, int(nsums), 0, u0, jscale)
+        out = (C.c_double * 6)()
+        xx = x if _is_torch(x) else _as_f64(x)
+        L.check(L.load().mhd_hunt_error_norms(self.handle, L.ptr(xx), C.byref(tab), C.byref(prm), out))
+        return dict(zip(("eu_l2", "eu_h1", "ej_l2", "uh_l2", "uh_h1", "jh_l2"), list(out)))
+
     # -- Krylov building blocks ------------------------------------------------------------------
     def spmv(self, x, y=None):
         self.allocate_jacobian()

@@ -48,6 +48,11 @@ class mhd_params_t(C.Structure):
                 ("g", C.c_double * 3), ("convection", C.c_int32)]
 
 
+class mhd_hunt_post_t(C.Structure):
+    _fields_ = [("a", C.c_double), ("mu", C.c_double), ("sigma", C.c_double), ("grad_pz", C.c_double), ("Ha", C.c_double),
+                ("nsums", C.c_int32), ("reserved", C.c_int32), ("u0", C.c_double), ("jscale", C.c_double)]
+
+
 class mhd_solver_opts_t(C.Structure):
     _fields_ = [("m", C.c_int32), ("maxiter", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("precond", C.c_int32), ("uj_inner_its", C.c_int32), ("uj_inner_restart", C.c_int32),
@@ -93,6 +98,7 @@ SIGNATURES = {
     "mhd_operator_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mhd_kernel_launch_count": (C.c_int, [C.POINTER(C.c_int64)]),
     "mhd_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
+    "mhd_hunt_error_norms": (C.c_int, [_P, _P, C.POINTER(mhd_tables_t), C.POINTER(mhd_hunt_post_t), C.POINTER(C.c_double)]),
     "mhd_map_entry_order": (C.c_int, [C.POINTER(C.c_uint16), C.POINTER(C.c_int64)]),
     "mhd_profile_enable": (C.c_int, [C.c_int]),
     "mhd_profile_get": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

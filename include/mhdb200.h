@@ -186,6 +186,19 @@ int mhd_solve(mhd_solver_t*, const double* b, double* x /* in: x0, out: solution
               double* resnorm, double* res_history /* nullable, maxiter+1 doubles */);
 int mhd_solver_destroy(mhd_solver_t*);
 
+/* ---- post-processing of GridapMHD.hunt (src/Applications/hunt.jl:239-260): norms of the discrete solution and its
+ * errors against the analytical Hunt series analytical_hunt_u / analytical_hunt_j (hunt.jl:372-457, square duct b = a),
+ * integrated with the tables `tab6` of the degree 2*(order+1) rule (nq <= 64; phi_val = the 8 vertex functions of the
+ * geometry map).  x: [n local] free values of the dimensionless solution; uh = u0 * ubar_h, jh = jscale * jbar_h
+ * (hunt.jl:212-217).  out[6] = { eu_l2, eu_h1, ej_l2, uh_l2, uh_h1, jh_l2 } over the LOCAL cells (square roots taken;
+ * with several ranks the caller sums the squares of the owned-cell results). */
+typedef struct {
+  double a, mu, sigma, grad_pz, Ha; /* semi-width, viscosity rho*nu, conductivity, pressure gradient -f_z/rho, Hartmann number */
+  int32_t nsums, reserved;          /* series terms k = 0..nsums */
+  double u0, jscale;
+} mhd_hunt_post_t;
+int mhd_hunt_error_norms(mhd_operator_t*, const double* x, const mhd_tables_t* tab6, const mhd_hunt_post_t* prm, double* out6);
+
 /* ---- introspection for tests / benches ---- */
 int mhd_operator_device_ptrs(mhd_operator_t*, void** rowptr_i64, void** colval_i32, void** nzval_f64);
 int mhd_kernel_launch_count(int64_t* count); /* kernels launched by the library since mhd_init */

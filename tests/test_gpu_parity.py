@@ -399,3 +399,26 @@ def test_hunt_solid_walls_values_and_solve(mhdlib):
     assert np.abs(s["j"] - so["j"]).max() < SOL_TOL * max(np.abs(so["j"]).max(), np.abs(so["u"]).max())
     print("solid: rel err j (own scale) =", relerr(s["j"], so["j"]))
     op.destroy()
+
+
+@pytest.mark.gpu
+def test_hunt_post_processing_norms_match_oracle(mhdlib):
+    """Device post-processing of hunt (hunt.jl:239-260): discrete norms and errors against the analytical Hunt series
+    (hunt.jl:372-457), degree-6 quadrature, against the oracle (itself pinned to the published error norms, K6)."""
+    from gridapmhd_jl_b200.host import reffe
+    from oracle import mhd_oracle as O
+
+    Ha = 30.0
+    params = hunt_params(nc=(5, 4), B=(0.0, Ha, 0.0))
+    fes = setup_spaces(params)
+    op = B200FEOperator(fes, params["fluid"])
+    # a smooth-ish state of the right magnitude plus noise: every term of the integrands is exercised
+    x = 1e-3 * np.random.default_rng(11).random(fes.ndofs)
+    T6 = reffe.make_tables(6)
+    for nsums in (0, 7, 200):
+        got = op.hunt_error_norms(x, T6, Ha, nsums, u0=1.3, jscale=Ha)
+        want = O.hunt_error_norms(fes, x, T6, Ha, nsums, u0=1.3, jscale=Ha)
+        want.update(O.solution_norms(fes, x, T6, u0=1.3, jscale=Ha))
+        for k, v in want.items():
+            assert abs(got[k] - v) <= 1e-11 * abs(v), (nsums, k, got[k], v)
+    op.destroy()
