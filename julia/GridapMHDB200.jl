@@ -114,6 +114,21 @@ end
 
 # ---------------------------------------------------------------------------------------------------------------
 # seam 2: the linear solver (FGMRES + block-triangular preconditioner, device resident)
+# ---- post-processing of _hunt (src/Applications/hunt.jl:239-260): replaces the ∫(...)dΩ_phys block between
+#      tic!(t) and toc!(t,"post_process"); `tables6` are the reference tables of Measure(Ω,2*(order+1))
+struct MhdHuntPost
+  a::Float64; mu::Float64; sigma::Float64; grad_pz::Float64; Ha::Float64
+  nsums::Int32; reserved::Int32
+  u0::Float64; jscale::Float64
+end
+function hunt_error_norms(op::B200FEOperator, x::AbstractVector, tables6::MhdTables; L, μ, σ, grad_pz, Ha, nsums, u0, jscale)
+  out = zeros(6)
+  prm = MhdHuntPost(L, μ, σ, grad_pz, Ha, nsums, 0, u0, jscale)
+  @check ccall((:mhd_hunt_error_norms, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{MhdTables}, Ref{MhdHuntPost}, Ptr{Float64}),
+               op.handle, x, tables6, prm, out)
+  (; eu_l2=out[1], eu_h1=out[2], ej_l2=out[3], uh_l2=out[4], uh_h1=out[5], jh_l2=out[6])
+end
+
 struct MhdSolverOpts
   m::Int32; maxiter::Int32; rtol::Float64; atol::Float64; precond::Int32
   uj_inner_its::Int32; uj_inner_restart::Int32; alpha_p::Float64; alpha_phi::Float64; uj_solver::Int32; reserved::Int32
