@@ -264,6 +264,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.samples and time.perf_counter() - t_wait < 5.0:  # nvidia-smi needs ~1 s to produce its first line
+            time.sleep(0.02)
     L.load().mhd_profile_enable(1)
     L.load().mhd_profile_reset()
     l0 = L.launch_count()

@@ -183,7 +183,7 @@ int mhd_fp64_peak(int32_t kind, double* tflops) {
   cudaEvent_t e0, e1;
   MHD_CUDA(cudaEventCreate(&e0));
   MHD_CUDA(cudaEventCreate(&e1));
-  const int iters = 20000, grid = sms * 8;
+  const int iters = 4000, grid = sms * 8;
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {  // first repetition = warm-up
     MHD_CUDA(cudaEventRecord(e0, g_stream));
