@@ -752,7 +752,7 @@ __device__ __forceinline__ void sweep(const int (&code)[KMAX], int n, const doub
       r = e / NCOL;      // NCOL is 4 or 8
       col = e % NCOL;
     }
-    const double v = Sw[r * LD + col];
+    const double v = code[k] != -1 ? Sw[r * LD + col] : 0.0;  // lanes of the padding may point past the tile
     double* p = reinterpret_cast<double*>(row[rowof(r)]) + (code[k] & 0x7FFF);
     scatter_pred(p, v, code[k]);
   }
