@@ -187,7 +187,9 @@ __device__ __forceinline__ void warp_mma_acc(const double* __restrict__ A, int l
 
 // Same product with GATHERED operand columns: this lane's column of row tile i is A[.][acol[i]], of column tile j
 // B[.][bcol[j]] (the caller resolves slots of the permuted numbering to panel columns once per job).
-template <int MT, int NTL, bool SCALE>
+// ALIAS0 >= 0: A and B are the same panel and row tile i of A is column tile ALIAS0 + i of B (products P^T P): the A
+// fragments are taken from the B fragments instead of being loaded again.
+template <int MT, int NTL, bool SCALE, int ALIAS0 = -1>
 __device__ __forceinline__ void warp_mma_cols(const double* __restrict__ A, int lda, const int (&acol)[MT],
                                               const double* __restrict__ B, int ldb, const int (&bcol)[NTL], int K,
                                               const double* __restrict__ sc, int scs, double (&acc)[MT][NTL][2]) {
@@ -201,17 +203,26 @@ __device__ __forceinline__ void warp_mma_cols(const double* __restrict__ A, int 
     const int kk = k0 + lk;
     const bool valid = kk < K;
     const int kc = valid ? kk : 0;
-    double a[MT], b[NTL];
+    double a[MT], b[NTL], braw[NTL];
     const double s = SCALE ? sc[kc * scs] : 1.0;
-#pragma unroll
-    for (int i = 0; i < MT; i++) {
-      const double v = A[kc * lda + acol[i]];
-      a[i] = valid ? v : 0.0;
-    }
 #pragma unroll
     for (int j = 0; j < NTL; j++) {
       const double v = B[kc * ldb + bcol[j]];
-      b[j] = valid ? (SCALE ? v * s : v) : 0.0;
+      braw[j] = valid ? v : 0.0;
+      b[j] = SCALE ? braw[j] * s : braw[j];
+    }
+#pragma unroll
+    for (int i = 0; i < MT; i++) {
+#ifdef MHD_NO_ALIAS
+      if (false) {
+#else
+      if (ALIAS0 >= 0 && ALIAS0 + i < NTL) {
+#endif
+        a[i] = braw[ALIAS0 + i < NTL ? ALIAS0 + i : 0];
+      } else {
+        const double v = A[kc * lda + acol[i]];
+        a[i] = valid ? v : 0.0;
+      }
     }
 #pragma unroll
     for (int i = 0; i < MT; i++)
@@ -752,7 +763,8 @@ __device__ __forceinline__ void sweep(const int (&code)[KMAX], int n, const doub
       r = e / NCOL;      // NCOL is 4 or 8
       col = e % NCOL;
     }
-    const double v = code[k] != -1 ? Sw[r * LD + col] : 0.0;  // lanes of the padding may point past the tile
+    const double v = Sw[r * LD + col];  // lanes of the padding (code SKIP) read at most 31 entries past the range: callers
+                                        // size LD so that this stays inside the warp's own tile
     double* p = reinterpret_cast<double*>(row[rowof(r)]) + (code[k] & 0x7FFF);
     scatter_pred(p, v, code[k]);
   }
@@ -885,11 +897,15 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
     if (!solid) {
       const int mt = warp >> 1, np = warp & 1;
       const int nrow = uu_nrow(mt), ncol = uu_ncol(np);
+      const int ldu = np ? 41 : 49;  // 8 rows + the padded tail of the 33-column sweep stay inside the SWN-double tile
       // operand columns of this lane: node slots resolved through the permutation (slots >= 27: the zero pad column)
       const int ca[1] = {8 * mt + lr};
       const int cb[2] = {16 * np + lr, 16 * np + 8 + lr};
       double base[1][2][2];
-      warp_mma_cols<1, 2, false>(sm + S_G, LDN, ca, sm + S_G, LDN, cb, 81, nullptr, 0, base);
+      // S = G'^T G': on the diagonal of the node-tile grid the A tile is one of the two B tiles
+      if (mt == 2 * np) warp_mma_cols<1, 2, false, 0>(sm + S_G, LDN, ca, sm + S_G, LDN, cb, 81, nullptr, 0, base);
+      else if (mt == 2 * np + 1) warp_mma_cols<1, 2, false, 1>(sm + S_G, LDN, ca, sm + S_G, LDN, cb, 81, nullptr, 0, base);
+      else warp_mma_cols<1, 2, false>(sm + S_G, LDN, ca, sm + S_G, LDN, cb, 81, nullptr, 0, base);
 #pragma unroll
       for (int j = 0; j < 2; j++)
 #pragma unroll
@@ -951,14 +967,15 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
               for (int r = 0; r < 2; r++) {
                 double v = acc[j][r];
                 if (d == c) v += base[0][j][r];
-                Sw[lr * 49 + 3 * (8 * j + 2 * lk + r) + d] = v;
+                const int bl = 8 * j + 2 * lk + r;
+                if (3 * bl < ncol) Sw[lr * ldu + 3 * bl + d] = v;  // (node slots >= 27 would run into the next row)
               }
           }
         }
         __syncwarp();
         if (CONV == 2 || ZU) {
           if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
-          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
+          else sweep<33, 41, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
         } else {
           // none / picard: only the diagonal component pairs carry values (the others stay at the memset zero)
 #pragma unroll
@@ -968,7 +985,7 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
             if (col % 3 != c) code[k] = -1;
           }
           if (np == 0) sweep<48, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
-          else sweep<33, 49, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
+          else sweep<33, 41, 12>(code, nuu, Sw, row, [&](int r) { return c * 27 + 8 * mt + r; });
         }
         __syncwarp();
       }
@@ -999,8 +1016,16 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
         int cb[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) cb[j] = 8 * j + lr;
-        if (P.zeta_j != 0.0) warp_mma_cols<2, 5, true>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
-        else warp_mma_cols<2, 5, false>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+        // the A tiles are B tiles 0,1 | 2,3 | 4 of the same panel: their fragments are reused
+        if (P.zeta_j != 0.0) {
+          if (job == 1) warp_mma_cols<2, 5, true, 0>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
+          else if (job == 2) warp_mma_cols<2, 5, true, 2>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
+          else warp_mma_cols<2, 5, true, 4>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 108, sm + S_SC, 1, acc);
+        } else {
+          if (job == 1) warp_mma_cols<2, 5, false, 0>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+          else if (job == 2) warp_mma_cols<2, 5, false, 2>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+          else warp_mma_cols<2, 5, false, 4>(sm + S_PSI, NJ, ca, sm + S_PSI, NJ, cb, 81, nullptr, 0, acc);
+        }
 #pragma unroll
         for (int j = 0; j < 5; j++) st2(Sw + lr * 40 + 8 * j + 2 * lk, acc[0][j][0], acc[0][j][1]);
         __syncwarp();
@@ -1148,20 +1173,21 @@ jacobian_kernel(int64_t ncells, int64_t nrows, CellArgs A, const double* __restr
           else sweep<4, 8, 12>(cuj, nuj, Sw, row, [&](int r) { return (r / 11) * 27 + 16 + r % 11; });
         }
         __syncwarp();
-        // ju part: Sw[ml * 50 + 3 * al + d]
+        // ju part: Sw[ml * ldb + 3 * al + d]; the padded tail of the 33-column sweep (8 rows + 24 entries) must stay in the tile
+        const int ldb = h == 0 ? 50 : 41;
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
           for (int c = 0; c < 3; c++) {
             const int al = 8 * i + lr;
             if (al < na) {
-              Sw[(2 * lk) * 50 + 3 * al + c] = sig_c * R[i][c][0];
-              Sw[(2 * lk + 1) * 50 + 3 * al + c] = sig_c * R[i][c][1];
+              Sw[(2 * lk) * ldb + 3 * al + c] = sig_c * R[i][c][0];
+              Sw[(2 * lk + 1) * ldb + 3 * al + c] = sig_c * R[i][c][1];
             }
           }
         __syncwarp();
         if (h == 0) sweep<48, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; });
-        else sweep<33, 50, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; });
+        else sweep<33, 41, 12>(cju, nuj, Sw, row, [&](int r) { return OFF_J + 8 * s_ + r; });
         __syncwarp();
       }
     }

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmhdb200.so")
+LIB_PATH = os.environ.get("MHDB200_LIBRARY") or os.path.join(_HERE, "csrc", "libmhdb200.so")  # same variable as the Julia binding
 
 MHD_OK = 0
 ERRORS = {-1: "MHD_E_INVALID", -2: "MHD_E_CUDA", -3: "MHD_E_STATE", -4: "MHD_E_CAPACITY", -5: "MHD_E_COMM", -6: "MHD_E_NOTCONV"}

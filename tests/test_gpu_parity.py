@@ -255,7 +255,8 @@ def test_hunt_solve_matches_oracle_and_published_norms(mhdlib):
     op = B200FEOperator(fes, params["fluid"])
     opts = B200SolverOptions(m=30, maxiter=30, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
     # two extra Newton steps act as iterative refinement of the (ill-conditioned, zeta-augmented) linear solve
-    nls = NewtonSolver(B200LinearSolver(opts), maxiter=3, rtol=1e-16)
+    # (stop once below 1e-12 |r0|: further steps only move the iterate around inside the rounding ball of the residual)
+    nls = NewtonSolver(B200LinearSolver(opts), maxiter=3, rtol=1e-12)
     x = nls.solve_b(np.zeros(fes.ndofs), op)
     assert nls.log[-1] < 1e-9 * nls.log[0], nls.log
     params0, fes0 = make_case(nc=(10, 10), B=(0.0, Ha, 0.0), BL_adapted=False, solver="badia2024")
@@ -389,7 +390,7 @@ def test_hunt_solid_walls_values_and_solve(mhdlib):
     assert relerr(op.residual(x), b) < 1e-14
     # solve (linear: the Hunt flow has no convection contribution)
     opts = B200SolverOptions(m=30, maxiter=30, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
-    nls = NewtonSolver(B200LinearSolver(opts), maxiter=6, rtol=1e-18)  # extra steps = iterative refinement
+    nls = NewtonSolver(B200LinearSolver(opts), maxiter=6, rtol=1e-12)  # extra steps = iterative refinement, until 1e-12 |r0|
     xs = nls.solve_b(np.zeros(fes.ndofs), op)
     xo, _ = O.newton_lu(fes, oracle_params(params["fluid"]), min_iters=6)
     s, so = fes.split(xs), fes.split(xo)
