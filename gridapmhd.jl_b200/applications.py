@@ -145,16 +145,30 @@ def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts
     return out
 
 
-def hunt(**kwargs):
-    """`hunt(;kwargs...)`: build params, call `main`, return the info dict (hunt.jl:282-303 subset)."""
+def hunt(nsums=10, post_process=True, **kwargs):
+    """`hunt(;kwargs...)`: build params, call `main`, post-process, return the info dict (hunt.jl:212-303 subset:
+    `time_*`, dof counts, and -- when `post_process` -- the norms `eu_l2 … jh_l2` of hunt.jl:247-260, integrated on the
+    device against the analytical series with `nsums` terms, default as in the reference, hunt.jl:70)."""
+    from .host.reffe import make_tables
+
     main_keys = ("solve", "res_assemble", "jac_assemble", "solver_opts", "newton_maxiter", "newton_rtol", "verbose")
     mk = {k: kwargs.pop(k) for k in main_keys if k in kwargs}
+    phys = {k: kwargs.get(k, d) for k, d in (("nu", 1.0), ("rho", 1.0), ("sigma", 1.0), ("f", (0.0, 0.0, 1.0)),
+                                              ("L", 1.0), ("u0", 1.0), ("B", (0.0, 10.0, 0.0)))}
     params = hunt_params(**kwargs)
     out = main(params, **mk)
     fes = out["fes"]
     info = dict(params["info"])
     info.update({"ndofs_u": fes.nfree["u"], "ndofs_p": fes.nfree["p"], "ndofs_j": fes.nfree["j"],
                  "ndofs_phi": fes.nfree["phi"], "ndofs": fes.ndofs})
+    if post_process and phys["L"] == 1.0:
+        t0 = time.perf_counter()
+        B0 = math.sqrt(sum(b * b for b in phys["B"]))
+        norms = out["op"].hunt_error_norms(
+            out["x"], make_tables(6), info["Ha"], nsums, u0=phys["u0"], jscale=phys["sigma"] * phys["u0"] * B0,  # hunt.jl:212-217
+            a=phys["L"], mu=phys["rho"] * phys["nu"], sigma=phys["sigma"], grad_pz=-phys["f"][2] / phys["rho"])
+        out["times"]["post_process"] = time.perf_counter() - t0
+        info.update(norms)
     for k, v in out["times"].items():
         info[f"time_{k}"] = v
     return info, out

@@ -423,3 +423,23 @@ def test_hunt_post_processing_norms_match_oracle(mhdlib):
         for k, v in want.items():
             assert abs(got[k] - v) <= 1e-11 * abs(v), (nsums, k, got[k], v)
     op.destroy()
+
+
+@pytest.mark.gpu
+def test_hunt_driver_end_to_end_reproduces_published_row(mhdlib):
+    """`hunt(nc=(10,10), B=(0,50,0), nsums=500)` through the driver mirror: device Newton/FGMRES solve, then the device
+    post-processing; all six norms of the reference's published run ha00050cx010 (hconv_ha00050ns500/summary.csv:7,
+    kmap=1 = unstretched mesh) are reproduced from end to end."""
+    from gridapmhd_jl_b200.applications import hunt
+    from gridapmhd_jl_b200.feoperator import B200SolverOptions
+
+    opts = B200SolverOptions(m=30, maxiter=30, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
+    info, out = hunt(nc=(10, 10), B=(0.0, 50.0, 0.0), BL_adapted=False, solver="badia2024", zeta_u=20.0, zeta_j=20.0,
+                     nsums=500, solve=True, solver_opts=opts, newton_maxiter=3, newton_rtol=1e-12)
+    assert info["ndofs"] == 17298 and info["Ha"] == 50.0
+    pins = dict(eu_l2=6.274034420523594e-5, eu_h1=0.0021489743289400043, ej_l2=0.0011055397108926523,
+                uh_l2=0.001125968494949451, uh_h1=0.009386206346670825, jh_l2=0.019669872964491745)
+    for k, v in pins.items():
+        assert abs(info[k] - v) / v < 1e-8, (k, info[k], v)
+    assert info["time_post_process"] < 5.0
+    out["op"].destroy()
