@@ -84,6 +84,23 @@ def test_k6_hunt_error_norms_against_the_analytical_solution(hunt_ha50_nc10_solu
             assert abs(e[k] - v) / v < 1e-9, (nsums, k, e[k], v)
 
 
+@pytest.mark.slow
+def test_k6_second_published_row_nc18():
+    """hconv_ha00050ns500/summary.csv, run ha00050cx018 (nc=18, 972 cells, 57 042 dofs): all six norms (~100 s of sparse LU)."""
+    Ha = 50.0
+    fes = hunt_fes(18, Ha, BL_adapted=False)
+    assert fes.ndofs == 57042
+    prm = O.FluidParams(alpha=1.0, beta=1.0, gamma=Ha**2, sigma=1.0, B=(0, 1, 0), f=(0, 0, 1), convection="newton")
+    x, hist = O.newton_lu(fes, prm)
+    T6 = reffe.make_tables(6)
+    got = O.hunt_error_norms(fes, x, T6, Ha, 500, u0=1.0, jscale=Ha)
+    got.update(O.solution_norms(fes, x, T6, u0=1.0, jscale=Ha))
+    pins = dict(eu_l2=1.4099417236975484e-5, eu_h1=0.0008916378834878792, ej_l2=0.0006661061529286713,
+                uh_l2=0.0011232728005488165, uh_h1=0.009581884653926384, jh_l2=0.019654422812794527)
+    for k, v in pins.items():
+        assert abs(got[k] - v) / v < 1e-9, (k, got[k], v)
+
+
 # K2 ------------------------------------------------------------------------------------------
 def _interpolate(fes, ufun, jconst, pconst, phiconst):
     """Interpolant of u (nodal), constant j (RT moments of a constant field), constant p and phi."""
