@@ -1253,7 +1253,13 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   P.cell_sigma = op->d_cell_sigma;
   const int conv = op->prm.convection;
   const bool zu = op->prm.zeta_u != 0.0;
-  const int64_t grid64 = (int64_t)sm_count() * 2;
+  static int ctas_per_sm = 0;  // resident CTAs per SM the kernel is built for (MHD_JAC_CTAS_PER_SM: A/B builds only)
+  if (!ctas_per_sm) {
+    const char* e = getenv("MHD_JAC_CTAS_PER_SM");
+    ctas_per_sm = e ? atoi(e) : 2;
+    if (ctas_per_sm < 1) ctas_per_sm = 2;
+  }
+  const int64_t grid64 = (int64_t)sm_count() * ctas_per_sm;
   const unsigned grid = (unsigned)(op->ncells < grid64 ? op->ncells : grid64);
 #define JK(C, Z, R)                                                                                          \
   do {                                                                                                       \
