@@ -9,10 +9,14 @@
 //   prep   : geometry Jacobians at the 27 Gauss points, physical gradients of the Q2 basis, Piola-mapped RT basis, all
 //            pre-scaled by sqrt(w_q |det J_q|) so that every block is a plain product sum_k A[k][m] B[k][n] of two
 //            shared-memory panels.  The reference tables arrive in panel layout with ONE bulk copy (cp.async.bulk +
-//            mbarrier) per cell, issued before the id / state loads, and are transformed in place.  Panels stay in
-//            reference order; the tensor-core jobs address their operand columns through the cell's permutation
-//            (each field sorted by global id, symbolic.cu) so that consecutive columns of a product are consecutive
-//            nnz of a CSR row.
+//            mbarrier) per cell, issued before the id / state loads, and are transformed IN PLACE AND PERMUTED: a warp
+//            owns the rows of a quadrature point, every lane gathers the reference column of its slot, the warp
+//            synchronises and writes the slot columns.  Slots follow the cell's permutation (each field sorted by
+//            global id, symbolic.cu), so consecutive columns of a product are consecutive nnz of a CSR row and the
+//            operand fragments are plain strided loads.
+//   residual: point values as (panel rows) x (state) products, a per-point coefficient stage, then the row products
+//            panel^T x coefficients -- all on the tensor cores; in the fused kernel the row products are jobs of the
+//            main phase.
 //   main   : one barrier-free phase.  Every warp runs tensor-core jobs (FP64 mma.sync m8n8k4): its tile of the uu block
 //            (all 9 component pairs) and then jobs drawn from a shared counter (jj strips, uj/ju, up/pu, j-phi/phi-j).
 //            A job's accumulators are transposed through a warp-private staging tile into destination order
