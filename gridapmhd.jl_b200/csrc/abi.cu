@@ -151,6 +151,7 @@ int mhd_init(int device_ordinal) {
 
 int mhd_finalize(void) {
   if (g_device >= 0) cudaStreamSynchronize(g_stream);
+  if (g_device >= 0) assembly_finalize();
   g_device = -1;
   g_stream = 0;
   return MHD_OK;
@@ -487,6 +488,7 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   MHD_TRY(check_ready(op));
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_jacobian: call mhd_operator_symbolic first");
   const double* dx;
+  MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
   MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
   MHD_TRY(launch_jacobian(op, dx, nullptr));
   if (nzval_out) return mhd_get_nzval(op, nzval_out);
@@ -499,9 +501,10 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_residual_and_jacobian: call mhd_operator_symbolic first");
   MHD_CHECK(r_out != nullptr, MHD_E_INVALID, "mhd_residual_and_jacobian: null residual output");
   const double* dx;
-  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
   const bool dev_out = is_device_ptr(r_out);
   double* dr = dev_out ? r_out : op->d_y;
+  MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
+  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
   MHD_TRY(launch_jacobian(op, dx, dr));
   if (!dev_out) {
     MHD_TRY(d2h(r_out, dr, op->nrows));

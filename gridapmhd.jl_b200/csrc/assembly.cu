@@ -1248,10 +1248,44 @@ static int set_smem(Kern k) {
   return 0;
 }
 
+// Clearing nzval (1.18 GB on cfg2, 0.12 ms) and the residual runs on a side stream so that it overlaps the host->device
+// copy of the state when the caller passes host buffers: begin_clear is called BEFORE that copy is enqueued, the kernel
+// launch waits for it.  The side stream first waits for everything already enqueued on the library stream (an earlier
+// SpMV / solve may still read the matrix).
+static cudaStream_t s_clear_stream = nullptr;
+static cudaEvent_t s_ev_in = nullptr, s_ev_done = nullptr;
+static int s_clear_device = -1;
+
+int begin_clear(mhd_operator* op, double* d_r) {
+  if (s_clear_device != g_device) {  // (re)created per mhd_init
+    MHD_CUDA(cudaStreamCreateWithFlags(&s_clear_stream, cudaStreamNonBlocking));
+    MHD_CUDA(cudaEventCreateWithFlags(&s_ev_in, cudaEventDisableTiming));
+    MHD_CUDA(cudaEventCreateWithFlags(&s_ev_done, cudaEventDisableTiming));
+    s_clear_device = g_device;
+  }
+  MHD_CUDA(cudaEventRecord(s_ev_in, g_stream));
+  MHD_CUDA(cudaStreamWaitEvent(s_clear_stream, s_ev_in, 0));
+  MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), s_clear_stream));
+  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), s_clear_stream));
+  MHD_CUDA(cudaEventRecord(s_ev_done, s_clear_stream));
+  op->clear_pending = true;
+  return 0;
+}
+
+void assembly_finalize() {
+  if (s_clear_device >= 0) {
+    cudaStreamDestroy(s_clear_stream);
+    cudaEventDestroy(s_ev_in);
+    cudaEventDestroy(s_ev_done);
+    s_clear_device = -1;
+  }
+}
+
 // d_r != nullptr: fused residual + Jacobian (residual_and_jacobian!)
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
-  MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), g_stream));
-  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
+  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r));
+  op->clear_pending = false;
+  MHD_CUDA(cudaStreamWaitEvent(g_stream, s_ev_done, 0));
   KParams P = make_kparams(op->prm);
   P.cell_solid = op->d_cell_solid;
   P.cell_sigma = op->d_cell_sigma;

@@ -137,6 +137,7 @@ struct mhd_operator {
   int64_t ndir_total = 0;
   mhd_params_t prm;
   bool has_symbolic = false;
+  bool clear_pending = false;      // begin_clear() has been enqueued for the next launch_jacobian
 
   // device data
   double* d_coords = nullptr;      // [nnodes*3]
@@ -235,6 +236,8 @@ void entry_order(std::vector<uint16_t>& ord);  // [NENT] (row slot << 8 | col sl
 // assembly.cu
 int pack_tables(mhd_operator* op, const mhd_tables_t* t);
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
+int begin_clear(mhd_operator* op, double* d_r /* nullable */);  // optional: start clearing before the state is copied in
+void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // krylov.cu
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);
