@@ -12,8 +12,9 @@ import time
 
 import numpy as np
 
-from .feoperator import B200FEOperator, B200LinearSolver, B200SolverOptions, FluidParams, NewtonSolver
+from .feoperator import B200FEOperator, B200H1H1FEOperator, B200LinearSolver, B200SolverOptions, FluidParams, NewtonSolver
 from .host.fespaces import FESpaces, setup_fe_spaces
+from .host.fespaces_h1h1 import H1H1Spaces, setup_fe_spaces_h1h1
 from .host.mesh import HexMesh, expansion_generate_mesh, hunt_generate_base_mesh
 
 
@@ -38,19 +39,28 @@ def hunt_reduced_quantities(nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0
 
 def hunt_params(nc=(4, 4), nu=1.0, rho=1.0, sigma=1.0, B=(0.0, 10.0, 0.0), f=(0.0, 0.0, 1.0), zeta_u=0.0, zeta_j=0.0,
                 L=1.0, u0=1.0, formulation="cfd", convection="newton", BL_adapted=True, kmap_x=1, kmap_y=1,
-                solver="julia", nz=3, periodic_z=True, z_extent=(0.0, 0.1), tw=0.0, sigma_w1=0.1, sigma_w2=10.0):
+                solver="julia", nz=3, periodic_z=True, z_extent=(0.0, 0.1), tw=0.0, sigma_w1=0.1, sigma_w2=10.0,
+                current_disc="RT"):
     """params Dict of `_hunt` (hunt.jl:88-193).  NOTE: `_hunt` never forwards its `convection` kwarg into
     params[:fluid] (hunt.jl:149-158), so the reference effectively runs Hunt with the `params_fluid` default
     `:newton` (parameters.jl:717); that is the default here too."""
     alpha, beta, gamma, fbar, Bbar, Re, Ha, N = hunt_reduced_quantities(nu, rho, sigma, B, f, L, u0, formulation)
     mesh = hunt_generate_base_mesh(nc, L=L, tw=tw, Ha=Ha, kmap_x=kmap_x, kmap_y=kmap_y, BL_adapted=BL_adapted, nz=nz,
                                    periodic_z=periodic_z, z_extent=z_extent)
+    bcs = {"u": {"tags": ("noslip",) + (("zwalls",) if not periodic_z else ()), "values": None},
+           "j": {"tags": ("insulating",)}}
+    if current_disc == "H1":  # hunt.jl:185-187
+        bcs["phi"] = {"tags": ("conducting",), "values": None}
+    elif current_disc != "RT":
+        raise ValueError("current_disc must be 'RT' (H1-HDiv) or 'H1' (H1-H1)")
     return {
         "model": mesh,
         "fluid": FluidParams(alpha=alpha, beta=beta, gamma=gamma, sigma=1.0, zeta_u=zeta_u, zeta_j=zeta_j, B=Bbar,
                              f=fbar, convection=convection),
-        "bcs": {"u": {"tags": ("noslip",) + (("zwalls",) if not periodic_z else ()), "values": None},
-                "j": {"tags": ("insulating",)}},
+        "bcs": bcs,
+        # params[:fespaces][:current_disc] (hunt.jl:165): :RT -> H1-HDiv, :H1 -> H1-H1 (select_formulation,
+        # parameters.jl:570-594)
+        "current_disc": current_disc,
         "solver": solver,
         # params[:solid] (hunt.jl:168-176): sigma per cell = sigma_w1/sigma on solid_1, sigma_w2/sigma on solid_2; zeta = zeta_j
         "solid": None if tw <= 0.0 else {"cells": mesh.cell_tags["solid"],
@@ -98,7 +108,7 @@ def expansion_params(level=1, Ha=1.0, N=1.0, zeta_u=0.0, zeta_j=0.0, formulation
     }
 
 
-def setup_spaces(params) -> FESpaces:
+def setup_spaces(params) -> FESpaces | H1H1Spaces:
     """`setup_fe_spaces(params)` (src/fespaces.jl:13-46) on the host."""
     bcs = params["bcs"]
     utags = tuple(bcs["u"]["tags"])
@@ -106,9 +116,20 @@ def setup_spaces(params) -> FESpaces:
     if uvals is None:
         uvals = (None,) * len(utags)
     solid = params.get("solid")
+    if params.get("current_disc", "RT") == "H1":
+        ftags = tuple(bcs["phi"]["tags"])
+        fvals = bcs["phi"].get("values") or (None,) * len(ftags)
+        return setup_fe_spaces_h1h1(params["model"], u_tags=utags, u_values=tuple(uvals), phi_tags=ftags,
+                                    phi_values=tuple(fvals), solid_cells=None if solid is None else solid["cells"])
     return setup_fe_spaces(params["model"], u_tags=utags, u_values=tuple(uvals), j_tags=tuple(bcs["j"]["tags"]),
                            solver=params.get("solver", "julia"), solid_cells=None if solid is None else solid["cells"],
                            cell_sigma=None if solid is None else solid["sigma"])
+
+
+def make_operator(fes, fluid: FluidParams, nowned=None):
+    """`_fe_operator(U,V,params)` (src/main.jl:207-233): the weak form follows the spaces (`weak_form`, weakforms.jl:2-31)."""
+    cls = B200H1H1FEOperator if isinstance(fes, H1H1Spaces) else B200FEOperator
+    return cls(fes, fluid, nowned)
 
 
 def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts: B200SolverOptions | None = None,
@@ -121,7 +142,7 @@ def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts
     t0 = time.perf_counter()
     fes = setup_spaces(params)
     times["fe_spaces"] = time.perf_counter() - t0
-    op = B200FEOperator(fes, params["fluid"])
+    op = make_operator(fes, params["fluid"])
     x = np.zeros(fes.ndofs)  # initial_guess(::Val{:zero}) main.jl:302
     out = {"fes": fes, "op": op}
     if solve:

@@ -488,9 +488,14 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   MHD_TRY(check_ready(op));
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_jacobian: call mhd_operator_symbolic first");
   const double* dx;
-  MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
-  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-  MHD_TRY(launch_jacobian(op, dx, nullptr));
+  if (op->formulation == FORM_H1H1) {
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(h1h1_launch_jacobian(op, dx));
+  } else {
+    MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(launch_jacobian(op, dx, nullptr));
+  }
   if (nzval_out) return mhd_get_nzval(op, nzval_out);
   if (!is_device_ptr(x)) MHD_CUDA(cudaStreamSynchronize(g_stream));
   return MHD_OK;
@@ -503,9 +508,15 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
   const double* dx;
   const bool dev_out = is_device_ptr(r_out);
   double* dr = dev_out ? r_out : op->d_y;
-  MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
-  MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-  MHD_TRY(launch_jacobian(op, dx, dr));
+  if (op->formulation == FORM_H1H1) {  // two launches (no fused variant yet)
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(h1h1_launch_residual(op, dx, dr));
+    MHD_TRY(h1h1_launch_jacobian(op, dx));
+  } else {
+    MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(launch_jacobian(op, dx, dr));
+  }
   if (!dev_out) {
     MHD_TRY(d2h(r_out, dr, op->nrows));
     MHD_CUDA(cudaStreamSynchronize(g_stream));
@@ -540,7 +551,8 @@ int mhd_residual(mhd_operator_t* op, const double* x, double* r_out) {
   MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
   bool dev_out = is_device_ptr(r_out);
   double* dr = dev_out ? r_out : op->d_y;
-  MHD_TRY(launch_residual(op, dx, dr));
+  if (op->formulation == FORM_H1H1) MHD_TRY(h1h1_launch_residual(op, dx, dr));
+  else MHD_TRY(launch_residual(op, dx, dr));
   if (!dev_out) {
     MHD_TRY(d2h(r_out, dr, op->nrows));
     MHD_CUDA(cudaStreamSynchronize(g_stream));
@@ -551,6 +563,7 @@ int mhd_residual(mhd_operator_t* op, const double* x, double* r_out) {
 int mhd_hunt_error_norms(mhd_operator_t* op, const double* x, const mhd_tables_t* tab6, const mhd_hunt_post_t* prm, double* out6) {
   MHD_TRY(check_ready(op));
   MHD_CHECK(x && tab6 && prm && out6, MHD_E_INVALID, "mhd_hunt_error_norms: null argument");
+  MHD_CHECK(op->formulation == FORM_HDIV, MHD_E_INVALID, "mhd_hunt_error_norms: H1-HDiv operators only");
   const double* dx;
   MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
   return hunt_error_norms(op, dx, tab6, prm, out6);

@@ -126,7 +126,13 @@ struct HaloDev {
 
 }  // namespace mhd
 
+namespace mhd {
+constexpr int FORM_HDIV = 0;  // H1-HDiv (u,p,j,phi), 129 local dofs: assembly.cu
+constexpr int FORM_H1H1 = 1;  // H1-H1 (u,p,phi), 149 local dofs: h1h1.cu (field slots: 0 = u, 1 = p, 3 = phi; slot 2 empty)
+}  // namespace mhd
+
 struct mhd_operator {
+  int formulation = mhd::FORM_HDIV;
   int64_t ncells = 0, nnodes = 0;
   int64_t nfree[4] = {0, 0, 0, 0}, nowned[4] = {0, 0, 0, 0}, ndir[4] = {0, 0, 0, 0};
   int32_t field_order[4] = {0, 1, 2, 3};
@@ -239,6 +245,9 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable
 int begin_clear(mhd_operator* op, double* d_r /* nullable */);  // optional: start clearing before the state is copied in
 void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
+// h1h1.cu
+int h1h1_launch_jacobian(mhd_operator* op, const double* d_x);
+int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // krylov.cu
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);
 // y[0..nr) = (A x)[0..nr) including the ghost exchange (fused peer-memory kernel when connected, NCCL otherwise)

@@ -414,6 +414,8 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
   MHD_CHECK(opts->m >= 1 && opts->m <= MAXM && opts->maxiter >= 1, MHD_E_INVALID, "bad m/maxiter");
   MHD_CUDA(cudaSetDevice(g_device));
   if (opts->precond == MHD_PC_BLOCK_TRI) {
+    MHD_CHECK(op->formulation == FORM_HDIV, MHD_E_INVALID,
+              "mhd_solver_create: the block-triangular preconditioner is built for H1-HDiv operators (use MHD_PC_JACOBI)");
     MHD_CHECK(op->field_order[0] == MHD_FIELD_U && op->field_order[1] == MHD_FIELD_J && op->field_order[2] == MHD_FIELD_P &&
                   op->field_order[3] == MHD_FIELD_PHI,
               MHD_E_INVALID, "block-triangular preconditioner needs field_order (u,j,p,phi) = ([u,j],p,phi) blocks");

@@ -13,18 +13,33 @@
 //      common.h) in its row -> 16-bit row-relative position;
 //      count contributions per nnz and flag the nnz that receive exactly one (plain store instead of atomic).
 #include "common.h"
+#include "h1h1_cell.h"
 
 namespace mhd {
 
-// ---- which local columns a local row couples to (the 8 touched blocks of jac_fluid_h1_hdiv,
-//      src/weakforms.jl:311): u-row: u,p,j | p-row: u | j-row: u,j,phi | phi-row: j
-__device__ __forceinline__ bool coupled(int li, int lj) {
-  int fi = li < OFF_P ? 0 : (li < OFF_J ? 1 : (li < OFF_F ? 2 : 3));
-  int fj = lj < OFF_P ? 0 : (lj < OFF_J ? 1 : (lj < OFF_F ? 2 : 3));
-  // 4 bits per row field: coupled column fields (bit fj): u:0b0111 p:0b0001 j:0b1101 phi:0b0100
-  const unsigned m = 0x4D17u;
-  return (m >> (fi * 4 + fj)) & 1u;
-}
+// ---- which local columns a local row couples to, per formulation (the kernels below are templates over this)
+// H1-HDiv: the 8 touched blocks of jac_fluid_h1_hdiv (src/weakforms.jl:311): u-row: u,p,j | p-row: u | j-row: u,j,phi | phi-row: j
+struct LayoutHDiv {
+  static constexpr int NLOC = mhd::NLOC;
+  __device__ static __forceinline__ bool coupled(int li, int lj) {
+    int fi = li < OFF_P ? 0 : (li < OFF_J ? 1 : (li < OFF_F ? 2 : 3));
+    int fj = lj < OFF_P ? 0 : (lj < OFF_J ? 1 : (lj < OFF_F ? 2 : 3));
+    // 4 bits per row field: coupled column fields (bit fj): u:0b0111 p:0b0001 j:0b1101 phi:0b0100
+    const unsigned m = 0x4D17u;
+    return (m >> (fi * 4 + fj)) & 1u;
+  }
+};
+// H1-H1: the 6 touched blocks of jac_fluid_h1_h1 (src/weakforms.jl:465): u-row: u,p,phi | p-row: u | phi-row: u,phi
+struct LayoutH1H1 {
+  static constexpr int NLOC = h1::NLOC;
+  __device__ static __forceinline__ bool coupled(int li, int lj) {
+    int fi = li < h1::OFF_P ? 0 : (li < h1::OFF_F ? 1 : 2);
+    int fj = lj < h1::OFF_P ? 0 : (lj < h1::OFF_F ? 1 : 2);
+    // 4 bits per row field (bit fj): u:0b111 p:0b001 phi:0b101
+    const unsigned m = 0x517u;
+    return (m >> (fi * 4 + fj)) & 1u;
+  }
+};
 
 // ---------------------------------------------------------------- 0. per-cell permutation (once per operator)
 // Inside each field the local dofs of a cell are sorted by global id (Dirichlet / absent dofs last, ties in reference
@@ -182,7 +197,7 @@ __global__ void fill_incidence(const int32_t* gids, int64_t nent, int64_t nrows,
 constexpr int ROW_CAP = 4096;       // candidate columns per row held in shared memory
 constexpr int ROW_WARPS = 2;        // warps (= rows) per CTA
 
-template <bool FILL>
+template <class L, bool FILL>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 row_columns(const int32_t* __restrict__ gids, const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ inc,
             int64_t nrows, int32_t* __restrict__ row_len, const int64_t* __restrict__ rowptr,
@@ -195,13 +210,13 @@ row_columns(const int32_t* __restrict__ gids, const int64_t* __restrict__ inc_pt
   int n = 0;
   for (int64_t p = inc_ptr[row]; p < inc_ptr[row + 1]; p++) {
     int64_t ci = inc[p];
-    int64_t cell = ci / NLOC;
-    int li = (int)(ci % NLOC);
-    const int32_t* g = gids + cell * NLOC;
-    for (int base = 0; base < NLOC; base += 32) {
+    int64_t cell = ci / L::NLOC;
+    int li = (int)(ci % L::NLOC);
+    const int32_t* g = gids + cell * L::NLOC;
+    for (int base = 0; base < L::NLOC; base += 32) {
       int lj = base + lane;
       int32_t c = -1;
-      if (lj < NLOC && coupled(li, lj)) c = g[lj];
+      if (lj < L::NLOC && L::coupled(li, lj)) c = g[lj];
       unsigned m = __ballot_sync(0xffffffffu, c >= 0);
       if (c >= 0) {
         int pos = n + __popc(m & ((1u << lane) - 1));
@@ -246,18 +261,19 @@ row_columns(const int32_t* __restrict__ gids, const int64_t* __restrict__ inc_pt
 }
 
 // ---------------------------------------------------------------- 3. scatter map
+template <class L>
 __global__ void __launch_bounds__(256)
-build_map(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order,
-          const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+build_map(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order, const int nent_cell,
+          const int nent_pad, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
           int64_t nrows, uint16_t* __restrict__ map, uint8_t* __restrict__ contrib) {
-  __shared__ int32_t g[NLOC];
+  __shared__ int32_t g[L::NLOC];
   int64_t cell = blockIdx.x;
-  for (int i = threadIdx.x; i < NLOC; i += blockDim.x) g[i] = gids[cell * NLOC + i];
+  for (int i = threadIdx.x; i < L::NLOC; i += blockDim.x) g[i] = gids[cell * L::NLOC + i];
   __syncthreads();
-  uint16_t* m = map + cell * NENT_PAD;
-  for (int e = threadIdx.x; e < NENT_PAD; e += blockDim.x) {
+  uint16_t* m = map + cell * nent_pad;
+  for (int e = threadIdx.x; e < nent_pad; e += blockDim.x) {
     uint16_t code = MAP_SKIP;
-    if (e < NENT) {
+    if (e < nent_cell) {
       const int li = order[e] >> 8, lj = order[e] & 0xFF;
       int32_t r = -1, c = -1;
       if (order[e] != ORDER_PAD) { r = g[li]; c = g[lj]; }
@@ -288,17 +304,18 @@ build_map(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __res
   }
 }
 
+template <class L>
 __global__ void __launch_bounds__(256)
-flag_exclusive(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order,
-               const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ contrib,
+flag_exclusive(const int32_t* __restrict__ gids /* permuted */, const uint16_t* __restrict__ order, const int nent_cell,
+               const int nent_pad, const int64_t* __restrict__ rowptr, const uint8_t* __restrict__ contrib,
                uint16_t* __restrict__ map, unsigned long long* __restrict__ stats) {
-  __shared__ int32_t g[NLOC];
+  __shared__ int32_t g[L::NLOC];
   int64_t cell = blockIdx.x;
-  for (int i = threadIdx.x; i < NLOC; i += blockDim.x) g[i] = gids[cell * NLOC + i];
+  for (int i = threadIdx.x; i < L::NLOC; i += blockDim.x) g[i] = gids[cell * L::NLOC + i];
   __syncthreads();
-  uint16_t* m = map + cell * NENT_PAD;
+  uint16_t* m = map + cell * nent_pad;
   unsigned nent = 0, nex = 0;
-  for (int e = threadIdx.x; e < NENT; e += blockDim.x) {
+  for (int e = threadIdx.x; e < nent_cell; e += blockDim.x) {
     uint16_t code = m[e];
     if (code == MAP_SKIP) continue;
     const int li = order[e] >> 8;
@@ -335,8 +352,11 @@ __global__ void max_row_len(const int32_t* row_len, int64_t nrows, int* out) {
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
-int symbolic_build(mhd_operator* op) {
-  const int64_t nent = op->ncells * NLOC;
+// map_gids: the cell -> local id table in the numbering the entry enumeration `order` refers to
+template <class L>
+static int symbolic_build_impl(mhd_operator* op, const int32_t* map_gids, const std::vector<uint16_t>& order, int nent_cell,
+                               int nent_pad) {
+  const int64_t nent = op->ncells * L::NLOC;
   const int64_t nrows = op->nrows;
   int32_t *d_cnt = nullptr, *d_cursor = nullptr, *d_rowlen = nullptr;
   int64_t *d_incptr = nullptr, *d_inc = nullptr;
@@ -372,7 +392,7 @@ int symbolic_build(mhd_operator* op) {
   if (!rc) { fill_incidence<<<gb, 256, 0, g_stream>>>(op->d_gids, nent, nrows, d_incptr, d_cursor, d_inc); SYL(); }
   const unsigned rb = (unsigned)((nrows + ROW_WARPS - 1) / ROW_WARPS);
   if (!rc) {
-    row_columns<false><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, d_rowlen, nullptr, nullptr, d_flags);
+    row_columns<L, false><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, d_rowlen, nullptr, nullptr, d_flags);
     SYL();
   }
   if (!rc) { max_row_len<<<(unsigned)((nrows + 255) / 256), 256, 0, g_stream>>>(d_rowlen, nrows, d_flags + 1); SYL(); }
@@ -398,26 +418,24 @@ int symbolic_build(mhd_operator* op) {
   cudaFree(op->d_map); op->d_map = nullptr;
   SY(dev_alloc(&op->d_colval, nnz));
   SY(dev_alloc(&op->d_nzval, nnz));
-  SY(dev_alloc(&op->d_map, op->ncells * NENT_PAD));
+  SY(dev_alloc(&op->d_map, op->ncells * nent_pad));
   if (!rc && !op->d_order) {
-    std::vector<uint16_t> ord;
-    entry_order(ord);
-    SY(dev_alloc(&op->d_order, NENT));
-    SY(h2d(op->d_order, ord.data(), NENT));
+    SY(dev_alloc(&op->d_order, nent_cell));
+    SY(h2d(op->d_order, order.data(), nent_cell));
     SYC(cudaStreamSynchronize(g_stream));
   }
   SY(dev_alloc(&d_contrib, (nnz + 3) / 4 * 4 + 4));
   SYC(cudaMemsetAsync(op->d_nzval, 0, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double), g_stream));
   SYC(cudaMemsetAsync(d_contrib, 0, (size_t)((nnz + 3) / 4 * 4 + 4), g_stream));
   if (!rc) {
-    row_columns<true><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, nullptr, op->d_rowptr, op->d_colval, d_flags);
+    row_columns<L, true><<<rb, ROW_WARPS * 32, 0, g_stream>>>(op->d_gids, d_incptr, d_inc, nrows, nullptr, op->d_rowptr, op->d_colval, d_flags);
     SYL();
   }
   cudaFree(op->d_rowstart); op->d_rowstart = nullptr;
   SY(dev_alloc(&op->d_rowstart, nent));
-  if (!rc) { cell_row_starts<<<gb, 256, 0, g_stream>>>(nent, nrows, op->d_pgids, op->d_rowptr, op->d_rowstart); SYL(); }
-  if (!rc) { build_map<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_pgids, op->d_order, op->d_rowptr, op->d_colval, nrows, op->d_map, d_contrib); SYL(); }
-  if (!rc) { flag_exclusive<<<(unsigned)op->ncells, 256, 0, g_stream>>>(op->d_pgids, op->d_order, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
+  if (!rc) { cell_row_starts<<<gb, 256, 0, g_stream>>>(nent, nrows, map_gids, op->d_rowptr, op->d_rowstart); SYL(); }
+  if (!rc) { build_map<L><<<(unsigned)op->ncells, 256, 0, g_stream>>>(map_gids, op->d_order, nent_cell, nent_pad, op->d_rowptr, op->d_colval, nrows, op->d_map, d_contrib); SYL(); }
+  if (!rc) { flag_exclusive<L><<<(unsigned)op->ncells, 256, 0, g_stream>>>(map_gids, op->d_order, nent_cell, nent_pad, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
   unsigned long long stats[2] = {0, 0};
   SY(d2h(stats, d_stats, 2));
   SYC(cudaStreamSynchronize(g_stream));
@@ -431,6 +449,21 @@ int symbolic_build(mhd_operator* op) {
 #undef SY
 #undef SYC
 #undef SYL
+}
+
+int symbolic_build(mhd_operator* op) {
+  if (op->formulation == FORM_H1H1) {
+    std::vector<uint16_t> ord(h1::NENT);
+    for (int e = 0; e < h1::NENT; e++) {
+      int li, lj;
+      h1::entry_rowcol(e, &li, &lj);
+      ord[e] = (uint16_t)(li << 8 | lj);
+    }
+    return symbolic_build_impl<LayoutH1H1>(op, op->d_gids, ord, h1::NENT, h1::NENT_PAD);
+  }
+  std::vector<uint16_t> ord;
+  entry_order(ord);
+  return symbolic_build_impl<LayoutHDiv>(op, op->d_pgids, ord, NENT, NENT_PAD);
 }
 
 }  // namespace mhd

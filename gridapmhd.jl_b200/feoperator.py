@@ -255,6 +255,50 @@ class B200FEOperator:
         return h
 
 
+class B200H1H1FEOperator(B200FEOperator):
+    """`FEOperator` of the H1-H1 formulation (`weak_form_h1_h1`, src/weakforms.jl:344-355; spaces (u,p,phi) of
+    src/fespaces.jl:32-41): same handle type and methods as `B200FEOperator` (jacobian, residual, spmv, dot, ...), created
+    through `mhd_h1h1_operator_create`.  `fes` is an `H1H1Spaces` (host/fespaces_h1h1.py)."""
+
+    H1H1_FIELD_IDS = {"u": 0, "p": 1, "phi": 2}
+
+    def __init__(self, fes, fluid: FluidParams, nowned: dict | None = None):
+        self.fes = fes
+        self.fluid = fluid
+        lib = L.load()
+        m = fes.mesh
+        T = fes.tables
+        keep = []
+
+        def hold(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        has_solid = fes.cell_solid is not None and bool(np.any(fes.cell_solid))
+        mesh = L.mhd_mesh_t(m.coords.shape[0], hold(m.coords, np.float64), m.ncells, hold(m.cell_nodes, np.int32), 0,
+                            hold(fes.cell_solid, np.uint8) if has_solid else None,
+                            hold(np.ones(m.ncells), np.float64) if has_solid else None)
+        tab = L.mhd_tables_h1h1_t(T.nq, hold(T.w, np.float64), hold(T.geo_grad, np.float64), hold(T.nu, np.float64),
+                                  hold(T.dnu, np.float64), hold(T.pp, np.float64), hold(T.dphi3, np.float64))
+        lay = L.mhd_layout_h1h1_t()
+        for f, i in self.H1H1_FIELD_IDS.items():
+            lay.cell_dofs[i] = hold(fes.cell_dofs[f], np.int32)
+            lay.nfree[i] = fes.nfree[f]
+            lay.nowned[i] = fes.nfree[f] if nowned is None else nowned[f]
+            lay.ndir[i] = fes.ndir[f]
+            dv = fes.dirichlet_values[f]
+            lay.dir_values[i] = hold(dv, np.float64) if len(dv) else None
+        for k, f in enumerate(fes.field_order):
+            lay.field_order[k] = self.H1H1_FIELD_IDS[f]
+        prm = fluid.to_c()
+        h = C.c_void_p()
+        L.check(lib.mhd_h1h1_operator_create(C.byref(mesh), C.byref(tab), C.byref(lay), C.byref(prm), C.byref(h)))
+        self.handle = h
+        self.nrows = self.ncols = self.nnz = None
+        self._A = None
+
+
 # ----------------------------------------------------------------------------------------------
 # linear solver seam
 

@@ -42,6 +42,16 @@ class mhd_layout_t(C.Structure):
                 ("field_order", C.c_int32 * 4)]
 
 
+class mhd_tables_h1h1_t(C.Structure):
+    _fields_ = [("nq", C.c_int32), ("w", C.c_void_p), ("geo_grad", C.c_void_p), ("u_val", C.c_void_p),
+                ("u_grad", C.c_void_p), ("p_val", C.c_void_p), ("phi_grad", C.c_void_p)]
+
+
+class mhd_layout_h1h1_t(C.Structure):
+    _fields_ = [("cell_dofs", C.c_void_p * 3), ("nfree", C.c_int64 * 3), ("nowned", C.c_int64 * 3),
+                ("ndir", C.c_int64 * 3), ("dir_values", C.c_void_p * 3), ("field_order", C.c_int32 * 3)]
+
+
 class mhd_params_t(C.Structure):
     _fields_ = [("alpha", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("sigma", C.c_double),
                 ("zeta_u", C.c_double), ("zeta_j", C.c_double), ("B", C.c_double * 3), ("f", C.c_double * 3),
@@ -100,6 +110,9 @@ SIGNATURES = {
     "mhd_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double)]),
     "mhd_hunt_error_norms": (C.c_int, [_P, _P, C.POINTER(mhd_tables_t), C.POINTER(mhd_hunt_post_t), C.POINTER(C.c_double)]),
     "mhd_map_entry_order": (C.c_int, [C.POINTER(C.c_uint16), C.POINTER(C.c_int64)]),
+    "mhd_h1h1_operator_create": (C.c_int, [C.POINTER(mhd_mesh_t), C.POINTER(mhd_tables_h1h1_t), C.POINTER(mhd_layout_h1h1_t),
+                                           C.POINTER(mhd_params_t), C.POINTER(_P)]),
+    "mhd_h1h1_entry_order": (C.c_int, [C.POINTER(C.c_uint16), C.POINTER(C.c_int64)]),
     "mhd_profile_enable": (C.c_int, [C.c_int]),
     "mhd_profile_get": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mhd_profile_reset": (C.c_int, []),

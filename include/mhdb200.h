@@ -199,6 +199,36 @@ typedef struct {
 } mhd_hunt_post_t;
 int mhd_hunt_error_norms(mhd_operator_t*, const double* x, const mhd_tables_t* tab6, const mhd_hunt_post_t* prm, double* out6);
 
+/* ---- H1-H1 formulation (u Q2, p P1disc, phi Q3 continuous; j = sigma (u x B - grad phi) eliminated):
+ * weak_form_h1_h1 -> jac_fluid_h1_h1 / res_fluid_h1_h1 (src/weakforms.jl:344-355,415-466), solid cells :468-478,
+ * spaces of the `formulation in (:H1H1,:HDivH1)` branch of setup_fe_spaces (src/fespaces.jl:32-41) with
+ * reffe_phi = LagrangianRefFE(Float64,HEX,k+1;space=:Q), conformity :H1 (src/parameters.jl:528-532),
+ * layout _multi_field_style(::Val{:h1h1blocks}) = (u,p,phi) (src/fespaces.jl:9).
+ * The handle is an mhd_operator_t: mhd_operator_symbolic / get_csr / mhd_jacobian / mhd_residual /
+ * mhd_residual_and_jacobian / mhd_spmv / mhd_dot / mhd_axpy / mhd_multi_dot_axpy / mhd_solver_* (MHD_PC_NONE and
+ * MHD_PC_JACOBI) / halo calls work on it as documented above.  Local dofs of a cell: u (a + 27 c) | p | phi (64, in
+ * whatever local order the host tabulated phi_grad), 149 in total; touched blocks uu, up, u-phi, pu, phi-u, phi-phi. */
+typedef struct {
+  int32_t nq;             /* must be 27: Quadrature(HEX,5), q = max(2,5,4,4,2*(3-1)) (src/parameters.jl:382-388) */
+  const double* w;        /* [nq] */
+  const double* geo_grad; /* [nq*8*3] */
+  const double* u_val;    /* [nq*27] */
+  const double* u_grad;   /* [nq*27*3] */
+  const double* p_val;    /* [nq*4] */
+  const double* phi_grad; /* [nq*64*3] reference gradients of the scalar Q3 basis */
+} mhd_tables_h1h1_t;
+typedef struct {
+  const int32_t* cell_dofs[3]; /* u [ncells*81], p [ncells*4], phi [ncells*64]; signed 1-based, 0 = absent (u, p on solid cells) */
+  int64_t nfree[3], nowned[3], ndir[3];
+  const double* dir_values[3];
+  int32_t field_order[3];      /* permutation of {0 = u, 1 = p, 2 = phi} */
+} mhd_layout_h1h1_t;
+int mhd_h1h1_operator_create(const mhd_mesh_t*, const mhd_tables_h1h1_t*, const mhd_layout_h1h1_t*, const mhd_params_t*,
+                             mhd_operator_t** out);
+/* enumeration of the touched entries of an H1-H1 cell (row << 8 | col, local numbering u|p|phi), = scatter-map order;
+ * needs no device */
+int mhd_h1h1_entry_order(uint16_t* order, int64_t* n);
+
 /* ---- introspection for tests / benches ---- */
 int mhd_operator_device_ptrs(mhd_operator_t*, void** rowptr_i64, void** colval_i32, void** nzval_f64);
 int mhd_kernel_launch_count(int64_t* count); /* kernels launched by the library since mhd_init */
