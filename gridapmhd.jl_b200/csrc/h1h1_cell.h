@@ -14,8 +14,10 @@
 
 #ifdef __CUDACC__
 #define MHD_HD __host__ __device__ __forceinline__
+#define MHD_UNROLL _Pragma("unroll")
 #else
 #define MHD_HD inline
+#define MHD_UNROLL
 #endif
 
 namespace mhd {
@@ -243,62 +245,172 @@ MHD_HD void phase_jac_projection(Shared& S, int tid, int nt) {
 }
 
 // ------------------------------------------------------------------ phase 6 (Jacobian): the entries
-// store(e, li, lj, v): entry e of the enumeration = local (row li, column lj), value v
+// store(e, li, lj, v): entry e of the enumeration = local (row li, column lj), value v.
+//
+// The phase is bound by shared-memory operand reads (ncu: L1TEX 87 % with one entry per thread), so every thread owns a
+// REGISTER TILE of entries and each operand it loads feeds several FMAs.  Tiles are strided (a, a+14 | l, l+16, ...) so
+// that the lanes of a warp read consecutive shared-memory words and consecutive map codes.  One job list per cell,
+// job kinds padded to whole warps:
+//   slots [0,224)   uu      196 jobs: 2 x 2 (a,b) node pairs x 9 components      (a in {ta, ta+14}, b in {tb, tb+14})
+//   slots [224,384) phi-phi 136 jobs: 4 x 4 tiles of the upper triangle, mirrored (l in {tl+16i}, m in {tm+16j}, tl <= tm)
+//   slots [384,544) u-phi   144 jobs: 3 x 4 (a,l) pairs x 3 directions -> u-phi and phi-u (a in {3ta..3ta+2}, l in {tl+16i})
+//   slots [544,868) up, pu  324 jobs: one (c,a,k) each (the integrals are the D of the coefficient phase)
+constexpr int JOB_UU = 0, JOB_FF = 224, JOB_UF = 384, JOB_UP = 544, JOB_END = 868;
+constexpr int NJOB_UU = 196, NJOB_FF = 136, NJOB_UF = 144;
+
 template <int CONV, bool ZU, class Store>
-MHD_HD void phase_jac_entries(const Shared& S, int tid, int nt, const Params& P, Store& store) {
-  // uu: beta grad du : grad v + gamma (du x B).(v x B) + zeta_u Pi_p(du) div v + alpha v.(conv(u,grad du) + conv(du,grad u))
-  for (int idx = tid; idx < 729; idx += nt) {
-    const int a = idx / 27, b = idx % 27;
-    double s = 0.0, t[9];
-    for (int i = 0; i < 9; i++) t[i] = 0.0;
-    for (int q = 0; q < NQ; q++) {
-      const double na = S.N[q][a];
-      double g = P.beta * (S.gU[q][0][a] * S.gU[q][0][b] + S.gU[q][1][a] * S.gU[q][1][b] + S.gU[q][2][a] * S.gU[q][2][b]);
-      if (CONV != 0) g += P.alpha * na * S.adv[q][b];
-      s += S.wdet[q] * g;
-      const double nn = na * S.N[q][b];
-      for (int i = 0; i < 9; i++) t[i] += nn * S.Mw[q][i];
-    }
-    for (int c = 0; c < 3; c++)
-      for (int d = 0; d < 3; d++) {
-        double v = t[c * 3 + d] + (c == d ? s : 0.0);
-        if (ZU) {
-          const int ra = c * 27 + a, cb = d * 27 + b;
-          v += P.zeta_u * (S.D[0][ra] * S.E[0][cb] + S.D[1][ra] * S.E[1][cb] + S.D[2][ra] * S.E[2][cb] + S.D[3][ra] * S.E[3][cb]);
+MHD_HD void job_uu(const Shared& S, int job, const Params& P, Store& store) {
+  const int ta = job / 14, tb = job % 14;
+  const int a[2] = {ta, ta + 14 < 27 ? ta + 14 : 26}, b[2] = {tb, tb + 14 < 27 ? tb + 14 : 26};
+  const int na_ok = ta + 14 < 27 ? 2 : 1, nb_ok = tb + 14 < 27 ? 2 : 1;
+  double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  double mass[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // CONV != 2: sum_q wdet N_a N_b
+  double t[2][2][9];                              // CONV == 2: sum_q N_a N_b Mw_cd
+  if (CONV == 2)
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++)
+        for (int k = 0; k < 9; k++) t[i][j][k] = 0.0;
+  for (int q = 0; q < NQ; q++) {
+    const double w = S.wdet[q];
+    double g[2][2], nn[2][2];
+    {
+      double na[2], ga[2][3], nb[2], gb[2][3], ab[2];
+      MHD_UNROLL
+      for (int i = 0; i < 2; i++) {
+        na[i] = S.N[q][a[i]];
+        nb[i] = S.N[q][b[i]];
+        for (int k = 0; k < 3; k++) {
+          ga[i][k] = S.gU[q][k][a[i]];
+          gb[i][k] = S.gU[q][k][b[i]];
         }
-        store(SEC_UU + (c * 3 + d) * 729 + idx, c * 27 + a, d * 27 + b, v);
+        ab[i] = CONV != 0 ? P.alpha * S.adv[q][b[i]] : 0.0;
+      }
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) {
+          double v = P.beta * (ga[i][0] * gb[j][0] + ga[i][1] * gb[j][1] + ga[i][2] * gb[j][2]);
+          if (CONV != 0) v += na[i] * ab[j];
+          g[i][j] = v;
+          nn[i][j] = na[i] * nb[j];
+        }
+    }
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 2; j++) {
+        s[i][j] += w * g[i][j];
+        if (CONV != 2) mass[i][j] += w * nn[i][j];
+      }
+    if (CONV == 2)
+      MHD_UNROLL
+      for (int k = 0; k < 9; k++) {
+        const double m = S.Mw[q][k];
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 2; j++) t[i][j][k] += nn[i][j] * m;
       }
   }
-  // up: -dp div v ; pu: -div du q
-  for (int idx = tid; idx < NU * NP; idx += nt) {
-    const int ca = idx / 4, k = idx % 4;
-    const double v = -S.D[k][ca];
-    store(SEC_UP + idx, ca, OFF_P + k, v);
-    store(SEC_PU + idx, OFF_P + k, ca, v);
+  const double B2 = P.B[0] * P.B[0] + P.B[1] * P.B[1] + P.B[2] * P.B[2];
+  MHD_UNROLL
+  for (int i = 0; i < 2; i++)
+    MHD_UNROLL
+    for (int j = 0; j < 2; j++)
+      MHD_UNROLL
+      for (int cd = 0; cd < 9; cd++) {
+        if (i < na_ok && j < nb_ok) {  // static loop bounds: the accumulators stay in registers
+          const int c = cd / 3, d = cd % 3;
+          double v = CONV == 2 ? t[i][j][c * 3 + d] : P.gamma * ((c == d ? B2 : 0.0) - P.B[c] * P.B[d]) * mass[i][j];
+          if (c == d) v += s[i][j];
+          const int ra = c * 27 + a[i], cb = d * 27 + b[j];
+          if (ZU)
+            v += P.zeta_u * (S.D[0][ra] * S.E[0][cb] + S.D[1][ra] * S.E[1][cb] + S.D[2][ra] * S.E[2][cb] + S.D[3][ra] * S.E[3][cb]);
+          store(SEC_UU + (c * 3 + d) * 729 + a[i] * 27 + b[j], ra, cb, v);
+        }
+      }
+}
+
+template <class Store>
+MHD_HD void job_ff(const Shared& S, int job, Store& store) {
+  int tl = 0, r = job;
+  while (r >= 16 - tl) {
+    r -= 16 - tl;
+    tl++;
+  }
+  const int tm = tl + r;
+  double acc[4][4];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  for (int q = 0; q < NQ; q++) {
+    const double w = S.wdet[q];
+    MHD_UNROLL
+    for (int k = 0; k < 3; k++) {
+      double gl[4], gm[4];
+      for (int i = 0; i < 4; i++) {
+        gl[i] = w * S.gF[q][k][tl + 16 * i];
+        gm[i] = S.gF[q][k][tm + 16 * i];
+      }
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) acc[i][j] += gl[i] * gm[j];
+    }
+  }
+  MHD_UNROLL
+  for (int i = 0; i < 4; i++)
+    MHD_UNROLL
+    for (int j = 0; j < 4; j++) {
+      const int l = tl + 16 * i, m = tm + 16 * j;
+      store(SEC_FF + l * NF + m, OFF_F + l, OFF_F + m, acc[i][j]);
+      if (tl != tm) store(SEC_FF + m * NF + l, OFF_F + m, OFF_F + l, acc[i][j]);
+    }
+}
+
+template <class Store>
+MHD_HD void job_uf(const Shared& S, int job, const Params& P, Store& store) {
+  const int ta = job / 16, tl = job % 16;
+  double acc[3][4][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++)
+      for (int k = 0; k < 3; k++) acc[i][j][k] = 0.0;
+  for (int q = 0; q < NQ; q++) {
+    const double w = S.wdet[q];
+    double wn[3];
+    for (int i = 0; i < 3; i++) wn[i] = w * S.N[q][3 * ta + i];
+    MHD_UNROLL
+    for (int k = 0; k < 3; k++) {
+      double g[4];
+      for (int j = 0; j < 4; j++) g[j] = S.gF[q][k][tl + 16 * j];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 4; j++) acc[i][j][k] += wn[i] * g[j];
+    }
   }
   // u-phi: -gamma grad dphi.(v x B) = -gamma N_a (B x grad phi_l)_c ; phi-u: -(du x B).grad w = -N_a (B x grad phi_l)_c
-  for (int idx = tid; idx < 27 * NF; idx += nt) {
-    const int a = idx / NF, l = idx % NF;
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-    for (int q = 0; q < NQ; q++) {
-      const double wn = S.wdet[q] * S.N[q][a];
-      v0 += wn * S.gF[q][0][l];
-      v1 += wn * S.gF[q][1][l];
-      v2 += wn * S.gF[q][2][l];
+  MHD_UNROLL
+  for (int i = 0; i < 3; i++)
+    MHD_UNROLL
+    for (int j = 0; j < 4; j++) {
+      const int a = 3 * ta + i, l = tl + 16 * j;
+      const double* v = acc[i][j];
+      const double x[3] = {P.B[1] * v[2] - P.B[2] * v[1], P.B[2] * v[0] - P.B[0] * v[2], P.B[0] * v[1] - P.B[1] * v[0]};
+      for (int c = 0; c < 3; c++) {
+        store(SEC_UF + c * 27 * NF + a * NF + l, c * 27 + a, OFF_F + l, -P.gamma * x[c]);
+        store(SEC_FU + c * 27 * NF + a * NF + l, OFF_F + l, c * 27 + a, -x[c]);
+      }
     }
-    const double x[3] = {P.B[1] * v2 - P.B[2] * v1, P.B[2] * v0 - P.B[0] * v2, P.B[0] * v1 - P.B[1] * v0};
-    for (int c = 0; c < 3; c++) {
-      store(SEC_UF + c * 27 * NF + idx, c * 27 + a, OFF_F + l, -P.gamma * x[c]);
-      store(SEC_FU + c * 27 * NF + idx, OFF_F + l, c * 27 + a, -x[c]);
+}
+
+template <int CONV, bool ZU, class Store>
+MHD_HD void phase_jac_entries(const Shared& S, int tid, int nt, const Params& P, Store& store) {
+  for (int slot = tid; slot < JOB_END; slot += nt) {
+    if (slot < JOB_FF) {
+      // uu: beta grad du : grad v + gamma (du x B).(v x B) + zeta_u Pi_p(du) div v + alpha v.(conv(u,grad du) + conv(du,grad u))
+      if (slot - JOB_UU < NJOB_UU) job_uu<CONV, ZU>(S, slot - JOB_UU, P, store);
+    } else if (slot < JOB_UF) {
+      // phi-phi: grad dphi . grad w (symmetric)
+      if (slot - JOB_FF < NJOB_FF) job_ff(S, slot - JOB_FF, store);
+    } else if (slot < JOB_UP) {
+      if (slot - JOB_UF < NJOB_UF) job_uf(S, slot - JOB_UF, P, store);
+    } else {
+      // up: -dp div v ; pu: -div du q
+      const int idx = slot - JOB_UP, ca = idx / 4, k = idx % 4;
+      const double v = -S.D[k][ca];
+      store(SEC_UP + idx, ca, OFF_P + k, v);
+      store(SEC_PU + idx, OFF_P + k, ca, v);
     }
-  }
-  // phi-phi: grad dphi . grad w
-  for (int idx = tid; idx < NF * NF; idx += nt) {
-    const int l = idx / NF, m = idx % NF;
-    double s = 0.0;
-    for (int q = 0; q < NQ; q++)
-      s += S.wdet[q] * (S.gF[q][0][l] * S.gF[q][0][m] + S.gF[q][1][l] * S.gF[q][1][m] + S.gF[q][2][l] * S.gF[q][2][m]);
-    store(SEC_FF + idx, OFF_F + l, OFF_F + m, s);
   }
 }
 
