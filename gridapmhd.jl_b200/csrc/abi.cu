@@ -123,7 +123,8 @@ int mhd_profile_reset(void) {
 }
 int mhd_profile_get(const char* name, double* total_ms, int64_t* launches) {
   MHD_CHECK(name != nullptr, MHD_E_INVALID, "null name");
-  int w = !strcmp(name, "jacobian") ? PROF_JAC : !strcmp(name, "residual") ? PROF_RES : !strcmp(name, "spmv") ? PROF_SPMV : -1;
+  int w = !strcmp(name, "jacobian") ? PROF_JAC : !strcmp(name, "residual") ? PROF_RES : !strcmp(name, "spmv") ? PROF_SPMV :
+          !strcmp(name, "patch_setup") ? PROF_PATCH_SETUP : !strcmp(name, "patch_apply") ? PROF_PATCH_APPLY : -1;
   MHD_CHECK(w >= 0, MHD_E_INVALID, "unknown profile slot '%s'", name);
   prof_collect();
   if (total_ms) *total_ms = g_prof[w].total_ms;

@@ -211,7 +211,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 bool is_device_ptr(const void* p);
 
 // event timing of the dominant kernels (bench.py roofline): prof_begin/prof_end bracket a launch
-enum { PROF_JAC = 0, PROF_RES = 1, PROF_SPMV = 2, PROF_N = 3 };
+enum { PROF_JAC = 0, PROF_RES = 1, PROF_SPMV = 2, PROF_PATCH_SETUP = 3, PROF_PATCH_APPLY = 4, PROF_N = 5 };
 extern bool g_prof_on;
 void prof_begin(int which);
 void prof_end(int which);
@@ -248,6 +248,13 @@ int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // h1h1.cu
 int h1h1_launch_jacobian(mhd_operator* op, const double* d_x);
 int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);
+// patch.cu: vertex-patch block-Jacobi smoother of the (u,j) block
+struct PatchData;
+int patch_create(PatchData** out, int64_t n_uj, int64_t npatch, const int64_t* ptr, const int32_t* dofs);
+void patch_destroy(PatchData* P);
+int patch_setup(PatchData* P, mhd_operator* op);  // gather the sub-blocks of the current Jacobian and invert them
+int patch_apply(PatchData* P, const double* d_r, double* d_z, double omega, bool accumulate);
+int64_t patch_bytes(const PatchData* P);
 // krylov.cu
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);
 // y[0..nr) = (A x)[0..nr) including the ghost exchange (fused peer-memory kernel when connected, NCCL otherwise)

@@ -293,6 +293,9 @@ struct mhd_solver {
   int* d_ipiv = nullptr;
   int* d_info = nullptr;
   int lu_lwork = 0;
+  // vertex-patch smoother of the (u,j) block (patch.cu)
+  mhd::PatchData* patches = nullptr;
+  double *d_t4 = nullptr, *d_t5 = nullptr;
 };
 
 namespace mhd {
@@ -402,7 +405,8 @@ int mhd_solver_default_opts(mhd_solver_opts_t* o) {
   o->alpha_p = -1.0;     // -1/(beta+zeta_u); the host overrides with the actual fluid parameters
   o->alpha_phi = -1.0;   // -1/(1+zeta_j)
   o->uj_solver = MHD_UJ_GMRES_JACOBI;
-  o->reserved = 0;
+  o->patch_its = 1;
+  o->patch_omega = 1.0;
   return MHD_OK;
 }
 
@@ -422,7 +426,13 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
     MHD_CHECK(opts->alpha_p != 0.0 && opts->alpha_phi != 0.0, MHD_E_INVALID, "alpha_p/alpha_phi must be nonzero");
     MHD_CHECK(opts->uj_inner_its >= 1 && opts->uj_inner_restart >= 1 && opts->uj_inner_restart <= MAXM, MHD_E_INVALID,
               "bad inner iteration counts");
-    MHD_CHECK(opts->uj_solver == MHD_UJ_GMRES_JACOBI || opts->uj_solver == MHD_UJ_DENSE_LU, MHD_E_INVALID, "unknown uj_solver");
+    MHD_CHECK(opts->uj_solver == MHD_UJ_GMRES_JACOBI || opts->uj_solver == MHD_UJ_DENSE_LU ||
+                  opts->uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_INVALID, "unknown uj_solver");
+    if (opts->uj_solver == MHD_UJ_GMRES_PATCH) {
+      MHD_CHECK(g_nranks == 1, MHD_E_INVALID, "the patch smoother runs on one GPU (patches across ranks are not exchanged yet)");
+      MHD_CHECK(opts->patch_its >= 1 && opts->patch_its <= 100 && opts->patch_omega > 0.0, MHD_E_INVALID,
+                "bad patch_its / patch_omega");
+    }
     if (opts->uj_solver == MHD_UJ_DENSE_LU) {
       MHD_CHECK(g_nranks == 1, MHD_E_INVALID, "MHD_UJ_DENSE_LU is a single-GPU option (the (u,j) block is distributed)");
       MHD_CHECK(op->nowned[MHD_FIELD_U] + op->nowned[MHD_FIELD_J] <= 24576, MHD_E_CAPACITY,
@@ -454,6 +464,10 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
   if (opts->precond == MHD_PC_BLOCK_TRI) {
     const int mi = opts->uj_inner_restart < opts->uj_inner_its ? opts->uj_inner_restart : opts->uj_inner_its;
     CR(s->inner.init(op, s->n_uj, op->ncols, mi, false));
+    if (opts->uj_solver == MHD_UJ_GMRES_PATCH) {
+      CR(dev_alloc(&s->d_t4, op->ncols));
+      CR(dev_alloc(&s->d_t5, op->ncols));
+    }
     if (opts->uj_solver == MHD_UJ_DENSE_LU) {
       CR(dev_alloc(&s->d_dense, s->n_uj * s->n_uj));
       CR(dev_alloc(&s->d_ipiv, s->n_uj));
@@ -493,8 +507,22 @@ int mhd_solver_destroy(mhd_solver_t* s) {
   cudaFree(s->d_dense); cudaFree(s->d_lu_work); cudaFree(s->d_ipiv); cudaFree(s->d_info);
   cudaFree(s->d_dinv); cudaFree(s->d_minv_p); cudaFree(s->d_minv_f);
   cudaFree(s->d_b); cudaFree(s->d_x); cudaFree(s->d_t1); cudaFree(s->d_t2); cudaFree(s->d_t3);
+  cudaFree(s->d_t4); cudaFree(s->d_t5);
+  patch_destroy(s->patches);
   delete s;
   return MHD_OK;
+}
+
+int mhd_solver_set_patches(mhd_solver_t* s, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs) {
+  MHD_CHECK(s != nullptr, MHD_E_INVALID, "null solver");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_STATE,
+            "mhd_solver_set_patches: the solver was not created with uj_solver = MHD_UJ_GMRES_PATCH");
+  MHD_CUDA(cudaSetDevice(g_device));
+  patch_destroy(s->patches);
+  s->patches = nullptr;
+  s->setup_done = false;
+  return patch_create(&s->patches, s->n_uj, npatch, patch_ptr, patch_dofs);
 }
 
 int mhd_solver_setup(mhd_solver_t* s) {
@@ -516,7 +544,33 @@ int mhd_solver_setup(mhd_solver_t* s) {
     MHD_CUDA(cudaStreamSynchronize(g_stream));
     MHD_CHECK(info == 0, MHD_E_INVALID, "dense LU of the (u,j) block failed: getrf info = %d", info);
   }
+  if (s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_GMRES_PATCH) {
+    MHD_CHECK(s->patches != nullptr, MHD_E_STATE, "mhd_solver_setup: call mhd_solver_set_patches first (uj_solver = MHD_UJ_GMRES_PATCH)");
+    MHD_TRY(patch_setup(s->patches, op));
+  }
   s->setup_done = true;
+  return MHD_OK;
+}
+
+int mhd_solver_patch_apply(mhd_solver_t* s, const double* r, double* z, double omega) {
+  MHD_CHECK(s && r && z, MHD_E_INVALID, "mhd_solver_patch_apply: null argument");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(s->patches != nullptr && s->setup_done, MHD_E_STATE,
+            "mhd_solver_patch_apply: call mhd_solver_set_patches and mhd_solver_setup first");
+  MHD_CUDA(cudaSetDevice(g_device));
+  const int64_t nuj = s->n_uj;
+  const bool rdev = is_device_ptr(r), zdev = is_device_ptr(z);
+  const double* dr = r;
+  if (!rdev) {
+    MHD_TRY(h2d(s->d_t4, r, nuj));
+    dr = s->d_t4;
+  }
+  double* dz = zdev ? z : s->d_t5;
+  MHD_TRY(patch_apply(s->patches, dr, dz, omega, false));
+  if (!zdev) {
+    MHD_TRY(d2h(z, dz, nuj));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
   return MHD_OK;
 }
 
@@ -547,6 +601,18 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
     MHD_LAUNCH_CHECK();
     return 0;
   };
+  // vertex-patch smoother: z = Richardson(patch_its, patch_omega) on A_uj with the additive patch solver (gmg.jl:62-81)
+  VecOp patch_uj = [s, nuj, &matvec_uj](const double* v, double* z) -> int {
+    const mhd_solver_opts_t& oo = s->opts;
+    MHD_TRY(patch_apply(s->patches, v, z, oo.patch_omega, false));
+    for (int it = 1; it < oo.patch_its; it++) {
+      MHD_TRY(matvec_uj(z, s->d_t4));
+      k_sub<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, v, s->d_t4, s->d_t5);
+      MHD_LAUNCH_CHECK();
+      MHD_TRY(patch_apply(s->patches, s->d_t5, z, oo.patch_omega, true));
+    }
+    return 0;
+  };
   VecOp precond;
   if (o.precond == MHD_PC_NONE) {
     precond = [n](const double* v, double* z) -> int {
@@ -561,7 +627,7 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
     };
   } else {
     // upper block-triangular solve (badia2024.jl:25-31): phi, p first, then the (u,j) block with the coupling
-    precond = [s, op, n, nuj, &matvec_uj, &jacobi_uj](const double* v, double* z) -> int {
+    precond = [s, op, n, nuj, &matvec_uj, &jacobi_uj, &patch_uj](const double* v, double* z) -> int {
       const mhd_solver_opts_t& oo = s->opts;
       MHD_CUDA(cudaMemsetAsync(z, 0, (size_t)op->ncols * 8, g_stream));
       k_apply_mass_inverses<<<(unsigned)((op->ncells * 12 + 127) / 128), 128, 0, g_stream>>>(
@@ -583,7 +649,8 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
       int done_its = 0;
       bool first = true;
       while (done_its < oo.uj_inner_its) {
-        MHD_TRY(s->inner.cycle(matvec_uj, jacobi_uj, s->d_t2, s->d_t3, 1e-2, 0.0, oo.uj_inner_its, first, true));
+        MHD_TRY(s->inner.cycle(matvec_uj, oo.uj_solver == MHD_UJ_GMRES_PATCH ? patch_uj : jacobi_uj, s->d_t2, s->d_t3, 1e-2, 0.0,
+                               oo.uj_inner_its, first, true));
         done_its += s->inner.m;
         first = false;
       }

@@ -314,7 +314,11 @@ class B200SolverOptions:
     precond: str = "block_tri"
     uj_inner_its: int = 30
     uj_inner_restart: int = 30
-    uj_solver: str = "gmres_jacobi"  # or "dense_lu": exact (u,j)-block solve on the device, small problems only
+    # (u,j) block: "gmres_jacobi" | "dense_lu" (exact, small problems) | "gmres_patch" (vertex-patch block-Jacobi smoother of
+    # gmg_block_jacobi_smoothers, src/Solvers/gmg.jl:62-81, inside the inner GMRES; any size, one GPU)
+    uj_solver: str = "gmres_jacobi"
+    patch_its: int = 1  # Richardson sweeps per application (the reference smoother: niter = 10)
+    patch_omega: float = 1.0  # damping (the reference smoother: w = 0.2)
 
 
 class B200LinearSolver:
@@ -347,11 +351,21 @@ class B200NumericalSetup:
         c.precond = L.PRECOND[o.precond]
         c.uj_inner_its, c.uj_inner_restart = o.uj_inner_its, o.uj_inner_restart
         c.uj_solver = L.UJ_SOLVER[o.uj_solver]
+        c.patch_its, c.patch_omega = o.patch_its, o.patch_omega
         c.alpha_p = -1.0 / (fl.beta + fl.zeta_u)  # badia2024.jl:11
         c.alpha_phi = -1.0 / (1.0 + fl.zeta_j)  # badia2024.jl:12
         h = C.c_void_p()
         L.check(L.load().mhd_solver_create(A.op.handle, C.byref(c), C.byref(h)))
         self.handle = h
+        if o.precond == "block_tri" and o.uj_solver == "gmres_patch":
+            # PatchTopology(ReferenceFE{0}, model) of the host (gmg.jl:69): vertex-star dof lists of the (u,j) block
+            from .host.patches import vertex_patches
+
+            ptr, dofs = vertex_patches(A.op.fes)
+            ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+            dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+            L.check(L.load().mhd_solver_set_patches(h, len(ptr) - 1, L.ptr(ptr), L.ptr(dofs)))
+            self.npatches, self.patch_entries = len(ptr) - 1, int((np.diff(ptr) ** 2).sum())
         self.iters = 0
         self.resnorm = float("nan")
         self.history = np.zeros(0)
@@ -361,6 +375,18 @@ class B200NumericalSetup:
         """numerical_setup!(ns,A): refresh preconditioner data after jacobian!"""
         L.check(L.load().mhd_solver_setup(self.handle))
         return self
+
+    def patch_apply(self, r, omega=1.0):
+        """solve!(z, BlockJacobiSolver, r): one additive sweep of the vertex-patch solver on the (u,j) block"""
+        rr = r if _is_torch(r) else _as_f64(r)
+        if _is_torch(r):
+            import torch
+
+            z = torch.empty_like(r)
+        else:
+            z = np.empty(len(rr))
+        L.check(L.load().mhd_solver_patch_apply(self.handle, L.ptr(rr), L.ptr(z), float(omega)))
+        return z
 
     def solve_b(self, x, b, raise_on_maxiter=False):
         """solve!(x,ns,b): x holds the initial guess on entry and the solution on exit."""

@@ -16,7 +16,7 @@ ERRORS = {-1: "MHD_E_INVALID", -2: "MHD_E_CUDA", -3: "MHD_E_STATE", -4: "MHD_E_C
 FIELD_IDS = {"u": 0, "p": 1, "j": 2, "phi": 3}
 CONVECTION = {"none": 0, "picard": 1, "newton": 2}
 PRECOND = {"none": 0, "jacobi": 1, "block_tri": 2}
-UJ_SOLVER = {"gmres_jacobi": 0, "dense_lu": 1}
+UJ_SOLVER = {"gmres_jacobi": 0, "dense_lu": 1, "gmres_patch": 2}
 
 
 class MhdError(RuntimeError):
@@ -66,7 +66,8 @@ class mhd_hunt_post_t(C.Structure):
 class mhd_solver_opts_t(C.Structure):
     _fields_ = [("m", C.c_int32), ("maxiter", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
                 ("precond", C.c_int32), ("uj_inner_its", C.c_int32), ("uj_inner_restart", C.c_int32),
-                ("alpha_p", C.c_double), ("alpha_phi", C.c_double), ("uj_solver", C.c_int32), ("reserved", C.c_int32)]
+                ("alpha_p", C.c_double), ("alpha_phi", C.c_double), ("uj_solver", C.c_int32), ("patch_its", C.c_int32),
+                ("patch_omega", C.c_double)]
 
 
 # every exported symbol of include/mhdb200.h with its signature (tests check the .so exports all of them)
@@ -102,7 +103,9 @@ SIGNATURES = {
     "mhd_multi_dot_axpy": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P, _P]),
     "mhd_solver_default_opts": (C.c_int, [C.POINTER(mhd_solver_opts_t)]),
     "mhd_solver_create": (C.c_int, [_P, C.POINTER(mhd_solver_opts_t), C.POINTER(_P)]),
+    "mhd_solver_set_patches": (C.c_int, [_P, C.c_int64, _P, _P]),
     "mhd_solver_setup": (C.c_int, [_P]),
+    "mhd_solver_patch_apply": (C.c_int, [_P, _P, _P, C.c_double]),
     "mhd_solve": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P]),
     "mhd_solver_destroy": (C.c_int, [_P]),
     "mhd_operator_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),

@@ -96,7 +96,10 @@ enum { MHD_PC_NONE = 0, MHD_PC_JACOBI = 1, MHD_PC_BLOCK_TRI = 2 };
 /* (u,j)-block solver of the block-triangular preconditioner: inner Jacobi-GMRES (any size, any rank count) or an
  * exact dense LU on the device (cuSOLVER getrf/getrs; single GPU, n_uj <= 24576) -- the device stand-in for the
  * reference's direct block solver on small problems. */
-enum { MHD_UJ_GMRES_JACOBI = 0, MHD_UJ_DENSE_LU = 1 };
+/* MHD_UJ_GMRES_PATCH: inner GMRES preconditioned by the vertex-patch block-Jacobi smoother of
+ * gmg_block_jacobi_smoothers (src/Solvers/gmg.jl:62-81): z = Richardson(patch_its sweeps, damping patch_omega) of the additive
+ * Schwarz operator sum_p R_p' inv(A_p) R_p over the vertex stars; needs mhd_solver_set_patches.  Any size, one GPU. */
+enum { MHD_UJ_GMRES_JACOBI = 0, MHD_UJ_DENSE_LU = 1, MHD_UJ_GMRES_PATCH = 2 };
 typedef struct {
   int32_t m;            /* restart length (niter_ls, default 15) */
   int32_t maxiter;      /* total Krylov iterations (reference: == m) */
@@ -106,7 +109,8 @@ typedef struct {
   int32_t uj_inner_restart;
   double alpha_p, alpha_phi; /* scalings of the p / phi mass blocks (badia2024.jl:11-12) */
   int32_t uj_solver;    /* MHD_UJ_*: how block_solvers[1] (LU/MUMPS in the reference, badia2024.jl:22) is realised */
-  int32_t reserved;
+  int32_t patch_its;    /* MHD_UJ_GMRES_PATCH: Richardson sweeps per preconditioner application (reference: niter = 10; default 1) */
+  double patch_omega;   /* damping of the sweeps (reference: w = 0.2, gmg.jl:62); irrelevant for patch_its = 1 under GMRES */
 } mhd_solver_opts_t;
 
 /* ---- library lifetime (GridapPETSc.with(args=...) do ... end; src/Applications/hunt.jl:202-206) ---- */
@@ -181,7 +185,15 @@ int mhd_multi_dot_axpy(mhd_operator_t*, int32_t k, const double* V, int64_t ldv,
  * (seam: _solver / get_block_solver, src/main.jl:181-190, src/Solvers/gridap.jl:2-3). ---- */
 int mhd_solver_default_opts(mhd_solver_opts_t*);
 int mhd_solver_create(mhd_operator_t*, const mhd_solver_opts_t*, mhd_solver_t** out);
+/* Vertex-star patches for MHD_UJ_GMRES_PATCH: what Geometry.PatchTopology(ReferenceFE{0},model) + the FE space give the
+ * reference's BlockJacobiSolver (src/Solvers/gmg.jl:69-73).  Patch k owns the rows patch_dofs[patch_ptr[k]..patch_ptr[k+1])
+ * (0-based local row ids inside the (u,j) block, strictly increasing, at most 256 per patch; empty patches allowed).
+ * Call before mhd_solver_setup; the lists are copied. */
+int mhd_solver_set_patches(mhd_solver_t*, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs);
 int mhd_solver_setup(mhd_solver_t*); /* numerical_setup!: refresh preconditioner data after mhd_jacobian */
+/* solve!(z, ns::BlockJacobiSolver, r) of the patch solver alone: z = omega * sum_p R_p' inv(A_p) R_p r on the (u,j) block
+ * (r, z: [n_uj], host or device).  After mhd_solver_set_patches + mhd_solver_setup. */
+int mhd_solver_patch_apply(mhd_solver_t*, const double* r, double* z, double omega);
 int mhd_solve(mhd_solver_t*, const double* b, double* x /* in: x0, out: solution */, int32_t* iters,
               double* resnorm, double* res_history /* nullable, maxiter+1 doubles */);
 int mhd_solver_destroy(mhd_solver_t*);

@@ -131,7 +131,17 @@ end
 
 struct MhdSolverOpts
   m::Int32; maxiter::Int32; rtol::Float64; atol::Float64; precond::Int32
-  uj_inner_its::Int32; uj_inner_restart::Int32; alpha_p::Float64; alpha_phi::Float64; uj_solver::Int32; reserved::Int32
+  uj_inner_its::Int32; uj_inner_restart::Int32; alpha_p::Float64; alpha_phi::Float64; uj_solver::Int32; patch_its::Int32
+  patch_omega::Float64
+end
+
+# uj_solver = 2 (MHD_UJ_GMRES_PATCH): hand the vertex-star dof lists of the (u,j) block to the solver before the first
+# numerical_setup! -- what gmg_block_jacobi_smoothers (src/Solvers/gmg.jl:62-81) gives PatchBasedSmoothers.BlockJacobiSolver:
+#   ptopo = Geometry.PatchTopology(ReferenceFE{0}, model); patch_ptr / patch_dofs = free (u,j) dof ids per patch, 0-based, sorted
+function set_patches!(ns, patch_ptr::Vector{Int64}, patch_dofs::Vector{Int32})
+  @check ccall((:mhd_solver_set_patches, libmhd), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}),
+               ns.handle, length(patch_ptr) - 1, patch_ptr, patch_dofs)
+  ns
 end
 
 struct B200LinearSolver <: Algebra.LinearSolver

@@ -57,12 +57,14 @@ def test_c_struct_layouts_match_header_sizes(tmp_path):
     from gridapmhd_jl_b200 import lib as L
 
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "mhdb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mhd_mesh_t),'
-                   " sizeof(mhd_tables_t), sizeof(mhd_layout_t), sizeof(mhd_params_t), sizeof(mhd_solver_opts_t), sizeof(mhd_hunt_post_t)); return 0;}\n")
+    src.write_text('#include <stdio.h>\n#include "mhdb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mhd_mesh_t),'
+                   " sizeof(mhd_tables_t), sizeof(mhd_layout_t), sizeof(mhd_params_t), sizeof(mhd_solver_opts_t), sizeof(mhd_hunt_post_t),"
+                   " sizeof(mhd_tables_h1h1_t), sizeof(mhd_layout_h1h1_t)); return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    mine = [ctypes.sizeof(t) for t in (L.mhd_mesh_t, L.mhd_tables_t, L.mhd_layout_t, L.mhd_params_t, L.mhd_solver_opts_t, L.mhd_hunt_post_t)]
+    mine = [ctypes.sizeof(t) for t in (L.mhd_mesh_t, L.mhd_tables_t, L.mhd_layout_t, L.mhd_params_t, L.mhd_solver_opts_t, L.mhd_hunt_post_t,
+                                       L.mhd_tables_h1h1_t, L.mhd_layout_h1h1_t)]
     assert mine == sizes, (mine, sizes)
 
 
