@@ -11,6 +11,8 @@
 //                           explicit inverses the right trade: the apply becomes one streaming pass)
 //   apply                 : z (+)= omega * sum_p R_p^T inv(A_p) R_p r : one CTA per patch, a warp per row, coalesced row
 //                           reads, warp-shuffle reduction, atomicAdd into z.  HBM-bound: 8 n_p^2 bytes per patch.
+#include <stdlib.h>
+
 #include "common.h"
 #include "patch_cell.h"
 
@@ -35,7 +37,8 @@ namespace {
   }
 
 // gather A[dofs, dofs] from the CSR into M (row-major n x n), then invert in place
-__global__ void __launch_bounds__(patch::NMAX)
+template <int MINB>
+__global__ void __launch_bounds__(patch::NMAX, MINB)
 patch_gather_invert(const int64_t* __restrict__ pptr, const int32_t* __restrict__ pdofs, const int64_t* __restrict__ matptr,
                     const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval, const double* __restrict__ nzval,
                     double* __restrict__ inv, int* __restrict__ flag) {
@@ -154,8 +157,20 @@ void patch_destroy(PatchData* P) {
 int patch_setup(PatchData* P, mhd_operator* op) {
   MHD_CUDA(cudaMemsetAsync(P->d_flag, 0, sizeof(int), g_stream));
   prof_begin(PROF_PATCH_SETUP);
-  patch_gather_invert<<<(unsigned)P->npatch, patch::NMAX, 0, g_stream>>>(P->d_ptr, P->d_dofs, P->d_matptr, op->d_rowptr,
-                                                                         op->d_colval, op->d_nzval, P->d_inv, P->d_flag);
+  static int minb = 0;  // resident CTAs per SM the kernel is compiled for (MHD_PATCH_CTAS: A/B builds, default 4)
+  if (!minb) {
+    const char* e = getenv("MHD_PATCH_CTAS");
+    minb = e ? atoi(e) : 4;
+  }
+  if (minb >= 4)
+    patch_gather_invert<4><<<(unsigned)P->npatch, patch::NMAX, 0, g_stream>>>(P->d_ptr, P->d_dofs, P->d_matptr, op->d_rowptr,
+                                                                              op->d_colval, op->d_nzval, P->d_inv, P->d_flag);
+  else if (minb == 3)
+    patch_gather_invert<3><<<(unsigned)P->npatch, patch::NMAX, 0, g_stream>>>(P->d_ptr, P->d_dofs, P->d_matptr, op->d_rowptr,
+                                                                              op->d_colval, op->d_nzval, P->d_inv, P->d_flag);
+  else
+    patch_gather_invert<2><<<(unsigned)P->npatch, patch::NMAX, 0, g_stream>>>(P->d_ptr, P->d_dofs, P->d_matptr, op->d_rowptr,
+                                                                              op->d_colval, op->d_nzval, P->d_inv, P->d_flag);
   prof_end(PROF_PATCH_SETUP);
   MHD_LAUNCH_CHECK();
   int nsing = 0;

@@ -35,7 +35,9 @@ constexpr int PB = 16;     // panel width
 constexpr int NLEAD = 16;  // leaders of the two-level pivot search (each scans NMAX / NLEAD rows)
 
 struct Shared {
-  double P[NMAX][PB];   // panel
+  double P[PB][NMAX + 1];  // panel, TRANSPOSED: P[s][i] = panel entry (row i, column s); thread i walks its row with
+                           // consecutive lanes on consecutive words (a row-major panel gave 32-way bank conflicts:
+                           // 112 ms -> see DESIGN 4.6), the odd leading dimension keeps the panel load conflict-free
   double prow[PB];      // scaled pivot row of the current sub-step
   double lead_val[NLEAD];
   int lead_idx[NLEAD];
@@ -47,7 +49,7 @@ MHD_PHD double dabs(double x) { return x < 0.0 ? -x : x; }
 
 // phase: load the panel columns [k0, k0+b)
 MHD_PHD void phase_load_panel(Shared& S, int tid, int nt, const double* A, int n, int k0, int b) {
-  for (int idx = tid; idx < n * b; idx += nt) S.P[idx / b][idx % b] = A[(int64_t)(idx / b) * n + k0 + idx % b];
+  for (int idx = tid; idx < n * b; idx += nt) S.P[idx % b][idx / b] = A[(int64_t)(idx / b) * n + k0 + idx % b];
 }
 // sub-step s, phase a: leaders scan their rows for the largest |P[i][s]|, i >= k0+s
 MHD_PHD void phase_pivot_leaders(Shared& S, int tid, int nt, int n, int k0, int s) {
@@ -57,7 +59,7 @@ MHD_PHD void phase_pivot_leaders(Shared& S, int tid, int nt, int n, int k0, int 
     int bi = -1;
     for (int i = tid * chunk; i < (tid + 1) * chunk && i < n; i++)
       if (i >= k0 + s) {
-        const double v = dabs(S.P[i][s]);
+        const double v = dabs(S.P[s][i]);
         if (v > best) { best = v; bi = i; }
       }
     S.lead_val[tid] = best;
@@ -78,30 +80,30 @@ MHD_PHD void phase_pivot_pick(Shared& S, int tid, int nt, int k0, int s) {
 MHD_PHD void phase_swap_panel_rows(Shared& S, int tid, int nt, int k0, int s, int b) {
   const int r = S.piv[k0 + s];
   if (tid < b && r != k0 + s) {
-    const double t = S.P[k0 + s][tid];
-    S.P[k0 + s][tid] = S.P[r][tid];
-    S.P[r][tid] = t;
+    const double t = S.P[tid][k0 + s];
+    S.P[tid][k0 + s] = S.P[tid][r];
+    S.P[tid][r] = t;
   }
 }
 // phase d: scaled pivot row into prow
 MHD_PHD void phase_scale_pivot_row(Shared& S, int tid, int nt, int k0, int s, int b) {
   if (tid < b) {
-    double p = S.P[k0 + s][s];
+    double p = S.P[s][k0 + s];
     if (p == 0.0) {
       p = 1.0;
       if (tid == 0) S.singular = 1;
     }
-    S.prow[tid] = (tid == s ? 1.0 : S.P[k0 + s][tid]) / p;
+    S.prow[tid] = (tid == s ? 1.0 : S.P[tid][k0 + s]) / p;
   }
 }
 // phase e: eliminate inside the panel (thread i owns row i)
 MHD_PHD void phase_eliminate_panel(Shared& S, int tid, int nt, int n, int k0, int s, int b) {
   for (int i = tid; i < n; i += nt) {
     if (i == k0 + s) {
-      for (int t = 0; t < b; t++) S.P[i][t] = S.prow[t];
+      for (int t = 0; t < b; t++) S.P[t][i] = S.prow[t];
     } else {
-      const double f = S.P[i][s];
-      for (int t = 0; t < b; t++) S.P[i][t] = (t == s ? 0.0 : S.P[i][t]) - f * S.prow[t];
+      const double f = S.P[s][i];
+      for (int t = 0; t < b; t++) S.P[t][i] = (t == s ? 0.0 : S.P[t][i]) - f * S.prow[t];
     }
   }
 }
@@ -109,7 +111,7 @@ MHD_PHD void phase_eliminate_panel(Shared& S, int tid, int nt, int n, int k0, in
 MHD_PHD void phase_update(const Shared& S, int tid, int nt, double* A, int n, int k0, int b) {
   for (int j = tid; j < n; j += nt) {
     if (j >= k0 && j < k0 + b) {
-      for (int i = 0; i < n; i++) A[(int64_t)i * n + j] = S.P[i][j - k0];
+      for (int i = 0; i < n; i++) A[(int64_t)i * n + j] = S.P[j - k0][i];
       continue;
     }
     double rb[PB];
@@ -128,18 +130,32 @@ MHD_PHD void phase_update(const Shared& S, int tid, int nt, double* A, int n, in
     MHD_PUNROLL
     for (int s = 0; s < PB; s++)
       if (s < b) rb[s] = A[(int64_t)(k0 + s) * n + j];
-    for (int i = 0; i < n; i++) {
-      double v = (i >= k0 && i < k0 + b) ? 0.0 : A[(int64_t)i * n + j];
+    // rows in chunks of RU: the loads of a chunk are issued together (the stores of the previous rows alias them as far as
+    // the compiler knows, so a row-at-a-time loop would pay the full memory latency per row)
+    constexpr int RU = 8;
+    for (int i0 = 0; i0 < n; i0 += RU) {
+      double v[RU];
       MHD_PUNROLL
-      for (int s = 0; s < PB; s++) v += S.P[i][s] * rb[s];  // P[i][s] = 0 for s >= b (see inverse_block_step)
-      A[(int64_t)i * n + j] = v;
+      for (int u = 0; u < RU; u++) {
+        const int i = i0 + u;
+        v[u] = (i < n && !(i >= k0 && i < k0 + b)) ? A[(int64_t)i * n + j] : 0.0;
+      }
+      MHD_PUNROLL
+      for (int u = 0; u < RU; u++) {
+        const int i = i0 + u < n ? i0 + u : n - 1;
+        MHD_PUNROLL
+        for (int s = 0; s < PB; s++) v[u] += S.P[s][i] * rb[s];  // P[i][s] = 0 for s >= b (phase_clear_panel_tail)
+      }
+      MHD_PUNROLL
+      for (int u = 0; u < RU; u++)
+        if (i0 + u < n) A[(int64_t)(i0 + u) * n + j] = v[u];
     }
   }
 }
 // phase: zero the unused panel columns of a short last block
 MHD_PHD void phase_clear_panel_tail(Shared& S, int tid, int nt, int n, int b) {
   if (b < PB)
-    for (int idx = tid; idx < n * (PB - b); idx += nt) S.P[idx / (PB - b)][b + idx % (PB - b)] = 0.0;
+    for (int idx = tid; idx < n * (PB - b); idx += nt) S.P[b + idx % (PB - b)][idx / (PB - b)] = 0.0;
 }
 // final phase: undo the row permutation on the columns, in reverse order (thread i owns row i)
 MHD_PHD void phase_unscramble(const Shared& S, int tid, int nt, double* A, int n) {
