@@ -147,6 +147,10 @@ def main(params, solve=True, res_assemble=False, jac_assemble=False, solver_opts
     out = {"fes": fes, "op": op}
     if solve:
         t0 = time.perf_counter()
+        if solver_opts is None and isinstance(fes, H1H1Spaces):
+            # default_solver_params(Val(:h1h1blocks)) (src/parameters.jl:274-287) with the patch-smoothed block solvers
+            solver_opts = B200SolverOptions(m=30, maxiter=60, rtol=newton_rtol / 10.0, atol=1e-14, precond="h1h1_blocks",
+                                            uj_solver="gmres_patch", uj_inner_its=30, uj_inner_restart=30)
         nls = NewtonSolver(B200LinearSolver(solver_opts), maxiter=newton_maxiter, rtol=newton_rtol, verbose=verbose)
         x = nls.solve_b(x, op)
         L.check(L.load().mhd_device_synchronize())

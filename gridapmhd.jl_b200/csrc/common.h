@@ -259,6 +259,7 @@ int64_t patch_bytes(const PatchData* P);
 int launch_spmv(mhd_operator* op, const double* d_x, double* d_y);
 // y[0..nr) = (A x)[0..nr) including the ghost exchange (fused peer-memory kernel when connected, NCCL otherwise)
 int spmv_with_halo(mhd_operator* op, int64_t nr, double* d_x, double* d_y);
+int spmv_row_range(mhd_operator* op, int64_t r0, int64_t r1, const double* d_x, double* d_y);
 int launch_dot(mhd_operator* op, int64_t n, const double* d_x, const double* d_y, double* d_out);
 int launch_axpy(int64_t n, double a, const double* d_x, double* d_y);
 int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int64_t ldv, const double* d_w, double* d_h);

@@ -192,6 +192,19 @@ spmv_rows_kernel(int64_t nr, const int64_t* __restrict__ rowptr, const int32_t* 
   }
 }
 
+// y[r0..r1) = (A x)[r0..r1): the rows of one diagonal block (single GPU; the block solvers of the H1-H1 preconditioner)
+int spmv_row_range(mhd_operator* op, int64_t r0, int64_t r1, const double* d_x, double* d_y) {
+  if (r1 <= r0) return 0;
+  MHD_CHECK(g_nranks == 1 && r0 >= 0 && r1 <= op->nrows, MHD_E_INVALID, "spmv_row_range: bad range / more than one rank");
+  int64_t blocks = (r1 - r0 + SPMV_WARPS - 1) / SPMV_WARPS;
+  const int64_t cap = (int64_t)sms() * 32 * 4;
+  if (blocks > cap) blocks = cap;
+  spmv_warp_row<2><<<(unsigned)blocks, SPMV_WARPS * 32, 0, g_stream>>>(r1 - r0, op->d_rowptr + r0, op->d_colval, op->d_nzval, d_x,
+                                                                       d_y + r0);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
 int spmv_with_halo(mhd_operator* op, int64_t nr, double* d_x, double* d_y) {
   if (nr <= 0) return 0;
   Halo& h = op->halo;

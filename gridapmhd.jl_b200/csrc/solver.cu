@@ -17,6 +17,7 @@
 #include <functional>
 
 #include "common.h"
+#include "h1h1_cell.h"
 
 namespace mhd {
 
@@ -296,6 +297,10 @@ struct mhd_solver {
   // vertex-patch smoother of the (u,j) block (patch.cu)
   mhd::PatchData* patches = nullptr;
   double *d_t4 = nullptr, *d_t5 = nullptr;
+  // H1-H1 block preconditioner: u block = `inner` + `patches`, phi block = `inner2` + `patches_phi`, p = d_minv_p
+  Fgmres inner2;
+  mhd::PatchData* patches_phi = nullptr;
+  int64_t off_p = 0, off_phi = 0;
 };
 
 namespace mhd {
@@ -389,6 +394,48 @@ k_apply_mass_inverses(int64_t ncells, int64_t nrows, const int32_t* __restrict__
   }
 }
 
+// ---- H1-H1 block preconditioner (src/Solvers/h1h1blocks.jl:2-43): inverse P1disc cell mass blocks from the H1-H1 tables
+__global__ void __launch_bounds__(64)
+k_h1h1_mass_inverse_p(int64_t ncells, const double* __restrict__ tab, const double* __restrict__ coords,
+                      const int32_t* __restrict__ cell_nodes, double* __restrict__ minv_p) {
+  const int64_t cell = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (cell >= ncells) return;
+  double X[8][3];
+  for (int v = 0; v < 8; v++)
+    for (int i = 0; i < 3; i++) X[v][i] = coords[(int64_t)cell_nodes[cell * 8 + v] * 3 + i];
+  double Mp[4][8];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) Mp[i][j] = (j - 4 == i) ? 1.0 : 0.0;
+  for (int q = 0; q < 27; q++) {
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int v = 0; v < 8; v++)
+      for (int i = 0; i < 3; i++)
+        for (int k = 0; k < 3; k++) J[i][k] += X[v][i] * tab[h1::T_GG + (q * 8 + v) * 3 + k];
+    const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                       J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    const double w = tab[h1::T_W + q] * fabs(det);
+    for (int k = 0; k < 4; k++)
+      for (int l = 0; l < 4; l++) Mp[k][l] += w * tab[h1::T_PP + q * 4 + k] * tab[h1::T_PP + q * 4 + l];
+  }
+  invert_spd<4>(&Mp[0][0]);
+  for (int k = 0; k < 4; k++) for (int l = 0; l < 4; l++) minv_p[cell * 16 + k * 4 + l] = Mp[k][4 + l];
+}
+
+// z[p rows of the cell] = (1/alpha_p) M_p^{-1} v
+__global__ void __launch_bounds__(128)
+k_h1h1_apply_mass_p(int64_t ncells, int64_t nrows, const int32_t* __restrict__ gids, const double* __restrict__ minv_p,
+                    double inv_alpha_p, const double* __restrict__ v, double* __restrict__ z) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t cell = t >> 2;
+  const int r = (int)(t & 3);
+  if (cell >= ncells) return;
+  const int32_t* g = gids + cell * h1::NLOC + h1::OFF_P;
+  const int32_t row = g[r];
+  if (row < 0 || row >= nrows) return;
+  double s = 0.0;
+  for (int l = 0; l < 4; l++) s = fma(minv_p[cell * 16 + r * 4 + l], v[g[l]], s);
+  z[row] = inv_alpha_p * s;
+}
+
 }  // namespace mhd
 
 extern "C" {
@@ -414,9 +461,22 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CHECK(op && opts && out, MHD_E_INVALID, "mhd_solver_create: null argument");
   MHD_CHECK(op->has_symbolic, MHD_E_STATE, "mhd_solver_create: call mhd_operator_symbolic first");
-  MHD_CHECK(opts->precond >= 0 && opts->precond <= 2, MHD_E_INVALID, "unknown preconditioner %d", opts->precond);
+  MHD_CHECK(opts->precond >= 0 && opts->precond <= 3, MHD_E_INVALID, "unknown preconditioner %d", opts->precond);
   MHD_CHECK(opts->m >= 1 && opts->m <= MAXM && opts->maxiter >= 1, MHD_E_INVALID, "bad m/maxiter");
   MHD_CUDA(cudaSetDevice(g_device));
+  if (opts->precond == MHD_PC_H1H1_BLOCKS) {
+    MHD_CHECK(op->formulation == FORM_H1H1, MHD_E_INVALID, "MHD_PC_H1H1_BLOCKS needs an operator from mhd_h1h1_operator_create");
+    MHD_CHECK(op->field_order[0] == MHD_FIELD_U && op->field_order[1] == MHD_FIELD_P && op->field_order[2] == MHD_FIELD_PHI,
+              MHD_E_INVALID, "MHD_PC_H1H1_BLOCKS needs field_order (u,p,phi) (_multi_field_style(::Val{:h1h1blocks}))");
+    MHD_CHECK(g_nranks == 1, MHD_E_INVALID, "MHD_PC_H1H1_BLOCKS runs on one GPU");
+    MHD_CHECK(opts->alpha_p != 0.0, MHD_E_INVALID, "alpha_p must be nonzero");
+    MHD_CHECK(opts->uj_inner_its >= 1 && opts->uj_inner_restart >= 1 && opts->uj_inner_restart <= MAXM, MHD_E_INVALID,
+              "bad inner iteration counts");
+    MHD_CHECK(opts->uj_solver == MHD_UJ_GMRES_JACOBI || opts->uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_INVALID,
+              "MHD_PC_H1H1_BLOCKS: block solvers are MHD_UJ_GMRES_JACOBI or MHD_UJ_GMRES_PATCH");
+    if (opts->uj_solver == MHD_UJ_GMRES_PATCH)
+      MHD_CHECK(opts->patch_its >= 1 && opts->patch_its <= 100 && opts->patch_omega > 0.0, MHD_E_INVALID, "bad patch_its / patch_omega");
+  }
   if (opts->precond == MHD_PC_BLOCK_TRI) {
     MHD_CHECK(op->formulation == FORM_HDIV, MHD_E_INVALID,
               "mhd_solver_create: the block-triangular preconditioner is built for H1-HDiv operators (use MHD_PC_JACOBI)");
@@ -461,6 +521,22 @@ int mhd_solver_create(mhd_operator_t* op, const mhd_solver_opts_t* opts, mhd_sol
     cudaMemsetAsync(s->d_t2, 0, op->ncols * 8, g_stream);
     cudaMemsetAsync(s->d_t3, 0, op->ncols * 8, g_stream);
   }
+  if (opts->precond == MHD_PC_H1H1_BLOCKS) {
+    const int mi = opts->uj_inner_restart < opts->uj_inner_its ? opts->uj_inner_restart : opts->uj_inner_its;
+    s->off_p = op->nowned[MHD_FIELD_U];
+    s->off_phi = s->off_p + op->nowned[MHD_FIELD_P];
+    CR(s->inner.init(op, s->n_uj, op->ncols, mi, false));     // u block: leading rows (n_uj = n_u, there is no j field)
+    CR(s->inner2.init(op, op->nrows, op->ncols, mi, false));  // phi block: full-length vectors, zero outside phi
+    CR(dev_alloc(&s->d_t4, op->ncols));
+    CR(dev_alloc(&s->d_t5, op->ncols));
+    CR(dev_alloc(&s->d_minv_p, op->ncells * 16));
+    if (!rc) {
+      k_h1h1_mass_inverse_p<<<(unsigned)((op->ncells + 63) / 64), 64, 0, g_stream>>>(op->ncells, op->d_tables, op->d_coords,
+                                                                                     op->d_cell_nodes, s->d_minv_p);
+      g_launches++;
+      if (cudaPeekAtLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "k_h1h1_mass_inverse_p", __FILE__, __LINE__);
+    }
+  }
   if (opts->precond == MHD_PC_BLOCK_TRI) {
     const int mi = opts->uj_inner_restart < opts->uj_inner_its ? opts->uj_inner_restart : opts->uj_inner_its;
     CR(s->inner.init(op, s->n_uj, op->ncols, mi, false));
@@ -503,6 +579,8 @@ int mhd_solver_destroy(mhd_solver_t* s) {
   cudaStreamSynchronize(g_stream);
   s->outer.release();
   s->inner.release();
+  s->inner2.release();
+  patch_destroy(s->patches_phi);
   if (s->cs) g_cs.Destroy(s->cs);
   cudaFree(s->d_dense); cudaFree(s->d_lu_work); cudaFree(s->d_ipiv); cudaFree(s->d_info);
   cudaFree(s->d_dinv); cudaFree(s->d_minv_p); cudaFree(s->d_minv_f);
@@ -516,13 +594,29 @@ int mhd_solver_destroy(mhd_solver_t* s) {
 int mhd_solver_set_patches(mhd_solver_t* s, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs) {
   MHD_CHECK(s != nullptr, MHD_E_INVALID, "null solver");
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
-  MHD_CHECK(s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_STATE,
+  MHD_CHECK((s->opts.precond == MHD_PC_BLOCK_TRI || s->opts.precond == MHD_PC_H1H1_BLOCKS) &&
+                s->opts.uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_STATE,
             "mhd_solver_set_patches: the solver was not created with uj_solver = MHD_UJ_GMRES_PATCH");
   MHD_CUDA(cudaSetDevice(g_device));
   patch_destroy(s->patches);
   s->patches = nullptr;
   s->setup_done = false;
   return patch_create(&s->patches, s->n_uj, npatch, patch_ptr, patch_dofs);
+}
+
+int mhd_solver_set_phi_patches(mhd_solver_t* s, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs) {
+  MHD_CHECK(s != nullptr, MHD_E_INVALID, "null solver");
+  MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
+  MHD_CHECK(s->opts.precond == MHD_PC_H1H1_BLOCKS && s->opts.uj_solver == MHD_UJ_GMRES_PATCH, MHD_E_STATE,
+            "mhd_solver_set_phi_patches: needs precond = MHD_PC_H1H1_BLOCKS and uj_solver = MHD_UJ_GMRES_PATCH");
+  MHD_CUDA(cudaSetDevice(g_device));
+  patch_destroy(s->patches_phi);
+  s->patches_phi = nullptr;
+  s->setup_done = false;
+  for (int64_t i = 0; patch_ptr && patch_dofs && i < patch_ptr[npatch > 0 ? npatch : 0]; i++)
+    MHD_CHECK(patch_dofs[i] >= s->off_phi, MHD_E_INVALID, "phi patches: dof %d is not a phi row (rows start at %lld)", patch_dofs[i],
+              (long long)s->off_phi);
+  return patch_create(&s->patches_phi, s->op->nrows, npatch, patch_ptr, patch_dofs);
 }
 
 int mhd_solver_setup(mhd_solver_t* s) {
@@ -544,9 +638,13 @@ int mhd_solver_setup(mhd_solver_t* s) {
     MHD_CUDA(cudaStreamSynchronize(g_stream));
     MHD_CHECK(info == 0, MHD_E_INVALID, "dense LU of the (u,j) block failed: getrf info = %d", info);
   }
-  if (s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_GMRES_PATCH) {
+  if ((s->opts.precond == MHD_PC_BLOCK_TRI || s->opts.precond == MHD_PC_H1H1_BLOCKS) && s->opts.uj_solver == MHD_UJ_GMRES_PATCH) {
     MHD_CHECK(s->patches != nullptr, MHD_E_STATE, "mhd_solver_setup: call mhd_solver_set_patches first (uj_solver = MHD_UJ_GMRES_PATCH)");
     MHD_TRY(patch_setup(s->patches, op));
+    if (s->opts.precond == MHD_PC_H1H1_BLOCKS) {
+      MHD_CHECK(s->patches_phi != nullptr, MHD_E_STATE, "mhd_solver_setup: call mhd_solver_set_phi_patches first");
+      MHD_TRY(patch_setup(s->patches_phi, op));
+    }
   }
   s->setup_done = true;
   return MHD_OK;
@@ -623,6 +721,70 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
     precond = [dinv, n](const double* v, double* z) -> int {
       k_mul<<<vgrid(n), 256, 0, g_stream>>>(n, dinv, v, z);
       MHD_LAUNCH_CHECK();
+      return 0;
+    };
+  } else if (o.precond == MHD_PC_H1H1_BLOCKS) {
+    // H1H1BlockSolver (src/Solvers/h1h1blocks.jl:17-26): BlockTriangularSolver(:upper) over (u, p, phi) with coefficients
+    // [1 1 1; 0 1 0; 0 0 1]: z_phi = S_phi v_phi ; z_p = (alpha_p M_p)^{-1} v_p ; z_u = S_u (v_u - A_up z_p - A_{u phi} z_phi),
+    // S_u / S_phi = inner GMRES on the assembled diagonal blocks, preconditioned by their vertex-patch solvers (or Jacobi)
+    precond = [s, op, n, nuj, &matvec_uj, &jacobi_uj, &patch_uj](const double* v, double* z) -> int {
+      const mhd_solver_opts_t& oo = s->opts;
+      const int64_t off = s->off_phi, nphi = n - off;
+      const bool use_patch = oo.uj_solver == MHD_UJ_GMRES_PATCH;
+      VecOp matvec_phi = [op, off, n](const double* x, double* y) -> int {
+        MHD_CUDA(cudaMemsetAsync(y, 0, (size_t)off * 8, g_stream));
+        return spmv_row_range(op, off, n, x, y);
+      };
+      double* dinv = s->d_dinv;
+      VecOp jacobi_phi = [dinv, off, n](const double* x, double* y) -> int {
+        MHD_CUDA(cudaMemsetAsync(y, 0, (size_t)off * 8, g_stream));
+        k_mul<<<vgrid(n - off), 256, 0, g_stream>>>(n - off, dinv + off, x + off, y + off);
+        MHD_LAUNCH_CHECK();
+        return 0;
+      };
+      VecOp patch_phi = [s, n, &matvec_phi](const double* x, double* y) -> int {
+        const mhd_solver_opts_t& o2 = s->opts;
+        MHD_TRY(patch_apply(s->patches_phi, x, y, o2.patch_omega, false));
+        for (int it = 1; it < o2.patch_its; it++) {
+          MHD_TRY(matvec_phi(y, s->d_t4));
+          k_sub<<<vgrid(n), 256, 0, g_stream>>>(n, x, s->d_t4, s->d_t5);
+          MHD_LAUNCH_CHECK();
+          MHD_TRY(patch_apply(s->patches_phi, s->d_t5, y, o2.patch_omega, true));
+        }
+        return 0;
+      };
+      MHD_CUDA(cudaMemsetAsync(z, 0, (size_t)op->ncols * 8, g_stream));
+      // phi block
+      if (nphi > 0) {
+        MHD_CUDA(cudaMemsetAsync(s->d_t2, 0, (size_t)op->ncols * 8, g_stream));
+        MHD_CUDA(cudaMemcpyAsync(s->d_t2 + off, v + off, (size_t)nphi * 8, cudaMemcpyDeviceToDevice, g_stream));
+        MHD_CUDA(cudaMemsetAsync(s->d_t3, 0, (size_t)op->ncols * 8, g_stream));
+        int done_its = 0;
+        bool first = true;
+        while (done_its < oo.uj_inner_its) {
+          MHD_TRY(s->inner2.cycle(matvec_phi, use_patch ? patch_phi : jacobi_phi, s->d_t2, s->d_t3, 1e-2, 0.0, oo.uj_inner_its, first, true));
+          done_its += s->inner2.m;
+          first = false;
+        }
+        MHD_CUDA(cudaMemcpyAsync(z + off, s->d_t3 + off, (size_t)nphi * 8, cudaMemcpyDeviceToDevice, g_stream));
+      }
+      // p block
+      k_h1h1_apply_mass_p<<<(unsigned)((op->ncells * 4 + 127) / 128), 128, 0, g_stream>>>(op->ncells, n, op->d_gids, s->d_minv_p,
+                                                                                          1.0 / oo.alpha_p, v, z);
+      MHD_LAUNCH_CHECK();
+      // u block with the coupling to p and phi
+      MHD_TRY(spmv_with_halo(op, nuj, z, s->d_t1));
+      k_sub<<<vgrid(nuj), 256, 0, g_stream>>>(nuj, v, s->d_t1, s->d_t2);
+      MHD_LAUNCH_CHECK();
+      MHD_CUDA(cudaMemsetAsync(s->d_t3, 0, (size_t)op->ncols * 8, g_stream));
+      int done_its = 0;
+      bool first = true;
+      while (done_its < oo.uj_inner_its) {
+        MHD_TRY(s->inner.cycle(matvec_uj, use_patch ? patch_uj : jacobi_uj, s->d_t2, s->d_t3, 1e-2, 0.0, oo.uj_inner_its, first, true));
+        done_its += s->inner.m;
+        first = false;
+      }
+      MHD_CUDA(cudaMemcpyAsync(z, s->d_t3, (size_t)nuj * 8, cudaMemcpyDeviceToDevice, g_stream));
       return 0;
     };
   } else {

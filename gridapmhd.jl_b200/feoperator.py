@@ -311,7 +311,7 @@ class B200SolverOptions:
     maxiter: int = 15
     rtol: float = 1e-7  # nl_rtol/10 (badia2024.jl:37)
     atol: float = 1e-8
-    precond: str = "block_tri"
+    precond: str = "block_tri"  # "none" | "jacobi" | "block_tri" (H1-HDiv, badia2024.jl) | "h1h1_blocks" (H1-H1, h1h1blocks.jl)
     uj_inner_its: int = 30
     uj_inner_restart: int = 30
     # (u,j) block: "gmres_jacobi" | "dense_lu" (exact, small problems) | "gmres_patch" (vertex-patch block-Jacobi smoother of
@@ -357,6 +357,16 @@ class B200NumericalSetup:
         h = C.c_void_p()
         L.check(L.load().mhd_solver_create(A.op.handle, C.byref(c), C.byref(h)))
         self.handle = h
+        if o.precond == "h1h1_blocks" and o.uj_solver == "gmres_patch":
+            from .host.patches import vertex_patches_h1h1
+
+            (pu, du), (pf, df) = vertex_patches_h1h1(A.op.fes)
+            keep = [np.ascontiguousarray(pu, dtype=np.int64), np.ascontiguousarray(du, dtype=np.int32),
+                    np.ascontiguousarray(pf, dtype=np.int64), np.ascontiguousarray(df, dtype=np.int32)]
+            L.check(L.load().mhd_solver_set_patches(h, len(pu) - 1, L.ptr(keep[0]), L.ptr(keep[1])))
+            L.check(L.load().mhd_solver_set_phi_patches(h, len(pf) - 1, L.ptr(keep[2]), L.ptr(keep[3])))
+            self.npatches = len(pu) - 1
+            self.patch_entries = int((np.diff(pu) ** 2).sum() + (np.diff(pf) ** 2).sum())
         if o.precond == "block_tri" and o.uj_solver == "gmres_patch":
             # PatchTopology(ReferenceFE{0}, model) of the host (gmg.jl:69): vertex-star dof lists of the (u,j) block
             from .host.patches import vertex_patches

@@ -32,6 +32,38 @@ def _corner_local_dofs():
 CORNER_DOFS = _corner_local_dofs()
 
 
+def _patches_from_corner_slots(fes, corner_slots: np.ndarray):
+    """CSR (ptr, dofs) of the vertex patches given, per cell corner, the local dof slots that belong to that corner's patch."""
+    gids = fes.cell_global_ids()
+    nc = gids.shape[0]
+    stride = int(gids.max()) + 2
+    verts = np.repeat(fes.mesh.cell_verts.reshape(nc, 8, 1), corner_slots.shape[1], axis=2)
+    dofs = gids[:, corner_slots]
+    ok = dofs >= 0
+    key = np.unique(verts[ok].astype(np.int64) * stride + dofs[ok])
+    v, d = key // stride, key % stride
+    ptr = np.zeros(fes.mesh.nverts + 1, dtype=np.int64)
+    np.add.at(ptr, v + 1, 1)
+    return np.cumsum(ptr), d.astype(np.int32)
+
+
+def vertex_patches_h1h1(fes):
+    """H1-H1 spaces (u,p,phi): ((ptr_u, dofs_u), (ptr_phi, dofs_phi)) -- the vertex-star patches of the velocity block (27
+    Q2 nodes x 3 = 81 dofs on an interior vertex) and of the potential block (5^3 = 125 Q3 nodes), global row ids of the
+    layout `fes.field_order`; what `gmg_block_jacobi_smoothers` builds for the u-block GMG of `gmg_solver(::Val{:H1H1},
+    ::Val{:h1h1blocks}, params)` (src/Solvers/gmg.jl:107-140)."""
+    from .fespaces_h1h1 import Q3_NODE_IJK
+
+    u_slots, f_slots = [], []
+    for k in range(8):
+        vk = HEX_VERTS[k]
+        nodes = [a for a in range(27) if all(Q2_NODE_IJK[a][d] != 2 * (1 - vk[d]) for d in range(3))]
+        u_slots.append([a + 27 * c for c in range(3) for a in nodes])
+        f_slots.append([85 + l for l in range(64) if all(Q3_NODE_IJK[l][d] != 3 * (1 - vk[d]) for d in range(3))])
+    return (_patches_from_corner_slots(fes, np.array(u_slots, dtype=np.int64)),
+            _patches_from_corner_slots(fes, np.array(f_slots, dtype=np.int64)))
+
+
 def vertex_patches(fes: FESpaces):
     """(patch_ptr int64 [nverts+1], patch_dofs int32) -- sorted global ids (0-based, layout of `fes.field_order`) of the
     free u and j dofs in the star of every vertex.  Empty patches (all dofs Dirichlet) are kept with zero length."""

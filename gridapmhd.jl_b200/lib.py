@@ -15,7 +15,7 @@ MHD_OK = 0
 ERRORS = {-1: "MHD_E_INVALID", -2: "MHD_E_CUDA", -3: "MHD_E_STATE", -4: "MHD_E_CAPACITY", -5: "MHD_E_COMM", -6: "MHD_E_NOTCONV"}
 FIELD_IDS = {"u": 0, "p": 1, "j": 2, "phi": 3}
 CONVECTION = {"none": 0, "picard": 1, "newton": 2}
-PRECOND = {"none": 0, "jacobi": 1, "block_tri": 2}
+PRECOND = {"none": 0, "jacobi": 1, "block_tri": 2, "h1h1_blocks": 3}
 UJ_SOLVER = {"gmres_jacobi": 0, "dense_lu": 1, "gmres_patch": 2}
 
 
@@ -104,6 +104,7 @@ SIGNATURES = {
     "mhd_solver_default_opts": (C.c_int, [C.POINTER(mhd_solver_opts_t)]),
     "mhd_solver_create": (C.c_int, [_P, C.POINTER(mhd_solver_opts_t), C.POINTER(_P)]),
     "mhd_solver_set_patches": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "mhd_solver_set_phi_patches": (C.c_int, [_P, C.c_int64, _P, _P]),
     "mhd_solver_setup": (C.c_int, [_P]),
     "mhd_solver_patch_apply": (C.c_int, [_P, _P, _P, C.c_double]),
     "mhd_solve": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P]),

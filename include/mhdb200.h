@@ -92,7 +92,12 @@ typedef struct {
 } mhd_params_t;
 
 /* FGMRES + preconditioner options (src/Solvers/badia2024.jl:32-45, src/parameters.jl:259-271). */
-enum { MHD_PC_NONE = 0, MHD_PC_JACOBI = 1, MHD_PC_BLOCK_TRI = 2 };
+/* MHD_PC_H1H1_BLOCKS: H1H1BlockSolver (src/Solvers/h1h1blocks.jl:2-43) for operators of mhd_h1h1_operator_create with layout
+ * (u,p,phi): upper block-triangular, coefficients [1 1 1; 0 1 0; 0 0 1], p block = alpha_p x mass (alpha_p = -1/(beta+zeta_u)),
+ * u and phi blocks = inner GMRES (uj_inner_its / uj_inner_restart) on the assembled diagonal blocks with Jacobi
+ * (MHD_UJ_GMRES_JACOBI) or their vertex-patch solvers (MHD_UJ_GMRES_PATCH: mhd_solver_set_patches = u patches,
+ * mhd_solver_set_phi_patches = phi patches; the reference puts GMG with the same patch smoothers there, gmg.jl:107-140). */
+enum { MHD_PC_NONE = 0, MHD_PC_JACOBI = 1, MHD_PC_BLOCK_TRI = 2, MHD_PC_H1H1_BLOCKS = 3 };
 /* (u,j)-block solver of the block-triangular preconditioner: inner Jacobi-GMRES (any size, any rank count) or an
  * exact dense LU on the device (cuSOLVER getrf/getrs; single GPU, n_uj <= 24576) -- the device stand-in for the
  * reference's direct block solver on small problems. */
@@ -190,6 +195,9 @@ int mhd_solver_create(mhd_operator_t*, const mhd_solver_opts_t*, mhd_solver_t** 
  * (0-based local row ids inside the (u,j) block, strictly increasing, at most 256 per patch; empty patches allowed).
  * Call before mhd_solver_setup; the lists are copied. */
 int mhd_solver_set_patches(mhd_solver_t*, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs);
+/* MHD_PC_H1H1_BLOCKS: vertex-star patches of the phi block (global row ids, i.e. >= n_u + n_p); the u patches go through
+ * mhd_solver_set_patches */
+int mhd_solver_set_phi_patches(mhd_solver_t*, int64_t npatch, const int64_t* patch_ptr, const int32_t* patch_dofs);
 int mhd_solver_setup(mhd_solver_t*); /* numerical_setup!: refresh preconditioner data after mhd_jacobian */
 /* solve!(z, ns::BlockJacobiSolver, r) of the patch solver alone: z = omega * sum_p R_p' inv(A_p) R_p r on the (u,j) block
  * (r, z: [n_uj], host or device).  After mhd_solver_set_patches + mhd_solver_setup. */

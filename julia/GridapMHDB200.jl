@@ -143,6 +143,12 @@ function set_patches!(ns, patch_ptr::Vector{Int64}, patch_dofs::Vector{Int32})
                ns.handle, length(patch_ptr) - 1, patch_ptr, patch_dofs)
   ns
 end
+# precond = 3 (MHD_PC_H1H1_BLOCKS, src/Solvers/h1h1blocks.jl): set_patches! carries the u patches, this one the phi patches
+function set_phi_patches!(ns, patch_ptr::Vector{Int64}, patch_dofs::Vector{Int32})
+  @check ccall((:mhd_solver_set_phi_patches, libmhd), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}),
+               ns.handle, length(patch_ptr) - 1, patch_ptr, patch_dofs)
+  ns
+end
 
 struct B200LinearSolver <: Algebra.LinearSolver
   op::B200FEOperator

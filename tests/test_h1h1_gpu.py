@@ -161,3 +161,56 @@ def test_h1h1_device_fgmres_reduces_the_residual(cfg1):
     with pytest.raises(MhdError):
         B200LinearSolver(B200SolverOptions(precond="block_tri")).symbolic_setup(A).numerical_setup()
     op.destroy()
+
+
+def test_h1h1_block_preconditioner_with_patch_solvers_converges(mhdlib):
+    """H1H1BlockSolver (src/Solvers/h1h1blocks.jl:2-43; hunt(..., solver=:h1h1blocks, zeta_u=10) of test/seq/hunt_tests.jl:90-103 at a
+    smaller mesh): outer FGMRES with the upper block-triangular preconditioner over (u,p,phi) whose u and phi blocks are
+    inner GMRES(30) with vertex-patch solvers.  The NumPy restatement of the same algorithm converges to 1e-8 in 19 outer
+    iterations; solution against sparse LU of the device matrix."""
+    p = hunt_params(nc=(6, 6), B=(0.0, 20.0, 0.0), zeta_u=10.0, current_disc="H1")
+    fes = setup_spaces(p)
+    op = make_operator(fes, p["fluid"])
+    A = op.allocate_jacobian()
+    b = np.empty(op.nrows)
+    op.residual_and_jacobian_b(b, A, np.zeros(fes.ndofs))
+    opts = B200SolverOptions(m=30, maxiter=60, rtol=1e-8, atol=0.0, precond="h1h1_blocks", uj_solver="gmres_patch", uj_inner_its=30,
+                             uj_inner_restart=30)
+    ns = B200LinearSolver(opts).symbolic_setup(A).numerical_setup()
+    dx = np.zeros(op.nrows)
+    ns.solve_b(dx, -b, raise_on_maxiter=True)
+    h = ns.history
+    assert ns.iters <= 40 and h[-1] <= 1e-8 * h[0]
+    As = A.to_scipy()
+    assert abs(np.linalg.norm(As @ dx + b) - ns.resnorm) < 1e-6 * h[0]
+    xo = spla.splu(As.tocsc()).solve(-b)
+    o = fes.offsets
+    for f in ("u", "phi"):
+        sl = slice(o[f], o[f] + fes.nfree[f])
+        assert relerr(dx[sl], xo[sl]) < 1e-5
+    ns.destroy()
+    # the Jacobi variant of the block solvers runs too (and is much weaker)
+    nsj = B200LinearSolver(B200SolverOptions(m=30, maxiter=30, rtol=1e-8, atol=0.0, precond="h1h1_blocks", uj_solver="gmres_jacobi",
+                                             uj_inner_its=30, uj_inner_restart=30)).symbolic_setup(A).numerical_setup()
+    dj = np.zeros(op.nrows)
+    nsj.solve_b(dj, -b)
+    assert nsj.history[-1] < nsj.history[0] and nsj.history[-1] > h[-1]
+    nsj.destroy()
+    op.destroy()
+
+
+def test_h1h1_hunt_driver_solves_on_the_device(mhdlib):
+    """`main(params)` for `current_disc = :H1`: Newton + device FGMRES with the H1-H1 block preconditioner (no host solve);
+    u and phi within 1e-5 of the oracle's Newton/LU solution"""
+    from gridapmhd_jl_b200.applications import main
+
+    p = hunt_params(nc=(6, 6), B=(0.0, 20.0, 0.0), zeta_u=10.0, current_disc="H1")
+    out = main(p, newton_rtol=1e-9)
+    fes = out["fes"]
+    assert out["newton_log"][-1] <= 1e-8 * out["newton_log"][0], out["newton_log"]
+    xo, _ = H.newton_lu(fes, oprm(p["fluid"]), rtol=1e-12)
+    o = fes.offsets
+    for f in ("u", "phi"):
+        sl = slice(o[f], o[f] + fes.nfree[f])
+        assert relerr(out["x"][sl], xo[sl]) < 1e-5
+    out["op"].destroy()

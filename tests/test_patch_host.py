@@ -105,3 +105,19 @@ def test_patch_smoother_makes_the_inner_gmres_converge_on_the_oracle_matrix():
     assert hj[-1] > 0.5 * hj[0]
     assert ha[-1] < 0.05 * ha[0]
     assert hr[-1] < 1e-2 * hr[0]
+
+
+def test_vertex_patches_of_the_h1h1_spaces():
+    from gridapmhd_jl_b200.host.patches import vertex_patches_h1h1
+
+    p = hunt_params(nc=(4, 4), B=(0.0, 10.0, 0.0), current_disc="H1")
+    fes = setup_spaces(p)
+    (pu, du), (pf, df) = vertex_patches_h1h1(fes)
+    nu, npp = fes.nfree["u"], fes.nfree["p"]
+    assert np.diff(pu).max() == 81 and np.diff(pf).max() == 125  # 27 Q2 nodes x 3 ; 5^3 Q3 nodes
+    assert du.min() >= 0 and du.max() < nu and df.min() >= nu + npp and df.max() < fes.ndofs
+    assert np.bincount(du, minlength=nu).min() >= 1
+    assert np.bincount(df - (nu + npp), minlength=fes.nfree["phi"]).min() >= 1
+    for ptr, d in ((pu, du), (pf, df)):
+        for k in range(len(ptr) - 1):
+            assert np.all(np.diff(d[ptr[k] : ptr[k + 1]]) > 0)
