@@ -14,15 +14,21 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .fespaces import FIELDS, FESpaces
+from .fespaces import FESpaces
+from .fespaces_h1h1 import H1H1Spaces
 from .mesh import HexMesh, build_topology, cartesian_partition
+
+
+def _fields(fes) -> tuple:
+    """("u","p","j","phi") for the H1-HDiv spaces, ("u","p","phi") for the H1-H1 spaces"""
+    return tuple(fes.cell_dofs.keys())
 
 
 def dof_owners(fes: FESpaces, cell_part: np.ndarray) -> dict:
     """field -> owner rank of each free dof (0-based per-field id): the lowest part among the cells around it."""
     out = {}
     nparts = int(cell_part.max()) + 1
-    for f in FIELDS:
+    for f in _fields(fes):
         ids = fes.cell_dofs[f]
         own = np.full(fes.nfree[f], nparts, dtype=np.int64)
         free = ids > 0
@@ -43,7 +49,7 @@ class LocalSets:
 def local_sets(fes: FESpaces, cell_part: np.ndarray, owners: dict, rank: int) -> LocalSets:
     owned_cells = np.nonzero(cell_part == rank)[0]
     touch = np.zeros(fes.mesh.ncells, dtype=bool)
-    for f in FIELDS:
+    for f in _fields(fes):
         ids = fes.cell_dofs[f]
         free = ids > 0
         mine = np.zeros(ids.shape, dtype=bool)
@@ -52,7 +58,7 @@ def local_sets(fes: FESpaces, cell_part: np.ndarray, owners: dict, rank: int) ->
     ghost_cells = np.nonzero(touch & (cell_part != rank))[0]
     cells = np.concatenate([owned_cells, ghost_cells])
     owned, ghost = {}, {}
-    for f in FIELDS:
+    for f in _fields(fes):
         ids = fes.cell_dofs[f][cells]
         g = np.unique(ids[ids > 0] - 1)
         o = owners[f][g] == rank
@@ -123,7 +129,7 @@ def partition_fespaces(fes: FESpaces, cell_part: np.ndarray, rank: int) -> Parti
     lmesh = HexMesh(coords=m.coords[used], cell_nodes=inv.reshape(cn.shape), cell_verts=m.cell_verts[me.cells])
     # ---- local dof tables
     cell_dofs, nfree, nowned = {}, {}, {}
-    for f in FIELDS:
+    for f in _fields(fes):
         ids = fes.cell_dofs[f][me.cells]
         lut = np.zeros(fes.nfree[f] + 1, dtype=np.int64)
         no, ng = len(me.owned[f]), len(me.ghost[f])
@@ -132,11 +138,17 @@ def partition_fespaces(fes: FESpaces, cell_part: np.ndarray, rank: int) -> Parti
         cell_dofs[f] = np.where(ids > 0, lut[np.where(ids > 0, ids, 0)], ids)
         nfree[f] = no + ng
         nowned[f] = no
-    lfes = FESpaces(mesh=lmesh, tables=fes.tables, cell_dofs=cell_dofs, nfree=nfree, ndir=dict(fes.ndir),
-                    dirichlet_values=fes.dirichlet_values, j_sign=fes.j_sign[me.cells], field_order=fes.field_order,
-                    u_node_coords=None if fes.u_node_coords is None else fes.u_node_coords[me.cells],
-                    cell_solid=None if fes.cell_solid is None else fes.cell_solid[me.cells],
-                    cell_sigma=None if fes.cell_sigma is None else fes.cell_sigma[me.cells])
+    if isinstance(fes, H1H1Spaces):
+        lfes = H1H1Spaces(mesh=lmesh, tables=fes.tables, cell_dofs=cell_dofs, nfree=nfree, ndir=dict(fes.ndir),
+                          dirichlet_values=fes.dirichlet_values, field_order=fes.field_order,
+                          cell_solid=None if fes.cell_solid is None else fes.cell_solid[me.cells],
+                          phi_node_coords=None if fes.phi_node_coords is None else fes.phi_node_coords[me.cells])
+    else:
+        lfes = FESpaces(mesh=lmesh, tables=fes.tables, cell_dofs=cell_dofs, nfree=nfree, ndir=dict(fes.ndir),
+                        dirichlet_values=fes.dirichlet_values, j_sign=fes.j_sign[me.cells], field_order=fes.field_order,
+                        u_node_coords=None if fes.u_node_coords is None else fes.u_node_coords[me.cells],
+                        cell_solid=None if fes.cell_solid is None else fes.cell_solid[me.cells],
+                        cell_sigma=None if fes.cell_sigma is None else fes.cell_sigma[me.cells])
     ps = PartitionedSpaces(fes=lfes, rank=rank, nparts=nparts, nowned=nowned, nowned_cells=me.nowned_cells, cells=me.cells,
                            own_global=me.owned, ghost_global=me.ghost)
     ps._global_offsets = fes.offsets
@@ -187,7 +199,7 @@ def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: i
     import ctypes as C
 
     from .. import lib as L
-    from ..feoperator import B200FEOperator
+    from ..feoperator import B200FEOperator, B200H1H1FEOperator
 
     cell_part = hunt_cell_partition(fes_global.mesh, np_xy)
     ps = partition_fespaces(fes_global, cell_part, rank)
@@ -205,7 +217,8 @@ def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: i
         dist.broadcast(idbuf, src=0)
         raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
         L.check(lib.mhd_comm_init(rank, world, raw))
-    op = B200FEOperator(ps.fes, params["fluid"], nowned=ps.nowned)
+    cls = B200H1H1FEOperator if isinstance(fes_global, H1H1Spaces) else B200FEOperator
+    op = cls(ps.fes, params["fluid"], nowned=ps.nowned)
     L.check(lib.mhd_operator_set_halo(op.handle, len(ps.neigh), L.ptr(ps.neigh), L.ptr(ps.send_ptr), L.ptr(ps.send_idx),
                                       L.ptr(ps.recv_ptr), L.ptr(ps.recv_idx)))
     if world > 1 and len(ps.neigh) > 0 and use_peer_memory:

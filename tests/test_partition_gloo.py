@@ -142,3 +142,54 @@ def test_halo_exchange_and_allreduce_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] == (True, True, True) and ret[1] == (True, True, True)
+
+
+def test_h1h1_spaces_partition_and_local_rows_reproduce_global_rows():
+    """the same decomposition for the H1-H1 spaces (u, p, continuous Q3 phi): every free dof owned once, the halo plans
+    of neighbours match, and the rows a rank assembles from its owned + ghost cells are the global rows"""
+    import scipy.sparse as sp
+
+    from oracle import mhd_oracle as O
+    from oracle import mhd_oracle_h1h1 as H
+
+    params = hunt_params(nc=(4, 3), B=(0.0, 20.0, 0.0), current_disc="H1")
+    fes = setup_spaces(params)
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    x = np.random.default_rng(0).random(fes.ndofs)
+    A = H.jacobian(fes, x, prm)
+    cell_part = hunt_cell_partition(fes.mesh, (2, 2))
+    parts = [partition_fespaces(fes, cell_part, r) for r in range(4)]
+    for f in ("u", "p", "phi"):
+        allown = np.concatenate([p.own_global[f] for p in parts])
+        assert len(allown) == fes.nfree[f] and len(np.unique(allown)) == fes.nfree[f]
+    for r, pr in enumerate(parts):
+        gr = pr.local_vector_ids()
+        for k, s in enumerate(pr.neigh):
+            ps = parts[s]
+            ks = list(ps.neigh).index(r)
+            sent = gr[pr.send_idx[pr.send_ptr[k] : pr.send_ptr[k + 1]]]
+            recv = ps.local_vector_ids()[ps.recv_idx[ps.recv_ptr[ks] : ps.recv_ptr[ks + 1]]]
+            assert np.array_equal(sent, recv)
+        assert len(np.unique(pr.recv_idx)) == pr.ncols - pr.nrows == len(pr.recv_idx)
+        # local assembly on the local spaces in the library layout [owned | ghosts]
+        lf = pr.fes
+        own_off, gh_off = pr.offsets()
+        cols = []
+        for f in ("u", "p", "phi"):
+            ids, no = lf.cell_dofs[f], pr.nowned[f]
+            cols.append(np.where(ids > 0, np.where(ids <= no, own_off[f] + ids - 1, gh_off[f] + ids - 1 - no), -1))
+        gids = np.concatenate(cols, axis=1)
+        xl = x[gr]
+        st = np.where(gids >= 0, xl[np.where(gids >= 0, gids, 0)], 0.0)
+        for f, (s0, s1) in zip(("u", "p", "phi"), ((0, 81), (81, 85), (85, 149))):
+            ids = lf.cell_dofs[f]
+            if len(lf.dirichlet_values[f]):
+                st[:, s0:s1] = np.where(ids < 0, lf.dirichlet_values[f][np.where(ids < 0, -ids - 1, 0)], st[:, s0:s1])
+        K = H.cell_jacobians(lf.tables, lf.mesh.cell_coords(), st, prm)
+        li, lj = np.nonzero(H.touched_mask())
+        rr, cc, vv = np.where(gids < pr.nrows, gids, -1)[:, li], gids[:, lj], K[:, li, lj]
+        ok = (rr >= 0) & (cc >= 0)
+        Al = sp.coo_matrix((vv[ok], (rr[ok], cc[ok])), shape=(pr.nrows, pr.ncols)).tocsr()
+        Aref = A[gr[: pr.nrows]][:, gr]
+        assert abs(Al - Aref).max() < 1e-12 * abs(Aref).max()
