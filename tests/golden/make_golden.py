@@ -30,5 +30,25 @@ def main():
     print("wrote", out, os.path.getsize(out), "bytes; nnz", A.nnz)
 
 
+def main_h1h1():
+    """H1-H1 formulation (oracle/mhd_oracle_h1h1.py): Hunt nc=(2,2), Ha=20, zeta_u=5, Newton convection."""
+    from oracle import mhd_oracle_h1h1 as H
+
+    params = hunt_params(nc=(2, 2), B=(0.0, 20.0, 0.0), zeta_u=5.0, current_disc="H1")
+    fes = setup_spaces(params)
+    fl = params["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, fl.g, fl.convection)
+    rng = np.random.default_rng(20261018)
+    x = rng.random(fes.ndofs)
+    v = rng.standard_normal(fes.ndofs)
+    A = H.jacobian(fes, x, prm)
+    r = H.residual(fes, x, prm)
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hunt_h1h1_nc2_ha20.npz")
+    np.savez_compressed(out, x=x, v=v, rowptr=A.indptr.astype(np.int64), colval=A.indices.astype(np.int32), nzval=A.data,
+                        residual=r, Av=A @ v, ndofs=np.array([fes.nfree[f] for f in ("u", "p", "phi")]))
+    print("wrote", out, os.path.getsize(out), "bytes; nnz", A.nnz)
+
+
 if __name__ == "__main__":
     main()
+    main_h1h1()

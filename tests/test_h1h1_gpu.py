@@ -214,3 +214,20 @@ def test_h1h1_hunt_driver_solves_on_the_device(mhdlib):
         sl = slice(o[f], o[f] + fes.nfree[f])
         assert relerr(out["x"][sl], xo[sl]) < 1e-5
     out["op"].destroy()
+
+
+def test_h1h1_golden_fixture(mhdlib):
+    """Committed golden vectors (tests/golden/make_golden.py::main_h1h1, generated with the oracle)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hunt_h1h1_nc2_ha20.npz"))
+    p = hunt_params(nc=(2, 2), B=(0.0, 20.0, 0.0), zeta_u=5.0, current_disc="H1")
+    fes = setup_spaces(p)
+    op = make_operator(fes, p["fluid"])
+    A = op.jacobian(g["x"])
+    rowptr, colval = A.pattern()
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(colval, g["colval"])
+    assert relerr(A.nzval(), g["nzval"]) < VAL_TOL
+    assert relerr(op.residual(g["x"]), g["residual"]) < VAL_TOL
+    assert relerr(op.spmv(g["v"]), g["Av"]) < VAL_TOL
+    op.destroy()

@@ -314,3 +314,25 @@ def test_entry_enumeration_exported_by_the_library_covers_the_touched_blocks_onc
     hit = np.zeros((149, 149), dtype=np.int64)
     np.add.at(hit, (order >> 8, order & 0xFF), 1)
     assert np.array_equal(hit, H.touched_mask().astype(np.int64))
+
+
+def test_golden_fixture_h1h1_oracle_and_emulated_device_code(emul):
+    """Committed golden vectors of the H1-H1 path (tests/golden/make_golden.py::main_h1h1): the oracle reproduces them, and
+    so does the device cell code run on the CPU, assembled with the oracle's scatter."""
+    g = np.load(os.path.join(HERE, "golden", "hunt_h1h1_nc2_ha20.npz"))
+    p = hunt_params(nc=(2, 2), B=(0.0, 20.0, 0.0), zeta_u=5.0, current_disc="H1")
+    fes = setup_spaces(p)
+    assert [fes.nfree[f] for f in ("u", "p", "phi")] == g["ndofs"].tolist()
+    prm = oracle_params(p["fluid"])
+    A = H.jacobian(fes, g["x"], prm)
+    assert np.array_equal(A.indptr, g["rowptr"]) and np.array_equal(A.indices, g["colval"])
+    assert np.abs(A.data - g["nzval"]).max() <= 1e-13 * np.abs(g["nzval"]).max()
+    assert np.abs(H.residual(fes, g["x"], prm) - g["residual"]).max() <= 1e-13 * np.abs(g["residual"]).max()
+    nbad, K, R = run_emul(emul, fes, g["x"], prm)
+    assert nbad == 0
+    gids = fes.cell_global_ids()
+    data = H._assemble(K, gids, fes.ndofs, (g["rowptr"], g["colval"].astype(np.int64)))
+    assert np.abs(data - g["nzval"]).max() <= 1e-12 * np.abs(g["nzval"]).max()
+    r = np.zeros(fes.ndofs)
+    np.add.at(r, gids[gids >= 0], R[gids >= 0])
+    assert np.abs(r - g["residual"]).max() <= 1e-12 * np.abs(g["residual"]).max()
