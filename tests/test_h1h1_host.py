@@ -336,3 +336,17 @@ def test_golden_fixture_h1h1_oracle_and_emulated_device_code(emul):
     r = np.zeros(fes.ndofs)
     np.add.at(r, gids[gids >= 0], R[gids >= 0])
     assert np.abs(r - g["residual"]).max() <= 1e-12 * np.abs(g["residual"]).max()
+
+
+def test_device_code_is_clean_under_address_sanitizer(tmp_path):
+    """h1h1_cell.h and patch_cell.h under -fsanitize=address,undefined (tests/emul/sanitize_main.cpp): no out-of-range index
+    into the cell's shared data for any template variant / thread count / patch size"""
+    exe = tmp_path / "sanitize_emul"
+    srcs = [os.path.join(HERE, "emul", f) for f in ("sanitize_main.cpp", "emul_h1h1.cpp", "emul_patch.cpp")]
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c++17", "-o", str(exe)] + srcs,
+                           capture_output=True, text=True)
+    if build.returncode != 0 and ("asan" in build.stderr or "ubsan" in build.stderr or "sanitize" in build.stderr):
+        pytest.skip("sanitizer runtime not installed: " + build.stderr[-200:])
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "bad=0" in run.stdout, run.stdout + run.stderr
