@@ -89,6 +89,28 @@ function B200FEOperator(U, V, params; tables, mesh, layout, fluid)
 end
 destroy!(op::B200FEOperator) = (ccall((:mhd_operator_destroy, libmhd), Cint, (Ptr{Cvoid},), op.handle); op.handle = C_NULL)
 
+# ---- H1-H1 formulation (params[:fespaces][:current_disc] = :H1 => U = (U_u,U_p,U_φ), src/fespaces.jl:32-41;
+#      weak_form_h1_h1, src/weakforms.jl:344-355).  Same operator type and methods; only the creation call differs.
+struct MhdTablesH1H1
+  nq::Int32; w::Ptr{Float64}; geo_grad::Ptr{Float64}; u_val::Ptr{Float64}; u_grad::Ptr{Float64}
+  p_val::Ptr{Float64}; phi_grad::Ptr{Float64}     # phi_grad: ∇(shape functions of reffe_φ = LagrangianRefFE(Float64,HEX,3)) at the points
+end
+struct MhdLayoutH1H1
+  cell_dofs::NTuple{3,Ptr{Int32}}                  # get_cell_dof_ids of V_u, V_p, V_φ
+  nfree::NTuple{3,Int64}; nowned::NTuple{3,Int64}; ndir::NTuple{3,Int64}
+  dir_values::NTuple{3,Ptr{Float64}}; field_order::NTuple{3,Int32}
+end
+function B200H1H1FEOperator(U, V, params; tables::MhdTablesH1H1, mesh::MhdMesh, layout::MhdLayoutH1H1, fluid::MhdParams)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  @check ccall((:mhd_h1h1_operator_create, libmhd), Cint,
+               (Ref{MhdMesh}, Ref{MhdTablesH1H1}, Ref{MhdLayoutH1H1}, Ref{MhdParams}, Ref{Ptr{Cvoid}}), mesh, tables, layout, fluid, h)
+  nr = Ref{Int64}(0); nc = Ref{Int64}(0); nnz = Ref{Int64}(0)
+  @check ccall((:mhd_operator_symbolic, libmhd), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h[], nr, nc, nnz)
+  rowptr = Vector{Int64}(undef, nr[] + 1); colval = Vector{Int64}(undef, nnz[])
+  @check ccall((:mhd_operator_get_csr, libmhd), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint, Cint), h[], rowptr, colval, 8, 0)
+  B200FEOperator(U, V, h[], nr[], nnz[], rowptr, colval)
+end
+
 # Gridap NonlinearOperator API used by solve!(xh,solver,op) (src/main.jl:275) and by main.jl:158,163
 function Algebra.allocate_residual(op::B200FEOperator, x::AbstractVector)
   zeros(Float64, op.nrows)
