@@ -613,7 +613,10 @@ int mhd_solver_set_phi_patches(mhd_solver_t* s, int64_t npatch, const int64_t* p
   patch_destroy(s->patches_phi);
   s->patches_phi = nullptr;
   s->setup_done = false;
-  for (int64_t i = 0; patch_ptr && patch_dofs && i < patch_ptr[npatch > 0 ? npatch : 0]; i++)
+  MHD_CHECK(npatch > 0 && patch_ptr != nullptr, MHD_E_INVALID, "mhd_solver_set_phi_patches: bad arguments");
+  const int64_t ndofs = patch_ptr[npatch];
+  MHD_CHECK(ndofs == 0 || patch_dofs != nullptr, MHD_E_INVALID, "mhd_solver_set_phi_patches: null dof list");
+  for (int64_t i = 0; i < ndofs; i++)
     MHD_CHECK(patch_dofs[i] >= s->off_phi, MHD_E_INVALID, "phi patches: dof %d is not a phi row (rows start at %lld)", patch_dofs[i],
               (long long)s->off_phi);
   return patch_create(&s->patches_phi, s->op->nrows, npatch, patch_ptr, patch_dofs);
