@@ -1,5 +1,6 @@
 // C ABI entry points of libmhdb200.so (see include/mhdb200.h for the contract of each function).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -491,7 +492,7 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   const double* dx;
   if (op->formulation == FORM_H1H1) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(h1h1_launch_jacobian(op, dx));
+    MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
   } else {
     MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
@@ -509,10 +510,21 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
   const double* dx;
   const bool dev_out = is_device_ptr(r_out);
   double* dr = dev_out ? r_out : op->d_y;
-  if (op->formulation == FORM_H1H1) {  // two launches (no fused variant yet)
+  if (op->formulation == FORM_H1H1) {
+    // two launches by default; MHD_H1H1_FUSED=1 selects the fused kernel (shared preparation), which is verified on the CPU
+    // emulation but has not been timed on a B200 yet
+    static int fused = -1;
+    if (fused < 0) {
+      const char* e = getenv("MHD_H1H1_FUSED");
+      fused = e ? atoi(e) : 0;
+    }
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(h1h1_launch_residual(op, dx, dr));
-    MHD_TRY(h1h1_launch_jacobian(op, dx));
+    if (fused) {
+      MHD_TRY(h1h1_launch_jacobian(op, dx, dr));
+    } else {
+      MHD_TRY(h1h1_launch_residual(op, dx, dr));
+      MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
+    }
   } else {
     MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));

@@ -246,7 +246,7 @@ int begin_clear(mhd_operator* op, double* d_r /* nullable */);  // optional: sta
 void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // h1h1.cu
-int h1h1_launch_jacobian(mhd_operator* op, const double* d_x);
+int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // patch.cu: vertex-patch block-Jacobi smoother of the (u,j) block
 struct PatchData;

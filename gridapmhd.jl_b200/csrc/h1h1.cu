@@ -51,10 +51,12 @@ struct DevAdd {
   }
 };
 
-template <int CONV, bool ZU>
+// RES: also assemble the residual (residual_and_jacobian!): the preparation phases are shared, the residual adds three
+// short phases after the entries.  Enabled with MHD_H1H1_FUSED=1 until it has been measured on a B200 (next round).
+template <int CONV, bool ZU, bool RES>
 __global__ void __launch_bounds__(H1_NT, 2)
-h1h1_jacobian_kernel(int64_t ncells, H1Args A, const double* __restrict__ x, const uint16_t* __restrict__ map,
-                     double* __restrict__ nzval, h1::Params P) {
+h1h1_jacobian_kernel(int64_t ncells, int64_t nrows, H1Args A, const double* __restrict__ x, const uint16_t* __restrict__ map,
+                     double* __restrict__ nzval, double* __restrict__ r, h1::Params P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   h1::Shared& S = *reinterpret_cast<h1::Shared*>(smem_raw);
   const int tid = threadIdx.x;
@@ -66,7 +68,7 @@ h1h1_jacobian_kernel(int64_t ncells, H1Args A, const double* __restrict__ x, con
     __syncthreads();
     h1::phase_gradients(S, tid, H1_NT, A.tab);
     __syncthreads();
-    if (CONV != 0) {
+    if (CONV != 0 || RES) {
       h1::phase_point_values(S, tid, H1_NT);
       __syncthreads();
     }
@@ -78,7 +80,16 @@ h1h1_jacobian_kernel(int64_t ncells, H1Args A, const double* __restrict__ x, con
     }
     DevStore store{map + cell * h1::NENT_PAD, nzval, S.rowstart};
     h1::phase_jac_entries<CONV, ZU>(S, tid, H1_NT, P, store);
-    __syncthreads();  // the next cell overwrites the shared data
+    __syncthreads();  // the next cell (or the residual phases) overwrite the shared data
+    if (RES) {
+      h1::phase_res_points<ZU>(S, tid, H1_NT);
+      __syncthreads();
+      h1::phase_res_coefficients<(CONV != 0 ? 1 : 0), ZU>(S, tid, H1_NT, P);
+      __syncthreads();
+      DevAdd add{S.gid, r, nrows};
+      h1::phase_res_rows(S, tid, H1_NT, add);
+      __syncthreads();
+    }
   }
 }
 
@@ -140,23 +151,27 @@ int opt_in_smem(K kernel) {
 
 }  // namespace
 
-int h1h1_launch_jacobian(mhd_operator* op, const double* d_x) {
+int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), g_stream));
+  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
   const h1::Params P = make_params(op->prm);
   const unsigned grid = persistent_grid(op->ncells);
   const size_t smem = sizeof(h1::Shared);
   const int conv = op->prm.convection;
   const bool zu = op->prm.zeta_u != 0.0;
-#define JK(C, Z)                                                                                                  \
+#define JKR(C, Z, R)                                                                                              \
   do {                                                                                                            \
-    MHD_TRY(opt_in_smem(h1h1_jacobian_kernel<C, Z>));                                                             \
-    h1h1_jacobian_kernel<C, Z><<<grid, H1_NT, smem, g_stream>>>(op->ncells, make_args(op), d_x, op->d_map, op->d_nzval, P); \
+    MHD_TRY(opt_in_smem(h1h1_jacobian_kernel<C, Z, R>));                                                          \
+    h1h1_jacobian_kernel<C, Z, R><<<grid, H1_NT, smem, g_stream>>>(op->ncells, op->nrows, make_args(op), d_x, op->d_map, \
+                                                                   op->d_nzval, d_r, P);                          \
   } while (0)
+#define JK(C, Z) do { if (d_r) JKR(C, Z, true); else JKR(C, Z, false); } while (0)
   prof_begin(PROF_JAC);
   if (conv == 0) { if (zu) JK(0, true); else JK(0, false); }
   else if (conv == 1) { if (zu) JK(1, true); else JK(1, false); }
   else { if (zu) JK(2, true); else JK(2, false); }
 #undef JK
+#undef JKR
   prof_end(PROF_JAC);
   MHD_LAUNCH_CHECK();
   return 0;

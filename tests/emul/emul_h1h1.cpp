@@ -33,16 +33,23 @@ struct HostAdd {
   void operator()(int li, double v) { R[li] += v; }
 };
 
+// fused = the phase sequence of h1h1_jacobian_kernel<CONV, ZU, RES = true>: Jacobian phases, then the residual phases on the
+// same cell data (no reload)
 template <int CONV, bool ZU>
-void jac_cell(Shared& S, int nt, const Params& P, HostStore& st, const double* tab) {
+void jac_cell(Shared& S, int nt, const Params& P, HostStore& st, const double* tab, bool fused = false, HostAdd* add = nullptr) {
   FOR_T phase_geometry(S, t, nt, tab);
   FOR_T phase_gradients(S, t, nt, tab);
-  if (CONV != 0)
+  if (CONV != 0 || fused)
     FOR_T phase_point_values(S, t, nt);
   FOR_T phase_jac_coefficients<CONV, ZU>(S, t, nt, P);
   if (ZU)
     FOR_T phase_jac_projection(S, t, nt);
   FOR_T phase_jac_entries<CONV, ZU>(S, t, nt, P, st);
+  if (fused) {
+    FOR_T phase_res_points<ZU>(S, t, nt);
+    FOR_T phase_res_coefficients<(CONV != 0 ? 1 : 0), ZU>(S, t, nt, P);
+    FOR_T phase_res_rows(S, t, nt, *add);
+  }
 }
 
 template <int CONV, bool ZU>
@@ -64,7 +71,8 @@ long long emul_h1h1_cells(long long ncells, const double* coords, const int* cel
                           const double* x, const double* w, const double* geo_grad, const double* u_val, const double* u_grad,
                           const double* p_val, const double* phi_grad, const double* prm, int conv, int nt, int reverse,
                           double* K_out, double* R_out) {
-  g_reverse = reverse != 0;
+  const bool fused = (reverse & 2) != 0;  // bit 1 of `reverse`: fused residual + Jacobian sequence (needs K_out and R_out)
+  g_reverse = (reverse & 1) != 0;
   std::vector<double> T(T_TOTAL);
   pack_tables(w, geo_grad, u_val, u_grad, p_val, phi_grad, T.data());
   Params P;
@@ -80,12 +88,14 @@ long long emul_h1h1_cells(long long ncells, const double* coords, const int* cel
     if (K_out) {
       std::fill(hit.begin(), hit.end(), 0);
       HostStore st{K_out + c * NLOC * NLOC, &nbad, hit.data()};
-      if (conv == 0) { if (zu) jac_cell<0, true>(*S, nt, P, st, T.data()); else jac_cell<0, false>(*S, nt, P, st, T.data()); }
-      else if (conv == 1) { if (zu) jac_cell<1, true>(*S, nt, P, st, T.data()); else jac_cell<1, false>(*S, nt, P, st, T.data()); }
-      else { if (zu) jac_cell<2, true>(*S, nt, P, st, T.data()); else jac_cell<2, false>(*S, nt, P, st, T.data()); }
+      HostAdd fadd{R_out ? R_out + c * NLOC : nullptr};
+      const bool f = fused && R_out;
+      if (conv == 0) { if (zu) jac_cell<0, true>(*S, nt, P, st, T.data(), f, &fadd); else jac_cell<0, false>(*S, nt, P, st, T.data(), f, &fadd); }
+      else if (conv == 1) { if (zu) jac_cell<1, true>(*S, nt, P, st, T.data(), f, &fadd); else jac_cell<1, false>(*S, nt, P, st, T.data(), f, &fadd); }
+      else { if (zu) jac_cell<2, true>(*S, nt, P, st, T.data(), f, &fadd); else jac_cell<2, false>(*S, nt, P, st, T.data(), f, &fadd); }
       for (int e = 0; e < NENT; e++) nbad += hit[e] != 1;
     }
-    if (R_out) {
+    if (R_out && !(fused && K_out)) {
       if (K_out) {
         memset(S, 0xFF, sizeof(Shared));
         FOR_T phase_load(*S, t, nt, coords, cell_nodes + c * 8, gids + c * NLOC, nullptr, dir, x, T.data());

@@ -287,6 +287,11 @@ def test_device_cell_code_matches_the_oracle(emul, small_case, conv, zu):
                     (slice(0, 81), slice(85, 149)), (slice(85, 149), slice(0, 81)), (slice(85, 149), slice(85, 149))):
             assert np.abs(K[:, blk[0], blk[1]] - Ko[:, blk[0], blk[1]]).max() <= 1e-13 * np.abs(Ko[:, blk[0], blk[1]]).max()
         assert np.abs(R - Ro).max() <= 1e-13 * np.abs(Ro).max()
+    # the fused residual + Jacobian phase sequence (h1h1_jacobian_kernel<.,.,RES=true>, MHD_H1H1_FUSED=1): same results
+    for rev in (2, 3):
+        nbad, K, R = run_emul(emul, fes, x, prm, nt=256, reverse=rev)
+        assert nbad == 0 and np.isfinite(K).all() and np.isfinite(R).all()
+        assert np.abs(K - Ko).max() <= 1e-13 * np.abs(Ko).max() and np.abs(R - Ro).max() <= 1e-13 * np.abs(Ro).max()
 
 
 def test_device_cell_code_on_nonaffine_cells_with_dirichlet_data(emul):
