@@ -257,3 +257,13 @@ def test_gmsh_reader_on_the_reference_expansion_mesh():
     eps = 1e-6
     fd = (O.residual(fes, x + eps * d, prm) - O.residual(fes, x - eps * d, prm)) / (2 * eps)
     assert np.abs(fd - A @ d).max() / np.abs(A @ d).max() < 1e-6
+
+
+def test_sum_factorised_uu_block_matches_the_oracle():
+    """design study for the next Jacobian kernel: the uu block by sum factorisation = the oracle's dense block"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("sumfac", os.path.join(ROOT, "tools_sumfac_study.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()  # asserts < 1e-12
