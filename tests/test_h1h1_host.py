@@ -355,3 +355,28 @@ def test_device_code_is_clean_under_address_sanitizer(tmp_path):
     assert build.returncode == 0, build.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and "bad=0" in run.stdout, run.stdout + run.stderr
+
+
+REF_MESH = "/root/reference/meshes/Expansion_710.msh"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MESH), reason="reference checkout not present (GPU box)")
+def test_h1h1_spaces_on_the_reference_gmsh_expansion_mesh(emul):
+    """the reference's own Gmsh fixture (240 graded hexes, Gmsh vertex order permuted by the reader): the Q3 space is
+    continuous on it, the oracle Jacobian is the derivative of the residual, and the device cell code agrees with the oracle"""
+    from gridapmhd_jl_b200.applications import u_inlet_parabolic
+
+    m = M.read_gmsh41(REF_MESH)
+    fes = setup_fe_spaces_h1h1(m, u_tags=("inlet", "wall"), u_values=(u_inlet_parabolic(), None), phi_tags=("outlet",))
+    _check_continuity(fes)
+    assert fes.ndir["phi"] > 0 and fes.ndir["u"] > 0
+    prm = O.FluidParams(alpha=1.0 / 5.0, beta=1.0 / 100.0, gamma=1.0, B=(0.0, 1.0, 0.0), convection="newton")
+    rng = np.random.default_rng(0)
+    x, d = rng.random(fes.ndofs), rng.standard_normal(fes.ndofs)
+    A = H.jacobian(fes, x, prm)
+    eps = 1e-6
+    fd = (H.residual(fes, x + eps * d, prm) - H.residual(fes, x - eps * d, prm)) / (2 * eps)
+    assert np.abs(fd - A @ d).max() / np.abs(A @ d).max() < 1e-7
+    Ko = H.cell_jacobians(fes.tables, m.cell_coords(), fes.cell_state(x), prm)
+    nbad, K, R = run_emul(emul, fes, x, prm, res=False)
+    assert nbad == 0 and np.abs(K - Ko).max() <= 1e-12 * np.abs(Ko).max()
