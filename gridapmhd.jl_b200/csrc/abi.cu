@@ -389,6 +389,7 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_cell_sigma);
   cudaFree(op->d_dir);
   cudaFree(op->d_tables);
+  cudaFree(op->d_sftab);
   cudaFree(op->d_rowptr);
   cudaFree(op->d_colval);
   cudaFree(op->d_nzval);
@@ -493,6 +494,9 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   if (op->formulation == FORM_H1H1) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
+  } else if (op->jac_version == 6) {
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(v6_launch_jacobian(op, dx));
   } else {
     MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
@@ -525,6 +529,10 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
       MHD_TRY(h1h1_launch_residual(op, dx, dr));
       MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
     }
+  } else if (op->jac_version == 6) {  // v6 has no fused residual: the residual kernel of assembly.cu + the v6 Jacobian
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(launch_residual(op, dx, dr));
+    MHD_TRY(v6_launch_jacobian(op, dx));
   } else {
     MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));

@@ -60,6 +60,7 @@ int pack_tables(mhd_operator* op, const mhd_tables_t* t) {
   MHD_TRY(dev_alloc(&op->d_tables, T_TOTAL));
   MHD_TRY(h2d(op->d_tables, h.data(), T_TOTAL));
   MHD_CUDA(cudaStreamSynchronize(g_stream));
+  op->h_tables = h;  // kept for mhd_operator_set_tensor_structure (hdiv_v6.cu)
   return 0;
 }
 

@@ -133,6 +133,9 @@ constexpr int FORM_H1H1 = 1;  // H1-H1 (u,p,phi), 149 local dofs: h1h1.cu (field
 
 struct mhd_operator {
   int formulation = mhd::FORM_HDIV;
+  int jac_version = 5;             // 5: tensor-core panel products (assembly.cu); 6: structure-exploiting kernel (hdiv_v6.cu, opt-in)
+  void* d_sftab = nullptr;         // v6: 1-D factors of the velocity tables (sf::Tables)
+  std::vector<double> h_tables;    // host copy of the packed reference tables (T_* layout)
   int64_t ncells = 0, nnodes = 0;
   int64_t nfree[4] = {0, 0, 0, 0}, nowned[4] = {0, 0, 0, 0}, ndir[4] = {0, 0, 0, 0};
   int32_t field_order[4] = {0, 1, 2, 3};
@@ -245,6 +248,9 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable
 int begin_clear(mhd_operator* op, double* d_r /* nullable */);  // optional: start clearing before the state is copied in
 void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
+// hdiv_v6.cu
+void v6_entry_order(std::vector<uint16_t>& ord);
+int v6_launch_jacobian(mhd_operator* op, const double* d_x);
 // h1h1.cu
 int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);

@@ -16,6 +16,7 @@ marshals arrays (numpy or torch) across the C ABI.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -140,6 +141,12 @@ class B200FEOperator:
         L.check(lib.mhd_operator_create(C.byref(mesh), C.byref(tab), C.byref(lay), C.byref(prm), C.byref(h)))
         self.handle = h
         self._keep = []
+        if os.environ.get("MHD_JAC_V6"):
+            # opt-in sum-factorised Jacobian kernel (hdiv_v6.cu): hand over the tensor structure of the Q2 node numbering
+            from .host.reffe import Q2_NODE_IJK
+
+            ijk = np.ascontiguousarray(Q2_NODE_IJK, dtype=np.int8)
+            L.check(lib.mhd_operator_set_tensor_structure(h, L.ptr(ijk)))
         self.nrows = self.ncols = self.nnz = None
         self._A = None
 

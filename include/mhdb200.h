@@ -137,6 +137,13 @@ int mhd_operator_create(const mhd_mesh_t*, const mhd_tables_t*, const mhd_layout
 int mhd_operator_destroy(mhd_operator_t*);
 int mhd_operator_set_params(mhd_operator_t*, const mhd_params_t*); /* continuation: src/main.jl:243-260 */
 
+/* Optional, before mhd_operator_symbolic: tell the library that the velocity basis and the quadrature are tensor products.
+ * node_ijk[27*3]: (i,j,k) in {0,1,2}^3 of every local velocity node in the order of the tables (what
+ * get_node_coordinates(reffe_u) gives the host).  The library derives the 1-D factors from the tables, checks the product
+ * structure (MHD_E_INVALID otherwise) and may then use the sum-factorised Jacobian kernel (opt-in: MHD_JAC_V6=1 in the
+ * environment of this call; the default kernel does not need the information). */
+int mhd_operator_set_tensor_structure(mhd_operator_t*, const int8_t* node_ijk);
+
 /* Ghost exchange plan of the operator's vectors (PartitionedArrays consistent!/PVector):
  * for neighbour k: send x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned local ids, 0-based) and receive into
  * local ids recv_idx[recv_ptr[k]..) (ghost ids). */
