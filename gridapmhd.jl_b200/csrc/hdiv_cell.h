@@ -271,10 +271,10 @@ MHD_6HD void phase_projection(Shared& S, int tid, int nt) {
 // job list (slots padded to whole warps):
 //   [0,736)     uu   729 pairs (a,b): third contraction of the sum factorisation, 9 entries each (+ zeta_u D' E)
 //   [736,832)   uj   81 jobs: 3 x 4 (a,m) tiles x 3 components -> uj and ju      (a in {3ta..3ta+2}, m in {tm + 9i})
-//   [832,896)   jj   45 jobs: 4 x 4 tiles of the upper triangle, mirrored            (m in {tm+9i}, n in {tn+9j}, tm <= tn)
-//   [896,1184)  jphi 288 (m,l) pairs -> j-phi and phi-j
-//   [1184,1508) up   324 (c,a,k) -> up and pu
-constexpr int JOB_UU = 0, JOB_UJ = 736, JOB_JJ = 832, JOB_JF = 896, JOB_UP = 1184, JOB_END = 1508;
+//   [832,928)   jj   78 jobs: 3 x 3 tiles of the upper triangle, mirrored            (m in {tm+12i}, n in {tn+12j}, tm <= tn)
+//   [928,1216)  jphi 288 (m,l) pairs -> j-phi and phi-j
+//   [1216,1540) up   324 (c,a,k) -> up and pu
+constexpr int JOB_UU = 0, JOB_UJ = 736, JOB_JJ = 832, JOB_JF = 928, JOB_UP = 1216, JOB_END = 1540;
 
 template <bool ZU, class Store>
 MHD_6HD void job_uu(const Shared& S, const sf::Tables& T, int ab, const Params& P, Store& store) {
@@ -342,52 +342,54 @@ MHD_6HD void job_uj(const Shared& S, int job, const Params& P, Store& store) {
     }
 }
 
+// jj: 3 x 3 tiles of the upper triangle (m in {tm, tm+12, tm+24}, n in {tn, tn+12, tn+24}, tm <= tn < 12): 78 jobs.
+// (4 x 4 tiles would need fewer operand loads but leave only 45 threads on the longest jobs of the cell.)
 template <bool ZJ, class Store>
 MHD_6HD void job_jj(const Shared& S, int job, const Params& P, Store& store) {
   int tm = 0, r = job;
-  while (r >= 9 - tm) {
-    r -= 9 - tm;
+  while (r >= 12 - tm) {
+    r -= 12 - tm;
     tm++;
   }
   const int tn = tm + r;
-  double acc[4][4];
+  double acc[3][3];
   MHD_6UNROLL
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 3; i++)
     MHD_6UNROLL
-    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int j = 0; j < 3; j++) acc[i][j] = 0.0;
   for (int q = 0; q < NQ; q++) {
     const double w = S.wdet[q];
     MHD_6UNROLL
     for (int k = 0; k < 3; k++) {
-      double gm[4], gn[4];
+      double gm[3], gn[3];
       MHD_6UNROLL
-      for (int i = 0; i < 4; i++) {
-        gm[i] = w * S.Psi[q][k][tm + 9 * i];
-        gn[i] = S.Psi[q][k][tn + 9 * i];
+      for (int i = 0; i < 3; i++) {
+        gm[i] = w * S.Psi[q][k][tm + 12 * i];
+        gn[i] = S.Psi[q][k][tn + 12 * i];
       }
       MHD_6UNROLL
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 3; i++)
         MHD_6UNROLL
-        for (int j = 0; j < 4; j++) acc[i][j] += gm[i] * gn[j];
+        for (int j = 0; j < 3; j++) acc[i][j] += gm[i] * gn[j];
     }
     if (ZJ) {  // zeta_j div dj div s
-      double gm[4], gn[4];
+      double gm[3], gn[3];
       MHD_6UNROLL
-      for (int i = 0; i < 4; i++) {
-        gm[i] = w * P.zeta_j * S.Dv[q][tm + 9 * i];
-        gn[i] = S.Dv[q][tn + 9 * i];
+      for (int i = 0; i < 3; i++) {
+        gm[i] = w * P.zeta_j * S.Dv[q][tm + 12 * i];
+        gn[i] = S.Dv[q][tn + 12 * i];
       }
       MHD_6UNROLL
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < 3; i++)
         MHD_6UNROLL
-        for (int j = 0; j < 4; j++) acc[i][j] += gm[i] * gn[j];
+        for (int j = 0; j < 3; j++) acc[i][j] += gm[i] * gn[j];
     }
   }
   MHD_6UNROLL
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 3; i++)
     MHD_6UNROLL
-    for (int j = 0; j < 4; j++) {
-      const int m = tm + 9 * i, n = tn + 9 * j;
+    for (int j = 0; j < 3; j++) {
+      const int m = tm + 12 * i, n = tn + 12 * j;
       store(SEC_JJ + m * NJ + n, OFF_J + m, OFF_J + n, acc[i][j]);
       if (tm != tn) store(SEC_JJ + n * NJ + m, OFF_J + n, OFF_J + m, acc[i][j]);
     }
@@ -401,7 +403,7 @@ MHD_6HD void phase_entries(const Shared& S, const sf::Tables& T, int tid, int nt
     } else if (slot < JOB_JJ) {
       if (slot - JOB_UJ < 81) job_uj(S, slot - JOB_UJ, P, store);
     } else if (slot < JOB_JF) {
-      if (slot - JOB_JJ < 45) job_jj<ZJ>(S, slot - JOB_JJ, P, store);
+      if (slot - JOB_JJ < 78) job_jj<ZJ>(S, slot - JOB_JJ, P, store);
     } else if (slot < JOB_UP) {
       // j-phi: -sigma dphi div s ; phi-j: -(+ on solid cells) div dj w
       const int idx = slot - JOB_JF, m = idx / NF, l = idx % NF;
