@@ -430,7 +430,8 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": "Mcells/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * op.ncols,
                 "d2h_bytes_per_step": 8 * op.nrows},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "jacobian_kernel<CONV=newton,RES=1> (fused residual_and_jacobian!)", "bound": "hbm", "achieved": jac_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"kernel": ("hdiv_v6_jacobian_kernel<newton> (opt-in MHD_JAC_V6=1; residual in its own launch)" if os.environ.get("MHD_JAC_V6")
+                                else "jacobian_kernel<CONV=newton,RES=1> (fused residual_and_jacobian!)"), "bound": "hbm", "achieved": jac_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": jac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": jac_kernel_ms,
                      "algorithmic_bytes": jac_bytes, "jacobian_only_Mcells_s": ncells_local / (jac_kernel_ms * 1e-3) / 1e6,
                      # second roofline of the same kernel: FP64 work.  Algorithmic count of DESIGN.md 4.2
