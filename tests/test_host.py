@@ -263,7 +263,7 @@ def test_sum_factorised_uu_block_matches_the_oracle():
     """design study for the next Jacobian kernel: the uu block by sum factorisation = the oracle's dense block"""
     import importlib.util
 
-    spec = importlib.util.spec_from_file_location("sumfac", os.path.join(ROOT, "tools_sumfac_study.py"))
+    spec = importlib.util.spec_from_file_location("sumfac", os.path.join(ROOT, "tools", "sumfac_study.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.main()  # asserts < 1e-12

@@ -8,7 +8,8 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, ".")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gridapmhd_jl_b200  # noqa: E402,F401
 from gridapmhd_jl_b200 import lib as L  # noqa: E402
 from gridapmhd_jl_b200.applications import hunt_params, make_operator, setup_spaces  # noqa: E402
