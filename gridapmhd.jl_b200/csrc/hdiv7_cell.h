@@ -1,0 +1,687 @@
+// "v7" Jacobian of the H1-HDiv formulation: jac_fluid_h1_hdiv / jac_solid_h1_hdiv (src/weakforms.jl:283-312, :327-338) with
+// EVERY block evaluated by sum factorisation, written as barrier-separated PHASES of a cooperative thread array so that
+// tests/emul/emul_hdiv7.cpp runs the same code on the CPU against the oracle (forward / reverse thread order, NaN-filled data).
+//
+// With tensor-product bases on the tensor Gauss rule (hdiv7_tables.h) every block is a sum of terms
+//     K[a][b] = sum_q F(q) a(q) b(q),   a = a_0(q_d0) a_1(q_d1) a_2(q_d2),  b likewise,  F a per-cell coefficient field,
+// contracted one direction at a time:  T1[(a2,b2)][q_d0,q_d1] -> T2[(a1,b1)][(a2,b2)][q_d0] -> K.   Per fluid cell ~0.13 M FMA
+// instead of 0.43 M (panel products of assembly.cu) and operands of a few hundred bytes instead of 27 x 27 panels:
+//   uu   21 fields (9 Newton alpha w d_d u_c | 9 stiffness beta w Jinv Jinv^T | 3 convection), merged into 9 + 4 arrays at stage 2
+//   uj   9 fields E_ck = w/det (J[c+1][k] B[c+2] - J[c+2][k] B[c+1]) (Piola map and cross product folded into the field),
+//        K_uj = -gamma sgn V, K_ju = +sigma sgn V^T from the same V
+//   jj   6 fields w/det^2 (J^T J)_kk' over the symmetric half + 1 field zeta_j w/det^2 (div-div)
+//   jphi 1 field w/det ;  up: 36 fields w pi_k Jinv[k'][c] contracted with one basis function (the result D also feeds the
+//        zeta_u projection term zeta_u D^T Mp^-1 D)
+// The values are staged in shared memory in DESTINATION order (permuted local numbering of assembly.cu: every field sorted by
+// global id) chunk by chunk -- uu rows of component 0 | 1 | 2, uj, ju, the rest -- and swept out 32 consecutive map entries per
+// instruction while the next chunk is being computed (two staging buffers).
+#pragma once
+#include <stdint.h>
+
+#include "hdiv7_tables.h"
+
+#ifdef __CUDACC__
+#define MHD_7HD __host__ __device__ __forceinline__
+#define MHD_7UNROLL _Pragma("unroll")
+#else
+#define MHD_7HD inline
+#define MHD_7UNROLL
+#endif
+
+namespace mhd {
+namespace h7 {
+
+constexpr int NU = 81, NP = 4, NJ = 36, NF = 8;
+constexpr int OFF_P = 81, OFF_J = 85, OFF_F = 121, NLOC = 129;
+
+// ---- enumeration of the touched entries = order of this kernel's u16 scatter map (chunks padded to multiples of 32)
+constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
+constexpr int CH_UU = 27 * 81, CH_UU_PAD = pad32(CH_UU);         // rows (c, slot) x cols (slot, d), one chunk per row component c
+constexpr int CH_UJ = 81 * 36, CH_UJ_PAD = pad32(CH_UJ);
+constexpr int E_UU = 0, E_UJ = 3 * CH_UU_PAD, E_JU = E_UJ + CH_UJ_PAD, E_REST = E_JU + CH_UJ_PAD;
+constexpr int R_JJ = 0, R_JF = R_JJ + NJ * NJ, R_FJ = R_JF + NJ * NF, R_UP = R_FJ + NF * NJ, R_PU = R_UP + NU * NP, CH_REST = R_PU + NP * NU;
+constexpr int NENT = E_REST + pad32(CH_REST);  // 15 040 codes per cell, 14 913 of them entries
+constexpr int BUF = CH_UJ_PAD;                 // doubles per staging buffer
+
+// (row slot, col slot) of map entry e in the permuted local numbering (u: c*27 + slot | p | j: 85 + slot | phi); false: padding
+inline bool entry_rowcol(int e, int* li, int* lj) {
+  auto ucol = [](int col) { return (col % 3) * 27 + col / 3; };
+  if (e < E_UJ) {
+    const int c = e / CH_UU_PAD, i = e % CH_UU_PAD;
+    if (i >= CH_UU) return false;
+    *li = c * 27 + i / 81;
+    *lj = ucol(i % 81);
+  } else if (e < E_JU) {
+    const int i = e - E_UJ;
+    if (i >= CH_UJ) return false;
+    *li = i / 36;
+    *lj = OFF_J + i % 36;
+  } else if (e < E_REST) {
+    const int i = e - E_JU;
+    if (i >= CH_UJ) return false;
+    *li = OFF_J + i / 81;
+    *lj = ucol(i % 81);
+  } else {
+    const int i = e - E_REST;
+    if (i >= CH_REST) return false;
+    if (i < R_JF) { *li = OFF_J + i / 36; *lj = OFF_J + i % 36; }
+    else if (i < R_FJ) { *li = OFF_J + (i - R_JF) / 8; *lj = OFF_F + (i - R_JF) % 8; }
+    else if (i < R_UP) { *li = OFF_F + (i - R_FJ) / 36; *lj = OFF_J + (i - R_FJ) % 36; }
+    else if (i < R_PU) { *li = (i - R_UP) / 4; *lj = OFF_P + (i - R_UP) % 4; }
+    else { *li = OFF_P + (i - R_PU) / 81; *lj = ucol((i - R_PU) % 81); }
+  }
+  return true;
+}
+
+struct Params {
+  double alpha, beta, gamma, sigma, zeta_u, zeta_j;
+  double B[3];
+};
+
+// small cell-independent tables kept in shared memory (copied once per CTA from Tab7)
+struct Small7 {
+  double LV[3][3][3], LD[3][3][3];
+  double RV[3][3][3][3], RD[3][3][3];
+  double XV[3][2][3];
+  double Puu[3][4][9][3];
+  double Puj[3][9][3];
+  double pp[27][4];
+  uint8_t node_t[27], jdof_t[36], t_phi[8], pad_[1];
+};
+MHD_7HD void small_from_tab(Small7& s, const Tab7& T, int tid, int nt) {
+  for (int i = tid; i < 27; i += nt) { (&s.LV[0][0][0])[i] = (&T.LV[0][0][0])[i]; (&s.LD[0][0][0])[i] = (&T.LD[0][0][0])[i]; (&s.RD[0][0][0])[i] = (&T.RD[0][0][0])[i]; }
+  for (int i = tid; i < 81; i += nt) { (&s.RV[0][0][0][0])[i] = (&T.RV[0][0][0][0])[i]; (&s.Puj[0][0][0])[i] = (&T.Puj[0][0][0])[i]; }
+  for (int i = tid; i < 18; i += nt) (&s.XV[0][0][0])[i] = (&T.XV[0][0][0])[i];
+  for (int i = tid; i < 324; i += nt) (&s.Puu[0][0][0][0])[i] = (&T.Puu[0][0][0][0])[i];
+  for (int i = tid; i < 108; i += nt) (&s.pp[0][0])[i] = (&T.pp[0][0])[i];
+  for (int i = tid; i < 27; i += nt) s.node_t[i] = T.node_t[i];
+  for (int i = tid; i < 36; i += nt) s.jdof_t[i] = T.jdof_t[i];
+  for (int i = tid; i < 8; i += nt) s.t_phi[i] = T.t_phi[i];
+}
+
+// ---- field / intermediate layouts (doubles)
+constexpr int NFIELD = 74;
+constexpr int FO_UU = 0, FO_UJ = 21, FO_JJ = 30, FO_DD = 36, FO_JF = 37, FO_UP = 38;
+constexpr int T1_UU = 0, T1_UJ = T1_UU + 21 * 81, T1_JA = T1_UJ + 9 * 54, T1_JB = T1_JA + 6 * 36, T1_JF = T1_JB + 6 * 36,
+              T1_UP = T1_JF + 3 * 36, T1_END = T1_UP + 36 * 27;  // 3699
+constexpr int T2_N = 0, T2_B = T2_N + 9 * 243, T2_UJ = T2_B + 4 * 243, T2_JA = T2_UJ + 9 * 108, T2_JB = T2_JA + 6 * 48,
+              T2_JF = T2_JB + 6 * 72, T2_END = T2_JF + 3 * 48;  // 4995
+constexpr int R1_DE = BUF;  // D and E live behind staging buffer 0 inside region 1 (T1 is dead by then)
+static_assert(R1_DE + 2 * 324 <= T1_END, "D/E do not fit behind staging buffer 0");
+constexpr int R3_T2UP = NFIELD * 27;  // 1998
+constexpr int R3_END = R3_T2UP + 36 * 27;  // 2970
+static_assert(R3_END >= BUF, "staging buffer 1 does not fit region 3");
+
+struct Cell7 {
+  double r1[T1_END];   // stage-1 results; later staging buffer 0 [0,BUF) | D [4][81] | E [4][81]
+  double r2[T2_END];   // stage-2 results; its head first holds the temporaries of the point evaluation
+  double r3[R3_END];   // coefficient fields [74][27] | T2up [36][27]; later staging buffer 1
+  double J[27][9];     // J[q][i*3+k] = d x_i / d xi_k
+  double invJ[27][9];  // invJ[q][k*3+i] = d xi_k / d x_i
+  double W[27];        // w |det J|
+  double idet[27];     // 1 / det J
+  double X[24];
+  double ut[81];       // velocity dofs in tensor order [c][i0 + 3 i1 + 9 i2]
+  double uq[27][3];
+  double gur[27][9];   // reference gradient of u: gur[q][k*3+c]
+  double Mp[16], Minv[16];
+  double sgn[36];      // RT sign flip by tensor id
+  double sigma_cell, phi_sign;
+  long long rowaddr[NLOC];  // permuted numbering: first nnz of the row (-1: dropped)
+  int32_t gid[NLOC];
+  uint8_t slot_u[32];  // tensor node index -> slot of the permuted numbering
+  uint8_t slot_j[40];  // tensor RT id -> slot
+};
+MHD_7HD double* cellD(Cell7& S) { return S.r1 + R1_DE; }
+MHD_7HD double* cellE(Cell7& S) { return S.r1 + R1_DE + 324; }
+
+MHD_7HD int pow3(int d) { return d == 0 ? 1 : (d == 1 ? 3 : 9); }
+// derivative flags (row side, col side) of uu field f in direction ax (fields: 0..8 mass type, 9..17 stiffness (m,n), 18..20 convection n)
+MHD_7HD int pat_uu(int f, int ax) {
+  int m = 0, n = 0;
+  if (f >= 9 && f < 18) { m = ((f - 9) / 3 == ax); n = ((f - 9) % 3 == ax); }
+  else if (f >= 18) n = (f - 18 == ax);
+  return 2 * m + n;
+}
+MHD_7HD void jjb_pair(int blk, int* k, int* kp) { *k = blk == 2 ? 1 : 0; *kp = blk == 0 ? 1 : 2; }
+
+// ------------------------------------------------------------------ phase 0: gather (permuted ids, row starts, state, vertices)
+MHD_7HD void phase_load(Cell7& S, const Small7& C, int tid, int nt, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129,
+                        const long long* rowstart129, const uint8_t* perm64, const double* dir, const double* x, bool need_u, bool solid,
+                        double sigma_cell, double sigma_fluid) {
+  for (int i = tid; i < 24; i += nt) S.X[i] = coords[(long long)cell_nodes8[i / 3] * 3 + i % 3];
+  for (int i = tid; i < NLOC; i += nt) {
+    S.gid[i] = pgids129[i];
+    S.rowaddr[i] = rowstart129 ? rowstart129[i] : -1;
+  }
+  for (int i = tid; i < 81; i += nt) {
+    const int c = i / 27, s = i % 27, t = C.node_t[perm64[s]];
+    if (c == 0) S.slot_u[t] = (uint8_t)s;
+    const int32_t g = pgids129[c * 27 + s];
+    S.ut[c * 27 + t] = need_u ? (g >= 0 ? x[g] : dir[-(long long)g - 1]) : 0.0;
+  }
+  for (int s = tid; s < 36; s += nt) {
+    const int pm = perm64[27 + s], tj = C.jdof_t[pm & 0x7F];
+    S.slot_j[tj] = (uint8_t)s;
+    S.sgn[tj] = (pm & 0x80) ? -1.0 : 1.0;
+  }
+  if (tid == 0) {
+    S.sigma_cell = solid ? sigma_cell : sigma_fluid;
+    S.phi_sign = solid ? 1.0 : -1.0;
+  }
+}
+
+// ------------------------------------------------------------------ phase 1a: J at the points | first contraction of the point evaluation
+template <int CONV>
+MHD_7HD void phase_geom_a(Cell7& S, const Small7& C, int tid, int nt, const double* gg /* Tab7::gg */) {
+  const int n = 243 + (CONV != 0 ? 162 : 0);
+  for (int it = tid; it < n; it += nt) {
+    if (it < 243) {
+      const int q = it / 9, i = (it / 3) % 3, k = it % 3;
+      double s = 0.0;
+      MHD_7UNROLL
+      for (int v = 0; v < 8; v++) s += S.X[v * 3 + i] * gg[q * 24 + v * 3 + k];
+      S.J[q][i * 3 + k] = s;
+    } else {
+      // A1[var][c][q0 + 3 a12] = sum_a0 (var ? LD : LV)[0][a0][q0] ut[c][a0 + 3 a12]
+      const int r = it - 243, var = r / 81, c = (r / 27) % 3, q0 = r % 3, a12 = (r / 3) % 9;
+      const double* tb = var ? C.LD[0][0] : C.LV[0][0];
+      const double* u = S.ut + c * 27 + 3 * a12;
+      S.r2[(var * 3 + c) * 27 + q0 + 3 * a12] = tb[0 * 3 + q0] * u[0] + tb[1 * 3 + q0] * u[1] + tb[2 * 3 + q0] * u[2];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase 1b: inverse / determinant | second contraction
+template <int CONV>
+MHD_7HD void phase_geom_b(Cell7& S, const Small7& C, int tid, int nt, const double* w) {
+  const int n = 27 + (CONV != 0 ? 243 : 0);
+  for (int it = tid; it < n; it += nt) {
+    if (it < 27) {
+      const int q = it;
+      const double* J = S.J[q];
+      const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+      const double det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+      const double id = 1.0 / det;
+      double* I = S.invJ[q];
+      I[0] = c00 * id;
+      I[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+      I[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+      I[3] = c01 * id;
+      I[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+      I[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+      I[6] = c02 * id;
+      I[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+      I[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+      S.idet[q] = id;
+      S.W[q] = w[q] * (det < 0.0 ? -det : det);
+    } else {
+      // Bv[var][c][q0 + 3 q1 + 9 a2] = sum_a1 T[a1][q1] A1[src][c][q0 + 3 (a1 + 3 a2)];  var 0: (v,v)  1: (d,v)  2: (v,d)
+      const int r = it - 27, var = r / 81, c = (r / 27) % 3, q01 = r % 9, a2 = (r / 9) % 3, q0 = q01 % 3, q1 = q01 / 3;
+      const double* tb = var == 2 ? C.LD[1][0] : C.LV[1][0];
+      const double* a1 = S.r2 + ((var == 1 ? 1 : 0) * 3 + c) * 27 + q0 + 9 * a2;
+      S.r2[162 + (var * 3 + c) * 27 + q01 + 9 * a2] = tb[0 * 3 + q1] * a1[0] + tb[1 * 3 + q1] * a1[3] + tb[2 * 3 + q1] * a1[6];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase 2: u and its reference gradient at the points
+MHD_7HD void phase_points(Cell7& S, const Small7& C, int tid, int nt) {
+  for (int it = tid; it < 324; it += nt) {
+    const int kind = it / 81, c = (it / 27) % 3, q = it % 27, q01 = q % 9, q2 = q / 9;
+    const double* tb = kind == 3 ? C.LD[2][0] : C.LV[2][0];
+    const int var = kind == 1 ? 1 : (kind == 2 ? 2 : 0);
+    const double* b = S.r2 + 162 + (var * 3 + c) * 27 + q01;
+    const double v = tb[0 * 3 + q2] * b[0] + tb[1 * 3 + q2] * b[9] + tb[2 * 3 + q2] * b[18];
+    if (kind == 0) S.uq[q][c] = v;
+    else S.gur[q][(kind - 1) * 3 + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------ phase 3: coefficient fields
+template <int CONV, bool ZJ>
+MHD_7HD void phase_fields(Cell7& S, const Small7& C, int tid, int nt, const Params& P) {
+  for (int it = tid; it < NFIELD * 27; it += nt) {
+    const int f = it / 27, q = it % 27;
+    const double* I = S.invJ[q];
+    const double* J = S.J[q];
+    const double w = S.W[q], id = S.idet[q];
+    double v = 0.0;
+    if (f < 9) {
+      if (CONV == 2) {
+        const int c = f / 3, d = f % 3;  // alpha w d_d u_c
+        v = P.alpha * w * (I[0 * 3 + d] * S.gur[q][0 * 3 + c] + I[1 * 3 + d] * S.gur[q][1 * 3 + c] + I[2 * 3 + d] * S.gur[q][2 * 3 + c]);
+      }
+    } else if (f < 18) {
+      const int m = (f - 9) / 3, n = (f - 9) % 3;
+      v = P.beta * w * (I[m * 3 + 0] * I[n * 3 + 0] + I[m * 3 + 1] * I[n * 3 + 1] + I[m * 3 + 2] * I[n * 3 + 2]);
+    } else if (f < FO_UJ) {
+      if (CONV != 0) {
+        const int n = f - 18;
+        v = P.alpha * w * (I[n * 3 + 0] * S.uq[q][0] + I[n * 3 + 1] * S.uq[q][1] + I[n * 3 + 2] * S.uq[q][2]);
+      }
+    } else if (f < FO_JJ) {
+      const int c = (f - FO_UJ) / 3, k = (f - FO_UJ) % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+      v = w * id * (J[c1 * 3 + k] * P.B[c2] - J[c2 * 3 + k] * P.B[c1]);
+    } else if (f < FO_DD) {
+      const int b = f - FO_JJ;
+      int k = b, kp = b;
+      if (b >= 3) jjb_pair(b - 3, &k, &kp);
+      v = w * id * id * (J[0 * 3 + k] * J[0 * 3 + kp] + J[1 * 3 + k] * J[1 * 3 + kp] + J[2 * 3 + k] * J[2 * 3 + kp]);
+    } else if (f == FO_DD) {
+      v = ZJ ? P.zeta_j * w * id * id : 0.0;
+    } else if (f == FO_JF) {
+      v = w * id;
+    } else {
+      const int r = f - FO_UP, kp = r / 9, c = (r / 3) % 3, kk = r % 3;
+      v = w * C.pp[q][kp] * I[kk * 3 + c];
+    }
+    S.r3[it] = v;
+  }
+}
+
+// ------------------------------------------------------------------ phase 4: first contraction (direction d2) of every block
+template <bool ZJ>
+MHD_7HD void phase_stage1(Cell7& S, const Small7& C, int tid, int nt) {
+  constexpr int N_UU = 189, N_UJ = N_UU + 81, N_JA = N_UJ + 54, N_JB = N_JA + 54, N_JF = N_JB + 27, N_UP = N_JF + 324;
+  const double* F = S.r3;
+  for (int it = tid; it < N_UP; it += nt) {
+    if (it < N_UU) {
+      const int f = it / 9, r = it % 9;
+      const double x0 = F[f * 27 + r], x1 = F[f * 27 + r + 9], x2 = F[f * 27 + r + 18];
+      const double* p = C.Puu[2][pat_uu(f, 2)][0];
+      double* o = S.r1 + T1_UU + f * 81 + r;
+      MHD_7UNROLL
+      for (int ab = 0; ab < 9; ab++) o[ab * 9] = p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+    } else if (it < N_UJ) {
+      const int i = it - N_UU, inst = i / 9, r = i % 9, k = inst % 3;
+      const int s0 = pow3(k), s1 = pow3((k + 1) % 3), d2 = (k + 2) % 3, s2 = pow3(d2);
+      const double* f = F + (FO_UJ + inst) * 27 + (r % 3) * s0 + (r / 3) * s1;
+      const double x0 = f[0], x1 = f[s2], x2 = f[2 * s2];
+      double* o = S.r1 + T1_UJ + inst * 54 + r;
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++)
+        MHD_7UNROLL
+        for (int j = 0; j < 2; j++) {
+          const double* la = C.LV[d2][a];
+          const double* rb = C.RV[k][2][j];
+          o[(a * 2 + j) * 9] = la[0] * rb[0] * x0 + la[1] * rb[1] * x1 + la[2] * rb[2] * x2;
+        }
+    } else if (it < N_JB) {
+      const bool typeb = it >= N_JA;
+      const int i = it - (typeb ? N_JA : N_UJ), blk = i / 18, kind = (i / 9) % 2, r = i % 9;
+      if (kind == 1 && !ZJ) continue;
+      int k = blk, kp = blk;
+      if (typeb) jjb_pair(blk, &k, &kp);
+      const int d0 = k, d1 = typeb ? kp : (k + 1) % 3, d2 = 3 - d0 - d1;
+      const int s0 = pow3(d0), s1 = pow3(d1), s2 = pow3(d2);
+      const double* f = F + (kind ? FO_DD : FO_JJ + (typeb ? 3 : 0) + blk) * 27 + (r % 3) * s0 + (r / 3) * s1;
+      const double x0 = f[0], x1 = f[s2], x2 = f[2 * s2];
+      const double* ra = C.RV[k][(d2 - k + 3) % 3][0];
+      const double* rb = C.RV[kp][(d2 - kp + 3) % 3][0];
+      double* o = S.r1 + (typeb ? T1_JB : T1_JA) + (blk * 2 + kind) * 36 + r;
+      MHD_7UNROLL
+      for (int a = 0; a < 2; a++)
+        MHD_7UNROLL
+        for (int b = 0; b < 2; b++)
+          o[(a * 2 + b) * 9] = ra[a * 3] * rb[b * 3] * x0 + ra[a * 3 + 1] * rb[b * 3 + 1] * x1 + ra[a * 3 + 2] * rb[b * 3 + 2] * x2;
+    } else if (it < N_JF) {
+      const int i = it - N_JB, k = i / 9, r = i % 9;
+      const int s0 = pow3(k), s1 = pow3((k + 1) % 3), d2 = (k + 2) % 3, s2 = pow3(d2);
+      const double* f = F + FO_JF * 27 + (r % 3) * s0 + (r / 3) * s1;
+      const double x0 = f[0], x1 = f[s2], x2 = f[2 * s2];
+      double* o = S.r1 + T1_JF + k * 36 + r;
+      MHD_7UNROLL
+      for (int a = 0; a < 2; a++)
+        MHD_7UNROLL
+        for (int l = 0; l < 2; l++) {
+          const double* ra = C.RV[k][2][a];
+          const double* xl = C.XV[d2][l];
+          o[(a * 2 + l) * 9] = ra[0] * xl[0] * x0 + ra[1] * xl[1] * x1 + ra[2] * xl[2] * x2;
+        }
+    } else {
+      const int i = it - N_JF, inst = i / 9, r = i % 9, kk = inst % 3;
+      const double* f = F + (FO_UP + inst) * 27 + r;
+      const double x0 = f[0], x1 = f[9], x2 = f[18];
+      const double* tb = kk == 2 ? C.LD[2][0] : C.LV[2][0];
+      double* o = S.r1 + T1_UP + inst * 27 + r;
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++) o[a * 9] = tb[a * 3] * x0 + tb[a * 3 + 1] * x1 + tb[a * 3 + 2] * x2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase 5: second contraction (direction d1)
+template <int CONV, bool ZJ>
+MHD_7HD void phase_stage2(Cell7& S, const Small7& C, int tid, int nt) {
+  constexpr int N_N = 243, N_B = N_N + 108, N_UJ = N_B + 162, N_JA = N_UJ + 72, N_JB = N_JA + 72, N_JF = N_JB + 36, N_UP = N_JF + 324;
+  const double* T1 = S.r1;
+  for (int it = tid; it < N_UP; it += nt) {
+    if (it < N_N) {
+      if (CONV != 2) continue;
+      const int f = it / 27, p2 = (it / 3) % 9, q0 = it % 3;
+      const double* x = T1 + T1_UU + f * 81 + p2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      const double* p = C.Puu[1][0][0];
+      double* o = S.r2 + T2_N + f * 243 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int ab = 0; ab < 9; ab++) o[ab * 27] = p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+    } else if (it < N_B) {
+      const int i = it - N_N, pc = i / 27, p2 = (i / 3) % 9, q0 = i % 3;
+      double acc[9];
+      MHD_7UNROLL
+      for (int ab = 0; ab < 9; ab++) acc[ab] = 0.0;
+      for (int f = 9; f < (CONV != 0 ? 21 : 18); f++) {
+        if (pat_uu(f, 0) != pc) continue;
+        const double* x = T1 + T1_UU + f * 81 + p2 * 9 + q0;
+        const double x0 = x[0], x1 = x[3], x2 = x[6];
+        const double* p = C.Puu[1][pat_uu(f, 1)][0];
+        MHD_7UNROLL
+        for (int ab = 0; ab < 9; ab++) acc[ab] += p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+      }
+      double* o = S.r2 + T2_B + pc * 243 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int ab = 0; ab < 9; ab++) o[ab * 27] = acc[ab];
+    } else if (it < N_UJ) {
+      const int i = it - N_B, inst = i / 18, p2 = (i / 3) % 6, q0 = i % 3, k = inst % 3, d1 = (k + 1) % 3;
+      const double* x = T1 + T1_UJ + inst * 54 + p2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      double* o = S.r2 + T2_UJ + inst * 108 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++)
+        MHD_7UNROLL
+        for (int j = 0; j < 2; j++) {
+          const double* la = C.LV[d1][a];
+          const double* rb = C.RV[k][1][j];
+          o[(a * 2 + j) * 18] = la[0] * rb[0] * x0 + la[1] * rb[1] * x1 + la[2] * rb[2] * x2;
+        }
+    } else if (it < N_JA) {
+      const int i = it - N_UJ, blk = i / 24, kind = (i / 12) % 2, p2 = (i / 3) % 4, q0 = i % 3, k = blk;
+      if (kind == 1 && !ZJ) continue;
+      const double* x = T1 + T1_JA + (blk * 2 + kind) * 36 + p2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      const double* r = C.RV[k][1][0];
+      double* o = S.r2 + T2_JA + (blk * 2 + kind) * 48 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int a = 0; a < 2; a++)
+        MHD_7UNROLL
+        for (int b = 0; b < 2; b++) o[(a * 2 + b) * 12] = r[a * 3] * r[b * 3] * x0 + r[a * 3 + 1] * r[b * 3 + 1] * x1 + r[a * 3 + 2] * r[b * 3 + 2] * x2;
+    } else if (it < N_JB) {
+      const int i = it - N_JA, blk = i / 24, kind = (i / 12) % 2, p2 = (i / 3) % 4, q0 = i % 3;
+      if (kind == 1 && !ZJ) continue;
+      int k, kp;
+      jjb_pair(blk, &k, &kp);
+      const int d1 = kp;
+      const double* x = T1 + T1_JB + (blk * 2 + kind) * 36 + p2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      const double* ra = C.RV[k][(d1 - k + 3) % 3][0];                 // row: a linear factor of component k (2 classes)
+      const double* rb = kind ? C.RD[kp][0] : C.RV[kp][0][0];          // col: the quadratic factor of component k' (3 classes)
+      double* o = S.r2 + T2_JB + (blk * 2 + kind) * 72 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int a = 0; a < 2; a++)
+        MHD_7UNROLL
+        for (int b = 0; b < 3; b++) o[(a * 3 + b) * 12] = ra[a * 3] * rb[b * 3] * x0 + ra[a * 3 + 1] * rb[b * 3 + 1] * x1 + ra[a * 3 + 2] * rb[b * 3 + 2] * x2;
+    } else if (it < N_JF) {
+      const int i = it - N_JB, k = i / 12, p2 = (i / 3) % 4, q0 = i % 3, d1 = (k + 1) % 3;
+      const double* x = T1 + T1_JF + k * 36 + p2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      double* o = S.r2 + T2_JF + k * 48 + p2 * 3 + q0;
+      MHD_7UNROLL
+      for (int a = 0; a < 2; a++)
+        MHD_7UNROLL
+        for (int l = 0; l < 2; l++) {
+          const double* ra = C.RV[k][1][a];
+          const double* xl = C.XV[d1][l];
+          o[(a * 2 + l) * 12] = ra[0] * xl[0] * x0 + ra[1] * xl[1] * x1 + ra[2] * xl[2] * x2;
+        }
+    } else {
+      const int i = it - N_JF, inst = i / 9, a2 = (i / 3) % 3, q0 = i % 3, kk = inst % 3;
+      const double* x = T1 + T1_UP + inst * 27 + a2 * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      const double* tb = kk == 1 ? C.LD[1][0] : C.LV[1][0];
+      double* o = S.r3 + R3_T2UP + inst * 27 + a2 * 3 + q0;
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++) o[a * 9] = tb[a * 3] * x0 + tb[a * 3 + 1] * x1 + tb[a * 3 + 2] * x2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase 5b: D[k][(c, tensor node)] = int pi_k d_c N, pressure mass matrix
+template <bool ZU>
+MHD_7HD void phase_D(Cell7& S, const Small7& C, int tid, int nt) {
+  double* D = cellD(S);
+  for (int it = tid; it < 108 + (ZU ? 16 : 0); it += nt) {
+    if (it < 108) {
+      const int kc = it / 9, a1 = (it / 3) % 3, a2 = it % 3, kp = kc / 3, c = kc % 3;
+      double acc[3] = {0.0, 0.0, 0.0};
+      MHD_7UNROLL
+      for (int kk = 0; kk < 3; kk++) {
+        const double* x = S.r3 + R3_T2UP + (kc * 3 + kk) * 27 + a1 * 9 + a2 * 3;
+        const double* tb = kk == 0 ? C.LD[0][0] : C.LV[0][0];
+        MHD_7UNROLL
+        for (int a0 = 0; a0 < 3; a0++) acc[a0] += tb[a0 * 3] * x[0] + tb[a0 * 3 + 1] * x[1] + tb[a0 * 3 + 2] * x[2];
+      }
+      MHD_7UNROLL
+      for (int a0 = 0; a0 < 3; a0++) D[kp * 81 + c * 27 + a0 + 3 * a1 + 9 * a2] = acc[a0];
+    } else {
+      const int i = it - 108;
+      double s = 0.0;
+      for (int q = 0; q < 27; q++) s += S.W[q] * C.pp[q][i / 4] * C.pp[q][i % 4];
+      S.Mp[i] = s;
+    }
+  }
+}
+
+MHD_7HD void invert4(const double* M, double* out) {
+  double a[4][8];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      a[i][j] = M[i * 4 + j];
+      a[i][4 + j] = i == j ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < 4; c++) {
+    int p = c;
+    double best = a[c][c] < 0 ? -a[c][c] : a[c][c];
+    for (int r = c + 1; r < 4; r++) {
+      const double v = a[r][c] < 0 ? -a[r][c] : a[r][c];
+      if (v > best) { best = v; p = r; }
+    }
+    if (p != c)
+      for (int j = 0; j < 8; j++) { const double t = a[c][j]; a[c][j] = a[p][j]; a[p][j] = t; }
+    const double ip = 1.0 / a[c][c];
+    for (int j = 0; j < 8; j++) a[c][j] *= ip;
+    for (int r = 0; r < 4; r++)
+      if (r != c) {
+        const double fct = a[r][c];
+        for (int j = 0; j < 8; j++) a[r][j] -= fct * a[c][j];
+      }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) out[i * 4 + j] = a[i][4 + j];
+}
+
+MHD_7HD void phase_Minv(Cell7& S, int tid, int nt) {
+  if (tid == nt - 1) invert4(S.Mp, S.Minv);
+}
+MHD_7HD void phase_E(Cell7& S, int tid, int nt, double zeta_u) {
+  const double* D = cellD(S);
+  double* E = cellE(S);
+  for (int it = tid; it < 324; it += nt) {
+    const int k = it / 81, ca = it % 81;
+    E[it] = zeta_u * (S.Minv[k * 4 + 0] * D[ca] + S.Minv[k * 4 + 1] * D[81 + ca] + S.Minv[k * 4 + 2] * D[162 + ca] + S.Minv[k * 4 + 3] * D[243 + ca]);
+  }
+}
+
+// ------------------------------------------------------------------ chunks: last contraction (direction d0) -> staging buffer
+// uu rows of component c: buf[slot(a) * 81 + 3 slot(b) + d]
+template <int CONV, bool ZU>
+MHD_7HD void chunk_uu(Cell7& S, const Small7& C, int tid, int nt, int c, double* buf) {
+  const double* D = cellD(S);
+  const double* E = cellE(S);
+  for (int it = tid; it < 243; it += nt) {
+    const int a0 = it / 81, p1 = (it / 9) % 9, p2 = it % 9, bi = p1 * 27 + p2 * 3;
+    const int a1 = p1 / 3, b1 = p1 % 3, a2 = p2 / 3, b2 = p2 % 3;
+    const int ta = a0 + 3 * a1 + 9 * a2, tb12 = 3 * b1 + 9 * b2;
+    double tb[4][3], tn[3][3];
+    MHD_7UNROLL
+    for (int pc = 0; pc < 4; pc++)
+      MHD_7UNROLL
+      for (int q = 0; q < 3; q++) tb[pc][q] = S.r2[T2_B + pc * 243 + bi + q];
+    if (CONV == 2) {
+      MHD_7UNROLL
+      for (int d = 0; d < 3; d++)
+        MHD_7UNROLL
+        for (int q = 0; q < 3; q++) tn[d][q] = S.r2[T2_N + (c * 3 + d) * 243 + bi + q];
+    }
+    const int rowoff = S.slot_u[ta] * 81;
+    MHD_7UNROLL
+    for (int b0 = 0; b0 < 3; b0++) {
+      const int ab = a0 * 3 + b0, tbn = b0 + tb12;
+      double base = 0.0;
+      MHD_7UNROLL
+      for (int pc = 0; pc < 4; pc++) {
+        const double* p = C.Puu[0][pc][ab];
+        base += p[0] * tb[pc][0] + p[1] * tb[pc][1] + p[2] * tb[pc][2];
+      }
+      const double* pv = C.Puu[0][0][ab];
+      const int col = 3 * S.slot_u[tbn];
+      MHD_7UNROLL
+      for (int d = 0; d < 3; d++) {
+        double v = d == c ? base : 0.0;
+        if (CONV == 2) v += pv[0] * tn[d][0] + pv[1] * tn[d][1] + pv[2] * tn[d][2];
+        if (ZU) v += D[c * 27 + ta] * E[d * 27 + tbn] + D[81 + c * 27 + ta] * E[81 + d * 27 + tbn] + D[162 + c * 27 + ta] * E[162 + d * 27 + tbn] +
+                     D[243 + c * 27 + ta] * E[243 + d * 27 + tbn];
+        buf[rowoff + col + d] = v;
+      }
+    }
+  }
+}
+
+// uj (JU = false): buf[(c*27 + slot(a)) * 36 + slot(m)] = -gamma sgn V ;  ju (JU = true): buf[slot(m) * 81 + 3 slot(a) + c] = +sigma sgn V
+template <bool JU>
+MHD_7HD void chunk_uj(Cell7& S, const Small7& C, int tid, int nt, const Params& P, double* buf) {
+  for (int it = tid; it < 324; it += nt) {
+    const int inst = it / 36, p1 = (it / 6) % 6, p2 = it % 6, c = inst / 3, k = inst % 3;
+    const int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+    const double* x = S.r2 + T2_UJ + inst * 108 + p1 * 18 + p2 * 3;
+    const double x0 = x[0], x1 = x[1], x2 = x[2];
+    const int a1 = p1 / 2, i1 = p1 % 2, a2 = p2 / 2, i2 = p2 % 2;
+    const int ta12 = a1 * pow3(d1) + a2 * pow3(d2), s0 = pow3(k), tj12 = 12 * k + 3 * (i1 + 2 * i2);
+    const double coef = JU ? P.sigma : -P.gamma;
+    MHD_7UNROLL
+    for (int a = 0; a < 3; a++) {
+      const int su = S.slot_u[ta12 + a * s0];
+      MHD_7UNROLL
+      for (int i0 = 0; i0 < 3; i0++) {
+        const double* p = C.Puj[k][a * 3 + i0];
+        const int tj = tj12 + i0;
+        const double v = coef * S.sgn[tj] * (p[0] * x0 + p[1] * x1 + p[2] * x2);
+        if (JU) buf[S.slot_j[tj] * 81 + 3 * su + c] = v;
+        else buf[(c * 27 + su) * 36 + S.slot_j[tj]] = v;
+      }
+    }
+  }
+}
+
+// the rest: jj | j-phi | phi-j | up | pu
+template <bool ZJ>
+MHD_7HD void chunk_rest(Cell7& S, const Small7& C, int tid, int nt, double* buf) {
+  constexpr int N_JA = 48, N_JB = N_JA + 72, N_JF = N_JB + 48, N_UP = N_JF + 324;
+  const double* D = cellD(S);
+  for (int it = tid; it < N_UP; it += nt) {
+    if (it < N_JA) {
+      const int blk = it / 16, p1 = (it / 4) % 4, p2 = it % 4, k = blk;
+      const double* x = S.r2 + T2_JA + (blk * 2) * 48 + p1 * 12 + p2 * 3;
+      const int tm12 = 12 * k + 3 * ((p1 / 2) + 2 * (p2 / 2)), tn12 = 12 * k + 3 * ((p1 % 2) + 2 * (p2 % 2));
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++)
+        MHD_7UNROLL
+        for (int j = 0; j < 3; j++) {
+          const double* ra = C.RV[k][0][i];
+          const double* rb = C.RV[k][0][j];
+          double v = ra[0] * rb[0] * x[0] + ra[1] * rb[1] * x[1] + ra[2] * rb[2] * x[2];
+          if (ZJ) {
+            const double* da = C.RD[k][i];
+            const double* db = C.RD[k][j];
+            v += da[0] * db[0] * x[48] + da[1] * db[1] * x[49] + da[2] * db[2] * x[50];
+          }
+          const int tm = tm12 + i, tn = tn12 + j;
+          buf[R_JJ + S.slot_j[tm] * 36 + S.slot_j[tn]] = S.sgn[tm] * S.sgn[tn] * v;
+        }
+    } else if (it < N_JB) {
+      const int r = it - N_JA, blk = r / 24, p1 = (r / 4) % 6, p2 = r % 4;
+      int k, kp;
+      jjb_pair(blk, &k, &kp);
+      const int d0 = k, d1 = kp, d2 = 3 - d0 - d1;
+      const double* x = S.r2 + T2_JB + (blk * 2) * 72 + p1 * 12 + p2 * 3;
+      const int i1 = p1 / 3, j1 = p1 % 3, i2 = p2 / 2, j2 = p2 % 2;   // row classes (i) | col classes (j) in directions d1, d2
+      // tensor ids: class of rotated direction r of a component sits at weight (1, 3, 6)[r]
+      auto wgt = [](int r) { return r == 0 ? 1 : (r == 1 ? 3 : 6); };
+      const int tm12 = 12 * k + i1 * wgt((d1 - k + 3) % 3) + i2 * wgt((d2 - k + 3) % 3);
+      const int tn12 = 12 * kp + j1 /* its quadratic factor */ + j2 * wgt((d2 - kp + 3) % 3);
+      const int wn0 = wgt((d0 - kp + 3) % 3);
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++)
+        MHD_7UNROLL
+        for (int j = 0; j < 2; j++) {
+          const double* ra = C.RV[k][0][i];
+          const double* rb = C.RV[kp][(d0 - kp + 3) % 3][j];
+          double v = ra[0] * rb[0] * x[0] + ra[1] * rb[1] * x[1] + ra[2] * rb[2] * x[2];
+          if (ZJ) {
+            const double* da = C.RD[k][i];
+            v += da[0] * rb[0] * x[72] + da[1] * rb[1] * x[73] + da[2] * rb[2] * x[74];
+          }
+          const int tm = tm12 + i, tn = tn12 + j * wn0;
+          const double vv = S.sgn[tm] * S.sgn[tn] * v;
+          buf[R_JJ + S.slot_j[tm] * 36 + S.slot_j[tn]] = vv;
+          buf[R_JJ + S.slot_j[tn] * 36 + S.slot_j[tm]] = vv;
+        }
+    } else if (it < N_JF) {
+      const int r = it - N_JB, k = r / 16, p1 = (r / 4) % 4, p2 = r % 4, d1 = (k + 1) % 3, d2 = (k + 2) % 3;
+      const double* x = S.r2 + T2_JF + k * 48 + p1 * 12 + p2 * 3;
+      const int tm12 = 12 * k + 3 * ((p1 / 2) + 2 * (p2 / 2));
+      const int lt12 = (p1 % 2) * (1 << d1) + (p2 % 2) * (1 << d2);
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++)
+        MHD_7UNROLL
+        for (int l0 = 0; l0 < 2; l0++) {
+          const double* da = C.RD[k][i];
+          const double* xl = C.XV[k][l0];
+          const int tm = tm12 + i, l = C.t_phi[lt12 + l0 * (1 << k)];
+          const double v = S.sgn[tm] * (da[0] * xl[0] * x[0] + da[1] * xl[1] * x[1] + da[2] * xl[2] * x[2]);
+          buf[R_JF + S.slot_j[tm] * 8 + l] = -S.sigma_cell * v;
+          buf[R_FJ + l * 36 + S.slot_j[tm]] = S.phi_sign * v;
+        }
+    } else {
+      const int r = it - N_JF, kp = r / 81, ct = r % 81, c = ct / 27, su = S.slot_u[ct % 27];
+      const double v = -D[r];
+      buf[R_UP + (c * 27 + su) * 4 + kp] = v;
+      buf[R_PU + kp * 81 + 3 * su + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sweeps: store(e, local row (permuted numbering), value)
+template <class Store>
+MHD_7HD void sweep_section(const double* buf, int e0, int n, int ncol, int row0, int tid, int nt, Store& store) {
+  for (int i = tid; i < n; i += nt) store(e0 + i, row0 + i / ncol, buf[i]);
+}
+template <class Store>
+MHD_7HD void sweep_uu(const double* buf, int c, int tid, int nt, Store& store) {
+  sweep_section(buf, E_UU + c * CH_UU_PAD, CH_UU, 81, c * 27, tid, nt, store);
+}
+template <class Store>
+MHD_7HD void sweep_uj(const double* buf, int tid, int nt, Store& store) { sweep_section(buf, E_UJ, CH_UJ, 36, 0, tid, nt, store); }
+template <class Store>
+MHD_7HD void sweep_ju(const double* buf, int tid, int nt, Store& store) { sweep_section(buf, E_JU, CH_UJ, 81, OFF_J, tid, nt, store); }
+template <class Store>
+MHD_7HD void sweep_rest(const double* buf, int tid, int nt, Store& store) {
+  sweep_section(buf + R_JJ, E_REST + R_JJ, NJ * NJ, 36, OFF_J, tid, nt, store);
+  sweep_section(buf + R_JF, E_REST + R_JF, NJ * NF, 8, OFF_J, tid, nt, store);
+  sweep_section(buf + R_FJ, E_REST + R_FJ, NF * NJ, 36, OFF_F, tid, nt, store);
+  sweep_section(buf + R_UP, E_REST + R_UP, NU * NP, 4, 0, tid, nt, store);
+  sweep_section(buf + R_PU, E_REST + R_PU, NP * NU, 81, OFF_P, tid, nt, store);
+}
+
+}  // namespace h7
+}  // namespace mhd

@@ -46,8 +46,12 @@ def _p(a):
 class COracle:
     """Holds contiguous copies of the FE tables of a `FESpaces` and calls the C restatement."""
 
-    def __init__(self, fes, prm):
+    def __init__(self, fes, prm, cells=None, threads=None):
+        """`cells`: optional index array -- the oracle then only knows these cells (bounded parity samples).
+        `threads`: OpenMP threads (default: the runtime's choice, i.e. OMP_NUM_THREADS or all cores)."""
         self.lib = load()
+        if threads:
+            self.lib.oracle_set_num_threads(int(threads))
         T = fes.tables
         self._t = [np.ascontiguousarray(a, dtype=np.float64) for a in (T.w, T.geo_grad, T.nu, T.dnu, T.pp, T.psi, T.dpsi, T.chi)]
         self.tab = oracle_tables_t(*[a.ctypes.data for a in self._t])
@@ -59,8 +63,10 @@ class COracle:
         self.prm = p
         self.fes = fes
         self.coords = np.ascontiguousarray(fes.mesh.coords, dtype=np.float64)
-        self.cell_nodes = np.ascontiguousarray(fes.mesh.cell_nodes, dtype=np.int32)
-        gids = fes.cell_global_ids()
+        sel = slice(None) if cells is None else np.asarray(cells, dtype=np.int64)
+        self.cell_nodes = np.ascontiguousarray(fes.mesh.cell_nodes[sel], dtype=np.int32)
+        self.ncells = len(self.cell_nodes)
+        gids = fes.cell_global_ids()[sel]
         # Dirichlet entries: -(index into the concatenated Dirichlet array + 1)
         dir_off, o = {}, 0
         for f in _FIELDS:
@@ -68,16 +74,16 @@ class COracle:
             o += fes.ndir[f]
         g = gids.copy()
         for f in _FIELDS:
-            ids = fes.cell_dofs[f]
+            ids = fes.cell_dofs[f][sel]
             sl = slice(_LO[f], _LO[f] + ids.shape[1])
             g[:, sl] = np.where(ids > 0, gids[:, sl], -(dir_off[f] + (-ids - 1)) - 1)
         self.gids = np.ascontiguousarray(g, dtype=np.int32)
         self.dirv = np.ascontiguousarray(np.concatenate([fes.dirichlet_values[f] for f in _FIELDS] + [np.zeros(1)]))
-        self.jsign = np.ascontiguousarray(fes.j_sign, dtype=np.int8)
+        self.jsign = np.ascontiguousarray(fes.j_sign[sel], dtype=np.int8)
         self.threads = self.lib.oracle_num_threads()
 
     def jacobian_values(self, x, rowptr, colval, c0=0, c1=None, out=None):
-        c1 = self.fes.mesh.ncells if c1 is None else c1
+        c1 = self.ncells if c1 is None else c1
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
         colval = np.ascontiguousarray(colval, dtype=np.int64)
         nz = np.zeros(len(colval)) if out is None else out
@@ -88,7 +94,7 @@ class COracle:
         return nz
 
     def residual(self, x, c0=0, c1=None):
-        c1 = self.fes.mesh.ncells if c1 is None else c1
+        c1 = self.ncells if c1 is None else c1
         r = np.zeros(self.fes.ndofs)
         x = np.ascontiguousarray(x, dtype=np.float64)
         self.lib.oracle_assemble_residual(C.byref(self.tab), C.byref(self.prm), C.c_int64(c0), C.c_int64(c1), _p(self.coords),

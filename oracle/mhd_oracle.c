@@ -42,6 +42,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1, the CPU arm uses every host core at every N */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* geometry + mapped bases at one quadrature point */
 static void point_bases(const oracle_tables_t* T, int q, const double* X, const int8_t* sign, double* wq, double gN[27][3],
                         double psi[36][3], double dpsi[36]) {
