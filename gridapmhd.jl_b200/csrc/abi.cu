@@ -365,6 +365,7 @@ int mhd_operator_create(const mhd_mesh_t* mesh, const mhd_tables_t* tab, const m
     CR(h2d(op->d_cell_sigma, mesh->cell_sigma, op->ncells));
   }
   CR(pack_tables(op, tab));
+  CR(v7_try_enable(op));
   CR(build_permutation(op));
   CR(ensure_red(op, 4096 + 65 * 1024));
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
@@ -390,6 +391,9 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_dir);
   cudaFree(op->d_tables);
   cudaFree(op->d_sftab);
+  cudaFree(op->d_tab7);
+  cudaFree(op->d_shared_mask);
+  cudaFree(op->d_color_cells);
   cudaFree(op->d_rowptr);
   cudaFree(op->d_colval);
   cudaFree(op->d_nzval);
@@ -414,6 +418,61 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->halo.d_send_buf);
   cudaFree(op->halo.d_recv_buf);
   delete op;
+  return MHD_OK;
+}
+
+int mhd_operator_get_kernel_version(mhd_operator_t* op, int32_t* version) {
+  MHD_CHECK(op != nullptr && version != nullptr, MHD_E_INVALID, "mhd_operator_get_kernel_version: null argument");
+  *version = op->formulation == FORM_HDIV ? op->jac_version : 0;
+  return MHD_OK;
+}
+
+int mhd_operator_set_deterministic(mhd_operator_t* op, int32_t on, int32_t* ncolors) {
+  MHD_TRY(check_ready(op));
+  if (ncolors) *ncolors = 0;
+  if (!on) {
+    op->deterministic = false;
+    return MHD_OK;
+  }
+  MHD_CHECK(op->formulation == FORM_HDIV && op->jac_version == 7, MHD_E_STATE,
+            "deterministic assembly needs the sum-factorised kernel (version 7); this operator runs version %d",
+            op->formulation == FORM_HDIV ? op->jac_version : 0);
+  if (op->color_ptr.empty()) {
+    // greedy colouring on the host: a cell takes the lowest colour none of its free dofs has seen yet
+    std::vector<int32_t> g((size_t)op->ncells * NLOC);
+    MHD_TRY(d2h(g.data(), op->d_gids, op->ncells * NLOC));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    std::vector<uint64_t> seen((size_t)op->ncols, 0);
+    std::vector<int32_t> color((size_t)op->ncells);
+    int nc = 0;
+    for (int64_t c = 0; c < op->ncells; c++) {
+      uint64_t m = 0;
+      for (int k = 0; k < NLOC; k++) {
+        const int32_t id = g[(size_t)c * NLOC + k];
+        if (id >= 0) m |= seen[id];
+      }
+      int col = 0;
+      while (col < 64 && ((m >> col) & 1)) col++;
+      MHD_CHECK(col < 64, MHD_E_CAPACITY, "cell colouring needs more than 64 colours");
+      color[c] = col;
+      if (col + 1 > nc) nc = col + 1;
+      for (int k = 0; k < NLOC; k++) {
+        const int32_t id = g[(size_t)c * NLOC + k];
+        if (id >= 0) seen[id] |= 1ull << col;
+      }
+    }
+    op->color_ptr.assign(nc + 1, 0);
+    for (int64_t c = 0; c < op->ncells; c++) op->color_ptr[color[c] + 1]++;
+    for (int i = 0; i < nc; i++) op->color_ptr[i + 1] += op->color_ptr[i];
+    std::vector<int64_t> cur(op->color_ptr.begin(), op->color_ptr.end() - 1);
+    std::vector<int32_t> cells((size_t)op->ncells);
+    for (int64_t c = 0; c < op->ncells; c++) cells[cur[color[c]]++] = (int32_t)c;
+    MHD_TRY(dev_alloc(&op->d_color_cells, op->ncells));
+    MHD_TRY(h2d(op->d_color_cells, cells.data(), op->ncells));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+  }
+  op->deterministic = true;
+  if (ncolors) *ncolors = (int32_t)op->color_ptr.size() - 1;
   return MHD_OK;
 }
 
@@ -497,6 +556,9 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   } else if (op->jac_version == 6) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(v6_launch_jacobian(op, dx));
+  } else if (op->jac_version == 7) {
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(v7_launch_jacobian(op, dx, nullptr));
   } else {
     MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
@@ -533,6 +595,9 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(launch_residual(op, dx, dr));
     MHD_TRY(v6_launch_jacobian(op, dx));
+  } else if (op->jac_version == 7) {
+    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
+    MHD_TRY(v7_launch_jacobian(op, dx, dr));
   } else {
     MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));

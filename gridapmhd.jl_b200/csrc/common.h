@@ -133,8 +133,15 @@ constexpr int FORM_H1H1 = 1;  // H1-H1 (u,p,phi), 149 local dofs: h1h1.cu (field
 
 struct mhd_operator {
   int formulation = mhd::FORM_HDIV;
-  int jac_version = 5;             // 5: tensor-core panel products (assembly.cu); 6: structure-exploiting kernel (hdiv_v6.cu, opt-in)
+  int jac_version = 5;             // 5: tensor-core panel products (assembly.cu); 6: hdiv_v6.cu (opt-in, superseded);
+                                   // 7: fully sum-factorised kernel (hdiv_v7.cu), chosen when the tables have the tensor structure
   void* d_sftab = nullptr;         // v6: 1-D factors of the velocity tables (sf::Tables)
+  unsigned char* d_tab7 = nullptr; // v7: h7::Tab7
+  std::vector<unsigned char> h_small7;  // v7: h7::Small7 (uploaded to constant memory before a launch when it is not the current one)
+  uint32_t* d_shared_mask = nullptr;  // v7: bit i set <=> nnz i receives != 1 contributions (cleared before, RED-accumulated in, an assembly)
+  bool deterministic = false;      // v7: one launch per colour => run-to-run identical bits
+  int32_t* d_color_cells = nullptr;   // cells sorted by colour
+  std::vector<int64_t> color_ptr;  // [ncolors + 1]
   std::vector<double> h_tables;    // host copy of the packed reference tables (T_* layout)
   int64_t ncells = 0, nnodes = 0;
   int64_t nfree[4] = {0, 0, 0, 0}, nowned[4] = {0, 0, 0, 0}, ndir[4] = {0, 0, 0, 0};
@@ -251,6 +258,11 @@ int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 // hdiv_v6.cu
 void v6_entry_order(std::vector<uint16_t>& ord);
 int v6_launch_jacobian(mhd_operator* op, const double* d_x);
+// hdiv_v7.cu
+void v7_entry_order(std::vector<uint16_t>& ord);
+int v7_try_enable(mhd_operator* op);                                  // at operator creation: discovers the tensor structure of the tables
+int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib); // end of the symbolic phase
+int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 // h1h1.cu
 int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);

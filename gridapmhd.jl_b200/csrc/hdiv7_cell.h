@@ -23,9 +23,11 @@
 #ifdef __CUDACC__
 #define MHD_7HD __host__ __device__ __forceinline__
 #define MHD_7UNROLL _Pragma("unroll")
+#define MHD_7NOUNROLL _Pragma("unroll 1")
 #else
 #define MHD_7HD inline
 #define MHD_7UNROLL
+#define MHD_7NOUNROLL
 #endif
 
 namespace mhd {
@@ -40,7 +42,8 @@ constexpr int CH_UU = 27 * 81, CH_UU_PAD = pad32(CH_UU);         // rows (c, slo
 constexpr int CH_UJ = 81 * 36, CH_UJ_PAD = pad32(CH_UJ);
 constexpr int E_UU = 0, E_UJ = 3 * CH_UU_PAD, E_JU = E_UJ + CH_UJ_PAD, E_REST = E_JU + CH_UJ_PAD;
 constexpr int R_JJ = 0, R_JF = R_JJ + NJ * NJ, R_FJ = R_JF + NJ * NF, R_UP = R_FJ + NF * NJ, R_PU = R_UP + NU * NP, CH_REST = R_PU + NP * NU;
-constexpr int NENT = E_REST + pad32(CH_REST);  // 15 040 codes per cell, 14 913 of them entries
+constexpr int CH_REST_PAD = pad32(CH_REST);
+constexpr int NENT = E_REST + CH_REST_PAD;  // 15 040 codes per cell, 14 913 of them entries
 constexpr int BUF = CH_UJ_PAD;                 // doubles per staging buffer
 
 // (row slot, col slot) of map entry e in the permuted local numbering (u: c*27 + slot | p | j: 85 + slot | phi); false: padding
@@ -76,27 +79,35 @@ inline bool entry_rowcol(int e, int* li, int* lj) {
 struct Params {
   double alpha, beta, gamma, sigma, zeta_u, zeta_j;
   double B[3];
+  double f[3], g[3];  // body forces of the u and j equations (residual only)
 };
 
-// small cell-independent tables kept in shared memory (copied once per CTA from Tab7)
-struct Small7 {
+// small cell-independent tables: SmallDyn = what is looked up with thread-dependent indices (kernel: shared memory, copied once
+// per CTA from Tab7); Small7 = SmallDyn + the pair tables, which are only indexed at compile time (kernel: constant memory)
+struct SmallDyn {
   double LV[3][3][3], LD[3][3][3];
   double RV[3][3][3][3], RD[3][3][3];
   double XV[3][2][3];
-  double Puu[3][4][9][3];
-  double Puj[3][9][3];
   double pp[27][4];
   uint8_t node_t[27], jdof_t[36], t_phi[8], pad_[1];
 };
-MHD_7HD void small_from_tab(Small7& s, const Tab7& T, int tid, int nt) {
+struct Small7 : SmallDyn {
+  double Puu[3][4][9][3];
+  double Puj[3][9][3];
+};
+MHD_7HD void small_from_tab(SmallDyn& s, const Tab7& T, int tid, int nt) {
   for (int i = tid; i < 27; i += nt) { (&s.LV[0][0][0])[i] = (&T.LV[0][0][0])[i]; (&s.LD[0][0][0])[i] = (&T.LD[0][0][0])[i]; (&s.RD[0][0][0])[i] = (&T.RD[0][0][0])[i]; }
-  for (int i = tid; i < 81; i += nt) { (&s.RV[0][0][0][0])[i] = (&T.RV[0][0][0][0])[i]; (&s.Puj[0][0][0])[i] = (&T.Puj[0][0][0])[i]; }
+  for (int i = tid; i < 81; i += nt) (&s.RV[0][0][0][0])[i] = (&T.RV[0][0][0][0])[i];
   for (int i = tid; i < 18; i += nt) (&s.XV[0][0][0])[i] = (&T.XV[0][0][0])[i];
-  for (int i = tid; i < 324; i += nt) (&s.Puu[0][0][0][0])[i] = (&T.Puu[0][0][0][0])[i];
   for (int i = tid; i < 108; i += nt) (&s.pp[0][0])[i] = (&T.pp[0][0])[i];
   for (int i = tid; i < 27; i += nt) s.node_t[i] = T.node_t[i];
   for (int i = tid; i < 36; i += nt) s.jdof_t[i] = T.jdof_t[i];
   for (int i = tid; i < 8; i += nt) s.t_phi[i] = T.t_phi[i];
+}
+MHD_7HD void small_from_tab(Small7& s, const Tab7& T, int tid, int nt) {
+  small_from_tab(static_cast<SmallDyn&>(s), T, tid, nt);
+  for (int i = tid; i < 81; i += nt) (&s.Puj[0][0][0])[i] = (&T.Puj[0][0][0])[i];
+  for (int i = tid; i < 324; i += nt) (&s.Puu[0][0][0][0])[i] = (&T.Puu[0][0][0][0])[i];
 }
 
 // ---- field / intermediate layouts (doubles)
@@ -112,6 +123,11 @@ constexpr int R3_T2UP = NFIELD * 27;  // 1998
 constexpr int R3_END = R3_T2UP + 36 * 27;  // 2970
 static_assert(R3_END >= BUF, "staging buffer 1 does not fit region 3");
 
+// residual scratch (Cell7::rs) and the residual's intermediates inside r3[0, 1998) (free between stage 1 and chunk_uu(1))
+constexpr int RS_JH = 0, RS_DJ = 81, RS_P = 162, RS_F = 189, RS_DIVU = 216, RS_D = 243, RS_PST = 247, RS_FST = 251, RS_JT = 259, RS_END = 296;
+constexpr int RF_G = 0, RF_H = 243, RF_V = 324, RF_S = 405, RF_DJ = 432, RR_A = 459, RR_JP = 783, RR_B = 855, RR_END = 1179;
+static_assert(RR_END <= NFIELD * 27, "residual intermediates must stay below T2up in r3");
+
 struct Cell7 {
   double r1[T1_END];   // stage-1 results; later staging buffer 0 [0,BUF) | D [4][81] | E [4][81]
   double r2[T2_END];   // stage-2 results; its head first holds the temporaries of the point evaluation
@@ -125,9 +141,10 @@ struct Cell7 {
   double uq[27][3];
   double gur[27][9];   // reference gradient of u: gur[q][k*3+c]
   double Mp[16], Minv[16];
+  double rs[RS_END];   // residual: point values of j^, div^ j^, p, phi, div u | d | p, phi, j state (offsets RS_*)
   double sgn[36];      // RT sign flip by tensor id
   double sigma_cell, phi_sign;
-  long long rowaddr[NLOC];  // permuted numbering: first nnz of the row (-1: dropped)
+  long long rowaddr[NLOC];  // permuted numbering: byte address of the first nnz of the row (kernel) / unused (emulation)
   int32_t gid[NLOC];
   uint8_t slot_u[32];  // tensor node index -> slot of the permuted numbering
   uint8_t slot_j[40];  // tensor RT id -> slot
@@ -136,6 +153,7 @@ MHD_7HD double* cellD(Cell7& S) { return S.r1 + R1_DE; }
 MHD_7HD double* cellE(Cell7& S) { return S.r1 + R1_DE + 324; }
 
 MHD_7HD int pow3(int d) { return d == 0 ? 1 : (d == 1 ? 3 : 9); }
+MHD_7HD int qdir(int q, int d) { return d == 0 ? q % 3 : (d == 1 ? (q / 3) % 3 : q / 9); }  // index of point q in direction d
 // derivative flags (row side, col side) of uu field f in direction ax (fields: 0..8 mass type, 9..17 stiffness (m,n), 18..20 convection n)
 MHD_7HD int pat_uu(int f, int ax) {
   int m = 0, n = 0;
@@ -146,13 +164,14 @@ MHD_7HD int pat_uu(int f, int ax) {
 MHD_7HD void jjb_pair(int blk, int* k, int* kp) { *k = blk == 2 ? 1 : 0; *kp = blk == 0 ? 1 : 2; }
 
 // ------------------------------------------------------------------ phase 0: gather (permuted ids, row starts, state, vertices)
-MHD_7HD void phase_load(Cell7& S, const Small7& C, int tid, int nt, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129,
+MHD_7HD void phase_load(Cell7& S, const SmallDyn& C, int tid, int nt, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129,
                         const long long* rowstart129, const uint8_t* perm64, const double* dir, const double* x, bool need_u, bool solid,
-                        double sigma_cell, double sigma_fluid) {
+                        double sigma_cell, double sigma_fluid, const double* nzval = nullptr, bool with_res = false) {
   for (int i = tid; i < 24; i += nt) S.X[i] = coords[(long long)cell_nodes8[i / 3] * 3 + i % 3];
   for (int i = tid; i < NLOC; i += nt) {
     S.gid[i] = pgids129[i];
-    S.rowaddr[i] = rowstart129 ? rowstart129[i] : -1;
+    // device: absolute byte address of the first nnz of the row (dropped rows are never dereferenced: their codes are MAP_SKIP)
+    S.rowaddr[i] = rowstart129 ? (long long)(nzval + rowstart129[i]) : -1;
   }
   for (int i = tid; i < 81; i += nt) {
     const int c = i / 27, s = i % 27, t = C.node_t[perm64[s]];
@@ -163,8 +182,18 @@ MHD_7HD void phase_load(Cell7& S, const Small7& C, int tid, int nt, const double
   for (int s = tid; s < 36; s += nt) {
     const int pm = perm64[27 + s], tj = C.jdof_t[pm & 0x7F];
     S.slot_j[tj] = (uint8_t)s;
-    S.sgn[tj] = (pm & 0x80) ? -1.0 : 1.0;
+    const double sg = (pm & 0x80) ? -1.0 : 1.0;
+    S.sgn[tj] = sg;
+    if (with_res) {
+      const int32_t g = pgids129[OFF_J + s];
+      S.rs[RS_JT + tj] = sg * (g >= 0 ? x[g] : dir[-(long long)g - 1]);
+    }
   }
+  if (with_res)
+    for (int i = tid; i < 12; i += nt) {  // p (4) and phi (8) are not permuted
+      const int32_t g = pgids129[i < 4 ? OFF_P + i : OFF_F + i - 4];
+      S.rs[RS_PST + i] = g >= 0 ? x[g] : dir[-(long long)g - 1];
+    }
   if (tid == 0) {
     S.sigma_cell = solid ? sigma_cell : sigma_fluid;
     S.phi_sign = solid ? 1.0 : -1.0;
@@ -173,7 +202,7 @@ MHD_7HD void phase_load(Cell7& S, const Small7& C, int tid, int nt, const double
 
 // ------------------------------------------------------------------ phase 1a: J at the points | first contraction of the point evaluation
 template <int CONV>
-MHD_7HD void phase_geom_a(Cell7& S, const Small7& C, int tid, int nt, const double* gg /* Tab7::gg */) {
+MHD_7HD void phase_geom_a(Cell7& S, const SmallDyn& C, int tid, int nt, const double* gg /* Tab7::gg */) {
   const int n = 243 + (CONV != 0 ? 162 : 0);
   for (int it = tid; it < n; it += nt) {
     if (it < 243) {
@@ -194,7 +223,7 @@ MHD_7HD void phase_geom_a(Cell7& S, const Small7& C, int tid, int nt, const doub
 
 // ------------------------------------------------------------------ phase 1b: inverse / determinant | second contraction
 template <int CONV>
-MHD_7HD void phase_geom_b(Cell7& S, const Small7& C, int tid, int nt, const double* w) {
+MHD_7HD void phase_geom_b(Cell7& S, const SmallDyn& C, int tid, int nt, const double* w) {
   const int n = 27 + (CONV != 0 ? 243 : 0);
   for (int it = tid; it < n; it += nt) {
     if (it < 27) {
@@ -226,7 +255,7 @@ MHD_7HD void phase_geom_b(Cell7& S, const Small7& C, int tid, int nt, const doub
 }
 
 // ------------------------------------------------------------------ phase 2: u and its reference gradient at the points
-MHD_7HD void phase_points(Cell7& S, const Small7& C, int tid, int nt) {
+MHD_7HD void phase_points(Cell7& S, const SmallDyn& C, int tid, int nt) {
   for (int it = tid; it < 324; it += nt) {
     const int kind = it / 81, c = (it / 27) % 3, q = it % 27, q01 = q % 9, q2 = q / 9;
     const double* tb = kind == 3 ? C.LD[2][0] : C.LV[2][0];
@@ -240,7 +269,7 @@ MHD_7HD void phase_points(Cell7& S, const Small7& C, int tid, int nt) {
 
 // ------------------------------------------------------------------ phase 3: coefficient fields
 template <int CONV, bool ZJ>
-MHD_7HD void phase_fields(Cell7& S, const Small7& C, int tid, int nt, const Params& P) {
+MHD_7HD void phase_fields(Cell7& S, const SmallDyn& C, int tid, int nt, const Params& P) {
   for (int it = tid; it < NFIELD * 27; it += nt) {
     const int f = it / 27, q = it % 27;
     const double* I = S.invJ[q];
@@ -282,17 +311,34 @@ MHD_7HD void phase_fields(Cell7& S, const Small7& C, int tid, int nt, const Para
 
 // ------------------------------------------------------------------ phase 4: first contraction (direction d2) of every block
 template <bool ZJ>
-MHD_7HD void phase_stage1(Cell7& S, const Small7& C, int tid, int nt) {
+MHD_7HD void phase_stage1(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
   constexpr int N_UU = 189, N_UJ = N_UU + 81, N_JA = N_UJ + 54, N_JB = N_JA + 54, N_JF = N_JB + 27, N_UP = N_JF + 324;
   const double* F = S.r3;
   for (int it = tid; it < N_UP; it += nt) {
     if (it < N_UU) {
-      const int f = it / 9, r = it % 9;
+      // items grouped by the direction-2 derivative pattern of their field so that the pattern switch is (nearly) warp-uniform
+      // and every table operand a compile-time constant: pattern 0: Newton 0..8, stiffness 9 10 12 13, convection 18 19 |
+      // 1: 11 14 20 | 2: 15 16 | 3: 17
+      const int fi = it / 9, r = it % 9;
+      int f, pat;
+      if (fi < 9) { f = fi; pat = 0; }
+      else if (fi < 13) { f = fi + (fi >= 11 ? 1 : 0); pat = 0; }
+      else if (fi < 15) { f = fi + 5; pat = 0; }
+      else if (fi < 18) { f = fi == 17 ? 20 : 11 + 3 * (fi - 15); pat = 1; }
+      else if (fi < 20) { f = fi - 3; pat = 2; }
+      else { f = 17; pat = 3; }
       const double x0 = F[f * 27 + r], x1 = F[f * 27 + r + 9], x2 = F[f * 27 + r + 18];
-      const double* p = C.Puu[2][pat_uu(f, 2)][0];
       double* o = S.r1 + T1_UU + f * 81 + r;
-      MHD_7UNROLL
-      for (int ab = 0; ab < 9; ab++) o[ab * 9] = p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+#define MHD_7S1(PAT_)                                                                                                   \
+  MHD_7UNROLL                                                                                                           \
+  for (int ab = 0; ab < 9; ab++) o[ab * 9] = K.Puu[2][PAT_][ab][0] * x0 + K.Puu[2][PAT_][ab][1] * x1 + K.Puu[2][PAT_][ab][2] * x2
+      switch (pat) {
+        case 0: MHD_7S1(0); break;
+        case 1: MHD_7S1(1); break;
+        case 2: MHD_7S1(2); break;
+        default: MHD_7S1(3); break;
+      }
+#undef MHD_7S1
     } else if (it < N_UJ) {
       const int i = it - N_UU, inst = i / 9, r = i % 9, k = inst % 3;
       const int s0 = pow3(k), s1 = pow3((k + 1) % 3), d2 = (k + 2) % 3, s2 = pow3(d2);
@@ -353,7 +399,7 @@ MHD_7HD void phase_stage1(Cell7& S, const Small7& C, int tid, int nt) {
 
 // ------------------------------------------------------------------ phase 5: second contraction (direction d1)
 template <int CONV, bool ZJ>
-MHD_7HD void phase_stage2(Cell7& S, const Small7& C, int tid, int nt) {
+MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
   constexpr int N_N = 243, N_B = N_N + 108, N_UJ = N_B + 162, N_JA = N_UJ + 72, N_JB = N_JA + 72, N_JF = N_JB + 36, N_UP = N_JF + 324;
   const double* T1 = S.r1;
   for (int it = tid; it < N_UP; it += nt) {
@@ -362,22 +408,46 @@ MHD_7HD void phase_stage2(Cell7& S, const Small7& C, int tid, int nt) {
       const int f = it / 27, p2 = (it / 3) % 9, q0 = it % 3;
       const double* x = T1 + T1_UU + f * 81 + p2 * 9 + q0;
       const double x0 = x[0], x1 = x[3], x2 = x[6];
-      const double* p = C.Puu[1][0][0];
       double* o = S.r2 + T2_N + f * 243 + p2 * 3 + q0;
       MHD_7UNROLL
-      for (int ab = 0; ab < 9; ab++) o[ab * 27] = p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+      for (int ab = 0; ab < 9; ab++) o[ab * 27] = K.Puu[1][0][ab][0] * x0 + K.Puu[1][0][ab][1] * x1 + K.Puu[1][0][ab][2] * x2;
     } else if (it < N_B) {
       const int i = it - N_N, pc = i / 27, p2 = (i / 3) % 9, q0 = i % 3;
       double acc[9];
       MHD_7UNROLL
       for (int ab = 0; ab < 9; ab++) acc[ab] = 0.0;
-      for (int f = 9; f < (CONV != 0 ? 21 : 18); f++) {
-        if (pat_uu(f, 0) != pc) continue;
-        const double* x = T1 + T1_UU + f * 81 + p2 * 9 + q0;
-        const double x0 = x[0], x1 = x[3], x2 = x[6];
-        const double* p = C.Puu[1][pat_uu(f, 1)][0];
-        MHD_7UNROLL
-        for (int ab = 0; ab < 9; ab++) acc[ab] += p[ab * 3] * x0 + p[ab * 3 + 1] * x1 + p[ab * 3 + 2] * x2;
+      // The fields whose direction-0 derivative pattern is pc, grouped by their direction-1 pattern (stiffness f = 9 + 3 m + n has
+      // pattern 2 (m == ax) + (n == ax) in direction ax, convection f = 18 + n has (n == ax)); fields of one group are summed
+      // before the contraction.  The loop over the pattern is NOT unrolled (27 compile-time table operands per pattern).
+      const double* xb = T1 + T1_UU + p2 * 9 + q0;
+      MHD_7NOUNROLL
+      for (int pat = 0; pat < 4; pat++) {
+        int f1 = -1, f2 = -1;
+        switch (pc * 4 + pat) {
+          case 12: f1 = 9; break;
+          case 9: f1 = 10; break;
+          case 8: f1 = 11; break;
+          case 6: f1 = 12; break;
+          case 4: f1 = 15; f2 = 18; break;
+          case 3: f1 = 13; break;
+          case 2: f1 = 14; break;
+          case 1: f1 = 16; f2 = 19; break;
+          case 0: f1 = 17; f2 = 20; break;
+          default: break;
+        }
+        if (f1 < 0) continue;
+        double x0 = xb[f1 * 81], x1 = xb[f1 * 81 + 3], x2 = xb[f1 * 81 + 6];
+        if (CONV != 0 && f2 >= 0) { x0 += xb[f2 * 81]; x1 += xb[f2 * 81 + 3]; x2 += xb[f2 * 81 + 6]; }
+#define MHD_7ACC(PAT1_)                                                                                                  \
+  MHD_7UNROLL                                                                                                            \
+  for (int ab = 0; ab < 9; ab++) acc[ab] += K.Puu[1][PAT1_][ab][0] * x0 + K.Puu[1][PAT1_][ab][1] * x1 + K.Puu[1][PAT1_][ab][2] * x2
+        switch (pat) {
+          case 0: MHD_7ACC(0); break;
+          case 1: MHD_7ACC(1); break;
+          case 2: MHD_7ACC(2); break;
+          default: MHD_7ACC(3); break;
+        }
+#undef MHD_7ACC
       }
       double* o = S.r2 + T2_B + pc * 243 + p2 * 3 + q0;
       MHD_7UNROLL
@@ -447,27 +517,32 @@ MHD_7HD void phase_stage2(Cell7& S, const Small7& C, int tid, int nt) {
 }
 
 // ------------------------------------------------------------------ phase 5b: D[k][(c, tensor node)] = int pi_k d_c N, pressure mass matrix
+// pressure mass matrix (zeta_u projection): 16 entries
+MHD_7HD void phase_Mp(Cell7& S, const SmallDyn& C, int tid, int nt) {
+  for (int i = tid; i < 16; i += nt) {
+    double s = 0.0;
+    for (int q = 0; q < 27; q++) s += S.W[q] * C.pp[q][i / 4] * C.pp[q][i % 4];
+    S.Mp[i] = s;
+  }
+}
+
 template <bool ZU>
-MHD_7HD void phase_D(Cell7& S, const Small7& C, int tid, int nt) {
+MHD_7HD void phase_D(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
   double* D = cellD(S);
-  for (int it = tid; it < 108 + (ZU ? 16 : 0); it += nt) {
-    if (it < 108) {
+  for (int it = tid; it < 108; it += nt) {
+    {
       const int kc = it / 9, a1 = (it / 3) % 3, a2 = it % 3, kp = kc / 3, c = kc % 3;
       double acc[3] = {0.0, 0.0, 0.0};
       MHD_7UNROLL
       for (int kk = 0; kk < 3; kk++) {
         const double* x = S.r3 + R3_T2UP + (kc * 3 + kk) * 27 + a1 * 9 + a2 * 3;
-        const double* tb = kk == 0 ? C.LD[0][0] : C.LV[0][0];
         MHD_7UNROLL
-        for (int a0 = 0; a0 < 3; a0++) acc[a0] += tb[a0 * 3] * x[0] + tb[a0 * 3 + 1] * x[1] + tb[a0 * 3 + 2] * x[2];
+        for (int a0 = 0; a0 < 3; a0++)
+          acc[a0] += (kk == 0 ? K.LD[0][a0][0] : K.LV[0][a0][0]) * x[0] + (kk == 0 ? K.LD[0][a0][1] : K.LV[0][a0][1]) * x[1] +
+                     (kk == 0 ? K.LD[0][a0][2] : K.LV[0][a0][2]) * x[2];
       }
       MHD_7UNROLL
       for (int a0 = 0; a0 < 3; a0++) D[kp * 81 + c * 27 + a0 + 3 * a1 + 9 * a2] = acc[a0];
-    } else {
-      const int i = it - 108;
-      double s = 0.0;
-      for (int q = 0; q < 27; q++) s += S.W[q] * C.pp[q][i / 4] * C.pp[q][i % 4];
-      S.Mp[i] = s;
     }
   }
 }
@@ -515,40 +590,43 @@ MHD_7HD void phase_E(Cell7& S, int tid, int nt, double zeta_u) {
 // ------------------------------------------------------------------ chunks: last contraction (direction d0) -> staging buffer
 // uu rows of component c: buf[slot(a) * 81 + 3 slot(b) + d]
 template <int CONV, bool ZU>
-MHD_7HD void chunk_uu(Cell7& S, const Small7& C, int tid, int nt, int c, double* buf) {
+MHD_7HD void chunk_uu(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt, int c, double* buf) {
   const double* D = cellD(S);
   const double* E = cellE(S);
   for (int it = tid; it < 243; it += nt) {
     const int a0 = it / 81, p1 = (it / 9) % 9, p2 = it % 9, bi = p1 * 27 + p2 * 3;
     const int a1 = p1 / 3, b1 = p1 % 3, a2 = p2 / 3, b2 = p2 % 3;
     const int ta = a0 + 3 * a1 + 9 * a2, tb12 = 3 * b1 + 9 * b2;
+    // Puu[0][2 m + n][3 a0 + b0][q] = (m ? LD : LV)[0][a0][q] * (n ? LD : LV)[0][b0][q]: fold the row factor (thread-dependent
+    // class a0) into the stage-2 data once, the column factor (unrolled b0) is a compile-time table operand
+    double rv[3], rd[3];
+    MHD_7UNROLL
+    for (int q = 0; q < 3; q++) { rv[q] = C.LV[0][a0][q]; rd[q] = C.LD[0][a0][q]; }
     double tb[4][3], tn[3][3];
     MHD_7UNROLL
     for (int pc = 0; pc < 4; pc++)
       MHD_7UNROLL
-      for (int q = 0; q < 3; q++) tb[pc][q] = S.r2[T2_B + pc * 243 + bi + q];
+      for (int q = 0; q < 3; q++) tb[pc][q] = ((pc & 2) ? rd[q] : rv[q]) * S.r2[T2_B + pc * 243 + bi + q];
     if (CONV == 2) {
       MHD_7UNROLL
       for (int d = 0; d < 3; d++)
         MHD_7UNROLL
-        for (int q = 0; q < 3; q++) tn[d][q] = S.r2[T2_N + (c * 3 + d) * 243 + bi + q];
+        for (int q = 0; q < 3; q++) tn[d][q] = rv[q] * S.r2[T2_N + (c * 3 + d) * 243 + bi + q];
     }
     const int rowoff = S.slot_u[ta] * 81;
     MHD_7UNROLL
     for (int b0 = 0; b0 < 3; b0++) {
-      const int ab = a0 * 3 + b0, tbn = b0 + tb12;
+      const int tbn = b0 + tb12;
       double base = 0.0;
       MHD_7UNROLL
-      for (int pc = 0; pc < 4; pc++) {
-        const double* p = C.Puu[0][pc][ab];
-        base += p[0] * tb[pc][0] + p[1] * tb[pc][1] + p[2] * tb[pc][2];
-      }
-      const double* pv = C.Puu[0][0][ab];
+      for (int pc = 0; pc < 4; pc++)
+        MHD_7UNROLL
+        for (int q = 0; q < 3; q++) base += ((pc & 1) ? K.LD[0][b0][q] : K.LV[0][b0][q]) * tb[pc][q];
       const int col = 3 * S.slot_u[tbn];
       MHD_7UNROLL
       for (int d = 0; d < 3; d++) {
         double v = d == c ? base : 0.0;
-        if (CONV == 2) v += pv[0] * tn[d][0] + pv[1] * tn[d][1] + pv[2] * tn[d][2];
+        if (CONV == 2) v += K.LV[0][b0][0] * tn[d][0] + K.LV[0][b0][1] * tn[d][1] + K.LV[0][b0][2] * tn[d][2];
         if (ZU) v += D[c * 27 + ta] * E[d * 27 + tbn] + D[81 + c * 27 + ta] * E[81 + d * 27 + tbn] + D[162 + c * 27 + ta] * E[162 + d * 27 + tbn] +
                      D[243 + c * 27 + ta] * E[243 + d * 27 + tbn];
         buf[rowoff + col + d] = v;
@@ -558,34 +636,45 @@ MHD_7HD void chunk_uu(Cell7& S, const Small7& C, int tid, int nt, int c, double*
 }
 
 // uj (JU = false): buf[(c*27 + slot(a)) * 36 + slot(m)] = -gamma sgn V ;  ju (JU = true): buf[slot(m) * 81 + 3 slot(a) + c] = +sigma sgn V
+template <bool JU, int KD>
+MHD_7HD void chunk_uj_k(Cell7& S, const Small7& K, const Params& P, double* buf, int c, int p1, int p2) {
+  constexpr int d1 = (KD + 1) % 3, d2 = (KD + 2) % 3;
+  constexpr int s0 = KD == 0 ? 1 : (KD == 1 ? 3 : 9), s1 = d1 == 0 ? 1 : (d1 == 1 ? 3 : 9), s2 = d2 == 0 ? 1 : (d2 == 1 ? 3 : 9);
+  const double* x = S.r2 + T2_UJ + (c * 3 + KD) * 108 + p1 * 18 + p2 * 3;
+  const double x0 = x[0], x1 = x[1], x2 = x[2];
+  const int a1 = p1 / 2, i1 = p1 % 2, a2 = p2 / 2, i2 = p2 % 2;
+  const int ta12 = a1 * s1 + a2 * s2, tj12 = 12 * KD + 3 * (i1 + 2 * i2);
+  const double coef = JU ? P.sigma : -P.gamma;
+  double sg[3];
+  int sj[3];
+  MHD_7UNROLL
+  for (int i0 = 0; i0 < 3; i0++) { sg[i0] = coef * S.sgn[tj12 + i0]; sj[i0] = S.slot_j[tj12 + i0]; }
+  MHD_7UNROLL
+  for (int a = 0; a < 3; a++) {
+    const int su = S.slot_u[ta12 + a * s0];
+    MHD_7UNROLL
+    for (int i0 = 0; i0 < 3; i0++) {
+      const double v = sg[i0] * (K.Puj[KD][a * 3 + i0][0] * x0 + K.Puj[KD][a * 3 + i0][1] * x1 + K.Puj[KD][a * 3 + i0][2] * x2);
+      if (JU) buf[sj[i0] * 81 + 3 * su + c] = v;
+      else buf[(c * 27 + su) * 36 + sj[i0]] = v;
+    }
+  }
+}
 template <bool JU>
-MHD_7HD void chunk_uj(Cell7& S, const Small7& C, int tid, int nt, const Params& P, double* buf) {
+MHD_7HD void chunk_uj(Cell7& S, const Small7& K, int tid, int nt, const Params& P, double* buf) {
   for (int it = tid; it < 324; it += nt) {
     const int inst = it / 36, p1 = (it / 6) % 6, p2 = it % 6, c = inst / 3, k = inst % 3;
-    const int d1 = (k + 1) % 3, d2 = (k + 2) % 3;
-    const double* x = S.r2 + T2_UJ + inst * 108 + p1 * 18 + p2 * 3;
-    const double x0 = x[0], x1 = x[1], x2 = x[2];
-    const int a1 = p1 / 2, i1 = p1 % 2, a2 = p2 / 2, i2 = p2 % 2;
-    const int ta12 = a1 * pow3(d1) + a2 * pow3(d2), s0 = pow3(k), tj12 = 12 * k + 3 * (i1 + 2 * i2);
-    const double coef = JU ? P.sigma : -P.gamma;
-    MHD_7UNROLL
-    for (int a = 0; a < 3; a++) {
-      const int su = S.slot_u[ta12 + a * s0];
-      MHD_7UNROLL
-      for (int i0 = 0; i0 < 3; i0++) {
-        const double* p = C.Puj[k][a * 3 + i0];
-        const int tj = tj12 + i0;
-        const double v = coef * S.sgn[tj] * (p[0] * x0 + p[1] * x1 + p[2] * x2);
-        if (JU) buf[S.slot_j[tj] * 81 + 3 * su + c] = v;
-        else buf[(c * 27 + su) * 36 + S.slot_j[tj]] = v;
-      }
+    switch (k) {
+      case 0: chunk_uj_k<JU, 0>(S, K, P, buf, c, p1, p2); break;
+      case 1: chunk_uj_k<JU, 1>(S, K, P, buf, c, p1, p2); break;
+      default: chunk_uj_k<JU, 2>(S, K, P, buf, c, p1, p2); break;
     }
   }
 }
 
 // the rest: jj | j-phi | phi-j | up | pu
 template <bool ZJ>
-MHD_7HD void chunk_rest(Cell7& S, const Small7& C, int tid, int nt, double* buf) {
+MHD_7HD void chunk_rest(Cell7& S, const SmallDyn& C, int tid, int nt, double* buf) {
   constexpr int N_JA = 48, N_JB = N_JA + 72, N_JF = N_JB + 48, N_UP = N_JF + 324;
   const double* D = cellD(S);
   for (int it = tid; it < N_UP; it += nt) {
@@ -658,6 +747,216 @@ MHD_7HD void chunk_rest(Cell7& S, const Small7& C, int tid, int nt, double* buf)
       buf[R_UP + (c * 27 + su) * 4 + kp] = v;
       buf[R_PU + kp * 81 + 3 * su + c] = v;
     }
+  }
+}
+
+// =================================================================== residual (res_fluid_h1_hdiv / res_solid_h1_hdiv,
+// src/weakforms.jl:255-281, :314-325) by sum factorisation, interleaved with the Jacobian phases of the same cell: every
+// res_* phase shares a barrier interval with a Jacobian phase (see hdiv_v7.cu).  radd(local row (permuted numbering), value)
+// accumulates into the global vector.
+//   r_u[(a,c)] = sum_q [ G^k_c d^_k N_a + H_c N_a ],  G^k_c = w sum_i invJ[k][i] (beta (grad u)[i][c] + delta_ic (zeta_u Pi_p - p)),
+//                                                      H_c   = w (alpha ((u.grad)u)_c - gamma (j x B)_c - f_c)
+//   r_p[k]     = - sum_q w pi_k div u
+//   r_j[m]     = sgn_m sum_q [ V_k psi^_m,k + S div^ psi^_m ],  V = w/det J^T (j - sigma u x B - g),  S = w/det (zeta_j div j - sigma_c phi)
+//   r_phi[l]   = phi_sign sum_q w chi_l div j          (phi_sign = -1 fluid, +1 solid)
+
+// interval of phase_geom_a: reference current j^_k, its divergence by component, p and phi at the points (state only)
+MHD_7HD void res_pv(Cell7& S, const SmallDyn& C, int tid, int nt) {
+  for (int it = tid; it < 216; it += nt) {
+    if (it < 162) {
+      const bool dv = it >= 81;
+      const int r = dv ? it - 81 : it, k = r / 27, q = r % 27;
+      const int q0 = qdir(q, k), q1 = qdir(q, (k + 1) % 3), q2 = qdir(q, (k + 2) % 3);
+      const double* jt = S.rs + RS_JT + 12 * k;
+      double s = 0.0;
+      MHD_7UNROLL
+      for (int i2 = 0; i2 < 2; i2++)
+        MHD_7UNROLL
+        for (int i1 = 0; i1 < 2; i1++) {
+          const double f12 = C.RV[k][1][i1][q1] * C.RV[k][2][i2][q2];
+          MHD_7UNROLL
+          for (int i0 = 0; i0 < 3; i0++) s += jt[i0 + 3 * (i1 + 2 * i2)] * (dv ? C.RD[k][i0][q0] : C.RV[k][0][i0][q0]) * f12;
+        }
+      S.rs[(dv ? RS_DJ : RS_JH) + r] = s;
+    } else if (it < 189) {
+      const int q = it - 162;
+      const double* ps = S.rs + RS_PST;
+      S.rs[RS_P + q] = C.pp[q][0] * ps[0] + C.pp[q][1] * ps[1] + C.pp[q][2] * ps[2] + C.pp[q][3] * ps[3];
+    } else {
+      const int q = it - 189, q0 = q % 3, q1 = (q / 3) % 3, q2 = q / 9;
+      double s = 0.0;
+      MHD_7UNROLL
+      for (int l = 0; l < 8; l++)
+        s += S.rs[RS_FST + C.t_phi[l]] * C.XV[0][l & 1][q0] * C.XV[1][(l >> 1) & 1][q1] * C.XV[2][l >> 2][q2];
+      S.rs[RS_F + q] = s;
+    }
+  }
+}
+
+// interval of phase_fields: div u at the points
+MHD_7HD void res_divu(Cell7& S, int tid, int nt) {
+  for (int q = tid; q < 27; q += nt) {
+    const double* I = S.invJ[q];
+    const double* G = S.gur[q];
+    double s = 0.0;
+    MHD_7UNROLL
+    for (int k = 0; k < 3; k++)
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++) s += I[k * 3 + i] * G[k * 3 + i];
+    S.rs[RS_DIVU + q] = s;
+  }
+}
+
+// interval of phase_stage1: d_k = sum_q w pi_k div u ; r_p = -d
+template <class RAdd>
+MHD_7HD void res_d(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& radd) {
+  for (int k = tid; k < 4; k += nt) {
+    double s = 0.0;
+    for (int q = 0; q < 27; q++) s += S.W[q] * C.pp[q][k] * S.rs[RS_DIVU + q];
+    S.rs[RS_D + k] = s;
+    radd(OFF_P + k, -s);
+  }
+}
+
+// interval of phase_stage2: the coefficient fields of the residual -> r3[RF_*]
+template <int CONV, bool ZU, bool ZJ>
+MHD_7HD void res_fields(Cell7& S, const SmallDyn& C, int tid, int nt, const Params& P) {
+  double* F = S.r3;
+  for (int it = tid; it < 162; it += nt) {
+    const int q = it % 27, grp = it / 27;
+    const double* I = S.invJ[q];
+    const double* J = S.J[q];
+    const double* G = S.gur[q];
+    const double w = S.W[q], id = S.idet[q];
+    if (grp < 3) {  // G^k_c, c = grp
+      const int c = grp;
+      double s = -S.rs[RS_P + q];
+      if (ZU) {
+        double pr = 0.0;
+        MHD_7UNROLL
+        for (int k = 0; k < 4; k++)
+          pr += C.pp[q][k] * (S.Minv[k * 4 + 0] * S.rs[RS_D] + S.Minv[k * 4 + 1] * S.rs[RS_D + 1] + S.Minv[k * 4 + 2] * S.rs[RS_D + 2] +
+                              S.Minv[k * 4 + 3] * S.rs[RS_D + 3]);
+        s += P.zeta_u * pr;
+      }
+      double t[3];  // beta (grad u)[i][c] + delta_ic s
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++) t[i] = P.beta * (I[0 * 3 + i] * G[0 * 3 + c] + I[1 * 3 + i] * G[1 * 3 + c] + I[2 * 3 + i] * G[2 * 3 + c]) + (i == c ? s : 0.0);
+      MHD_7UNROLL
+      for (int k = 0; k < 3; k++) F[RF_G + (c * 3 + k) * 27 + q] = w * (I[k * 3 + 0] * t[0] + I[k * 3 + 1] * t[1] + I[k * 3 + 2] * t[2]);
+    } else if (grp == 3 || grp == 4) {  // H_c | V_k: both need the physical current
+      double jp[3];
+      MHD_7UNROLL
+      for (int i = 0; i < 3; i++)
+        jp[i] = id * (J[i * 3 + 0] * S.rs[RS_JH + q] + J[i * 3 + 1] * S.rs[RS_JH + 27 + q] + J[i * 3 + 2] * S.rs[RS_JH + 54 + q]);
+      const double* u = S.uq[q];
+      if (grp == 3) {
+        MHD_7UNROLL
+        for (int c = 0; c < 3; c++) {
+          const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+          double h = -P.gamma * (jp[c1] * P.B[c2] - jp[c2] * P.B[c1]) - P.f[c];
+          if (CONV != 0) {
+            double cv = 0.0;  // ((u . grad) u)_c = sum_i u_i d_i u_c
+            MHD_7UNROLL
+            for (int i = 0; i < 3; i++) cv += u[i] * (I[0 * 3 + i] * G[0 * 3 + c] + I[1 * 3 + i] * G[1 * 3 + c] + I[2 * 3 + i] * G[2 * 3 + c]);
+            h += P.alpha * cv;
+          }
+          F[RF_H + c * 27 + q] = w * h;
+        }
+      } else {
+        double v[3];
+        MHD_7UNROLL
+        for (int i = 0; i < 3; i++) {
+          const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+          v[i] = jp[i] - P.sigma * (u[i1] * P.B[i2] - u[i2] * P.B[i1]) - P.g[i];
+        }
+        MHD_7UNROLL
+        for (int k = 0; k < 3; k++) F[RF_V + k * 27 + q] = w * id * (J[0 * 3 + k] * v[0] + J[1 * 3 + k] * v[1] + J[2 * 3 + k] * v[2]);
+      }
+    } else {  // S and w div j
+      const double dj = id * (S.rs[RS_DJ + q] + S.rs[RS_DJ + 27 + q] + S.rs[RS_DJ + 54 + q]);
+      F[RF_S + q] = w * id * ((ZJ ? P.zeta_j * dj : 0.0) - S.sigma_cell * S.rs[RS_F + q]);
+      F[RF_DJ + q] = w * dj;
+    }
+  }
+}
+
+// interval of phase_D: first contraction of the u rows | partial sums of the j rows | phi rows
+template <class RAdd>
+MHD_7HD void res_stage_a(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& radd) {
+  double* F = S.r3;
+  for (int it = tid; it < 152; it += nt) {
+    if (it < 108) {
+      const int c = it / 36, f = (it / 9) % 4, q01 = it % 9;
+      const double* x = F + (f < 3 ? RF_G + (c * 3 + f) * 27 : RF_H + c * 27) + q01;
+      const double x0 = x[0], x1 = x[9], x2 = x[18];
+      const double* tb = f == 2 ? C.LD[2][0] : C.LV[2][0];
+      double* o = F + RR_A + ((c * 4 + f) * 3) * 9 + q01;
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++) o[a * 9] = tb[a * 3] * x0 + tb[a * 3 + 1] * x1 + tb[a * 3 + 2] * x2;
+    } else if (it < 144) {
+      const int r = it - 108, k = r / 12, i1 = (r / 6) % 2, i2 = (r / 3) % 2, qk = r % 3;
+      const int s0 = pow3(k), s1 = pow3((k + 1) % 3), s2 = pow3((k + 2) % 3);
+      double pv = 0.0, ps = 0.0;
+      MHD_7UNROLL
+      for (int q2 = 0; q2 < 3; q2++)
+        MHD_7UNROLL
+        for (int q1 = 0; q1 < 3; q1++) {
+          const int q = qk * s0 + q1 * s1 + q2 * s2;
+          const double t = C.RV[k][1][i1][q1] * C.RV[k][2][i2][q2];
+          pv += t * F[RF_V + k * 27 + q];
+          ps += t * F[RF_S + q];
+        }
+      F[RR_JP + ((k * 4 + i1 + 2 * i2) * 3 + qk) * 2] = pv;
+      F[RR_JP + ((k * 4 + i1 + 2 * i2) * 3 + qk) * 2 + 1] = ps;
+    } else {
+      const int lt = it - 144, l0 = lt & 1, l1 = (lt >> 1) & 1, l2 = lt >> 2;
+      double s = 0.0;
+      for (int q = 0; q < 27; q++) s += F[RF_DJ + q] * C.XV[0][l0][q % 3] * C.XV[1][l1][(q / 3) % 3] * C.XV[2][l2][q / 9];
+      radd(OFF_F + C.t_phi[lt], S.phi_sign * s);
+    }
+  }
+}
+
+// next interval: second contraction of the u rows | j rows
+template <class RAdd>
+MHD_7HD void res_stage_b(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& radd) {
+  double* F = S.r3;
+  for (int it = tid; it < 144; it += nt) {
+    if (it < 108) {
+      const int cf = it / 9, f = cf % 4, a2 = (it / 3) % 3, q0 = it % 3;
+      const double* x = F + RR_A + (cf * 3 + a2) * 9 + q0;
+      const double x0 = x[0], x1 = x[3], x2 = x[6];
+      const double* tb = f == 1 ? C.LD[1][0] : C.LV[1][0];
+      double* o = F + RR_B + (cf * 9 + a2) * 3 + q0;  // [(cf * 3 + a1) * 3 + a2] * 3 + q0
+      MHD_7UNROLL
+      for (int a = 0; a < 3; a++) o[a * 9] = tb[a * 3] * x0 + tb[a * 3 + 1] * x1 + tb[a * 3 + 2] * x2;
+    } else {
+      const int r = it - 108, k = r / 12, i0 = r % 3, i12 = (r / 3) % 4;
+      const double* jp = F + RR_JP + ((k * 4 + i12) * 3) * 2;
+      double s = 0.0;
+      MHD_7UNROLL
+      for (int qk = 0; qk < 3; qk++) s += jp[qk * 2] * C.RV[k][0][i0][qk] + jp[qk * 2 + 1] * C.RD[k][i0][qk];
+      const int tj = 12 * k + i0 + 3 * i12;
+      radd(OFF_J + S.slot_j[tj], S.sgn[tj] * s);
+    }
+  }
+}
+
+// interval of chunk_uu(0): last contraction of the u rows
+template <class RAdd>
+MHD_7HD void res_stage_c(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& radd) {
+  const double* F = S.r3;
+  for (int it = tid; it < 81; it += nt) {
+    const int c = it / 27, t = it % 27, a0 = t % 3, a12 = ((t / 3) % 3) * 3 + t / 9;  // a1 * 3 + a2: layout of res_stage_b
+    double s = 0.0;
+    MHD_7UNROLL
+    for (int f = 0; f < 4; f++) {
+      const double* x = F + RR_B + (((c * 4 + f) * 9) + a12) * 3;
+      const double* tb = f == 0 ? C.LD[0][a0] : C.LV[0][a0];
+      s += tb[0] * x[0] + tb[1] * x[1] + tb[2] * x[2];
+    }
+    radd(c * 27 + S.slot_u[t], s);
   }
 }
 

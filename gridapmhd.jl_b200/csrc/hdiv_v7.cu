@@ -1,0 +1,490 @@
+// "v7" Jacobian kernel of the H1-HDiv formulation (jac_fluid_h1_hdiv / jac_solid_h1_hdiv, src/weakforms.jl:283-312,:327-338):
+// the fully sum-factorised cell code of hdiv7_cell.h run by one CTA of 256 threads per cell on a persistent grid (2 CTAs per
+// SM).  ~0.13 M FMA per cell instead of 0.43 M, operands of a few hundred bytes instead of 27 x 27 panels, so the kernel's
+// time goes where the roofline says it should: into streaming the 14 913 values of a cell out through the u16 scatter map.
+//
+// * The 1-D factors are DISCOVERED from the plain tables of mhd_tables_t when the operator is created (hdiv7_tables.h); an
+//   operator whose tables lack the tensor structure keeps the generic tensor-core kernel of assembly.cu.
+// * Values are staged in shared memory in destination order (permuted local numbering: every field sorted by global id),
+//   chunk by chunk in two buffers; while chunk n+1 is computed, chunk n is swept out 32 consecutive map entries per
+//   instruction.  The map codes of a chunk are fetched into registers one barrier interval before they are needed.
+// * nnz that receive exactly one contribution (67 % on Hunt meshes) are stored plainly; the others are accumulated with
+//   RED.ADD.F64 after `zero_shared` cleared just those (a bit mask from the symbolic phase) -- no 1.2 GB memset.
+#include <stdlib.h>
+
+#include "common.h"
+#include "hdiv7_cell.h"
+
+namespace mhd {
+
+namespace {
+
+constexpr int V7_NT = 256;
+
+struct V7Args {
+  const double* coords;
+  const int32_t* cell_nodes;
+  const int32_t* pgids;
+  const long long* rowstart;
+  const uint8_t* perm;
+  const uint8_t* cell_solid;
+  const double* cell_sigma;
+  const double* dir;
+  const h7::Tab7* tab;
+  const int32_t* cell_list;  // nullable: cells of one colour (deterministic mode)
+  unsigned long long* clk;   // nullable: phase clocks
+};
+
+// ids of the NEXT cell, fetched with cp.async while the current cell is being integrated (phase_load then only gathers x)
+struct NextIds {
+  uint8_t perm[64];   // 16-byte copies
+  int32_t nodes[8];   // 16-byte copies
+  long long rowstart[h7::NLOC];
+  int32_t gid[h7::NLOC];
+  int32_t pad_[1];
+};
+static_assert(sizeof(NextIds) % 16 == 0, "NextIds must keep 16-byte alignment");
+
+constexpr int V7_CODES = h7::CH_UJ_PAD;  // u16 codes of the largest chunk
+constexpr size_t V7_SMEM_CELL = (sizeof(h7::Cell7) + 15) / 16 * 16;
+constexpr size_t V7_SMEM_SMALL = (sizeof(h7::SmallDyn) + 15) / 16 * 16;
+constexpr size_t V7_OFF_NEXT = V7_SMEM_CELL + V7_SMEM_SMALL;
+constexpr size_t V7_OFF_CODES = V7_OFF_NEXT + sizeof(NextIds);
+constexpr size_t V7_SMEM = V7_OFF_CODES + V7_CODES * sizeof(uint16_t);
+static_assert(2 * (V7_SMEM + 64 + 1024) <= 233472, "two CTAs of the v7 kernel must fit one SM");
+
+// The cell-independent 1-D tables exist twice: the ones looked up with thread-dependent indices in shared memory (SmallDyn C),
+// everything in constant memory (Small7 K): a table operand whose index is known at compile time (the unrolled inner loops of
+// the hot phases) becomes an immediate constant-bank operand of its DFMA -- no shared-memory wavefront, which is what bounds
+// the kernel.  (Measured: routing the thread-dependent lookups through the constant cache as well -- LDC with divergent
+// addresses -- is slower than shared memory.)  One copy per module: v7_launch_jacobian re-uploads it when an operator with
+// different tables comes along.
+__constant__ h7::Small7 c_small7;
+std::vector<unsigned char> g_small7_loaded;  // host copy of what c_small7 holds (compared by content: 5.6 KB)
+int g_small7_device = -1;
+
+extern __shared__ __align__(16) unsigned char v7_smem[];
+__device__ __forceinline__ h7::Cell7& sm_cell() { return *reinterpret_cast<h7::Cell7*>(v7_smem); }
+__device__ __forceinline__ h7::SmallDyn& sm_small() { return *reinterpret_cast<h7::SmallDyn*>(v7_smem + V7_SMEM_CELL); }
+__device__ __forceinline__ NextIds& sm_next() { return *reinterpret_cast<NextIds*>(v7_smem + V7_OFF_NEXT); }
+__device__ __forceinline__ uint16_t* sm_codes() { return reinterpret_cast<uint16_t*>(v7_smem + V7_OFF_CODES); }
+template <int B>
+__device__ __forceinline__ double* sm_buf() { return B == 0 ? sm_cell().r1 : sm_cell().r3; }
+
+// Each heavy phase is its own (non-inlined) function: one register allocation per phase, nothing hoisted across phases --
+// inlined into one body ptxas wants 164 registers and spills at the 128 the two resident CTAs allow.  The functions re-derive
+// their shared-memory references from the extern array (a reference PARAMETER would turn every access into a generic LD/ST).
+#define V7_NI static __device__ __noinline__
+template <int CONV, bool ZJ>
+V7_NI void ni_fields(int tid, const h7::Params& P) { h7::phase_fields<CONV, ZJ>(sm_cell(), sm_small(), tid, V7_NT, P); }
+template <bool ZJ>
+V7_NI void ni_stage1(int tid) { h7::phase_stage1<ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
+template <int CONV, bool ZJ>
+V7_NI void ni_stage2(int tid) { h7::phase_stage2<CONV, ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
+template <int CONV, bool ZU, int CC>
+V7_NI void ni_chunk_uu(int tid) { h7::chunk_uu<CONV, ZU>(sm_cell(), sm_small(), c_small7, tid, V7_NT, CC, sm_buf<CC & 1>()); }
+template <bool JU>
+V7_NI void ni_chunk_uj(int tid, const h7::Params& P) { h7::chunk_uj<JU>(sm_cell(), c_small7, tid, V7_NT, P, sm_buf<JU ? 0 : 1>()); }
+template <bool ZJ>
+V7_NI void ni_chunk_rest(int tid) { h7::chunk_rest<ZJ>(sm_cell(), sm_small(), tid, V7_NT, sm_buf<1>()); }
+
+#define V7_CLK(slot)                                                        \
+  do {                                                                      \
+    if (A.clk != nullptr && tid == 0) {                                     \
+      const long long now_ = clock64();                                     \
+      clk_acc[slot] += (unsigned long long)(now_ - (long long)clk_acc[7]);  \
+      clk_acc[7] = (unsigned long long)now_;                                \
+    }                                                                       \
+  } while (0)
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// ids of `cell` -> staging (one or two copies per thread), and its scatter map -> L2
+__device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const uint16_t* __restrict__ map, int64_t cell, int tid) {
+  for (int i = tid; i < h7::NLOC; i += V7_NT) {
+    cp_async8(&N.rowstart[i], A.rowstart + cell * h7::NLOC + i);
+    cp_async4(&N.gid[i], A.pgids + cell * h7::NLOC + i);
+  }
+  if (tid >= 192 && tid < 196) cp_async16(&N.perm[(tid - 192) * 16], A.perm + cell * PERM_STRIDE + (tid - 192) * 16);
+  if (tid >= 224 && tid < 226) cp_async16(&N.nodes[(tid - 224) * 4], A.cell_nodes + cell * 8 + (tid - 224) * 4);
+  const char* mp = reinterpret_cast<const char*>(map + cell * h7::NENT);
+  if (tid * 128 < h7::NENT * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + tid * 128));
+}
+
+// Scatter-map codes of a chunk: global -> shared with cp.async, issued BEFORE the chunk is computed, consumed by the sweep one
+// barrier interval later.  Warp w owns the 32-entry segments w, w + 8, ...: it alone writes (lanes 0..3, 16 bytes each) and
+// reads them, so one buffer serves all chunks -- a warp refills its segments as soon as its own sweep is through with them.
+template <int NSEG>
+__device__ __forceinline__ void codes_fetch(const uint16_t* __restrict__ m, int tid) {
+  const int w = tid >> 5, lane = tid & 31;
+  __syncwarp();
+  if (lane < 4) {
+#pragma unroll
+    for (int j = 0; j < (NSEG + 7) / 8; j++) {
+      const int seg = w + 8 * j;
+      if (seg < NSEG) cp_async16(sm_codes() + seg * 32 + lane * 8, m + seg * 32 + lane * 8);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// value buf[i] of entry i goes to rowbase[row(i)] + 8 * code: plain store (MAP_EXCL) or reduction, predicated -- no branch
+__device__ __forceinline__ void scatter_one(unsigned code, unsigned long long rowbase, double v) {
+  const unsigned long long addr = rowbase + (unsigned long long)((code & 0x7FFFu) << 3);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pst, prd;\n\t"
+      "setp.ge.u32 pst, %2, 0x8000;\n\t"
+      "setp.lt.u32 prd, %2, 0x8000;\n\t"
+      "setp.ne.and.u32 pst, %2, 0xFFFF, pst;\n\t"
+      "@pst st.global.f64 [%0], %1;\n\t"
+      "@prd red.global.add.f64 [%0], %1;\n\t"
+      "}" ::"l"(addr), "d"(v), "r"(code)
+      : "memory");
+}
+
+// sweep of a chunk of NSEG 32-entry segments with NCOL entries per row, rows from row0 (pads carry MAP_SKIP)
+template <int NSEG, int NCOL>
+__device__ __forceinline__ void sweep(const double* __restrict__ buf, int row0, int tid) {
+  const int w = tid >> 5, lane = tid & 31;
+  const uint16_t* codes = sm_codes();
+  const long long* rowbase = sm_cell().rowaddr;
+#pragma unroll
+  for (int j = 0; j < (NSEG + 7) / 8; j++) {
+    const int seg = w + 8 * j;
+    if (seg < NSEG) {
+      const int i = seg * 32 + lane;
+      int row = row0 + i / NCOL;
+      if (row > h7::NLOC - 1) row = h7::NLOC - 1;  // pad entries of the last segment
+      scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
+    }
+  }
+}
+// the last chunk holds five sections: jj | j-phi | phi-j | up | pu
+__device__ __forceinline__ void sweep_rest(const double* __restrict__ buf, int tid) {
+  constexpr int NSEG = h7::CH_REST_PAD / 32;
+  constexpr int R_JF = h7::R_JF, R_FJ = h7::R_FJ, R_UP = h7::R_UP, R_PU = h7::R_PU;
+  constexpr int OFF_P = h7::OFF_P, OFF_J = h7::OFF_J, OFF_F = h7::OFF_F, NLOC = h7::NLOC;
+  const int w = tid >> 5, lane = tid & 31;
+  const uint16_t* codes = sm_codes();
+  const long long* rowbase = sm_cell().rowaddr;
+#pragma unroll
+  for (int j = 0; j < (NSEG + 7) / 8; j++) {
+    const int seg = w + 8 * j;
+    if (seg < NSEG) {
+      const int i = seg * 32 + lane;
+      int row;
+      if (i < R_JF) row = OFF_J + i / 36;
+      else if (i < R_FJ) row = OFF_J + (i - R_JF) / 8;
+      else if (i < R_UP) row = OFF_F + (i - R_FJ) / 36;
+      else if (i < R_PU) row = (i - R_UP) / 4;
+      else row = OFF_P + (i - R_PU) / 81;
+      if (row > NLOC - 1) row = NLOC - 1;
+      scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
+    }
+  }
+}
+
+struct DevRAdd {
+  double* r;
+  int64_t nrows;
+  __device__ __forceinline__ void operator()(int row, double v) const {
+    const int32_t g = sm_cell().gid[row];
+    if (g >= 0 && g < nrows) atomicAdd(r + g, v);
+  }
+};
+template <int CONV, bool ZU, bool ZJ>
+V7_NI void ni_res_fields(int tid, const h7::Params& P) { h7::res_fields<CONV, ZU, ZJ>(sm_cell(), sm_small(), tid, V7_NT, P); }
+
+// RES: residual_and_jacobian! -- the residual phases ride in the barrier intervals of the Jacobian phases
+template <int CONV, bool ZU, bool ZJ, bool RES>
+__global__ void __launch_bounds__(V7_NT, 2)
+hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* __restrict__ x, const uint16_t* __restrict__ map,
+                        double* __restrict__ nzval, double* __restrict__ rout, const __grid_constant__ h7::Params P) {
+  using namespace h7;
+  constexpr int WU = (CONV != 0 || RES) ? 1 : 0;  // velocity and its gradient at the points are needed
+  constexpr int SEG_UU = CH_UU_PAD / 32, SEG_UJ = CH_UJ_PAD / 32, SEG_REST = CH_REST_PAD / 32;
+  Cell7& S = sm_cell();
+  SmallDyn& C = sm_small();
+  NextIds& N = sm_next();
+  const Small7& K = c_small7;
+  small_from_tab(C, *A.tab, threadIdx.x, V7_NT);
+  __shared__ unsigned long long clk_acc[8];  // [7] = time of the last stamp
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 7; i++) clk_acc[i] = 0;
+    clk_acc[7] = (unsigned long long)clock64();
+  }
+  if ((int64_t)blockIdx.x < ncells) {
+    fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[blockIdx.x] : (int64_t)blockIdx.x, threadIdx.x);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  DevRAdd radd{rout, nrows};
+  for (int64_t it = blockIdx.x; it < ncells; it += gridDim.x) {
+    // re-read the thread id inside the loop: keeps the index arithmetic of the phases from being hoisted out of the cell
+    // loop (and spilled) -- it is a handful of integer instructions per phase
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int64_t cell = A.cell_list ? (int64_t)A.cell_list[it] : it;
+    const uint16_t* m = map + cell * h7::NENT;
+    const bool solid = A.cell_solid != nullptr && A.cell_solid[cell] != 0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // the ids of this cell have landed in N (and the previous cell's sweeps are done with S)
+    phase_load(S, C, tid, V7_NT, A.coords, N.nodes, N.gid, N.rowstart, N.perm, A.dir, x, WU != 0, solid,
+               solid ? A.cell_sigma[cell] : 0.0, P.sigma, nzval, RES);
+    __syncthreads();
+    if (it + gridDim.x < ncells) {
+      fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[it + gridDim.x] : it + gridDim.x, tid);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    V7_CLK(0);
+    phase_geom_a<WU>(S, C, tid, V7_NT, &A.tab->gg[0][0]);
+    if (RES) res_pv(S, C, tid, V7_NT);
+    __syncthreads();
+    phase_geom_b<WU>(S, C, tid, V7_NT, A.tab->w);
+    __syncthreads();
+    if (WU || ZU) {
+      if (WU) phase_points(S, C, tid, V7_NT);
+      if (ZU) phase_Mp(S, C, tid, V7_NT);
+      __syncthreads();
+    }
+    V7_CLK(1);
+    ni_fields<CONV, ZJ>(tid, P);
+    if (RES) res_divu(S, tid, V7_NT);
+    if (ZU) phase_Minv(S, tid, V7_NT);
+    __syncthreads();
+    V7_CLK(2);
+    ni_stage1<ZJ>(tid);
+    if (RES) res_d(S, C, tid, V7_NT, radd);
+    __syncthreads();
+    ni_stage2<CONV, ZJ>(tid);
+    if (RES) ni_res_fields<CONV, ZU, ZJ>(tid, P);
+    __syncthreads();
+    phase_D<ZU>(S, C, K, tid, V7_NT);
+    if (RES) res_stage_a(S, C, tid, V7_NT, radd);
+    __syncthreads();
+    if (ZU || RES) {
+      if (ZU) phase_E(S, tid, V7_NT, P.zeta_u);
+      if (RES) res_stage_b(S, C, tid, V7_NT, radd);
+      __syncthreads();
+    }
+    V7_CLK(3);
+    // Every interval: fetch the codes of the chunk about to be computed (cp.async, behind the sweep of the previous chunk:
+    // a warp refills only its own segments), sweep the chunk staged in the previous interval, compute the next one.
+    codes_fetch<SEG_UU>(m + E_UU, tid);
+    ni_chunk_uu<CONV, ZU, 0>(tid);
+    if (RES) res_stage_c(S, C, tid, V7_NT, radd);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    sweep<SEG_UU, 81>(sm_buf<0>(), 0, tid);
+    codes_fetch<SEG_UU>(m + E_UU + CH_UU_PAD, tid);
+    ni_chunk_uu<CONV, ZU, 1>(tid);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    sweep<SEG_UU, 81>(sm_buf<1>(), 27, tid);
+    codes_fetch<SEG_UU>(m + E_UU + 2 * CH_UU_PAD, tid);
+    ni_chunk_uu<CONV, ZU, 2>(tid);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    V7_CLK(4);
+    sweep<SEG_UU, 81>(sm_buf<0>(), 54, tid);
+    codes_fetch<SEG_UJ>(m + E_UJ, tid);
+    ni_chunk_uj<false>(tid, P);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    sweep<SEG_UJ, 36>(sm_buf<1>(), 0, tid);
+    codes_fetch<SEG_UJ>(m + E_JU, tid);
+    ni_chunk_uj<true>(tid, P);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    V7_CLK(5);
+    sweep<SEG_UJ, 81>(sm_buf<0>(), h7::OFF_J, tid);
+    codes_fetch<SEG_REST>(m + E_REST, tid);
+    ni_chunk_rest<ZJ>(tid);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    sweep_rest(sm_buf<1>(), tid);
+    V7_CLK(6);
+  }
+  if (A.clk != nullptr && threadIdx.x == 0)
+    for (int i = 0; i < 7; i++) atomicAdd(A.clk + i, clk_acc[i]);
+}
+
+// nnz that receive more than one contribution are accumulated with RED: clear exactly those (bit mask of the symbolic phase)
+__global__ void __launch_bounds__(256)
+zero_shared_kernel(int64_t nwords, const uint32_t* __restrict__ mask, double* __restrict__ nz, int64_t nnz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t w0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; w0 < nwords; w0 += nwarps * 32) {
+    const uint32_t mine = w0 + lane < nwords ? __ldg(mask + w0 + lane) : 0u;
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+      const uint32_t wd = __shfl_sync(0xffffffffu, mine, j);
+      if (wd == 0u) continue;
+      const int64_t i = (w0 + j) * 32 + lane;
+      if ((wd >> lane) & 1u) nz[i] = 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+build_shared_mask(int64_t nwords, int64_t nnz, const uint8_t* __restrict__ contrib, uint32_t* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one nnz per thread, one word per warp
+  const bool sh = i < nnz && contrib[i] != 1;                        // 0 contributions: never written -> keep it cleared
+  const uint32_t b = __ballot_sync(0xffffffffu, sh);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < nwords) mask[i >> 5] = b;
+}
+
+template <class K>
+int v7_opt_in(K kernel) {  // (K is the same function-pointer type for every instantiation: no per-type caching here)
+  MHD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM));
+  return 0;
+}
+
+int sm_count7() {
+  static int sms = 0;
+  if (!sms) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace
+
+void v7_entry_order(std::vector<uint16_t>& ord) {
+  ord.assign(h7::NENT, ORDER_PAD);
+  for (int e = 0; e < h7::NENT; e++) {
+    int li, lj;
+    if (h7::entry_rowcol(e, &li, &lj)) ord[e] = (uint16_t)(li << 8 | lj);
+  }
+}
+
+// Called at operator creation: discover the tensor structure; returns 0 also when there is none (jac_version stays 5)
+int v7_try_enable(mhd_operator* op) {
+  const char* e = getenv("MHD_JAC_V7");  // MHD_JAC_V7=0: keep the generic kernel (A/B runs, tests of assembly.cu)
+  const bool want = e ? (atoi(e) != 0) : true;
+  if (!want || op->formulation != FORM_HDIV) return 0;
+  const double* h = op->h_tables.data();
+  h7::Tab7* T = new h7::Tab7;
+  const bool ok = h7::build_tab7(h + T_W, h + T_GG, h + T_NU, h + T_DNU, h + T_PP, h + T_PSI, h + T_DPSI, h + T_CHI, T);
+  int rc = 0;
+  if (ok) {
+    rc = dev_alloc((unsigned char**)&op->d_tab7, (int64_t)sizeof(h7::Tab7));
+    if (!rc && cudaMemcpyAsync(op->d_tab7, T, sizeof(h7::Tab7), cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+      rc = cuda_fail(cudaGetLastError(), "copy of the v7 tables", __FILE__, __LINE__);
+    if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+    if (!rc) {
+      h7::Small7 sm;
+      h7::small_from_tab(sm, *T, 0, 1);
+      op->h_small7.assign((const unsigned char*)&sm, (const unsigned char*)&sm + sizeof(sm));
+      op->jac_version = 7;
+    }
+  }
+  delete T;
+  return rc;
+}
+
+// symbolic phase: bit mask of the nnz with != 1 contributions
+int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib) {
+  const int64_t nwords = (op->nnz + 31) / 32;
+  cudaFree(op->d_shared_mask);
+  op->d_shared_mask = nullptr;
+  MHD_TRY(dev_alloc(&op->d_shared_mask, nwords));
+  const int64_t nthreads = nwords * 32;
+  build_shared_mask<<<(unsigned)((nthreads + 255) / 256), 256, 0, g_stream>>>(nwords, op->nnz, d_contrib, op->d_shared_mask);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+int v7_zero_shared(mhd_operator* op) {
+  const int64_t nwords = (op->nnz + 31) / 32;
+  const int64_t want = (nwords + 32 * 8 - 1) / (32 * 8);
+  const int64_t cap = (int64_t)sm_count7() * 16;
+  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, g_stream>>>(nwords, op->d_shared_mask, op->d_nzval, op->nnz);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
+  MHD_CHECK(op->jac_version == 7 && op->d_tab7 != nullptr && op->d_shared_mask != nullptr, MHD_E_STATE,
+            "v7 Jacobian kernel is not enabled on this operator");
+  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
+  h7::Params P;
+  P.alpha = op->prm.alpha; P.beta = op->prm.beta; P.gamma = op->prm.gamma; P.sigma = op->prm.sigma;
+  P.zeta_u = op->prm.zeta_u; P.zeta_j = op->prm.zeta_j;
+  for (int i = 0; i < 3; i++) { P.B[i] = op->prm.B[i]; P.f[i] = op->prm.f[i]; P.g[i] = op->prm.g[i]; }
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("MHD_JAC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  static unsigned long long* d_clk = nullptr;
+  if ((dbg & 16) && !d_clk) MHD_CUDA(cudaMalloc((void**)&d_clk, 8 * sizeof(unsigned long long)));
+  if (dbg & 16) MHD_CUDA(cudaMemsetAsync(d_clk, 0, 8 * sizeof(unsigned long long), g_stream));
+  if (g_small7_device != g_device || g_small7_loaded != op->h_small7) {
+    g_small7_loaded = op->h_small7;  // the copy below reads this buffer asynchronously: it must outlive the call
+    MHD_CUDA(cudaMemcpyToSymbolAsync(c_small7, g_small7_loaded.data(), sizeof(h7::Small7), 0, cudaMemcpyHostToDevice, g_stream));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    g_small7_device = g_device;
+  }
+  V7Args A{op->d_coords, op->d_cell_nodes, op->d_pgids, (const long long*)op->d_rowstart, op->d_perm, op->d_cell_solid,
+           op->d_cell_sigma, op->d_dir, (const h7::Tab7*)op->d_tab7, nullptr, (dbg & 16) ? d_clk : nullptr};
+  const int64_t g64 = (int64_t)sm_count7() * 2;
+  const int conv = op->prm.convection;
+  const bool zu = op->prm.zeta_u != 0.0, zj = op->prm.zeta_j != 0.0;
+  int64_t ncells = op->ncells;
+  unsigned grid = (unsigned)(ncells < g64 ? ncells : g64);
+#define VK(C, U, J)                                                                                                        \
+  do {                                                                                                                     \
+    if (d_r) {                                                                                                             \
+      MHD_TRY(v7_opt_in(hdiv_v7_jacobian_kernel<C, U, J, true>));                                                           \
+      hdiv_v7_jacobian_kernel<C, U, J, true><<<grid, V7_NT, V7_SMEM, g_stream>>>(ncells, op->nrows, A, d_x, op->d_map,      \
+                                                                                 op->d_nzval, d_r, P);                     \
+    } else {                                                                                                               \
+      MHD_TRY(v7_opt_in(hdiv_v7_jacobian_kernel<C, U, J, false>));                                                          \
+      hdiv_v7_jacobian_kernel<C, U, J, false><<<grid, V7_NT, V7_SMEM, g_stream>>>(ncells, op->nrows, A, d_x, op->d_map,     \
+                                                                                  op->d_nzval, nullptr, P);                \
+    }                                                                                                                      \
+  } while (0)
+#define VKJ(C, U) do { if (zj) VK(C, U, true); else VK(C, U, false); } while (0)
+#define VKU(C) do { if (zu) VKJ(C, true); else VKJ(C, false); } while (0)
+#define VKC() do { if (conv == 0) VKU(0); else if (conv == 1) VKU(1); else VKU(2); } while (0)
+  MHD_TRY(v7_zero_shared(op));
+  prof_begin(PROF_JAC);
+  if (op->deterministic && op->d_color_cells != nullptr) {
+    // one launch per colour: cells of a colour share no dof, colours run in stream order => a fixed summation order
+    for (size_t c = 0; c + 1 < op->color_ptr.size(); c++) {
+      ncells = op->color_ptr[c + 1] - op->color_ptr[c];
+      if (ncells == 0) continue;
+      A.cell_list = op->d_color_cells + op->color_ptr[c];
+      grid = (unsigned)(ncells < g64 ? ncells : g64);
+      VKC();
+      MHD_LAUNCH_CHECK();
+    }
+  } else {
+    VKC();
+    MHD_LAUNCH_CHECK();
+  }
+  prof_end(PROF_JAC);
+#undef VKC
+#undef VKU
+#undef VKJ
+#undef VK
+  if (dbg & 16) {
+    unsigned long long h[8];
+    MHD_CUDA(cudaMemcpyAsync(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    const double per = 1.0 / (double)op->ncells;
+    fprintf(stderr, "[mhd v7 phase clocks / cell] load %.0f  geometry+points %.0f  fields %.0f  stages+D %.0f  uu %.0f  uj/ju %.0f  rest+tail %.0f\n",
+            h[0] * per, h[1] * per, h[2] * per, h[3] * per, h[4] * per, h[5] * per, h[6] * per);
+  }
+  return 0;
+}
+
+}  // namespace mhd

@@ -15,6 +15,7 @@
 #include "common.h"
 #include "h1h1_cell.h"
 #include "hdiv_cell.h"
+#include "hdiv7_cell.h"
 
 namespace mhd {
 
@@ -439,6 +440,10 @@ static int symbolic_build_impl(mhd_operator* op, const int32_t* map_gids, const 
   if (!rc) { flag_exclusive<L><<<(unsigned)op->ncells, 256, 0, g_stream>>>(map_gids, op->d_order, nent_cell, nent_pad, op->d_rowptr, d_contrib, op->d_map, d_stats); SYL(); }
   unsigned long long stats[2] = {0, 0};
   SY(d2h(stats, d_stats, 2));
+  if (!rc && op->formulation == FORM_HDIV && op->jac_version == 7) {
+    op->nnz = nnz;
+    SY(v7_build_shared_mask(op, d_contrib));
+  }
   SYC(cudaStreamSynchronize(g_stream));
   cleanup();
   if (rc) return rc;
@@ -466,6 +471,10 @@ int symbolic_build(mhd_operator* op) {
   if (op->jac_version == 6) {  // opt-in structure-exploiting kernel: its own enumeration, unpermuted local numbering
     v6_entry_order(ord);
     return symbolic_build_impl<LayoutHDiv>(op, op->d_gids, ord, h6::NENT, h6::NENT_PAD);
+  }
+  if (op->jac_version == 7) {  // sum-factorised kernel: its own enumeration in the permuted local numbering
+    v7_entry_order(ord);
+    return symbolic_build_impl<LayoutHDiv>(op, op->d_pgids, ord, h7::NENT, h7::NENT);
   }
   entry_order(ord);
   return symbolic_build_impl<LayoutHDiv>(op, op->d_pgids, ord, NENT, NENT_PAD);

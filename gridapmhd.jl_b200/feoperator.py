@@ -141,7 +141,7 @@ class B200FEOperator:
         L.check(lib.mhd_operator_create(C.byref(mesh), C.byref(tab), C.byref(lay), C.byref(prm), C.byref(h)))
         self.handle = h
         self._keep = []
-        if os.environ.get("MHD_JAC_V6"):
+        if os.environ.get("MHD_JAC_V6", "0") not in ("", "0"):  # same rule as the library: atoi(value) != 0
             # opt-in sum-factorised Jacobian kernel (hdiv_v6.cu): hand over the tensor structure of the Q2 node numbering
             from .host.reffe import Q2_NODE_IJK
 
@@ -161,6 +161,19 @@ class B200FEOperator:
             self.destroy()
         except Exception:
             pass
+
+    @property
+    def kernel_version(self) -> int:
+        """7: sum-factorised kernel (tables recognised as tensor products), 5: generic tensor-core kernel."""
+        v = C.c_int32()
+        L.check(L.load().mhd_operator_get_kernel_version(self.handle, C.byref(v)))
+        return v.value
+
+    def set_deterministic(self, on: bool = True) -> int:
+        """Coloured assembly: bit-identical results from run to run (returns the number of colours)."""
+        n = C.c_int32()
+        L.check(L.load().mhd_operator_set_deterministic(self.handle, 1 if on else 0, C.byref(n)))
+        return n.value
 
     def set_fluid(self, fluid: FluidParams):
         self.fluid = fluid

@@ -143,6 +143,16 @@ int mhd_operator_set_params(mhd_operator_t*, const mhd_params_t*); /* continuati
  * structure (MHD_E_INVALID otherwise) and may then use the sum-factorised Jacobian kernel (opt-in: MHD_JAC_V6=1 in the
  * environment of this call; the default kernel does not need the information). */
 int mhd_operator_set_tensor_structure(mhd_operator_t*, const int8_t* node_ijk);
+/* Which Jacobian kernel the operator runs: 7 = fully sum-factorised kernel (csrc/hdiv_v7.cu; chosen automatically at
+ * mhd_operator_create when the tables of mhd_tables_t turn out to be tensor products of 1-D factors on the tensor Gauss rule --
+ * true for the reference's HEX elements, src/parameters.jl:436-441,521-525 -- unless MHD_JAC_V7=0), 5 = generic tensor-core
+ * kernel (csrc/assembly.cu, any tables), 6 = superseded opt-in kernel.  H1-H1 operators report 0. */
+int mhd_operator_get_kernel_version(mhd_operator_t*, int32_t* version);
+/* Deterministic assembly ("offer a deterministic (coloured) mode"): cells are greedily coloured so that no two
+ * cells of a colour share a dof and the Jacobian / residual kernels run one launch per colour, which fixes the order in which
+ * contributions to a shared nnz / row are summed => bit-identical results from run to run (the reference's sequential
+ * assembly loop is deterministic by construction).  Needs kernel version 7.  on = 0 switches back to one launch. */
+int mhd_operator_set_deterministic(mhd_operator_t*, int32_t on, int32_t* ncolors /* nullable out */);
 
 /* Ghost exchange plan of the operator's vectors (PartitionedArrays consistent!/PVector):
  * for neighbour k: send x[send_idx[send_ptr[k]..send_ptr[k+1])] (owned local ids, 0-based) and receive into

@@ -28,24 +28,29 @@ struct HostStore {
   }
 };
 
-template <int CONV, bool ZU, bool ZJ>
-void cell(Cell7& S, const Small7& C, const mhd::h7::Tab7& T, int nt, const Params& P, HostStore& st) {
-  FOR_T phase_geom_a<CONV>(S, C, t, nt, &T.gg[0][0]);
-  FOR_T phase_geom_b<CONV>(S, C, t, nt, T.w);
-  if (CONV != 0) FOR_T phase_points(S, C, t, nt);
-  FOR_T phase_fields<CONV, ZJ>(S, C, t, nt, P);
-  FOR_T phase_stage1<ZJ>(S, C, t, nt);
-  FOR_T phase_stage2<CONV, ZJ>(S, C, t, nt);
-  FOR_T phase_D<ZU>(S, C, t, nt);
-  if (ZU) {
-    FOR_T phase_Minv(S, t, nt);
-    FOR_T phase_E(S, t, nt, P.zeta_u);
-  }
+struct HostRAdd {
+  double* R;          // [129] reference numbering, nullable
+  const int* unperm;
+  void operator()(int row, double v) { R[unperm[row]] += v; }
+};
+
+// the kernel's interval structure (hdiv_v7.cu): every FOR_T is one barrier interval
+template <int CONV, bool ZU, bool ZJ, bool RES>
+void cell(Cell7& S, const Small7& C, const mhd::h7::Tab7& T, int nt, const Params& P, HostStore& st, HostRAdd& ra) {
+  constexpr int WU = (CONV != 0 || RES) ? 1 : 0;
+  FOR_T { phase_geom_a<WU>(S, C, t, nt, &T.gg[0][0]); if (RES) res_pv(S, C, t, nt); }
+  FOR_T phase_geom_b<WU>(S, C, t, nt, T.w);
+  if (WU || ZU) FOR_T { if (WU) phase_points(S, C, t, nt); if (ZU) phase_Mp(S, C, t, nt); }
+  FOR_T { phase_fields<CONV, ZJ>(S, C, t, nt, P); if (RES) res_divu(S, t, nt); if (ZU) phase_Minv(S, t, nt); }
+  FOR_T { phase_stage1<ZJ>(S, C, C, t, nt); if (RES) res_d(S, C, t, nt, ra); }
+  FOR_T { phase_stage2<CONV, ZJ>(S, C, C, t, nt); if (RES) res_fields<CONV, ZU, ZJ>(S, C, t, nt, P); }
+  FOR_T { phase_D<ZU>(S, C, C, t, nt); if (RES) res_stage_a(S, C, t, nt, ra); }
+  if (ZU || RES) FOR_T { if (ZU) phase_E(S, t, nt, P.zeta_u); if (RES) res_stage_b(S, C, t, nt, ra); }
   double* b0 = S.r1;
   double* b1 = S.r3;
-  FOR_T chunk_uu<CONV, ZU>(S, C, t, nt, 0, b0);
-  FOR_T { sweep_uu(b0, 0, t, nt, st); chunk_uu<CONV, ZU>(S, C, t, nt, 1, b1); }
-  FOR_T { sweep_uu(b1, 1, t, nt, st); chunk_uu<CONV, ZU>(S, C, t, nt, 2, b0); }
+  FOR_T { chunk_uu<CONV, ZU>(S, C, C, t, nt, 0, b0); if (RES) res_stage_c(S, C, t, nt, ra); }
+  FOR_T { sweep_uu(b0, 0, t, nt, st); chunk_uu<CONV, ZU>(S, C, C, t, nt, 1, b1); }
+  FOR_T { sweep_uu(b1, 1, t, nt, st); chunk_uu<CONV, ZU>(S, C, C, t, nt, 2, b0); }
   FOR_T { sweep_uu(b0, 2, t, nt, st); chunk_uj<false>(S, C, t, nt, P, b1); }
   FOR_T { sweep_uj(b1, t, nt, st); chunk_uj<true>(S, C, t, nt, P, b0); }
   FOR_T { sweep_ju(b0, t, nt, st); chunk_rest<ZJ>(S, C, t, nt, b1); }
@@ -54,13 +59,13 @@ void cell(Cell7& S, const Small7& C, const mhd::h7::Tab7& T, int nt, const Param
 }  // namespace
 
 extern "C" {
-// raw tables in the layouts of mhd_tables_t.  prm = {alpha, beta, gamma, sigma, zeta_u, zeta_j, B[3]}.
+// raw tables in the layouts of mhd_tables_t.  prm = {alpha, beta, gamma, sigma, zeta_u, zeta_j, B[3], f[3], g[3]}.
 // returns -1 if the tables lack the tensor structure, else the number of mis-stored entries
 long long emul_hdiv7_cells(long long ncells, const double* coords, const int* cell_nodes, const int* gids, const signed char* jsign,
                            const unsigned char* cell_solid, const double* cell_sigma, const double* dir, const double* x,
                            const double* w, const double* geo_grad, const double* u_val, const double* u_grad, const double* p_val,
                            const double* j_val, const double* j_div, const double* phi_val, const double* prm, int conv, int nt,
-                           int reverse, double* K_out) {
+                           int reverse, double* K_out, double* R_out /* nullable: [ncells][129] cell residuals */) {
   g_rev = reverse != 0;
   mhd::h7::Tab7* T = new mhd::h7::Tab7;
   if (!build_tab7(w, geo_grad, u_val, u_grad, p_val, j_val, j_div, phi_val, T)) { delete T; return -1; }
@@ -68,7 +73,7 @@ long long emul_hdiv7_cells(long long ncells, const double* coords, const int* ce
   for (int t = 0; t < nt; t++) small_from_tab(*C, *T, t, nt);
   Params P;
   P.alpha = prm[0]; P.beta = prm[1]; P.gamma = prm[2]; P.sigma = prm[3]; P.zeta_u = prm[4]; P.zeta_j = prm[5];
-  for (int i = 0; i < 3; i++) P.B[i] = prm[6 + i];
+  for (int i = 0; i < 3; i++) { P.B[i] = prm[6 + i]; P.f[i] = prm[9 + i]; P.g[i] = prm[12 + i]; }
   const bool zu = P.zeta_u != 0.0, zj = P.zeta_j != 0.0;
   Cell7* S = new Cell7;
   std::vector<unsigned char> hit(NENT);
@@ -96,11 +101,12 @@ long long emul_hdiv7_cells(long long ncells, const double* coords, const int* ce
       unperm[i] = src;
     }
     const bool solid = cell_solid && cell_solid[c];
-    FOR_T phase_load(*S, *C, t, nt, coords, cell_nodes + c * 8, pg, nullptr, perm, dir, x, conv != 0, solid, solid ? cell_sigma[c] : 0.0,
-                     P.sigma);
+    FOR_T phase_load(*S, *C, t, nt, coords, cell_nodes + c * 8, pg, nullptr, perm, dir, x, conv != 0 || R_out != nullptr, solid,
+                     solid ? cell_sigma[c] : 0.0, P.sigma, nullptr, R_out != nullptr);
     std::fill(hit.begin(), hit.end(), 0);
     HostStore st{K_out + c * NLOC * NLOC, unperm, &nbad, hit.data()};
-#define RUN(CV, U, J) cell<CV, U, J>(*S, *C, *T, nt, P, st)
+    HostRAdd ra{R_out ? R_out + c * NLOC : nullptr, unperm};
+#define RUN(CV, U, J) do { if (R_out) cell<CV, U, J, true>(*S, *C, *T, nt, P, st, ra); else cell<CV, U, J, false>(*S, *C, *T, nt, P, st, ra); } while (0)
 #define RUNJ(CV, U) do { if (zj) RUN(CV, U, true); else RUN(CV, U, false); } while (0)
 #define RUNU(CV) do { if (zu) RUNJ(CV, true); else RUNJ(CV, false); } while (0)
     if (conv == 0) RUNU(0); else if (conv == 1) RUNU(1); else RUNU(2);

@@ -43,7 +43,7 @@ def device_gids(fes):
     return np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=np.int32), dirv
 
 
-def run(lib, fes, x, prm, nt=256, reverse=0, tables=None):
+def run(lib, fes, x, prm, nt=256, reverse=0, tables=None, residual=False):
     m, T = fes.mesh, tables or fes.tables
     gids, dirv = device_gids(fes)
     nc = m.ncells
@@ -54,12 +54,13 @@ def run(lib, fes, x, prm, nt=256, reverse=0, tables=None):
     solid = None if fes.cell_solid is None else a(fes.cell_solid, np.uint8)
     sig = None if fes.cell_sigma is None else a(fes.cell_sigma)
     tabs = [a(t) for t in (T.w, T.geo_grad, T.nu, T.dnu, T.pp, T.psi, T.dpsi, T.chi)]
-    pv = a([prm.alpha, prm.beta, prm.gamma, prm.sigma, prm.zeta_u, prm.zeta_j, *prm.B])
+    pv = a([prm.alpha, prm.beta, prm.gamma, prm.sigma, prm.zeta_u, prm.zeta_j, *prm.B, *prm.f, *prm.g])
+    R = np.zeros((nc, 129)) if residual else None
     xx = a(x)
     conv = {"none": 0, "picard": 1, "newton": 2}[prm.convection]
     nbad = lib.emul_hdiv7_cells(C.c_longlong(nc), P(coords), P(cn), P(gids), P(js), P(solid), P(sig), P(dirv), P(xx), *[P(t) for t in tabs],
-                                P(pv), conv, nt, reverse, P(K))
-    return nbad, K
+                                P(pv), conv, nt, reverse, P(K), P(R))
+    return (nbad, K, R) if residual else (nbad, K)
 
 
 def compare(K, Ko, solid=None):
@@ -129,3 +130,62 @@ def test_v7_structure_discovery_rejects_non_tensor_tables(emul):
     prm = O.FluidParams()
     nbad, _ = run(emul, fes, np.zeros(fes.ndofs), prm, tables=T)
     assert nbad == -1
+
+
+def compare_residual(R, Ro, solid=None):
+    assert np.isfinite(R).all()
+    if solid is not None:
+        R = R.copy()
+        R[solid, :85] = 0.0
+    for r in ((0, 81), (81, 85), (85, 121), (121, 129)):
+        blk = Ro[:, r[0] : r[1]]
+        assert np.abs(R[:, r[0] : r[1]] - blk).max() <= 1e-12 * max(np.abs(blk).max(), 1e-300), r
+
+
+@pytest.mark.parametrize("conv,zu,zj", [("none", 0.0, 0.0), ("picard", 0.0, 0.0), ("newton", 0.0, 0.0), ("none", 7.0, 3.0),
+                                         ("newton", 7.0, 3.0)])
+def test_v7_fused_residual_matches_the_oracle(emul, conv, zu, zj):
+    """res_fluid_h1_hdiv by sum factorisation, interleaved with the Jacobian phases (the Jacobian must come out unchanged)"""
+    p = hunt_params(nc=(3, 3), B=(0.0, 20.0, 0.0))
+    fes = setup_spaces(p)
+    fl = p["fluid"]
+    prm = O.FluidParams(alpha=fl.alpha, beta=fl.beta, gamma=fl.gamma, sigma=0.7, zeta_u=zu, zeta_j=zj, B=(0.2, 1.0, -0.3), f=(0.3, -0.1, 1.0),
+                        g=(0.1, 0.2, -0.3), convection=conv)
+    x = np.random.default_rng(11).random(fes.ndofs)
+    st = fes.cell_state(x)
+    Ko = O.cell_jacobians(fes.tables, fes.mesh.cell_coords(), st, fes.j_sign, prm)
+    Ro = O.cell_residuals(fes.tables, fes.mesh.cell_coords(), st, fes.j_sign, prm)
+    for nt, rev in ((256, 0), (256, 1), (96, 0)):
+        nbad, K, R = run(emul, fes, x, prm, nt=nt, reverse=rev, residual=True)
+        assert nbad == 0
+        compare(K, Ko)
+        compare_residual(R, Ro)
+
+
+def test_v7_fused_residual_on_nonaffine_cells_with_dirichlet_data(emul):
+    m = M.expansion_generate_mesh(0, perturb=0.2, seed=1)
+    from gridapmhd_jl_b200.applications import u_inlet_parabolic
+
+    fes = setup_fe_spaces(m, u_tags=("inlet", "wall"), u_values=(u_inlet_parabolic(), None), j_tags=("wall", "inlet", "outlet"))
+    prm = O.FluidParams(alpha=0.5, beta=0.01, gamma=1.0, sigma=1.0, zeta_u=2.0, zeta_j=2.0, B=(0.3, 1.0, 0.1), f=(0.1, 0.2, 0.3), g=(0.3, 0.2, 0.1),
+                        convection="newton")
+    x = np.random.default_rng(2).random(fes.ndofs)
+    st = fes.cell_state(x)
+    Ro = O.cell_residuals(fes.tables, m.cell_coords(), st, fes.j_sign, prm)
+    nbad, K, R = run(emul, fes, x, prm, residual=True)
+    assert nbad == 0
+    compare(K, O.cell_jacobians(fes.tables, m.cell_coords(), st, fes.j_sign, prm))
+    compare_residual(R, Ro)
+
+
+def test_v7_fused_residual_with_solid_walls(emul):
+    p = hunt_params(nc=(12, 12), B=(0.0, 50.0, 0.0), tw=0.2, BL_adapted=False, kmap_x=3, kmap_y=3, zeta_j=2.0)
+    fes = setup_spaces(p)
+    fl = p["fluid"]
+    prm = O.FluidParams(fl.alpha, fl.beta, fl.gamma, fl.sigma, fl.zeta_u, fl.zeta_j, fl.B, fl.f, (0.1, 0.2, 0.3), fl.convection)
+    x = np.random.default_rng(3).random(fes.ndofs)
+    st = fes.cell_state(x)
+    Ro = O.cell_residuals(fes.tables, fes.mesh.cell_coords(), st, fes.j_sign, prm, fes.cell_solid, fes.cell_sigma)
+    nbad, K, R = run(emul, fes, x, prm, residual=True)
+    assert nbad == 0
+    compare_residual(R, Ro, solid=fes.cell_solid)
