@@ -485,8 +485,7 @@ def run_ours(args):
                                 "note": "nzval also copied to pinned host memory every step (host-side direct solver)"},
         "parity": parity,
         "gpu_launches": int(launches),
-        "roofline": {"kernel": {7: "hdiv_v7_jacobian_kernel<newton> (sum-factorised; zero_shared + residual in their own launches)",
-                                6: "hdiv_v6_jacobian_kernel<newton> (opt-in MHD_JAC_V6=1; residual in its own launch)",
+        "roofline": {"kernel": {7: "hdiv_v7_jacobian_kernel<CONV=newton,RES=1> (sum-factorised, fused residual_and_jacobian!; zero_shared in its own launch)",
                                 5: "jacobian_kernel<CONV=newton,RES=1> (fused residual_and_jacobian!)"}[op.kernel_version], "bound": "hbm", "achieved": jac_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": jac_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": jac_kernel_ms,
                      "algorithmic_bytes": jac_bytes, "jacobian_only_Mcells_s": ncells_local / (jac_kernel_ms * 1e-3) / 1e6,

@@ -179,8 +179,7 @@ int mhd_fp64_peak(int32_t kind, double* tflops) {
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CHECK(tflops && (kind == 0 || kind == 1), MHD_E_INVALID, "mhd_fp64_peak: invalid argument");
   MHD_CUDA(cudaSetDevice(g_device));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
+  const int sms = device_sm_count();
   double* d_out = nullptr;
   MHD_CUDA(cudaMalloc((void**)&d_out, sizeof(double)));
   cudaEvent_t e0, e1;
@@ -390,7 +389,6 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_cell_sigma);
   cudaFree(op->d_dir);
   cudaFree(op->d_tables);
-  cudaFree(op->d_sftab);
   cudaFree(op->d_tab7);
   cudaFree(op->d_shared_mask);
   cudaFree(op->d_color_cells);
@@ -553,9 +551,6 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
   if (op->formulation == FORM_H1H1) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
-  } else if (op->jac_version == 6) {
-    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(v6_launch_jacobian(op, dx));
   } else if (op->jac_version == 7) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(v7_launch_jacobian(op, dx, nullptr));
@@ -591,10 +586,6 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
       MHD_TRY(h1h1_launch_residual(op, dx, dr));
       MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
     }
-  } else if (op->jac_version == 6) {  // v6 has no fused residual: the residual kernel of assembly.cu + the v6 Jacobian
-    MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(launch_residual(op, dx, dr));
-    MHD_TRY(v6_launch_jacobian(op, dx));
   } else if (op->jac_version == 7) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(v7_launch_jacobian(op, dx, dr));

@@ -60,7 +60,7 @@ int pack_tables(mhd_operator* op, const mhd_tables_t* t) {
   MHD_TRY(dev_alloc(&op->d_tables, T_TOTAL));
   MHD_TRY(h2d(op->d_tables, h.data(), T_TOTAL));
   MHD_CUDA(cudaStreamSynchronize(g_stream));
-  op->h_tables = h;  // kept for mhd_operator_set_tensor_structure (hdiv_v6.cu)
+  op->h_tables = h;  // kept for the structure discovery of hdiv_v7.cu (v7_try_enable)
   return 0;
 }
 
@@ -1237,10 +1237,8 @@ static CellArgs make_cell_args(const mhd_operator* op) {
   return a;
 }
 
-static int g_sm_count = 0;
 static int sm_count() {
-  if (!g_sm_count) cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, g_device);
-  return g_sm_count ? g_sm_count : 148;
+  return device_sm_count();
 }
 
 template <class Kern>

@@ -6,10 +6,10 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function"
 OBJS=""
 PIDS=""
-for f in abi symbolic assembly krylov solver comm postprocess h1h1 patch hdiv_v6 hdiv_v7; do
+for f in abi symbolic assembly krylov solver comm postprocess h1h1 patch hdiv_v7; do
   stale=0
   [ -f $f.o ] || stale=1
-  for dep in $f.cu common.h h1h1_cell.h patch_cell.h hdiv_cell.h hdiv7_cell.h hdiv7_tables.h sumfac_uu.h ../../include/mhdb200.h; do
+  for dep in $f.cu common.h h1h1_cell.h patch_cell.h hdiv7_cell.h hdiv7_tables.h ../../include/mhdb200.h; do
     [ $dep -nt $f.o ] && stale=1
   done
   if [ $stale = 1 ]; then

@@ -133,9 +133,8 @@ constexpr int FORM_H1H1 = 1;  // H1-H1 (u,p,phi), 149 local dofs: h1h1.cu (field
 
 struct mhd_operator {
   int formulation = mhd::FORM_HDIV;
-  int jac_version = 5;             // 5: tensor-core panel products (assembly.cu); 6: hdiv_v6.cu (opt-in, superseded);
+  int jac_version = 5;             // 5: tensor-core panel products (assembly.cu, any tables);
                                    // 7: fully sum-factorised kernel (hdiv_v7.cu), chosen when the tables have the tensor structure
-  void* d_sftab = nullptr;         // v6: 1-D factors of the velocity tables (sf::Tables)
   unsigned char* d_tab7 = nullptr; // v7: h7::Tab7
   std::vector<unsigned char> h_small7;  // v7: h7::Small7 (uploaded to constant memory before a launch when it is not the current one)
   uint32_t* d_shared_mask = nullptr;  // v7: bit i set <=> nnz i receives != 1 contributions (cleared before, RED-accumulated in, an assembly)
@@ -219,6 +218,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 bool is_device_ptr(const void* p);
+int device_sm_count();  // multiprocessors of g_device (queried once per mhd_init; abi.cu)
 
 // event timing of the dominant kernels (bench.py roofline): prof_begin/prof_end bracket a launch
 enum { PROF_JAC = 0, PROF_RES = 1, PROF_SPMV = 2, PROF_PATCH_SETUP = 3, PROF_PATCH_APPLY = 4, PROF_N = 5 };
@@ -255,9 +255,6 @@ int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable
 int begin_clear(mhd_operator* op, double* d_r /* nullable */);  // optional: start clearing before the state is copied in
 void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
-// hdiv_v6.cu
-void v6_entry_order(std::vector<uint16_t>& ord);
-int v6_launch_jacobian(mhd_operator* op, const double* d_x);
 // hdiv_v7.cu
 void v7_entry_order(std::vector<uint16_t>& ord);
 int v7_try_enable(mhd_operator* op);                                  // at operator creation: discovers the tensor structure of the tables

@@ -137,9 +137,7 @@ H1Args make_args(const mhd_operator* op) {
 }
 
 unsigned persistent_grid(int64_t ncells) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device);
-  const int64_t g = (int64_t)sms * 2;
+  const int64_t g = (int64_t)device_sm_count() * 2;
   return (unsigned)(ncells < g ? ncells : g);
 }
 

@@ -636,8 +636,9 @@ MHD_7HD void chunk_uu(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int
 }
 
 // uj (JU = false): buf[(c*27 + slot(a)) * 36 + slot(m)] = -gamma sgn V ;  ju (JU = true): buf[slot(m) * 81 + 3 slot(a) + c] = +sigma sgn V
-template <bool JU, int KD>
-MHD_7HD void chunk_uj_k(Cell7& S, const Small7& K, const Params& P, double* buf, int c, int p1, int p2) {
+// (JU is a run-time flag: one copy of the code, the kernel is instruction-cache bound otherwise)
+template <int KD>
+MHD_7HD void chunk_uj_k(Cell7& S, const Small7& K, const Params& P, double* buf, int c, int p1, int p2, bool JU) {
   constexpr int d1 = (KD + 1) % 3, d2 = (KD + 2) % 3;
   constexpr int s0 = KD == 0 ? 1 : (KD == 1 ? 3 : 9), s1 = d1 == 0 ? 1 : (d1 == 1 ? 3 : 9), s2 = d2 == 0 ? 1 : (d2 == 1 ? 3 : 9);
   const double* x = S.r2 + T2_UJ + (c * 3 + KD) * 108 + p1 * 18 + p2 * 3;
@@ -655,19 +656,17 @@ MHD_7HD void chunk_uj_k(Cell7& S, const Small7& K, const Params& P, double* buf,
     MHD_7UNROLL
     for (int i0 = 0; i0 < 3; i0++) {
       const double v = sg[i0] * (K.Puj[KD][a * 3 + i0][0] * x0 + K.Puj[KD][a * 3 + i0][1] * x1 + K.Puj[KD][a * 3 + i0][2] * x2);
-      if (JU) buf[sj[i0] * 81 + 3 * su + c] = v;
-      else buf[(c * 27 + su) * 36 + sj[i0]] = v;
+      buf[JU ? sj[i0] * 81 + 3 * su + c : (c * 27 + su) * 36 + sj[i0]] = v;
     }
   }
 }
-template <bool JU>
-MHD_7HD void chunk_uj(Cell7& S, const Small7& K, int tid, int nt, const Params& P, double* buf) {
+MHD_7HD void chunk_uj(Cell7& S, const Small7& K, int tid, int nt, const Params& P, double* buf, bool JU) {
   for (int it = tid; it < 324; it += nt) {
     const int inst = it / 36, p1 = (it / 6) % 6, p2 = it % 6, c = inst / 3, k = inst % 3;
     switch (k) {
-      case 0: chunk_uj_k<JU, 0>(S, K, P, buf, c, p1, p2); break;
-      case 1: chunk_uj_k<JU, 1>(S, K, P, buf, c, p1, p2); break;
-      default: chunk_uj_k<JU, 2>(S, K, P, buf, c, p1, p2); break;
+      case 0: chunk_uj_k<0>(S, K, P, buf, c, p1, p2, JU); break;
+      case 1: chunk_uj_k<1>(S, K, P, buf, c, p1, p2, JU); break;
+      default: chunk_uj_k<2>(S, K, P, buf, c, p1, p2, JU); break;
     }
   }
 }

@@ -81,10 +81,15 @@ template <bool ZJ>
 V7_NI void ni_stage1(int tid) { h7::phase_stage1<ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
 template <int CONV, bool ZJ>
 V7_NI void ni_stage2(int tid) { h7::phase_stage2<CONV, ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
-template <int CONV, bool ZU, int CC>
-V7_NI void ni_chunk_uu(int tid) { h7::chunk_uu<CONV, ZU>(sm_cell(), sm_small(), c_small7, tid, V7_NT, CC, sm_buf<CC & 1>()); }
-template <bool JU>
-V7_NI void ni_chunk_uj(int tid, const h7::Params& P) { h7::chunk_uj<JU>(sm_cell(), c_small7, tid, V7_NT, P, sm_buf<JU ? 0 : 1>()); }
+// (the component / direction of a chunk is a run-time argument: ONE copy of the code -- the loop body of the kernel is several
+// times the 32 KB instruction cache and every duplicated phase shows up as no_inst stalls)
+template <int CONV, bool ZU>
+V7_NI void ni_chunk_uu(int tid, int cc) {
+  h7::chunk_uu<CONV, ZU>(sm_cell(), sm_small(), c_small7, tid, V7_NT, cc, (cc & 1) ? sm_cell().r3 : sm_cell().r1);
+}
+V7_NI void ni_chunk_uj(int tid, const h7::Params& P, bool ju) {
+  h7::chunk_uj(sm_cell(), c_small7, tid, V7_NT, P, ju ? sm_cell().r1 : sm_cell().r3, ju);
+}
 template <bool ZJ>
 V7_NI void ni_chunk_rest(int tid) { h7::chunk_rest<ZJ>(sm_cell(), sm_small(), tid, V7_NT, sm_buf<1>()); }
 
@@ -121,16 +126,15 @@ __device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const ui
 // Scatter-map codes of a chunk: global -> shared with cp.async, issued BEFORE the chunk is computed, consumed by the sweep one
 // barrier interval later.  Warp w owns the 32-entry segments w, w + 8, ...: it alone writes (lanes 0..3, 16 bytes each) and
 // reads them, so one buffer serves all chunks -- a warp refills its segments as soon as its own sweep is through with them.
-template <int NSEG>
-__device__ __forceinline__ void codes_fetch(const uint16_t* __restrict__ m, int tid) {
+V7_NI void codes_fetch(const uint16_t* __restrict__ m, int nseg, int tid) {
   const int w = tid >> 5, lane = tid & 31;
   __syncwarp();
   if (lane < 4) {
-#pragma unroll
-    for (int j = 0; j < (NSEG + 7) / 8; j++) {
-      const int seg = w + 8 * j;
-      if (seg < NSEG) cp_async16(sm_codes() + seg * 32 + lane * 8, m + seg * 32 + lane * 8);
-    }
+    unsigned dst = (unsigned)__cvta_generic_to_shared(sm_codes()) + (unsigned)(w * 64 + lane * 16);
+    const char* src = reinterpret_cast<const char*>(m) + w * 64 + lane * 16;
+#pragma unroll 1
+    for (int seg = w; seg < nseg; seg += 8, dst += 512, src += 512)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -150,45 +154,41 @@ __device__ __forceinline__ void scatter_one(unsigned code, unsigned long long ro
       : "memory");
 }
 
-// sweep of a chunk of NSEG 32-entry segments with NCOL entries per row, rows from row0 (pads carry MAP_SKIP)
-template <int NSEG, int NCOL>
-__device__ __forceinline__ void sweep(const double* __restrict__ buf, int row0, int tid) {
+// sweep of a chunk of nseg 32-entry segments with ncol entries per row, rows from row0 (pads carry MAP_SKIP).  One copy of the
+// code for all chunks (run-time ncol; the division is a multiplication by a host-computed reciprocal: exact for i < 2^15).
+V7_NI void sweep(const double* __restrict__ buf, int nseg, int row0, unsigned ncol_recip /* ceil(2^20 / ncol) */, int tid) {
   const int w = tid >> 5, lane = tid & 31;
   const uint16_t* codes = sm_codes();
   const long long* rowbase = sm_cell().rowaddr;
-#pragma unroll
-  for (int j = 0; j < (NSEG + 7) / 8; j++) {
-    const int seg = w + 8 * j;
-    if (seg < NSEG) {
-      const int i = seg * 32 + lane;
-      int row = row0 + i / NCOL;
-      if (row > h7::NLOC - 1) row = h7::NLOC - 1;  // pad entries of the last segment
-      scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
-    }
+#pragma unroll 2
+  for (int seg = w; seg < nseg; seg += 8) {
+    const int i = seg * 32 + lane;
+    int row = row0 + (int)(((unsigned)i * ncol_recip) >> 20);
+    if (row > h7::NLOC - 1) row = h7::NLOC - 1;  // pad entries of the last segment
+    scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
   }
 }
+__host__ __device__ constexpr unsigned recip20(int n) { return (unsigned)(((1u << 20) + n - 1) / n); }
+static_assert((2943u * recip20(81)) >> 20 == 2943u / 81 && (2943u * recip20(36)) >> 20 == 2943u / 36, "reciprocal division");
 // the last chunk holds five sections: jj | j-phi | phi-j | up | pu
-__device__ __forceinline__ void sweep_rest(const double* __restrict__ buf, int tid) {
+V7_NI void sweep_rest(const double* __restrict__ buf, int tid) {
   constexpr int NSEG = h7::CH_REST_PAD / 32;
   constexpr int R_JF = h7::R_JF, R_FJ = h7::R_FJ, R_UP = h7::R_UP, R_PU = h7::R_PU;
   constexpr int OFF_P = h7::OFF_P, OFF_J = h7::OFF_J, OFF_F = h7::OFF_F, NLOC = h7::NLOC;
   const int w = tid >> 5, lane = tid & 31;
   const uint16_t* codes = sm_codes();
   const long long* rowbase = sm_cell().rowaddr;
-#pragma unroll
-  for (int j = 0; j < (NSEG + 7) / 8; j++) {
-    const int seg = w + 8 * j;
-    if (seg < NSEG) {
-      const int i = seg * 32 + lane;
-      int row;
-      if (i < R_JF) row = OFF_J + i / 36;
-      else if (i < R_FJ) row = OFF_J + (i - R_JF) / 8;
-      else if (i < R_UP) row = OFF_F + (i - R_FJ) / 36;
-      else if (i < R_PU) row = (i - R_UP) / 4;
-      else row = OFF_P + (i - R_PU) / 81;
-      if (row > NLOC - 1) row = NLOC - 1;
-      scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
-    }
+#pragma unroll 2
+  for (int seg = w; seg < NSEG; seg += 8) {
+    const int i = seg * 32 + lane;
+    int row;
+    if (i < R_JF) row = OFF_J + i / 36;
+    else if (i < R_FJ) row = OFF_J + (i - R_JF) / 8;
+    else if (i < R_UP) row = OFF_F + (i - R_FJ) / 36;
+    else if (i < R_PU) row = (i - R_UP) / 4;
+    else row = OFF_P + (i - R_PU) / 81;
+    if (row > NLOC - 1) row = NLOC - 1;
+    scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
   }
 }
 
@@ -277,35 +277,35 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     V7_CLK(3);
     // Every interval: fetch the codes of the chunk about to be computed (cp.async, behind the sweep of the previous chunk:
     // a warp refills only its own segments), sweep the chunk staged in the previous interval, compute the next one.
-    codes_fetch<SEG_UU>(m + E_UU, tid);
-    ni_chunk_uu<CONV, ZU, 0>(tid);
+    codes_fetch(m + E_UU, SEG_UU, tid);
+    ni_chunk_uu<CONV, ZU>(tid, 0);
     if (RES) res_stage_c(S, C, tid, V7_NT, radd);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep<SEG_UU, 81>(sm_buf<0>(), 0, tid);
-    codes_fetch<SEG_UU>(m + E_UU + CH_UU_PAD, tid);
-    ni_chunk_uu<CONV, ZU, 1>(tid);
+    sweep(sm_buf<0>(), SEG_UU, 0, recip20(81), tid);
+    codes_fetch(m + E_UU + CH_UU_PAD, SEG_UU, tid);
+    ni_chunk_uu<CONV, ZU>(tid, 1);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep<SEG_UU, 81>(sm_buf<1>(), 27, tid);
-    codes_fetch<SEG_UU>(m + E_UU + 2 * CH_UU_PAD, tid);
-    ni_chunk_uu<CONV, ZU, 2>(tid);
+    sweep(sm_buf<1>(), SEG_UU, 27, recip20(81), tid);
+    codes_fetch(m + E_UU + 2 * CH_UU_PAD, SEG_UU, tid);
+    ni_chunk_uu<CONV, ZU>(tid, 2);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     V7_CLK(4);
-    sweep<SEG_UU, 81>(sm_buf<0>(), 54, tid);
-    codes_fetch<SEG_UJ>(m + E_UJ, tid);
-    ni_chunk_uj<false>(tid, P);
+    sweep(sm_buf<0>(), SEG_UU, 54, recip20(81), tid);
+    codes_fetch(m + E_UJ, SEG_UJ, tid);
+    ni_chunk_uj(tid, P, false);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep<SEG_UJ, 36>(sm_buf<1>(), 0, tid);
-    codes_fetch<SEG_UJ>(m + E_JU, tid);
-    ni_chunk_uj<true>(tid, P);
+    sweep(sm_buf<1>(), SEG_UJ, 0, recip20(36), tid);
+    codes_fetch(m + E_JU, SEG_UJ, tid);
+    ni_chunk_uj(tid, P, true);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     V7_CLK(5);
-    sweep<SEG_UJ, 81>(sm_buf<0>(), h7::OFF_J, tid);
-    codes_fetch<SEG_REST>(m + E_REST, tid);
+    sweep(sm_buf<0>(), SEG_UJ, h7::OFF_J, recip20(81), tid);
+    codes_fetch(m + E_REST, SEG_REST, tid);
     ni_chunk_rest<ZJ>(tid);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -347,13 +347,7 @@ int v7_opt_in(K kernel) {  // (K is the same function-pointer type for every ins
   return 0;
 }
 
-int sm_count7() {
-  static int sms = 0;
-  if (!sms) {
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int sm_count7() { return device_sm_count(); }
 
 }  // namespace
 

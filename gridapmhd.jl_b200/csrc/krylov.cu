@@ -7,10 +7,19 @@
 
 namespace mhd {
 
-static int g_sms = 0;
+// Grid sizes are multiples of the SM count of the device actually in use -- queried, never assumed.
+int device_sm_count() {
+  static int dev = -1, sms = 0;
+  if (dev != g_device || sms <= 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g_device) != cudaSuccess || v <= 0) return 1;
+    sms = v;
+    dev = g_device;
+  }
+  return sms;
+}
 static int sms() {
-  if (!g_sms) cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, g_device);
-  return g_sms ? g_sms : 148;
+  return device_sm_count();
 }
 
 int ensure_red(mhd_operator* op, int64_t n) {

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256) k_mul(int64_t n, const double* __restrict
 
 static unsigned vgrid(int64_t n) {
   int64_t b = (n + 255) / 256;
-  if (b > 148 * 8) b = 148 * 8;
+  const int64_t cap = (int64_t)device_sm_count() * 8;
+  if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (unsigned)b;
 }

@@ -14,7 +14,6 @@
 //      count contributions per nnz and flag the nnz that receive exactly one (plain store instead of atomic).
 #include "common.h"
 #include "h1h1_cell.h"
-#include "hdiv_cell.h"
 #include "hdiv7_cell.h"
 
 namespace mhd {
@@ -468,10 +467,6 @@ int symbolic_build(mhd_operator* op) {
     return symbolic_build_impl<LayoutH1H1>(op, op->d_gids, ord, h1::NENT, h1::NENT_PAD);
   }
   std::vector<uint16_t> ord;
-  if (op->jac_version == 6) {  // opt-in structure-exploiting kernel: its own enumeration, unpermuted local numbering
-    v6_entry_order(ord);
-    return symbolic_build_impl<LayoutHDiv>(op, op->d_gids, ord, h6::NENT, h6::NENT_PAD);
-  }
   if (op->jac_version == 7) {  // sum-factorised kernel: its own enumeration in the permuted local numbering
     v7_entry_order(ord);
     return symbolic_build_impl<LayoutHDiv>(op, op->d_pgids, ord, h7::NENT, h7::NENT);

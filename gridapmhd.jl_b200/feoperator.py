@@ -141,12 +141,6 @@ class B200FEOperator:
         L.check(lib.mhd_operator_create(C.byref(mesh), C.byref(tab), C.byref(lay), C.byref(prm), C.byref(h)))
         self.handle = h
         self._keep = []
-        if os.environ.get("MHD_JAC_V6", "0") not in ("", "0"):  # same rule as the library: atoi(value) != 0
-            # opt-in sum-factorised Jacobian kernel (hdiv_v6.cu): hand over the tensor structure of the Q2 node numbering
-            from .host.reffe import Q2_NODE_IJK
-
-            ijk = np.ascontiguousarray(Q2_NODE_IJK, dtype=np.int8)
-            L.check(lib.mhd_operator_set_tensor_structure(h, L.ptr(ijk)))
         self.nrows = self.ncols = self.nnz = None
         self._A = None
 

@@ -85,7 +85,6 @@ SIGNATURES = {
                                       C.POINTER(mhd_params_t), C.POINTER(_P)]),
     "mhd_operator_destroy": (C.c_int, [_P]),
     "mhd_operator_set_params": (C.c_int, [_P, C.POINTER(mhd_params_t)]),
-    "mhd_operator_set_tensor_structure": (C.c_int, [_P, _P]),
     "mhd_operator_get_kernel_version": (C.c_int, [_P, _P]),
     "mhd_operator_set_deterministic": (C.c_int, [_P, C.c_int32, _P]),
     "mhd_operator_set_halo": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),

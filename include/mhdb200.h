@@ -137,16 +137,10 @@ int mhd_operator_create(const mhd_mesh_t*, const mhd_tables_t*, const mhd_layout
 int mhd_operator_destroy(mhd_operator_t*);
 int mhd_operator_set_params(mhd_operator_t*, const mhd_params_t*); /* continuation: src/main.jl:243-260 */
 
-/* Optional, before mhd_operator_symbolic: tell the library that the velocity basis and the quadrature are tensor products.
- * node_ijk[27*3]: (i,j,k) in {0,1,2}^3 of every local velocity node in the order of the tables (what
- * get_node_coordinates(reffe_u) gives the host).  The library derives the 1-D factors from the tables, checks the product
- * structure (MHD_E_INVALID otherwise) and may then use the sum-factorised Jacobian kernel (opt-in: MHD_JAC_V6=1 in the
- * environment of this call; the default kernel does not need the information). */
-int mhd_operator_set_tensor_structure(mhd_operator_t*, const int8_t* node_ijk);
 /* Which Jacobian kernel the operator runs: 7 = fully sum-factorised kernel (csrc/hdiv_v7.cu; chosen automatically at
  * mhd_operator_create when the tables of mhd_tables_t turn out to be tensor products of 1-D factors on the tensor Gauss rule --
  * true for the reference's HEX elements, src/parameters.jl:436-441,521-525 -- unless MHD_JAC_V7=0), 5 = generic tensor-core
- * kernel (csrc/assembly.cu, any tables), 6 = superseded opt-in kernel.  H1-H1 operators report 0. */
+ * kernel (csrc/assembly.cu, any tables).  H1-H1 operators report 0. */
 int mhd_operator_get_kernel_version(mhd_operator_t*, int32_t* version);
 /* Deterministic assembly ("offer a deterministic (coloured) mode"): cells are greedily coloured so that no two
  * cells of a colour share a dof and the Jacobian / residual kernels run one launch per colour, which fixes the order in which

@@ -12,6 +12,7 @@ module GridapMHDB200
 
 using Gridap, Gridap.FESpaces, Gridap.Algebra, Gridap.ReferenceFEs, Gridap.Geometry, Gridap.MultiField
 using SparseMatricesCSR
+using LinearAlgebra
 
 const libmhd = get(ENV, "MHDB200_LIBRARY", "libmhdb200.so")   # like JULIA_PETSC_LIBRARY (ci_mpi.yml:9)
 
@@ -23,6 +24,7 @@ macro check(ex)
     rc == 0 || error("libmhdb200: ", unsafe_string(ccall((:mhd_last_error_string, libmhd), Cstring, ())))
   end
 end
+const MHD_E_NOTCONV = Cint(-6)   # mhd_solve reached maxiter: a RESULT, not a failure (see solve! below)
 
 struct MhdMesh
   nnodes::Int64; coords::Ptr{Float64}; ncells::Int64; cell_nodes::Ptr{Int32}; index_base::Int32
@@ -59,6 +61,8 @@ mutable struct B200FEOperator <: FEOperator
   handle::Ptr{Cvoid}
   nrows::Int; nnz::Int
   rowptr::Vector{Int64}; colval::Vector{Int64}     # fetched once (0-based, SparseMatrixCSR{0})
+  device_resident::Bool                            # allocate_jacobian returns a B200DeviceMatrix (solver :b200) or a host CSR
+  keep::Any                                        # the host arrays the create call borrowed (kept only for debugging)
 end
 FESpaces.get_trial(op::B200FEOperator) = op.trial
 FESpaces.get_test(op::B200FEOperator) = op.test
@@ -75,7 +79,7 @@ Tables handed over (all borrowed for the call only):
     (`get_sign_flip`), free/Dirichlet counts, and the field order of `_multi_field_style(params)`
   * fluid parameters α β γ σ ζᵤ ζⱼ B f g convection from `params[:fluid]` (src/weakforms.jl:71-83)
 """
-function B200FEOperator(U, V, params; tables, mesh, layout, fluid)
+function B200FEOperator(U, V, params; tables, mesh, layout, fluid, device_resident=(params[:solver][:solver] == :b200), keep=nothing)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   @check ccall((:mhd_operator_create, libmhd), Cint,
                (Ref{MhdMesh}, Ref{MhdTables}, Ref{MhdLayout}, Ref{MhdParams}, Ref{Ptr{Cvoid}}), mesh, tables, layout, fluid, h)
@@ -83,11 +87,108 @@ function B200FEOperator(U, V, params; tables, mesh, layout, fluid)
   @check ccall((:mhd_operator_symbolic, libmhd), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h[], nr, nc, nnz)
   rowptr = Vector{Int64}(undef, nr[] + 1); colval = Vector{Int64}(undef, nnz[])
   @check ccall((:mhd_operator_get_csr, libmhd), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint, Cint), h[], rowptr, colval, 8, 0)
-  op = B200FEOperator(U, V, h[], nr[], nnz[], rowptr, colval)
+  op = B200FEOperator(U, V, h[], nr[], nnz[], rowptr, colval, device_resident, keep)
   finalizer(o -> nothing, op)   # explicit destroy only (collective objects must not be freed from GC; hunt.jl:204)
   return op
 end
 destroy!(op::B200FEOperator) = (ccall((:mhd_operator_destroy, libmhd), Cint, (Ptr{Cvoid},), op.handle); op.handle = C_NULL)
+
+# ---- Gridap -> C structs: the part of the seam that decides whether Gridap's own entries come out (src/main.jl:207-233,
+#      src/fespaces.jl:13-46).  Everything the kernels integrate with is READ OFF Gridap's objects -- reference tables from the
+#      reffes at the quadrature points, cell dof ids and RT sign flips from the FE spaces -- never re-derived.
+"""
+    b200_operator(U, V, params) -> B200FEOperator
+
+Drop-in for `_fe_operator(mfs,U,V,params)` of the H1-HDiv formulation on a sequential (or one rank's local) model.
+"""
+function b200_operator(U, V, params)
+  model = params[:model]
+  grid  = get_grid(model)
+  # -- mesh: HEX8 cells in Gridap's lexicographic vertex order (what the geometry tables below assume)
+  xs    = get_node_coordinates(grid)
+  coords = collect(Float64, reinterpret(reshape, Float64, collect(xs)))            # 3 x nnodes, column major = [node][3]
+  cn    = get_cell_node_ids(grid)
+  ncells = length(cn)
+  cell_nodes = Matrix{Int32}(undef, 8, ncells)
+  for (c, ids) in enumerate(cn); cell_nodes[:, c] .= ids; end
+  # -- solid cells (params[:solid], src/Applications/hunt.jl:168-176): u, p live on Ωf only => dof id 0 on solid cells
+  Ωf = params[:Ωf]
+  fluid_cells = Ωf === nothing ? collect(1:ncells) : get_cell_to_bgcell(Ωf) # Triangulation -> background cell ids (Gridap.Geometry; older: get_glue(Ωf,Val(3)).tface_to_mface)
+  is_solid = ones(UInt8, ncells); is_solid[fluid_cells] .= 0
+  has_solid = any(!iszero, is_solid)
+  cell_sigma = has_solid ? _cellwise_sigma(params, ncells, is_solid) : Float64[]
+  # -- reference tables at the points of Quadrature(HEX, q) (src/parameters.jl:381-389: q = 5 -> 27 Gauss points)
+  q     = params[:fespaces][:q]
+  quad  = Quadrature(HEX, q)
+  xq, wq = get_coordinates(quad), get_weights(quad)
+  @assert length(wq) == 27 "libmhdb200 integrates with the 27-point rule (order_u = order_j = 2)"
+  reffe_u, reffe_p = _reffe(params, :reffe_u), _reffe(params, :reffe_p)
+  reffe_j, reffe_φ = _reffe(params, :reffe_j), _reffe(params, :reffe_φ)
+  geo   = LagrangianRefFE(Float64, HEX, 1)                                             # trilinear geometry map
+  dgeo  = evaluate(Broadcasting(∇)(get_shapefuns(geo)), xq)                            # [q, v] VectorValue{3}
+  geo_grad = Float64[dgeo[iq, v][k] for k in 1:3, v in 1:8, iq in 1:27]                # C layout [q][v][k]
+  # velocity: the SCALAR Q2 basis (the library expands N_a e_c itself; Gridap's vector Lagrangian dofs are component major,
+  # dof = node + nnodes*(comp-1): checked below on the cell dof ids)
+  su    = get_shapefuns(LagrangianRefFE(Float64, HEX, get_order(reffe_u)))
+  uval  = evaluate(su, xq); ugrad = evaluate(Broadcasting(∇)(su), xq)
+  u_val = Float64[uval[iq, a] for a in 1:27, iq in 1:27]                               # [q][a]
+  u_grad = Float64[ugrad[iq, a][k] for k in 1:3, a in 1:27, iq in 1:27]                # [q][a][k]
+  pval  = evaluate(get_shapefuns(reffe_p), xq)
+  p_val = Float64[pval[iq, k] for k in 1:4, iq in 1:27]
+  sj    = get_shapefuns(reffe_j)
+  jval  = evaluate(sj, xq); jdiv = evaluate(Broadcasting(divergence)(sj), xq)
+  j_val = Float64[jval[iq, m][k] for k in 1:3, m in 1:36, iq in 1:27]                  # reference (un-mapped) RT basis
+  j_div = Float64[jdiv[iq, m] for m in 1:36, iq in 1:27]
+  fval  = evaluate(get_shapefuns(reffe_φ), xq)
+  phi_val = Float64[fval[iq, l] for l in 1:8, iq in 1:27]
+  w     = collect(Float64, wq)
+  # -- dof ids: signed, 1-based, negative = Dirichlet (Gridap's own convention); 0 = absent on a solid cell
+  V_u, V_p, V_j, V_φ = V[1], V[2], V[3], V[4]
+  U_u, U_j = U[1], U[3]
+  cd_u = _cell_dofs(V_u, 81, ncells, fluid_cells); cd_p = _cell_dofs(V_p, 4, ncells, fluid_cells)
+  cd_j = _cell_dofs(V_j, 36, ncells, 1:ncells);    cd_φ = _cell_dofs(V_φ, 8, ncells, 1:ncells)
+  # RT sign flips: Gridap keeps them with the cell map of the dof basis ("a cell flips the dofs of a facet iff it is the
+  # second cell around it"); get_sign_flip(model, cell_reffes) returns, per cell, a Bool per local dof
+  flips = ReferenceFEs.get_sign_flip(model, Fill(reffe_j, ncells))                    # Gridap.FESpaces (DivConformingFESpaces.jl)
+  j_sign = Matrix{Int8}(undef, 36, ncells)
+  for (c, f) in enumerate(flips); j_sign[:, c] .= ifelse.(f, Int8(-1), Int8(1)); end
+  dir_u = collect(Float64, get_dirichlet_dof_values(U_u)); dir_j = collect(Float64, get_dirichlet_dof_values(U_j))
+  nfree = (num_free_dofs(V_u), num_free_dofs(V_p), num_free_dofs(V_j), num_free_dofs(V_φ))
+  ndir  = (num_dirichlet_dofs(V_u), 0, num_dirichlet_dofs(V_j), 0)
+  order = _field_order(params)                                                       # (0,1,2,3) | (0,2,1,3) | (2,0,1,3): src/fespaces.jl:4-9
+  fl    = params[:fluid]
+  conv  = Dict(:none => 0, :picard => 1, :newton => 2)[get(fl, :convection, :newton)]
+  c3(v) = (Float64(v[1]), Float64(v[2]), Float64(v[3]))
+  fluid = MhdParams(fl[:α], fl[:β], fl[:γ], fl[:σ], fl[:ζᵤ], fl[:ζⱼ], c3(fl[:B]), c3(fl[:f]), c3(get(fl, :g, (0, 0, 0))), conv)
+  keep  = (coords, cell_nodes, is_solid, cell_sigma, w, geo_grad, u_val, u_grad, p_val, j_val, j_div, phi_val, cd_u, cd_p, cd_j, cd_φ,
+           j_sign, dir_u, dir_j)
+  GC.@preserve keep begin
+    mesh = MhdMesh(size(coords, 2), pointer(coords), ncells, pointer(cell_nodes), 1,
+                   has_solid ? pointer(is_solid) : C_NULL, has_solid ? pointer(cell_sigma) : C_NULL)
+    tables = MhdTables(27, pointer(w), pointer(geo_grad), pointer(u_val), pointer(u_grad), pointer(p_val), pointer(j_val),
+                       pointer(j_div), pointer(phi_val))
+    layout = MhdLayout((pointer(cd_u), pointer(cd_p), pointer(cd_j), pointer(cd_φ)), pointer(j_sign), nfree, nfree, ndir,
+                       (isempty(dir_u) ? C_NULL : pointer(dir_u), C_NULL, isempty(dir_j) ? C_NULL : pointer(dir_j), C_NULL), order)
+    return B200FEOperator(U, V, params; tables, mesh, layout, fluid)   # the library copies everything during the call
+  end
+end
+_reffe(params, key) = (r = params[:fespaces][key]; r isa Tuple ? ReferenceFE(HEX, r[1], r[2]...; r[3]...) : r)
+function _cell_dofs(V, n, ncells, cells)
+  ids = get_cell_dof_ids(V)                          # on the space's own triangulation: one entry per cell of `cells`
+  out = zeros(Int32, n, ncells)                      # 0 = the dof does not exist on this (solid) cell
+  for (i, c) in enumerate(cells); out[:, c] .= ids[i]; end
+  out
+end
+function _cellwise_sigma(params, ncells, is_solid)
+  σs = params[:solid] === nothing ? 0.0 : params[:solid][:σ]
+  Float64[is_solid[c] != 0 ? σs : params[:fluid][:σ] for c in 1:ncells]
+end
+function _field_order(params)
+  s = params[:solver][:solver]
+  s === :li2019 ? (Int32(2), Int32(0), Int32(1), Int32(3)) :                          # (j,u,p,φ)
+  (s === :badia2024 || s === :b200) ? (Int32(0), Int32(2), Int32(1), Int32(3)) :      # ([u,j],p,φ)
+  (Int32(0), Int32(1), Int32(2), Int32(3))                                           # Consecutive
+end
 
 # ---- H1-H1 formulation (params[:fespaces][:current_disc] = :H1 => U = (U_u,U_p,U_φ), src/fespaces.jl:32-41;
 #      weak_form_h1_h1, src/weakforms.jl:344-355).  Same operator type and methods; only the creation call differs.
@@ -108,7 +209,7 @@ function B200H1H1FEOperator(U, V, params; tables::MhdTablesH1H1, mesh::MhdMesh, 
   @check ccall((:mhd_operator_symbolic, libmhd), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), h[], nr, nc, nnz)
   rowptr = Vector{Int64}(undef, nr[] + 1); colval = Vector{Int64}(undef, nnz[])
   @check ccall((:mhd_operator_get_csr, libmhd), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Cint, Cint), h[], rowptr, colval, 8, 0)
-  B200FEOperator(U, V, h[], nr[], nnz[], rowptr, colval)
+  B200FEOperator(U, V, h[], nr[], nnz[], rowptr, colval, params[:solver][:solver] == :b200, nothing)
 end
 
 # Gridap NonlinearOperator API used by solve!(xh,solver,op) (src/main.jl:275) and by main.jl:158,163
@@ -116,15 +217,40 @@ function Algebra.allocate_residual(op::B200FEOperator, x::AbstractVector)
   zeros(Float64, op.nrows)
 end
 function Algebra.allocate_jacobian(op::B200FEOperator, x::AbstractVector)
-  SparseMatrixCSR{0}(op.nrows, op.nrows, op.rowptr, op.colval, zeros(Float64, op.nnz))
+  op.device_resident ? B200DeviceMatrix(op) : SparseMatrixCSR{0}(op.nrows, op.nrows, op.rowptr, op.colval, zeros(Float64, op.nnz))
 end
 function Algebra.residual!(b::AbstractVector, op::B200FEOperator, x::AbstractVector)
   @check ccall((:mhd_residual, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), op.handle, x, b)
   b
 end
+# Two matrix types (chosen by params[:solver][:matrix_type], src/main.jl:220):
+#  * B200DeviceMatrix: the values never leave the GPU -- the matrix IS the operator handle (1.2 GB per assembly stay where the
+#    device-resident Krylov solver reads them).  This is what :b200 solvers use; `nzval(A)` fetches a host copy on demand.
+#  * SparseMatrixCSR{0,Float64,Int64}: for host-side solvers (:julia LU, PETSc): the values are copied out after every assembly
+#    (bench.py reports both modes: `e2e` and `e2e_with_matrix_d2h`).
+struct B200DeviceMatrix <: AbstractMatrix{Float64}
+  op::B200FEOperator
+end
+Base.size(A::B200DeviceMatrix) = (A.op.nrows, A.op.nrows)
+Base.getindex(A::B200DeviceMatrix, i::Int, j::Int) = error("B200DeviceMatrix is device resident: use host_copy(A)")
+function host_copy(A::B200DeviceMatrix)
+  v = Vector{Float64}(undef, A.op.nnz)
+  @check ccall((:mhd_get_nzval, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}), A.op.handle, v)
+  SparseMatrixCSR{0}(A.op.nrows, A.op.nrows, A.op.rowptr, A.op.colval, v)
+end
+function LinearAlgebra.mul!(y::AbstractVector, A::B200DeviceMatrix, x::AbstractVector)
+  @check ccall((:mhd_spmv, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), A.op.handle, x, y)
+  y
+end
+function Algebra.jacobian!(A::B200DeviceMatrix, op::B200FEOperator, x::AbstractVector)
+  @check ccall((:mhd_jacobian, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), op.handle, x, C_NULL)   # no D2H of nzval
+  A
+end
+function Algebra.residual_and_jacobian!(b, A::B200DeviceMatrix, op::B200FEOperator, x)
+  @check ccall((:mhd_residual_and_jacobian, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), op.handle, x, b)
+  b, A
+end
 function Algebra.jacobian!(A::SparseMatrixCSR, op::B200FEOperator, x::AbstractVector)
-  # values are copied out only when the caller wants them on the host (direct solvers); the B200 linear solver
-  # below passes C_NULL and keeps the matrix on the device behind the handle
   @check ccall((:mhd_jacobian, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), op.handle, x, A.nzval)
   A
 end
@@ -175,29 +301,42 @@ end
 struct B200LinearSolver <: Algebra.LinearSolver
   op::B200FEOperator
   opts::MhdSolverOpts
+  verbose::Bool
 end
+B200LinearSolver(op, opts) = B200LinearSolver(op, opts, false)
 struct B200SymbolicSetup <: Algebra.SymbolicSetup
   solver::B200LinearSolver
 end
 mutable struct B200NumericalSetup <: Algebra.NumericalSetup
   solver::B200LinearSolver
   handle::Ptr{Cvoid}
+  last_iters::Int32
+  last_residual::Float64
 end
 Algebra.symbolic_setup(s::B200LinearSolver, A::AbstractMatrix) = B200SymbolicSetup(s)
 function Algebra.numerical_setup(ss::B200SymbolicSetup, A::AbstractMatrix)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   @check ccall((:mhd_solver_create, libmhd), Cint, (Ptr{Cvoid}, Ref{MhdSolverOpts}, Ref{Ptr{Cvoid}}), ss.solver.op.handle, ss.solver.opts, h)
-  ns = B200NumericalSetup(ss.solver, h[])
+  ns = B200NumericalSetup(ss.solver, h[], 0, 0.0)
   Algebra.numerical_setup!(ns, A)
 end
 function Algebra.numerical_setup!(ns::B200NumericalSetup, A::AbstractMatrix)
   @check ccall((:mhd_solver_setup, libmhd), Cint, (Ptr{Cvoid},), ns.handle)   # the matrix is already on the device
   ns
 end
+# GridapSolvers' FGMRESSolver(m,P;maxiter=m,...) (src/Solvers/badia2024.jl:40) RETURNS when it hits maxiter and the NewtonSolver
+# around it carries on as an inexact Newton method; with m = maxiter = 15 and rtol = nl_rtol/10 that is the common case.
+# So MHD_E_NOTCONV must not raise: it is reported through the (optional) log and the iteration count.
 function Algebra.solve!(x::AbstractVector, ns::B200NumericalSetup, b::AbstractVector)
   iters = Ref{Int32}(0); res = Ref{Float64}(0.0)
-  @check ccall((:mhd_solve, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}, Ref{Float64}, Ptr{Float64}),
-               ns.handle, b, x, iters, res, C_NULL)
+  rc = ccall((:mhd_solve, libmhd), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}, Ref{Float64}, Ptr{Float64}),
+             ns.handle, b, x, iters, res, C_NULL)
+  if rc == MHD_E_NOTCONV
+    ns.solver.verbose && @info "B200LinearSolver: maxiter reached" iterations=iters[] residual=res[]
+  elseif rc != 0
+    error("libmhdb200: ", unsafe_string(ccall((:mhd_last_error_string, libmhd), Cstring, ())))
+  end
+  ns.last_iters = iters[]; ns.last_residual = res[]
   x
 end
 

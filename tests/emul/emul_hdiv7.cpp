@@ -51,8 +51,8 @@ void cell(Cell7& S, const Small7& C, const mhd::h7::Tab7& T, int nt, const Param
   FOR_T { chunk_uu<CONV, ZU>(S, C, C, t, nt, 0, b0); if (RES) res_stage_c(S, C, t, nt, ra); }
   FOR_T { sweep_uu(b0, 0, t, nt, st); chunk_uu<CONV, ZU>(S, C, C, t, nt, 1, b1); }
   FOR_T { sweep_uu(b1, 1, t, nt, st); chunk_uu<CONV, ZU>(S, C, C, t, nt, 2, b0); }
-  FOR_T { sweep_uu(b0, 2, t, nt, st); chunk_uj<false>(S, C, t, nt, P, b1); }
-  FOR_T { sweep_uj(b1, t, nt, st); chunk_uj<true>(S, C, t, nt, P, b0); }
+  FOR_T { sweep_uu(b0, 2, t, nt, st); chunk_uj(S, C, t, nt, P, b1, false); }
+  FOR_T { sweep_uj(b1, t, nt, st); chunk_uj(S, C, t, nt, P, b0, true); }
   FOR_T { sweep_ju(b0, t, nt, st); chunk_rest<ZJ>(S, C, t, nt, b1); }
   FOR_T sweep_rest(b1, t, nt, st);
 }

@@ -337,7 +337,7 @@ def test_expansion_nonaffine_mesh_values(mhdlib):
     assert np.array_equal(rowptr, Ao.indptr) and np.array_equal(colval, Ao.indices)
     assert relerr(A.nzval(), Ao.data) < VAL_TOL
     assert relerr(b, O.residual(fes, x, oracle_params(params["fluid"]))) < VAL_TOL
-    assert relerr(op.residual(x), b) < 1e-14
+    assert relerr(op.residual(x), b) < 1e-13  # two kernels, different summation orders
     op.destroy()
 
 
@@ -387,7 +387,7 @@ def test_hunt_solid_walls_values_and_solve(mhdlib):
     assert np.array_equal(rowptr, Ao.indptr) and np.array_equal(colval, Ao.indices)
     assert relerr(A.nzval(), Ao.data) < VAL_TOL
     assert relerr(b, O.residual(fes, x, oracle_params(params["fluid"]))) < VAL_TOL
-    assert relerr(op.residual(x), b) < 1e-14
+    assert relerr(op.residual(x), b) < 1e-13  # two kernels, different summation orders
     # solve (linear: the Hunt flow has no convection contribution)
     opts = B200SolverOptions(m=30, maxiter=30, rtol=1e-13, atol=1e-30, precond="block_tri", uj_solver="dense_lu")
     nls = NewtonSolver(B200LinearSolver(opts), maxiter=6, rtol=1e-12)  # extra steps = iterative refinement, until 1e-12 |r0|

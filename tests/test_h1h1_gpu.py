@@ -216,6 +216,17 @@ def test_h1h1_hunt_driver_solves_on_the_device(mhdlib):
     out["op"].destroy()
 
 
+def test_hunt_driver_with_current_disc_h1_returns_its_info_dict(mhdlib):
+    """`hunt(current_disc=:H1, ...)` end to end (hunt.jl:212-303 subset): dof counts of the three fields, timings, solve log"""
+    from gridapmhd_jl_b200.applications import hunt
+
+    info, out = hunt(nc=(4, 4), B=(0.0, 20.0, 0.0), zeta_u=10.0, current_disc="H1", newton_rtol=1e-8)
+    assert info["ndofs_u"] + info["ndofs_p"] + info["ndofs_phi"] == info["ndofs"] and "ndofs_j" not in info
+    assert "skipped" in info["post_process"] and info["time_solve"] > 0.0
+    assert out["newton_log"][-1] <= 1e-7 * out["newton_log"][0]
+    out["op"].destroy()
+
+
 def test_h1h1_golden_fixture(mhdlib):
     """Committed golden vectors (tests/golden/make_golden.py::main_h1h1, generated with the oracle)."""
     import os

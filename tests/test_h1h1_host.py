@@ -344,10 +344,10 @@ def test_golden_fixture_h1h1_oracle_and_emulated_device_code(emul):
 
 
 def test_device_code_is_clean_under_address_sanitizer(tmp_path):
-    """h1h1_cell.h, patch_cell.h and hdiv_cell.h / sumfac_uu.h under -fsanitize=address,undefined (tests/emul/sanitize_main.cpp): no out-of-range index
+    """h1h1_cell.h, patch_cell.h and hdiv7_cell.h under -fsanitize=address,undefined (tests/emul/sanitize_main.cpp): no out-of-range index
     into the cell's shared data for any template variant / thread count / patch size"""
     exe = tmp_path / "sanitize_emul"
-    srcs = [os.path.join(HERE, "emul", f) for f in ("sanitize_main.cpp", "emul_h1h1.cpp", "emul_patch.cpp", "emul_hdiv.cpp")]
+    srcs = [os.path.join(HERE, "emul", f) for f in ("sanitize_main.cpp", "emul_h1h1.cpp", "emul_patch.cpp", "emul_hdiv7.cpp")]
     build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-std=c++17", "-o", str(exe)] + srcs,
                            capture_output=True, text=True)
     if build.returncode != 0 and ("asan" in build.stderr or "ubsan" in build.stderr or "sanitize" in build.stderr):

@@ -269,51 +269,3 @@ def test_sum_factorised_uu_block_matches_the_oracle():
     mod.main()  # asserts < 1e-12
 
 
-def test_sum_factorised_uu_device_phases_match_the_oracle(tmp_path):
-    """gridapmhd.jl_b200/csrc/sumfac_uu.h (the device phases of the sum-factorised uu block, not yet used by a kernel) run on
-    the CPU: Newton mass-type + stiffness + convection fields of non-affine cells against the oracle's dense uu block"""
-    import ctypes as C
-    import subprocess
-
-    from gridapmhd_jl_b200.host import mesh as M
-    from gridapmhd_jl_b200.host.fespaces import setup_fe_spaces
-    from gridapmhd_jl_b200.host.reffe import Q2_NODE_IJK, _lagrange_1d, gauss_legendre_01
-    from oracle import mhd_oracle as O
-
-    so = tmp_path / "libemul_sumfac.so"
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", str(so), os.path.join(ROOT, "tests", "emul", "emul_sumfac.cpp")])
-    lib = C.CDLL(str(so))
-    m = M.expansion_generate_mesh(0, perturb=0.2, seed=1)
-    fes = setup_fe_spaces(m, u_tags=("inlet", "wall"), u_values=(None, None), j_tags=("wall",))
-    T = fes.tables
-    prm = O.FluidParams(alpha=0.7, beta=0.3, gamma=50.0, sigma=1.0, B=(0.2, 1.0, -0.1), convection="newton")
-    x = np.random.default_rng(0).random(fes.ndofs)
-    X, st = m.cell_coords(), fes.cell_state(x)
-    Kref = O.cell_jacobians(T, X, st, fes.j_sign, prm)[:, :81, :81]
-    xq, _ = gauss_legendre_01(3)
-    v, d = _lagrange_1d(np.array([0.0, 0.5, 1.0]), xq)
-    D = (v, d)
-    P = np.ascontiguousarray(np.stack([np.einsum("iq,Iq->iIq", D[mm], D[nn]).reshape(9, 3) for mm in (0, 1) for nn in (0, 1)]))
-    ijk = np.ascontiguousarray(Q2_NODE_IJK, dtype=np.int8)
-    _, det, invJ = O.cell_geometry(T, X)
-    w = T.w[None, :] * np.abs(det)
-    nc = X.shape[0]
-    us = st[:, :81].reshape(nc, 3, 27)
-    uq = np.einsum("qa,cia->cqi", T.nu, us)
-    gN = np.einsum("qak,cqki->cqai", T.dnu, invJ)
-    gu = np.einsum("cqbd,cib->cqdi", gN, us)
-    for c in range(nc):
-        F = np.zeros((21, 27))
-        for ci in range(3):
-            for di in range(3):
-                F[ci * 3 + di] = w[c] * prm.alpha * gu[c, :, di, ci]
-        G = prm.beta * np.einsum("q,qmi,qni->qmn", w[c], invJ[c], invJ[c])
-        F[9:18] = G.reshape(27, 9).T
-        F[18:21] = (prm.alpha * np.einsum("q,qni,qi->qn", w[c], invJ[c], uq[c])).T
-        F = np.ascontiguousarray(F)
-        for nt, rev in ((256, 0), (256, 1), (100, 0)):
-            K = np.zeros((81, 81))
-            lib.emul_sumfac_uu(P.ctypes.data_as(C.c_void_p), ijk.ctypes.data_as(C.c_void_p), F.ctypes.data_as(C.c_void_p), nt, rev,
-                               K.ctypes.data_as(C.c_void_p))
-            assert np.isfinite(K).all()
-            assert np.abs(K - Kref[c]).max() <= 1e-13 * np.abs(Kref[c]).max()
