@@ -238,6 +238,80 @@ def h1h1_extra_leg(L, nc, reps=10):
     return out
 
 
+def expansion6k_extra_leg(L, reps=10):
+    """BASELINE configs 3/4 stand-in: the reference's own Expansion_6k.msh (4 320 non-affine hexes; fixture
+    tests/golden/expansion_6k_mesh.npz), Expansion parameterisation (expansion.jl:40-181), Newton convection, inlet Dirichlet
+    data: fused residual + Jacobian assembly and SpMV, with the parity of every row against the C oracle."""
+    import torch
+
+    from gridapmhd_jl_b200.applications import expansion_params, setup_spaces
+    from gridapmhd_jl_b200.feoperator import B200FEOperator
+    from gridapmhd_jl_b200.host import mesh as M
+    from oracle import parity as PAR
+
+    m = M.load_mesh_npz(os.path.join(ROOT, "tests", "golden", "expansion_6k_mesh.npz"))
+    params = expansion_params(Ha=100.0, N=3740.0, zeta_u=10.0, zeta_j=10.0, mesh=m)
+    fes = setup_spaces(params)
+    op = B200FEOperator(fes, params["fluid"])
+    A = op.allocate_jacobian()
+    xh = np.random.default_rng(6).random(fes.ndofs)
+    x = torch.from_numpy(xh).cuda()
+    r, y = torch.empty_like(x), torch.empty_like(x)
+    for _ in range(3):
+        op.residual_and_jacobian_b(r, A, x), op.spmv(x, y)
+    L.load().mhd_profile_enable(1)
+    L.load().mhd_profile_reset()
+    for _ in range(reps):
+        op.residual_and_jacobian_b(r, A, x), op.spmv(x, y)
+    jac, nj = L.profile_get("jacobian")
+    spmv, ns = L.profile_get("spmv")
+    L.load().mhd_profile_enable(0)
+    rowptr, colval = A.pattern()
+    par = PAR.assembly_parity(fes, oracle_params(params["fluid"]), xh, rowptr, colval, A.nzval(), r.cpu().numpy(), op.nrows, ncells=m.ncells)
+    out = {"workload": "Expansion_6k.msh (reference mesh, 4320 non-affine hexes), Ha=100 N=3740 zeta=10, newton convection, inlet profile",
+           "ncells": m.ncells, "ndofs": fes.ndofs, "nnz": op.nnz, "kernel_version": op.kernel_version,
+           "residual_and_jacobian_kernel_ms": jac / nj, "Mcells_s": m.ncells / (jac / nj) / 1e3, "spmv_kernel_ms": spmv / ns,
+           "spmv_GBs": (12.0 * op.nnz + 20.0 * op.nrows) / (spmv / ns) / 1e6,
+           "parity": {k: par[k] for k in ("jac_rel", "res_rel", "csr_bitexact", "rows_checked")}}
+    op.destroy()
+    return out
+
+
+def solve_extra_leg(L, nc):
+    """BASELINE config 2 "assembly + GMRES with block preconditioner", converging: Hunt nc=(64,64), Ha=1000 on the reference's
+    default (boundary-layer adapted) mesh, augmented Lagrangian zeta = 100 (the reference's tests use 10..100), one Newton step
+    from x = 0: FGMRES(30) + Badia2024 block-triangular preconditioner, (u,j) block = inner GMRES(30) preconditioned by the
+    vertex-patch block-Jacobi smoother -- all on the device.  Reports iterations, wall time and the TRUE relative residual."""
+    from gridapmhd_jl_b200.applications import hunt_params, setup_spaces
+    from gridapmhd_jl_b200.feoperator import B200FEOperator, B200LinearSolver, B200SolverOptions
+
+    p = hunt_params(nc=(nc[0], nc[1]), B=(0.0, HA, 0.0), zeta_u=100.0, zeta_j=100.0, solver="badia2024")
+    fes = setup_spaces(p)
+    op = B200FEOperator(fes, p["fluid"])
+    A = op.allocate_jacobian()
+    b = np.empty(op.nrows)
+    op.residual_and_jacobian_b(b, A, np.zeros(fes.ndofs))
+    t0 = time.perf_counter()
+    opts = B200SolverOptions(m=30, maxiter=120, rtol=1e-8, atol=0.0, precond="block_tri", uj_solver="gmres_patch", uj_inner_its=30,
+                             uj_inner_restart=30, patch_its=1, patch_omega=1.0)
+    ns = B200LinearSolver(opts).symbolic_setup(A).numerical_setup()
+    L.check(L.load().mhd_device_synchronize())
+    t_setup = time.perf_counter() - t0
+    dx = np.zeros(op.nrows)
+    t0 = time.perf_counter()
+    ns.solve_b(dx, -b)
+    t_solve = time.perf_counter() - t0
+    true = float(np.linalg.norm(op.spmv(dx) + b) / np.linalg.norm(b))
+    out = {"workload": f"Hunt nc=({nc[0]},{nc[1]},3) Ha={HA:g}, zeta_u=zeta_j=100, linear solve of the first Newton step, ndofs {fes.ndofs}",
+           "solver": "FGMRES(30) + block-triangular preconditioner (badia2024.jl); (u,j) block: GMRES(30) + vertex-patch smoother (gmg.jl:62-81); "
+                     "p, phi blocks: exact cell mass inverses", "iterations": int(ns.iters), "setup_ms": t_setup * 1e3, "solve_ms": t_solve * 1e3,
+           "true_relative_residual": true, "estimated_relative_residual": float(ns.history[-1] / ns.history[0]),
+           "converged_to_1e-8": bool(true <= 2e-8), "patch_inverse_bytes": 8 * ns.patch_entries}
+    ns.destroy()
+    op.destroy()
+    return out
+
+
 def patch_extra_leg(L, op, A, fes, reps=10):
     """Vertex-patch block-Jacobi smoother of the (u,j) block on the bench matrix: setup = gather + blocked
     Gauss-Jordan inversion of every patch, apply = one additive sweep (streams the explicit inverses once)."""
@@ -373,27 +447,45 @@ def run_ours(args):
     # the assembled matrix, enqueued as a whole on the stream (SpMV, fused CGS2 Gram-Schmidt, Givens on the device; the
     # host reads the scalars once per cycle).  Point-Jacobi preconditioner: the block preconditioner's (u,j) solve is
     # not scalable yet, so this times the Krylov machinery, not a converged solve.
+    # Runs at every N: the (m+1)-double all-reduces and the fused peer-memory halo are part of the iteration when N > 1.
     krylov = None
-    if world == 1:
+    try:
         from gridapmhd_jl_b200.feoperator import B200LinearSolver, B200SolverOptions
 
         ns = B200LinearSolver(B200SolverOptions(m=15, maxiter=15, rtol=1e-30, atol=0.0, precond="jacobi")).symbolic_setup(A).numerical_setup()
-        bb = np.random.default_rng(7).standard_normal(op.nrows)
-        xx = np.zeros(op.nrows)
-        ns.solve_b(xx, bb)  # warm-up
-        torch.cuda.synchronize()
-        reps = 3
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_k = time.perf_counter()
-        for _ in range(reps):
-            xx[:] = 0.0
+        bb = torch.from_numpy(np.random.default_rng(7 + rank).standard_normal(op.nrows)).cuda()
+        xx = torch.zeros(op.nrows, dtype=torch.float64, device="cuda")
+        ns.solve_b(xx, bb)  # warm-up (captures the CUDA graph of the restart cycle on one GPU)
+        reps = 5
+
+        def one_cycle():
+            xx.zero_()
             ns.solve_b(xx, bb)
-        torch.cuda.synchronize()
-        t_k = (time.perf_counter() - t_k) / reps
-        krylov = {"solver": "FGMRES(15), point-Jacobi, 15 iterations, host buffers for b and x", "ms_per_cycle": t_k * 1e3,
-                  "ms_per_iteration": t_k * 1e3 / 15, "iterations": int(ns.iters),
+
+        ms_cycle = timed(one_cycle, reps, 2)
+        krylov = {"solver": "FGMRES(15), point-Jacobi, 15 iterations = one restart cycle, device vectors; CGS2 fused into 4 launches per "
+                            "Arnoldi step, cycle replayed as a CUDA graph on one GPU (MHD_KRYLOV_GRAPH=0 disables)",
+                  "ms_per_cycle": ms_cycle, "ms_per_iteration": ms_cycle / 15, "iterations": int(ns.iters),
                   "residual_reduction": float(ns.history[-1] / ns.history[0]) if len(ns.history) else None}
         ns.destroy()
+    except Exception as e:  # keep the contract line alive
+        krylov = {"error": repr(e)}
+    # dot / axpy / fused multi-dot bandwidth (BASELINE metric names them): vectors of the operator's size, 31 of them for m = 15
+    blas1 = None
+    try:
+        nv = op.nrows
+        Vb = torch.from_numpy(np.random.default_rng(3).standard_normal((16, nv))).cuda()
+        wv = torch.from_numpy(np.random.default_rng(4).standard_normal(nv)).cuda()
+        hbuf = torch.zeros(16, dtype=torch.float64, device="cuda")
+        lib = L.load()
+        ms_dot = timed(lambda: L.check(lib.mhd_dot(op.handle, L.ptr(Vb[0]), L.ptr(wv), L.ptr(hbuf))), 50, 5)
+        ms_axpy = timed(lambda: L.check(lib.mhd_axpy(op.handle, 0.5, L.ptr(Vb[0]), L.ptr(wv))), 50, 5)
+        ms_gs = timed(lambda: L.check(lib.mhd_multi_dot_axpy(op.handle, 16, L.ptr(Vb), nv, L.ptr(wv), L.ptr(hbuf))), 20, 3)
+        blas1 = {"n": int(nv), "note": "vectors are L2-resident at this size (5.9 MB each): GB/s are L2, not HBM, figures",
+                 "dot_ms": ms_dot, "dot_GBs": 16 * nv / ms_dot / 1e6, "axpy_ms": ms_axpy, "axpy_GBs": 24 * nv / ms_axpy / 1e6,
+                 "multi_dot_axpy16_ms": ms_gs, "multi_dot_axpy16_GBs": (17 * 8 + 18 * 8) * nv / ms_gs / 1e6}
+    except Exception as e:
+        blas1 = {"error": repr(e)}
     # host wall-clock for the e2e leg (host buffers; copies inside): CUDA events bracket it too
     ms_e2e = timed(step_host, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
@@ -451,8 +543,16 @@ def run_ours(args):
         fp64[name] = v.value
     # extra legs (single GPU, after every number of the main line has been taken): the H1-H1 formulation on the same mesh
     # and the vertex-patch smoother of the (u,j) block.  Reported beside the main line, never part of `value`.
-    h1h1_leg = patch_leg = None
-    if world == 1:
+    h1h1_leg = patch_leg = exp6k_leg = solve_leg = None
+    if world == 1 and not args.no_extra:
+        try:
+            exp6k_leg = expansion6k_extra_leg(L)
+        except Exception as e:
+            exp6k_leg = {"error": repr(e)}
+        try:
+            solve_leg = solve_extra_leg(L, nc)
+        except Exception as e:
+            solve_leg = {"error": repr(e)}
         try:
             h1h1_leg = h1h1_extra_leg(L, nc)
         except Exception as e:  # keep the contract line alive
@@ -500,6 +600,9 @@ def run_ours(args):
                  "roofline": {"bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
                               "traffic": None, "algorithmic_bytes": spmv_bytes}},
         "krylov": krylov,
+        "blas1": blas1,
+        "solve": solve_leg,
+        "expansion6k": exp6k_leg,
         "h1h1": h1h1_leg,
         "patch_smoother": patch_leg,
         "clocks": clocks,
@@ -530,6 +633,7 @@ def main():
     ap.add_argument("--ref-cells", type=int, default=1536, help="cells per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check against the oracle")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (solve, expansion6k, H1-H1, patch smoother)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -553,7 +553,7 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
     MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
   } else if (op->jac_version == 7) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(v7_launch_jacobian(op, dx, nullptr));
+    MHD_TRY(v7_launch(op, dx, nullptr, 0));
   } else {
     MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
@@ -588,7 +588,7 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
     }
   } else if (op->jac_version == 7) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
-    MHD_TRY(v7_launch_jacobian(op, dx, dr));
+    MHD_TRY(v7_launch(op, dx, dr, 1));
   } else {
     MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
@@ -629,6 +629,7 @@ int mhd_residual(mhd_operator_t* op, const double* x, double* r_out) {
   bool dev_out = is_device_ptr(r_out);
   double* dr = dev_out ? r_out : op->d_y;
   if (op->formulation == FORM_H1H1) MHD_TRY(h1h1_launch_residual(op, dx, dr));
+  else if (op->jac_version == 7) MHD_TRY(v7_launch(op, dx, dr, 2));
   else MHD_TRY(launch_residual(op, dx, dr));
   if (!dev_out) {
     MHD_TRY(d2h(r_out, dr, op->nrows));
@@ -664,6 +665,7 @@ int mhd_spmv(mhd_operator_t* op, const double* x, double* y) {
   if (!dev_out) {
     MHD_TRY(d2h(y, dy, op->nrows));
     MHD_CUDA(cudaStreamSynchronize(g_stream));
+    MHD_TRY(halo_check(op));  // host sync point: a timed-out ghost exchange is an error, not a silent wrong product
   }
   return MHD_OK;
 }

@@ -96,6 +96,17 @@ int allreduce_sum(double* d_buf, int n) {
   return 0;
 }
 
+int halo_check(mhd_operator* op) {
+  if (!op->halo.fused || op->halo.d_err == nullptr) return 0;
+  int e = 0;
+  MHD_CUDA(cudaMemcpyAsync(&e, op->halo.d_err, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  MHD_CUDA(cudaStreamSynchronize(g_stream));
+  MHD_CHECK(e == 0, MHD_E_COMM,
+            "fused SpMV + ghost exchange: a neighbour's values did not arrive within the spin limit (stalled or dead peer); "
+            "results computed since are invalid");
+  return 0;
+}
+
 }  // namespace mhd
 
 using namespace mhd;

@@ -137,7 +137,7 @@ struct mhd_operator {
                                    // 7: fully sum-factorised kernel (hdiv_v7.cu), chosen when the tables have the tensor structure
   unsigned char* d_tab7 = nullptr; // v7: h7::Tab7
   std::vector<unsigned char> h_small7;  // v7: h7::Small7 (uploaded to constant memory before a launch when it is not the current one)
-  uint32_t* d_shared_mask = nullptr;  // v7: bit i set <=> nnz i receives != 1 contributions (cleared before, RED-accumulated in, an assembly)
+  uint32_t* d_shared_mask = nullptr;  // v7: bit s set <=> the 32-byte sector s of nzval holds an nnz with != 1 contributions (cleared before an assembly)
   bool deterministic = false;      // v7: one launch per colour => run-to-run identical bits
   int32_t* d_color_cells = nullptr;   // cells sorted by colour
   std::vector<int64_t> color_ptr;  // [ncolors + 1]
@@ -259,7 +259,7 @@ int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 void v7_entry_order(std::vector<uint16_t>& ord);
 int v7_try_enable(mhd_operator* op);                                  // at operator creation: discovers the tensor structure of the tables
 int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib); // end of the symbolic phase
-int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
+int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode /* 0: Jacobian, 1: residual + Jacobian, 2: residual */);
 // h1h1.cu
 int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
 int h1h1_launch_residual(mhd_operator* op, const double* d_x, double* d_r);
@@ -280,10 +280,18 @@ int launch_axpy(int64_t n, double a, const double* d_x, double* d_y);
 int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int64_t ldv, const double* d_w, double* d_h);
 int launch_multi_axpy(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, double sign, double* d_w);
 int ensure_red(mhd_operator* op, int64_t ndoubles);
+// fused Gram-Schmidt building blocks of FGMRES (one launch each; k + 1 <= 18)
+bool gs_fused_ok(int k);
+int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out);
+int launch_gs_update(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, const double* d_w, const double* d_scale,
+                     const int* d_dead, double* d_out);
 // postprocess.cu
 int hunt_error_norms(mhd_operator* op, const double* d_x, const mhd_tables_t* t, const mhd_hunt_post_t* p, double* out6);
 // comm.cu
 int halo_exchange(mhd_operator* op, double* d_x);
+// at a host synchronisation point: MHD_E_COMM if a fused SpMV + halo kernel gave up waiting for a neighbour (the products computed
+// since then used stale ghost values)
+int halo_check(mhd_operator* op);
 int allreduce_sum(double* d_buf, int n);
 
 }  // namespace mhd

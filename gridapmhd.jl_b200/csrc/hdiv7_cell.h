@@ -164,40 +164,60 @@ MHD_7HD int pat_uu(int f, int ax) {
 MHD_7HD void jjb_pair(int blk, int* k, int* kp) { *k = blk == 2 ? 1 : 0; *kp = blk == 0 ? 1 : 2; }
 
 // ------------------------------------------------------------------ phase 0: gather (permuted ids, row starts, state, vertices)
-MHD_7HD void phase_load(Cell7& S, const SmallDyn& C, int tid, int nt, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129,
-                        const long long* rowstart129, const uint8_t* perm64, const double* dir, const double* x, bool need_u, bool solid,
-                        double sigma_cell, double sigma_fluid, const double* nzval = nullptr, bool with_res = false) {
-  for (int i = tid; i < 24; i += nt) S.X[i] = coords[(long long)cell_nodes8[i / 3] * 3 + i % 3];
+// Every gathered VALUE is one item (u 81 | j 36 | p, phi 12 | vertex coordinates 24): load_gather fetches it from global memory,
+// load_scatter files it in the cell data.  The kernel runs load_gather for the NEXT cell one barrier interval early (one value
+// per thread, in a register) so that no global-memory latency is left at the top of a cell; phase_load is the plain sequence.
+constexpr int LOAD_ITEMS = 153;
+MHD_7HD double load_gather(int i, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129, const double* dir, const double* x,
+                           bool need_u, bool with_res) {
+  int32_t g;
+  if (i < 81) {
+    if (!need_u) return 0.0;
+    g = pgids129[i];
+  } else if (i < 129) {
+    if (!with_res) return 0.0;
+    g = pgids129[i < 117 ? OFF_J + (i - 81) : (i < 121 ? OFF_P + (i - 117) : OFF_F + (i - 121))];
+  } else {
+    const int k = i - 129;
+    return coords[(long long)cell_nodes8[k / 3] * 3 + k % 3];
+  }
+  return g >= 0 ? x[g] : dir[-(long long)g - 1];
+}
+MHD_7HD void load_scatter(Cell7& S, const SmallDyn& C, int i, double v, const uint8_t* perm64, bool with_res) {
+  if (i < 81) {
+    const int c = i / 27, s = i % 27, t = C.node_t[perm64[s]];
+    if (c == 0) S.slot_u[t] = (uint8_t)s;
+    S.ut[c * 27 + t] = v;
+  } else if (i < 117) {
+    const int s = i - 81, pm = perm64[27 + s], tj = C.jdof_t[pm & 0x7F];
+    S.slot_j[tj] = (uint8_t)s;
+    const double sg = (pm & 0x80) ? -1.0 : 1.0;
+    S.sgn[tj] = sg;
+    if (with_res) S.rs[RS_JT + tj] = sg * v;
+  } else if (i < 129) {
+    if (with_res) S.rs[RS_PST + (i - 117)] = v;  // p (4) and phi (8) are not permuted
+  } else {
+    S.X[i - 129] = v;
+  }
+}
+MHD_7HD void load_ids(Cell7& S, int tid, int nt, const int32_t* pgids129, const long long* rowstart129, const double* nzval, bool solid,
+                      double sigma_cell, double sigma_fluid) {
   for (int i = tid; i < NLOC; i += nt) {
     S.gid[i] = pgids129[i];
     // device: absolute byte address of the first nnz of the row (dropped rows are never dereferenced: their codes are MAP_SKIP)
     S.rowaddr[i] = rowstart129 ? (long long)(nzval + rowstart129[i]) : -1;
   }
-  for (int i = tid; i < 81; i += nt) {
-    const int c = i / 27, s = i % 27, t = C.node_t[perm64[s]];
-    if (c == 0) S.slot_u[t] = (uint8_t)s;
-    const int32_t g = pgids129[c * 27 + s];
-    S.ut[c * 27 + t] = need_u ? (g >= 0 ? x[g] : dir[-(long long)g - 1]) : 0.0;
-  }
-  for (int s = tid; s < 36; s += nt) {
-    const int pm = perm64[27 + s], tj = C.jdof_t[pm & 0x7F];
-    S.slot_j[tj] = (uint8_t)s;
-    const double sg = (pm & 0x80) ? -1.0 : 1.0;
-    S.sgn[tj] = sg;
-    if (with_res) {
-      const int32_t g = pgids129[OFF_J + s];
-      S.rs[RS_JT + tj] = sg * (g >= 0 ? x[g] : dir[-(long long)g - 1]);
-    }
-  }
-  if (with_res)
-    for (int i = tid; i < 12; i += nt) {  // p (4) and phi (8) are not permuted
-      const int32_t g = pgids129[i < 4 ? OFF_P + i : OFF_F + i - 4];
-      S.rs[RS_PST + i] = g >= 0 ? x[g] : dir[-(long long)g - 1];
-    }
   if (tid == 0) {
     S.sigma_cell = solid ? sigma_cell : sigma_fluid;
     S.phi_sign = solid ? 1.0 : -1.0;
   }
+}
+MHD_7HD void phase_load(Cell7& S, const SmallDyn& C, int tid, int nt, const double* coords, const int32_t* cell_nodes8, const int32_t* pgids129,
+                        const long long* rowstart129, const uint8_t* perm64, const double* dir, const double* x, bool need_u, bool solid,
+                        double sigma_cell, double sigma_fluid, const double* nzval = nullptr, bool with_res = false) {
+  load_ids(S, tid, nt, pgids129, rowstart129, nzval, solid, sigma_cell, sigma_fluid);
+  for (int i = tid; i < LOAD_ITEMS; i += nt)
+    load_scatter(S, C, i, load_gather(i, coords, cell_nodes8, pgids129, dir, x, need_u, with_res), perm64, with_res);
 }
 
 // ------------------------------------------------------------------ phase 1a: J at the points | first contraction of the point evaluation
@@ -268,44 +288,84 @@ MHD_7HD void phase_points(Cell7& S, const SmallDyn& C, int tid, int nt) {
 }
 
 // ------------------------------------------------------------------ phase 3: coefficient fields
+// Item = (group, point): a lane owns one quadrature point (27 of 32 lanes), loads its geometry once and evaluates all fields of
+// its group from registers; with 256 threads warp w = group w, so the group switch is warp-uniform and every field index a
+// compile-time constant.  Groups: 0 Newton (9) | 1 stiffness (9) | 2 convection (3) + jj (6) + div-div + j-phi | 3 uj (9) |
+// 4..7 up, pressure function kp = group - 4 (9 each).
 template <int CONV, bool ZJ>
 MHD_7HD void phase_fields(Cell7& S, const SmallDyn& C, int tid, int nt, const Params& P) {
-  for (int it = tid; it < NFIELD * 27; it += nt) {
-    const int f = it / 27, q = it % 27;
-    const double* I = S.invJ[q];
-    const double* J = S.J[q];
-    const double w = S.W[q], id = S.idet[q];
-    double v = 0.0;
-    if (f < 9) {
+  double* F = S.r3;
+  for (int it = tid; it < 8 * 32; it += nt) {
+    const int grp = it >> 5, q = it & 31;
+    if (q >= 27) continue;
+    const double w = S.W[q];
+    if (grp == 0) {
       if (CONV == 2) {
-        const int c = f / 3, d = f % 3;  // alpha w d_d u_c
-        v = P.alpha * w * (I[0 * 3 + d] * S.gur[q][0 * 3 + c] + I[1 * 3 + d] * S.gur[q][1 * 3 + c] + I[2 * 3 + d] * S.gur[q][2 * 3 + c]);
+        double I[9], G[9];
+        MHD_7UNROLL
+        for (int i = 0; i < 9; i++) { I[i] = S.invJ[q][i]; G[i] = S.gur[q][i]; }
+        const double aw = P.alpha * w;
+        MHD_7UNROLL
+        for (int c = 0; c < 3; c++)
+          MHD_7UNROLL
+          for (int d = 0; d < 3; d++) F[(c * 3 + d) * 27 + q] = aw * (I[0 * 3 + d] * G[0 * 3 + c] + I[1 * 3 + d] * G[1 * 3 + c] + I[2 * 3 + d] * G[2 * 3 + c]);
+      } else {
+        MHD_7UNROLL
+        for (int f = 0; f < 9; f++) F[f * 27 + q] = 0.0;
       }
-    } else if (f < 18) {
-      const int m = (f - 9) / 3, n = (f - 9) % 3;
-      v = P.beta * w * (I[m * 3 + 0] * I[n * 3 + 0] + I[m * 3 + 1] * I[n * 3 + 1] + I[m * 3 + 2] * I[n * 3 + 2]);
-    } else if (f < FO_UJ) {
+    } else if (grp == 1) {
+      double I[9];
+      MHD_7UNROLL
+      for (int i = 0; i < 9; i++) I[i] = S.invJ[q][i];
+      const double bw = P.beta * w;
+      MHD_7UNROLL
+      for (int m = 0; m < 3; m++)
+        MHD_7UNROLL
+        for (int n = m; n < 3; n++) {
+          const double v = bw * (I[m * 3 + 0] * I[n * 3 + 0] + I[m * 3 + 1] * I[n * 3 + 1] + I[m * 3 + 2] * I[n * 3 + 2]);
+          F[(9 + m * 3 + n) * 27 + q] = v;
+          if (n != m) F[(9 + n * 3 + m) * 27 + q] = v;
+        }
+    } else if (grp == 2) {
+      double J[9];
+      MHD_7UNROLL
+      for (int i = 0; i < 9; i++) J[i] = S.J[q][i];
+      const double id = S.idet[q], wii = w * id * id;
       if (CONV != 0) {
-        const int n = f - 18;
-        v = P.alpha * w * (I[n * 3 + 0] * S.uq[q][0] + I[n * 3 + 1] * S.uq[q][1] + I[n * 3 + 2] * S.uq[q][2]);
+        const double aw = P.alpha * w, u0 = S.uq[q][0], u1 = S.uq[q][1], u2 = S.uq[q][2];
+        MHD_7UNROLL
+        for (int n = 0; n < 3; n++) F[(18 + n) * 27 + q] = aw * (S.invJ[q][n * 3 + 0] * u0 + S.invJ[q][n * 3 + 1] * u1 + S.invJ[q][n * 3 + 2] * u2);
+      } else {
+        MHD_7UNROLL
+        for (int n = 0; n < 3; n++) F[(18 + n) * 27 + q] = 0.0;
       }
-    } else if (f < FO_JJ) {
-      const int c = (f - FO_UJ) / 3, k = (f - FO_UJ) % 3, c1 = (c + 1) % 3, c2 = (c + 2) % 3;
-      v = w * id * (J[c1 * 3 + k] * P.B[c2] - J[c2 * 3 + k] * P.B[c1]);
-    } else if (f < FO_DD) {
-      const int b = f - FO_JJ;
-      int k = b, kp = b;
-      if (b >= 3) jjb_pair(b - 3, &k, &kp);
-      v = w * id * id * (J[0 * 3 + k] * J[0 * 3 + kp] + J[1 * 3 + k] * J[1 * 3 + kp] + J[2 * 3 + k] * J[2 * 3 + kp]);
-    } else if (f == FO_DD) {
-      v = ZJ ? P.zeta_j * w * id * id : 0.0;
-    } else if (f == FO_JF) {
-      v = w * id;
+      MHD_7UNROLL
+      for (int b = 0; b < 6; b++) {
+        const int k = b < 3 ? b : (b == 5 ? 1 : 0), kp = b < 3 ? b : (b == 3 ? 1 : 2);  // jjb_pair
+        F[(FO_JJ + b) * 27 + q] = wii * (J[0 * 3 + k] * J[0 * 3 + kp] + J[1 * 3 + k] * J[1 * 3 + kp] + J[2 * 3 + k] * J[2 * 3 + kp]);
+      }
+      F[FO_DD * 27 + q] = ZJ ? P.zeta_j * wii : 0.0;
+      F[FO_JF * 27 + q] = w * id;
+    } else if (grp == 3) {
+      double J[9];
+      MHD_7UNROLL
+      for (int i = 0; i < 9; i++) J[i] = S.J[q][i];
+      const double wi = w * S.idet[q];
+      MHD_7UNROLL
+      for (int c = 0; c < 3; c++) {
+        const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+        MHD_7UNROLL
+        for (int k = 0; k < 3; k++) F[(FO_UJ + c * 3 + k) * 27 + q] = wi * (J[c1 * 3 + k] * P.B[c2] - J[c2 * 3 + k] * P.B[c1]);
+      }
     } else {
-      const int r = f - FO_UP, kp = r / 9, c = (r / 3) % 3, kk = r % 3;
-      v = w * C.pp[q][kp] * I[kk * 3 + c];
+      const int kp = grp - 4;
+      const double wp = w * C.pp[q][kp];
+      double* o = F + (FO_UP + kp * 9) * 27 + q;
+      MHD_7UNROLL
+      for (int c = 0; c < 3; c++)
+        MHD_7UNROLL
+        for (int kk = 0; kk < 3; kk++) o[(c * 3 + kk) * 27] = wp * S.invJ[q][kk * 3 + c];
     }
-    S.r3[it] = v;
   }
 }
 
@@ -589,13 +649,14 @@ MHD_7HD void phase_E(Cell7& S, int tid, int nt, double zeta_u) {
 
 // ------------------------------------------------------------------ chunks: last contraction (direction d0) -> staging buffer
 // uu rows of component c: buf[slot(a) * 81 + 3 slot(b) + d]
+// one item (of 243) of a uu chunk; the kernel calls it directly with item = tid (see chunk_uj_item)
 template <int CONV, bool ZU>
-MHD_7HD void chunk_uu(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt, int c, double* buf) {
+MHD_7HD void chunk_uu_item(Cell7& S, const SmallDyn& C, const Small7& K, int it, int c, double* buf) {
   const double* D = cellD(S);
   const double* E = cellE(S);
-  for (int it = tid; it < 243; it += nt) {
-    const int a0 = it / 81, p1 = (it / 9) % 9, p2 = it % 9, bi = p1 * 27 + p2 * 3;
-    const int a1 = p1 / 3, b1 = p1 % 3, a2 = p2 / 3, b2 = p2 % 3;
+  {
+    const int a0 = it / 81, r = it - 81 * a0, p1 = r / 9, p2 = r - 9 * p1, bi = p1 * 27 + p2 * 3;
+    const int a1 = p1 / 3, b1 = p1 - 3 * a1, a2 = p2 / 3, b2 = p2 - 3 * a2;
     const int ta = a0 + 3 * a1 + 9 * a2, tb12 = 3 * b1 + 9 * b2;
     // Puu[0][2 m + n][3 a0 + b0][q] = (m ? LD : LV)[0][a0][q] * (n ? LD : LV)[0][b0][q]: fold the row factor (thread-dependent
     // class a0) into the stage-2 data once, the column factor (unrolled b0) is a compile-time table operand
@@ -634,6 +695,10 @@ MHD_7HD void chunk_uu(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int
     }
   }
 }
+template <int CONV, bool ZU>
+MHD_7HD void chunk_uu(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt, int c, double* buf) {
+  for (int it = tid; it < 243; it += nt) chunk_uu_item<CONV, ZU>(S, C, K, it, c, buf);
+}
 
 // uj (JU = false): buf[(c*27 + slot(a)) * 36 + slot(m)] = -gamma sgn V ;  ju (JU = true): buf[slot(m) * 81 + 3 slot(a) + c] = +sigma sgn V
 // (JU is a run-time flag: one copy of the code, the kernel is instruction-cache bound otherwise)
@@ -642,33 +707,41 @@ MHD_7HD void chunk_uj_k(Cell7& S, const Small7& K, const Params& P, double* buf,
   constexpr int d1 = (KD + 1) % 3, d2 = (KD + 2) % 3;
   constexpr int s0 = KD == 0 ? 1 : (KD == 1 ? 3 : 9), s1 = d1 == 0 ? 1 : (d1 == 1 ? 3 : 9), s2 = d2 == 0 ? 1 : (d2 == 1 ? 3 : 9);
   const double* x = S.r2 + T2_UJ + (c * 3 + KD) * 108 + p1 * 18 + p2 * 3;
-  const double x0 = x[0], x1 = x[1], x2 = x[2];
-  const int a1 = p1 / 2, i1 = p1 % 2, a2 = p2 / 2, i2 = p2 % 2;
+  const int a1 = p1 >> 1, i1 = p1 & 1, a2 = p2 >> 1, i2 = p2 & 1;
   const int ta12 = a1 * s1 + a2 * s2, tj12 = 12 * KD + 3 * (i1 + 2 * i2);
   const double coef = JU ? P.sigma : -P.gamma;
-  double sg[3];
-  int sj[3];
+  // destination index = base + su * SU + sj * SJ   (ju: slot_j * 81 + 3 slot_u + c | uj: (c * 27 + slot_u) * 36 + slot_j)
+  const int SU = JU ? 3 : 36, SJ = JU ? 81 : 1, base = JU ? c : c * 972;
+  double xs[3][3];  // sign, coefficient and stage-2 data folded together
+  int oj[3];
   MHD_7UNROLL
-  for (int i0 = 0; i0 < 3; i0++) { sg[i0] = coef * S.sgn[tj12 + i0]; sj[i0] = S.slot_j[tj12 + i0]; }
+  for (int i0 = 0; i0 < 3; i0++) {
+    const double sg = coef * S.sgn[tj12 + i0];
+    oj[i0] = base + S.slot_j[tj12 + i0] * SJ;
+    MHD_7UNROLL
+    for (int q = 0; q < 3; q++) xs[i0][q] = sg * x[q];
+  }
   MHD_7UNROLL
   for (int a = 0; a < 3; a++) {
-    const int su = S.slot_u[ta12 + a * s0];
+    const int ou = S.slot_u[ta12 + a * s0] * SU;
     MHD_7UNROLL
-    for (int i0 = 0; i0 < 3; i0++) {
-      const double v = sg[i0] * (K.Puj[KD][a * 3 + i0][0] * x0 + K.Puj[KD][a * 3 + i0][1] * x1 + K.Puj[KD][a * 3 + i0][2] * x2);
-      buf[JU ? sj[i0] * 81 + 3 * su + c : (c * 27 + su) * 36 + sj[i0]] = v;
-    }
+    for (int i0 = 0; i0 < 3; i0++)
+      buf[ou + oj[i0]] = K.Puj[KD][a * 3 + i0][0] * xs[i0][0] + K.Puj[KD][a * 3 + i0][1] * xs[i0][1] + K.Puj[KD][a * 3 + i0][2] * xs[i0][2];
+  }
+}
+// one item (of 324): direction-major order, so that the direction switch is warp-uniform except at two boundaries.  The kernel
+// calls this for item = tid and, for tid < 68, item = tid + 256 -- NOT through the loop below: inside a loop ptxas hoists the
+// 81 constant-bank table values of the three cases into registers on every call (a 110-instruction prologue).
+MHD_7HD void chunk_uj_item(Cell7& S, const Small7& K, const Params& P, double* buf, int it, bool JU) {
+  const int k = it / 108, r = it - 108 * k, c = r / 36, r2 = r - 36 * c, p1 = r2 / 6, p2 = r2 - 6 * p1;
+  switch (k) {
+    case 0: chunk_uj_k<0>(S, K, P, buf, c, p1, p2, JU); break;
+    case 1: chunk_uj_k<1>(S, K, P, buf, c, p1, p2, JU); break;
+    default: chunk_uj_k<2>(S, K, P, buf, c, p1, p2, JU); break;
   }
 }
 MHD_7HD void chunk_uj(Cell7& S, const Small7& K, int tid, int nt, const Params& P, double* buf, bool JU) {
-  for (int it = tid; it < 324; it += nt) {
-    const int inst = it / 36, p1 = (it / 6) % 6, p2 = it % 6, c = inst / 3, k = inst % 3;
-    switch (k) {
-      case 0: chunk_uj_k<0>(S, K, P, buf, c, p1, p2, JU); break;
-      case 1: chunk_uj_k<1>(S, K, P, buf, c, p1, p2, JU); break;
-      default: chunk_uj_k<2>(S, K, P, buf, c, p1, p2, JU); break;
-    }
-  }
+  for (int it = tid; it < 324; it += nt) chunk_uj_item(S, K, P, buf, it, JU);
 }
 
 // the rest: jj | j-phi | phi-j | up | pu

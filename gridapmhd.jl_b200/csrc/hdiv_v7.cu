@@ -85,10 +85,14 @@ V7_NI void ni_stage2(int tid) { h7::phase_stage2<CONV, ZJ>(sm_cell(), sm_small()
 // times the 32 KB instruction cache and every duplicated phase shows up as no_inst stalls)
 template <int CONV, bool ZU>
 V7_NI void ni_chunk_uu(int tid, int cc) {
-  h7::chunk_uu<CONV, ZU>(sm_cell(), sm_small(), c_small7, tid, V7_NT, cc, (cc & 1) ? sm_cell().r3 : sm_cell().r1);
+  if (tid < 243) h7::chunk_uu_item<CONV, ZU>(sm_cell(), sm_small(), c_small7, tid, cc, (cc & 1) ? sm_cell().r3 : sm_cell().r1);
 }
-V7_NI void ni_chunk_uj(int tid, const h7::Params& P, bool ju) {
-  h7::chunk_uj(sm_cell(), c_small7, tid, V7_NT, P, ju ? sm_cell().r1 : sm_cell().r3, ju);
+V7_NI void ni_chunk_uj_item(int item, const h7::Params& P, bool ju) {
+  h7::chunk_uj_item(sm_cell(), c_small7, P, ju ? sm_cell().r1 : sm_cell().r3, item, ju);
+}
+__device__ __forceinline__ void ni_chunk_uj(int tid, const h7::Params& P, bool ju) {  // 324 items on 256 threads
+  ni_chunk_uj_item(tid, P, ju);
+  if (tid < 324 - V7_NT) ni_chunk_uj_item(tid + V7_NT, P, ju);
 }
 template <bool ZJ>
 V7_NI void ni_chunk_rest(int tid) { h7::chunk_rest<ZJ>(sm_cell(), sm_small(), tid, V7_NT, sm_buf<1>()); }
@@ -112,66 +116,62 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 // ids of `cell` -> staging (one or two copies per thread), and its scatter map -> L2
-__device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const uint16_t* __restrict__ map, int64_t cell, int tid) {
+__device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const uint16_t* __restrict__ map, int64_t cell, int tid, bool with_map = true) {
   for (int i = tid; i < h7::NLOC; i += V7_NT) {
-    cp_async8(&N.rowstart[i], A.rowstart + cell * h7::NLOC + i);
+    if (with_map) cp_async8(&N.rowstart[i], A.rowstart + cell * h7::NLOC + i);  // (residual! works before the symbolic phase)
     cp_async4(&N.gid[i], A.pgids + cell * h7::NLOC + i);
   }
   if (tid >= 192 && tid < 196) cp_async16(&N.perm[(tid - 192) * 16], A.perm + cell * PERM_STRIDE + (tid - 192) * 16);
   if (tid >= 224 && tid < 226) cp_async16(&N.nodes[(tid - 224) * 4], A.cell_nodes + cell * 8 + (tid - 224) * 4);
   const char* mp = reinterpret_cast<const char*>(map + cell * h7::NENT);
-  if (tid * 128 < h7::NENT * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + tid * 128));
+  if (with_map && tid * 128 < h7::NENT * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + tid * 128));
 }
 
-// Scatter-map codes of a chunk: global -> shared with cp.async, issued BEFORE the chunk is computed, consumed by the sweep one
-// barrier interval later.  Warp w owns the 32-entry segments w, w + 8, ...: it alone writes (lanes 0..3, 16 bytes each) and
-// reads them, so one buffer serves all chunks -- a warp refills its segments as soon as its own sweep is through with them.
-V7_NI void codes_fetch(const uint16_t* __restrict__ m, int nseg, int tid) {
-  const int w = tid >> 5, lane = tid & 31;
-  __syncwarp();
-  if (lane < 4) {
-    unsigned dst = (unsigned)__cvta_generic_to_shared(sm_codes()) + (unsigned)(w * 64 + lane * 16);
-    const char* src = reinterpret_cast<const char*>(m) + w * 64 + lane * 16;
-#pragma unroll 1
-    for (int seg = w; seg < nseg; seg += 8, dst += 512, src += 512)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// value buf[i] of entry i goes to rowbase[row(i)] + 8 * code: plain store (MAP_EXCL) or reduction, predicated -- no branch
+// value v of an entry goes to rowbase + 8 * code: plain store (MAP_EXCL set, not MAP_SKIP) or reduction, predicated -- no branch
 __device__ __forceinline__ void scatter_one(unsigned code, unsigned long long rowbase, double v) {
   const unsigned long long addr = rowbase + (unsigned long long)((code & 0x7FFFu) << 3);
   asm volatile(
       "{\n\t"
       ".reg .pred pst, prd;\n\t"
-      "setp.ge.u32 pst, %2, 0x8000;\n\t"
+      ".reg .u32 t;\n\t"
+      "xor.b32 t, %2, 0x8000;\n\t"
+      "setp.lt.u32 pst, t, 0x7FFF;\n\t"   // 0x8000 <= code < 0xFFFF
       "setp.lt.u32 prd, %2, 0x8000;\n\t"
-      "setp.ne.and.u32 pst, %2, 0xFFFF, pst;\n\t"
       "@pst st.global.f64 [%0], %1;\n\t"
       "@prd red.global.add.f64 [%0], %1;\n\t"
       "}" ::"l"(addr), "d"(v), "r"(code)
       : "memory");
 }
 
-// sweep of a chunk of nseg 32-entry segments with ncol entries per row, rows from row0 (pads carry MAP_SKIP).  One copy of the
-// code for all chunks (run-time ncol; the division is a multiplication by a host-computed reciprocal: exact for i < 2^15).
-V7_NI void sweep(const double* __restrict__ buf, int nseg, int row0, unsigned ncol_recip /* ceil(2^20 / ncol) */, int tid) {
+// One call per barrier interval: (1) sweep the chunk staged in the previous interval -- nseg 32-entry segments, ncol entries per
+// row, rows from row0 (pads carry MAP_SKIP; ncol_recip = ceil(2^20 / ncol): exact quotient for i < 2^15) -- and (2) start the
+// cp.async copy of the NEXT chunk's codes (consumed one interval later).  Warp w owns the segments w, w + 8, ...: it alone
+// reads and refills them, so one code buffer serves all chunks (__syncwarp between the two halves is the only ordering needed).
+// (bufsel: 0 = Cell7::r1, 1 = Cell7::r3 -- an index, not a pointer: a pointer PARAMETER makes every staged value a generic LD)
+V7_NI void sweep_and_fetch(int bufsel, int nseg, int row0, unsigned ncol_recip, const uint16_t* __restrict__ next, int next_nseg, int tid) {
   const int w = tid >> 5, lane = tid & 31;
+  const double* buf = bufsel ? sm_cell().r3 : sm_cell().r1;
   const uint16_t* codes = sm_codes();
-  const long long* rowbase = sm_cell().rowaddr;
-#pragma unroll 2
-  for (int seg = w; seg < nseg; seg += 8) {
-    const int i = seg * 32 + lane;
-    int row = row0 + (int)(((unsigned)i * ncol_recip) >> 20);
-    if (row > h7::NLOC - 1) row = h7::NLOC - 1;  // pad entries of the last segment
-    scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
-  }
+  const long long* rowbase = sm_cell().rowaddr + row0;
+#pragma unroll 3
+  for (int i = w * 32 + lane; i < nseg * 32; i += 256)
+    scatter_one(codes[i], (unsigned long long)rowbase[((unsigned)i * ncol_recip) >> 20], buf[i]);
+  __syncwarp();
+  // lane l copies 16 bytes of segment w + 8 (l / 4) (+ 64 per round): one instruction moves eight of the warp's segments
+  int seg = w + 8 * (lane >> 2);
+  const int off = seg * 64 + (lane & 3) * 16;
+  unsigned dst = (unsigned)__cvta_generic_to_shared(sm_codes()) + (unsigned)off;
+  const char* src = reinterpret_cast<const char*>(next) + off;
+#pragma unroll 1
+  for (; seg < next_nseg; seg += 64, dst += 4096, src += 4096)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __host__ __device__ constexpr unsigned recip20(int n) { return (unsigned)(((1u << 20) + n - 1) / n); }
 static_assert((2943u * recip20(81)) >> 20 == 2943u / 81 && (2943u * recip20(36)) >> 20 == 2943u / 36, "reciprocal division");
 // the last chunk holds five sections: jj | j-phi | phi-j | up | pu
-V7_NI void sweep_rest(const double* __restrict__ buf, int tid) {
+V7_NI void sweep_rest(int tid) {
+  const double* buf = sm_cell().r3;
   constexpr int NSEG = h7::CH_REST_PAD / 32;
   constexpr int R_JF = h7::R_JF, R_FJ = h7::R_FJ, R_UP = h7::R_UP, R_PU = h7::R_PU;
   constexpr int OFF_P = h7::OFF_P, OFF_J = h7::OFF_J, OFF_F = h7::OFF_F, NLOC = h7::NLOC;
@@ -203,12 +203,14 @@ struct DevRAdd {
 template <int CONV, bool ZU, bool ZJ>
 V7_NI void ni_res_fields(int tid, const h7::Params& P) { h7::res_fields<CONV, ZU, ZJ>(sm_cell(), sm_small(), tid, V7_NT, P); }
 
-// RES: residual_and_jacobian! -- the residual phases ride in the barrier intervals of the Jacobian phases
-template <int CONV, bool ZU, bool ZJ, bool RES>
+// MODE 0: jacobian! | 1: residual_and_jacobian! (the residual phases ride in the barrier intervals of the Jacobian phases) |
+// 2: residual! (the same residual phases alone)
+template <int CONV, bool ZU, bool ZJ, int MODE>
 __global__ void __launch_bounds__(V7_NT, 2)
 hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* __restrict__ x, const uint16_t* __restrict__ map,
                         double* __restrict__ nzval, double* __restrict__ rout, const __grid_constant__ h7::Params P) {
   using namespace h7;
+  constexpr bool RES = MODE != 0, JAC = MODE != 2;
   constexpr int WU = (CONV != 0 || RES) ? 1 : 0;  // velocity and its gradient at the points are needed
   constexpr int SEG_UU = CH_UU_PAD / 32, SEG_UJ = CH_UJ_PAD / 32, SEG_REST = CH_REST_PAD / 32;
   Cell7& S = sm_cell();
@@ -221,9 +223,13 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     for (int i = 0; i < 7; i++) clk_acc[i] = 0;
     clk_acc[7] = (unsigned long long)clock64();
   }
+  double v_pre = 0.0;  // this thread's gathered value (state / vertex coordinate) of the cell about to start
   if ((int64_t)blockIdx.x < ncells) {
-    fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[blockIdx.x] : (int64_t)blockIdx.x, threadIdx.x);
+    fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[blockIdx.x] : (int64_t)blockIdx.x, threadIdx.x, JAC);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < LOAD_ITEMS) v_pre = load_gather(threadIdx.x, A.coords, N.nodes, N.gid, A.dir, x, WU != 0, RES);
   }
   DevRAdd radd{rout, nrows};
   for (int64_t it = blockIdx.x; it < ncells; it += gridDim.x) {
@@ -234,13 +240,12 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     const int64_t cell = A.cell_list ? (int64_t)A.cell_list[it] : it;
     const uint16_t* m = map + cell * h7::NENT;
     const bool solid = A.cell_solid != nullptr && A.cell_solid[cell] != 0;
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();  // the ids of this cell have landed in N (and the previous cell's sweeps are done with S)
-    phase_load(S, C, tid, V7_NT, A.coords, N.nodes, N.gid, N.rowstart, N.perm, A.dir, x, WU != 0, solid,
-               solid ? A.cell_sigma[cell] : 0.0, P.sigma, nzval, RES);
+    __syncthreads();  // the previous cell's sweeps are done with S (the ids of this cell landed in N long ago)
+    load_ids(S, tid, V7_NT, N.gid, JAC ? N.rowstart : nullptr, nzval, solid, solid ? A.cell_sigma[cell] : 0.0, P.sigma);
+    if (tid < LOAD_ITEMS) load_scatter(S, C, tid, v_pre, N.perm, RES);
     __syncthreads();
     if (it + gridDim.x < ncells) {
-      fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[it + gridDim.x] : it + gridDim.x, tid);
+      fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[it + gridDim.x] : it + gridDim.x, tid, JAC);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     V7_CLK(0);
@@ -255,90 +260,99 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
       __syncthreads();
     }
     V7_CLK(1);
-    ni_fields<CONV, ZJ>(tid, P);
+    if (JAC) ni_fields<CONV, ZJ>(tid, P);
     if (RES) res_divu(S, tid, V7_NT);
     if (ZU) phase_Minv(S, tid, V7_NT);
     __syncthreads();
     V7_CLK(2);
-    ni_stage1<ZJ>(tid);
+    if (JAC) ni_stage1<ZJ>(tid);
     if (RES) res_d(S, C, tid, V7_NT, radd);
     __syncthreads();
-    ni_stage2<CONV, ZJ>(tid);
+    if (JAC) ni_stage2<CONV, ZJ>(tid);
     if (RES) ni_res_fields<CONV, ZU, ZJ>(tid, P);
     __syncthreads();
-    phase_D<ZU>(S, C, K, tid, V7_NT);
+    if (JAC) phase_D<ZU>(S, C, K, tid, V7_NT);
     if (RES) res_stage_a(S, C, tid, V7_NT, radd);
     __syncthreads();
     if (ZU || RES) {
-      if (ZU) phase_E(S, tid, V7_NT, P.zeta_u);
+      if (ZU && JAC) phase_E(S, tid, V7_NT, P.zeta_u);
       if (RES) res_stage_b(S, C, tid, V7_NT, radd);
       __syncthreads();
     }
     V7_CLK(3);
+    if (!JAC) {
+      res_stage_c(S, C, tid, V7_NT, radd);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();  // the next cell's ids have landed
+      if (it + gridDim.x < ncells && tid < LOAD_ITEMS) v_pre = load_gather(tid, A.coords, N.nodes, N.gid, A.dir, x, WU != 0, RES);
+      continue;
+    }
     // Every interval: fetch the codes of the chunk about to be computed (cp.async, behind the sweep of the previous chunk:
     // a warp refills only its own segments), sweep the chunk staged in the previous interval, compute the next one.
-    codes_fetch(m + E_UU, SEG_UU, tid);
+    sweep_and_fetch(0, 0, 0, 0, m + E_UU, SEG_UU, tid);
     ni_chunk_uu<CONV, ZU>(tid, 0);
     if (RES) res_stage_c(S, C, tid, V7_NT, radd);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep(sm_buf<0>(), SEG_UU, 0, recip20(81), tid);
-    codes_fetch(m + E_UU + CH_UU_PAD, SEG_UU, tid);
+    sweep_and_fetch(0, SEG_UU, 0, recip20(81), m + E_UU + CH_UU_PAD, SEG_UU, tid);
     ni_chunk_uu<CONV, ZU>(tid, 1);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep(sm_buf<1>(), SEG_UU, 27, recip20(81), tid);
-    codes_fetch(m + E_UU + 2 * CH_UU_PAD, SEG_UU, tid);
+    sweep_and_fetch(1, SEG_UU, 27, recip20(81), m + E_UU + 2 * CH_UU_PAD, SEG_UU, tid);
     ni_chunk_uu<CONV, ZU>(tid, 2);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     V7_CLK(4);
-    sweep(sm_buf<0>(), SEG_UU, 54, recip20(81), tid);
-    codes_fetch(m + E_UJ, SEG_UJ, tid);
+    sweep_and_fetch(0, SEG_UU, 54, recip20(81), m + E_UJ, SEG_UJ, tid);
     ni_chunk_uj(tid, P, false);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep(sm_buf<1>(), SEG_UJ, 0, recip20(36), tid);
-    codes_fetch(m + E_JU, SEG_UJ, tid);
+    sweep_and_fetch(1, SEG_UJ, 0, recip20(36), m + E_JU, SEG_UJ, tid);
     ni_chunk_uj(tid, P, true);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     V7_CLK(5);
-    sweep(sm_buf<0>(), SEG_UJ, h7::OFF_J, recip20(81), tid);
-    codes_fetch(m + E_REST, SEG_REST, tid);
+    sweep_and_fetch(0, SEG_UJ, h7::OFF_J, recip20(81), m + E_REST, SEG_REST, tid);
     ni_chunk_rest<ZJ>(tid);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    sweep_rest(sm_buf<1>(), tid);
+    // the next cell's ids landed before the barrier above: gather its state now, behind the last sweep
+    if (it + gridDim.x < ncells && tid < LOAD_ITEMS) v_pre = load_gather(tid, A.coords, N.nodes, N.gid, A.dir, x, WU != 0, RES);
+    sweep_rest(tid);
     V7_CLK(6);
   }
   if (A.clk != nullptr && threadIdx.x == 0)
     for (int i = 0; i < 7; i++) atomicAdd(A.clk + i, clk_acc[i]);
 }
 
-// nnz that receive more than one contribution are accumulated with RED: clear exactly those (bit mask of the symbolic phase)
+// nnz that receive more than one contribution are accumulated with RED and must start from zero.  Clearing them one by one
+// costs more than the 1.2 GB memset it replaces (0.18 ms against 0.12 ms: 8-byte stores leave partial 32-byte sectors that
+// the L2 has to fill from DRAM), so whole SECTORS are cleared: bit s of the mask <=> sector s (nnz 4 s .. 4 s + 3) holds a
+// shared nnz.  Exclusive nnz inside a cleared sector are overwritten by their plain store later in the same assembly.
 __global__ void __launch_bounds__(256)
-zero_shared_kernel(int64_t nwords, const uint32_t* __restrict__ mask, double* __restrict__ nz, int64_t nnz) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t w0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; w0 < nwords; w0 += nwarps * 32) {
-    const uint32_t mine = w0 + lane < nwords ? __ldg(mask + w0 + lane) : 0u;
-#pragma unroll 4
-    for (int j = 0; j < 32; j++) {
-      const uint32_t wd = __shfl_sync(0xffffffffu, mine, j);
-      if (wd == 0u) continue;
-      const int64_t i = (w0 + j) * 32 + lane;
-      if ((wd >> lane) & 1u) nz[i] = 0.0;
+zero_shared_kernel(int64_t nsectors, const uint32_t* __restrict__ mask, double* __restrict__ nz, int64_t nnz) {
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsectors; s += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t wd = __ldg(mask + (s >> 5));  // one word per warp: broadcast load
+    if (!((wd >> (s & 31)) & 1u)) continue;
+    const int64_t i = s * 4;
+    if (i + 4 <= nnz) {
+      double2* p = reinterpret_cast<double2*>(nz + i);
+      p[0] = make_double2(0.0, 0.0);
+      p[1] = make_double2(0.0, 0.0);
+    } else {
+      for (int64_t j = i; j < nnz; j++) nz[j] = 0.0;
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
-build_shared_mask(int64_t nwords, int64_t nnz, const uint8_t* __restrict__ contrib, uint32_t* __restrict__ mask) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one nnz per thread, one word per warp
-  const bool sh = i < nnz && contrib[i] != 1;                        // 0 contributions: never written -> keep it cleared
-  const uint32_t b = __ballot_sync(0xffffffffu, sh);
-  if ((threadIdx.x & 31) == 0 && (i >> 5) < nwords) mask[i >> 5] = b;
+build_shared_mask(int64_t nsectors, int64_t nnz, const uint8_t* __restrict__ contrib, uint32_t* __restrict__ mask) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one sector per thread, one mask word per warp
+  bool sh = false;
+  if (s < nsectors)
+    for (int64_t i = s * 4; i < s * 4 + 4 && i < nnz; i++) sh = sh || contrib[i] != 1;  // 0 contributions: keep it cleared too
+  const uint32_t bits = __ballot_sync(0xffffffffu, sh);
+  if ((threadIdx.x & 31) == 0 && s < (nsectors + 31) / 32 * 32) mask[s >> 5] = bits;
 }
 
 template <class K>
@@ -384,30 +398,32 @@ int v7_try_enable(mhd_operator* op) {
   return rc;
 }
 
-// symbolic phase: bit mask of the nnz with != 1 contributions
+// symbolic phase: bit mask of the 32-byte sectors of nzval that hold an nnz with != 1 contributions
 int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib) {
-  const int64_t nwords = (op->nnz + 31) / 32;
+  const int64_t nsectors = (op->nnz + 3) / 4, nwords = (nsectors + 31) / 32;
   cudaFree(op->d_shared_mask);
   op->d_shared_mask = nullptr;
   MHD_TRY(dev_alloc(&op->d_shared_mask, nwords));
   const int64_t nthreads = nwords * 32;
-  build_shared_mask<<<(unsigned)((nthreads + 255) / 256), 256, 0, g_stream>>>(nwords, op->nnz, d_contrib, op->d_shared_mask);
+  build_shared_mask<<<(unsigned)((nthreads + 255) / 256), 256, 0, g_stream>>>(nsectors, op->nnz, d_contrib, op->d_shared_mask);
   MHD_LAUNCH_CHECK();
   return 0;
 }
 
 int v7_zero_shared(mhd_operator* op) {
-  const int64_t nwords = (op->nnz + 31) / 32;
-  const int64_t want = (nwords + 32 * 8 - 1) / (32 * 8);
-  const int64_t cap = (int64_t)sm_count7() * 16;
-  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, g_stream>>>(nwords, op->d_shared_mask, op->d_nzval, op->nnz);
+  const int64_t nsectors = (op->nnz + 3) / 4;
+  const int64_t want = (nsectors + 255) / 256;
+  const int64_t cap = (int64_t)sm_count7() * 64;
+  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, g_stream>>>(nsectors, op->d_shared_mask, op->d_nzval, op->nnz);
   MHD_LAUNCH_CHECK();
   return 0;
 }
 
-int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
-  MHD_CHECK(op->jac_version == 7 && op->d_tab7 != nullptr && op->d_shared_mask != nullptr, MHD_E_STATE,
-            "v7 Jacobian kernel is not enabled on this operator");
+// mode 0: Jacobian (d_r unused) | 1: residual + Jacobian | 2: residual only
+int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode) {
+  MHD_CHECK(op->jac_version == 7 && op->d_tab7 != nullptr && (mode == 2 || op->d_shared_mask != nullptr), MHD_E_STATE,
+            "v7 kernel is not enabled on this operator");
+  if (mode == 0) d_r = nullptr;
   if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
   h7::Params P;
   P.alpha = op->prm.alpha; P.beta = op->prm.beta; P.gamma = op->prm.gamma; P.sigma = op->prm.sigma;
@@ -434,23 +450,18 @@ int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   const bool zu = op->prm.zeta_u != 0.0, zj = op->prm.zeta_j != 0.0;
   int64_t ncells = op->ncells;
   unsigned grid = (unsigned)(ncells < g64 ? ncells : g64);
-#define VK(C, U, J)                                                                                                        \
+#define VKM(C, U, J, M)                                                                                                    \
   do {                                                                                                                     \
-    if (d_r) {                                                                                                             \
-      MHD_TRY(v7_opt_in(hdiv_v7_jacobian_kernel<C, U, J, true>));                                                           \
-      hdiv_v7_jacobian_kernel<C, U, J, true><<<grid, V7_NT, V7_SMEM, g_stream>>>(ncells, op->nrows, A, d_x, op->d_map,      \
-                                                                                 op->d_nzval, d_r, P);                     \
-    } else {                                                                                                               \
-      MHD_TRY(v7_opt_in(hdiv_v7_jacobian_kernel<C, U, J, false>));                                                          \
-      hdiv_v7_jacobian_kernel<C, U, J, false><<<grid, V7_NT, V7_SMEM, g_stream>>>(ncells, op->nrows, A, d_x, op->d_map,     \
-                                                                                  op->d_nzval, nullptr, P);                \
-    }                                                                                                                      \
+    MHD_TRY(v7_opt_in(hdiv_v7_jacobian_kernel<C, U, J, M>));                                                                \
+    hdiv_v7_jacobian_kernel<C, U, J, M><<<grid, V7_NT, V7_SMEM, g_stream>>>(ncells, op->nrows, A, d_x, op->d_map,           \
+                                                                            op->d_nzval, d_r, P);                          \
   } while (0)
+#define VK(C, U, J) do { if (mode == 0) VKM(C, U, J, 0); else if (mode == 1) VKM(C, U, J, 1); else VKM(C, U, J, 2); } while (0)
 #define VKJ(C, U) do { if (zj) VK(C, U, true); else VK(C, U, false); } while (0)
 #define VKU(C) do { if (zu) VKJ(C, true); else VKJ(C, false); } while (0)
 #define VKC() do { if (conv == 0) VKU(0); else if (conv == 1) VKU(1); else VKU(2); } while (0)
-  MHD_TRY(v7_zero_shared(op));
-  prof_begin(PROF_JAC);
+  if (mode != 2) MHD_TRY(v7_zero_shared(op));
+  prof_begin(mode == 2 ? PROF_RES : PROF_JAC);
   if (op->deterministic && op->d_color_cells != nullptr) {
     // one launch per colour: cells of a colour share no dof, colours run in stream order => a fixed summation order
     for (size_t c = 0; c + 1 < op->color_ptr.size(); c++) {
@@ -465,11 +476,12 @@ int v7_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
     VKC();
     MHD_LAUNCH_CHECK();
   }
-  prof_end(PROF_JAC);
+  prof_end(mode == 2 ? PROF_RES : PROF_JAC);
 #undef VKC
 #undef VKU
 #undef VKJ
 #undef VK
+#undef VKM
   if (dbg & 16) {
     unsigned long long h[8];
     MHD_CUDA(cudaMemcpyAsync(h, d_clk, sizeof(h), cudaMemcpyDeviceToHost, g_stream));

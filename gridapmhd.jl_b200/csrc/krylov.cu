@@ -29,6 +29,7 @@ int ensure_red(mhd_operator* op, int64_t n) {
   op->d_red = nullptr;
   op->red_cap = 0;
   MHD_TRY(dev_alloc(&op->d_red, n));
+  MHD_CUDA(cudaMemsetAsync(op->d_red, 0, (size_t)(n < 4096 ? n : 4096) * sizeof(double), g_stream));  // tickets of the fused reductions
   op->red_cap = n;
   return 0;
 }
@@ -108,9 +109,25 @@ int launch_spmv(mhd_operator* op, const double* d_x, double* d_y) {
 //     meets its first ghost column.  Interior rows never wait: the exchange is overlapped with the bulk of the product.
 //   Inboxes are double-buffered by the parity of the product count and the counters are monotone (target = expected
 //   CTAs x use count), so nothing is ever reset and a fast neighbour cannot overwrite data still being read.
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+// Memory model of the exchange (PTX ISA "memory consistency model"): the pusher's value stores, fence.sc.sys
+// (__threadfence_system) and relaxed system-scope atomic on the counter form a release pattern; the consumer polls the counter
+// with ld.relaxed.sys and, once it has seen the target, performs ONE ld.acquire.sys -- an acquire pattern that synchronises with
+// the release, so every later load of the warp (ordered behind lane 0 by __syncwarp) observes the pushed values.  The ghost
+// values themselves are read with ld.relaxed.sys (coherent, served by L2): the non-coherent path (__ldg / ld.global.nc) is
+// only legal for data no one writes during the kernel, which is true for x and the matrix but not for the inbox.
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -157,23 +174,28 @@ spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, c
           for (int k = 0; k < nn; k++) {
             const unsigned target = H->expected[k] * round;
             unsigned spins = 0;
-            while (ld_volatile_u32(fl + k) < target) {
-              if (++spins > (1u << 28)) {  // never hang the GPU: report and go on
+            while (ld_relaxed_sys_u32(fl + k) < target) {
+              if (++spins > (1u << 28)) {  // never hang the GPU: flag the error (the host turns it into MHD_E_COMM) and go on
                 atomicExch(H->err, 1);
                 break;
               }
             }
+            (void)ld_acquire_sys_u32(fl + k);  // synchronises with the pusher's fence + atomic: its values are visible from here on
           }
-          // no __threadfence() here: a gpu-scope fence invalidates the SM's whole L1 (CCTL.IVALL) and with it the cached
-          // x entries of every warp on the SM.  The counters are read with ld.volatile (L2); inbox lines cannot be in
-          // L1 yet (L1 is empty at kernel start and nothing reads a ghost before this point).
         }
         __syncwarp();
         arrived = true;
       }
-      // L1 is invalidated at every kernel launch and no ghost is read before the arrival wait, so the cached path is safe
-      const double x0 = __ldg((g0 ? xg : x) + c0);
-      const double x1 = __ldg((g1 ? xg : x) + c1);
+      // warp-uniform choice (no divergence): chunks that touch ghost columns gather through the coherent path, all others
+      // keep the read-only path for x
+      double x0, x1;
+      if (__any_sync(0xffffffffu, g0 || g1)) {
+        x0 = ld_relaxed_sys_f64((g0 ? xg : x) + c0);
+        x1 = ld_relaxed_sys_f64((g1 ? xg : x) + c1);
+      } else {
+        x0 = __ldg(x + c0);
+        x1 = __ldg(x + c1);
+      }
       s0 = fma(v0, x0, s0);
       s1 = fma(v1, x1, s1);
     }
@@ -314,6 +336,94 @@ int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int6
     MHD_LAUNCH_CHECK();
   }
   reduce_partials<<<k, RED_T, 0, g_stream>>>(nb, RED_MAXB, partial, d_h);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+// One-pass Gram-Schmidt reductions: out[j] = <V_j, w> for j < k and, when with_norm, out[k] = <w, w> -- ONE launch: every block
+// writes its partial sums, the block that draws the last ticket adds them up in block order (deterministic).  k + with_norm <= KB.
+template <int KB>
+__global__ void __launch_bounds__(RED_T)
+gs_dots_kernel(int64_t n, int k, int with_norm, const double* __restrict__ V, int64_t ldv, const double* __restrict__ w,
+               double* __restrict__ partial, int pstride, unsigned* __restrict__ ticket, double* __restrict__ out) {
+  __shared__ double sh[RED_T / 32];
+  __shared__ bool last;
+  double acc[KB];
+#pragma unroll
+  for (int j = 0; j < KB; j++) acc[j] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * RED_T + threadIdx.x; i < n; i += (int64_t)gridDim.x * RED_T) {
+    const double wi = w[i];
+#pragma unroll
+    for (int j = 0; j < KB - 1; j++)
+      if (j < k) acc[j] = fma(wi, V[(int64_t)j * ldv + i], acc[j]);
+    acc[KB - 1] = fma(wi, wi, acc[KB - 1]);
+  }
+  const int nout = k + (with_norm ? 1 : 0);
+#pragma unroll
+  for (int j = 0; j < KB; j++) {
+    const bool is_norm = j == KB - 1;
+    if (j < k || (is_norm && with_norm)) {
+      const double r = block_sum(acc[j], sh);
+      if (threadIdx.x == 0) partial[(int64_t)(is_norm ? k : j) * pstride + blockIdx.x] = r;
+    }
+  }
+  __threadfence();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int j = 0; j < nout; j++) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_T) s += __ldcg(partial + (int64_t)j * pstride + i);
+    const double r = block_sum(s, sh);
+    if (threadIdx.x == 0) out[j] = r;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+constexpr int GS_KB = 18;  // m <= 16: h[0..j] and the norm in one pass
+
+bool gs_fused_ok(int k) { return k + 1 <= GS_KB; }
+
+int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out) {
+  MHD_CHECK(gs_fused_ok(k), MHD_E_INVALID, "launch_gs_dots: k = %d exceeds the fused kernel", k);
+  const int nb = red_blocks(n);
+  MHD_TRY(ensure_red(op, 4096 + (int64_t)GS_KB * RED_MAXB));
+  double* partial = op->d_red + 4096;
+  unsigned* ticket = reinterpret_cast<unsigned*>(op->d_red + 4000);  // zeroed by ensure_red, reset by the kernel
+  gs_dots_kernel<GS_KB><<<nb, RED_T, 0, g_stream>>>(n, k, with_norm ? 1 : 0, d_V, ldv, d_w, partial, RED_MAXB, ticket, d_out);
+  MHD_LAUNCH_CHECK();
+  return 0;
+}
+
+// out = scale * (w - sum_j h[j] V_j): the second Gram-Schmidt update fused with the normalisation of the next basis vector
+// (scale_ptr == nullptr: out = w - V h, plain update; dead_ptr != nullptr && *dead_ptr: out = 0)
+template <int KB>
+__global__ void __launch_bounds__(256)
+gs_update_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv, const double* __restrict__ h, const double* __restrict__ w,
+                 const double* __restrict__ scale_ptr, const int* __restrict__ dead_ptr, double* __restrict__ out) {
+  double hh[KB];
+#pragma unroll
+  for (int j = 0; j < KB; j++) hh[j] = j < k ? h[j] : 0.0;
+  const bool dead = dead_ptr != nullptr && *dead_ptr != 0;
+  const double sc = dead ? 0.0 : (scale_ptr ? *scale_ptr : 1.0);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    double s = w[i];
+#pragma unroll
+    for (int j = 0; j < KB; j++)
+      if (j < k) s = fma(-hh[j], V[(int64_t)j * ldv + i], s);
+    out[i] = dead ? 0.0 : sc * s;
+  }
+}
+
+int launch_gs_update(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, const double* d_w, const double* d_scale,
+                     const int* d_dead, double* d_out) {
+  if (n == 0) return 0;
+  MHD_CHECK(k <= GS_KB, MHD_E_INVALID, "launch_gs_update: k = %d exceeds the fused kernel", k);
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sms() * 8;
+  if (b > cap) b = cap;
+  gs_update_kernel<GS_KB><<<(unsigned)b, 256, 0, g_stream>>>(n, k, d_V, ldv, d_h, d_w, d_scale, d_dead, d_out);
   MHD_LAUNCH_CHECK();
   return 0;
 }

@@ -15,6 +15,8 @@
 #include <dlfcn.h>
 
 #include <functional>
+#include <map>
+#include <tuple>
 
 #include "common.h"
 #include "h1h1_cell.h"
@@ -34,6 +36,7 @@ struct KrylovScalars {  // lives in device memory
   double tol;
   double inv;           // scaling for the next basis vector
   double hist[4 * MAXM + 2];
+  int renorm;           // fused CGS2: the Pythagoras norm lost too many digits, use the explicitly computed one
   int done;             // converged (or breakdown): later steps of the cycle become no-ops
   int k;                // Arnoldi steps taken in this cycle
   int iters;            // total iterations
@@ -101,6 +104,24 @@ __global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
   if (S->beta <= S->tol || hn == 0.0 || S->iters >= maxiter) S->done = 1;
 }
 
+// fused CGS2 step: h (pass 1) and h2 | ||w1||^2 (pass 2, w1 = w - V h) are in; the norm of w2 = w1 - V h2 follows from
+// Pythagoras (V orthonormal): ||w2||^2 = ||w1||^2 - ||h2||^2, unless cancellation eats more than ~8 digits -- then the flag
+// `renorm` asks the host-free slow path (one extra reduction) to recompute it.  Leaves h += h2 and hn in place.
+__global__ void k_cgs2_scalars(KrylovScalars* S, int j) {
+  double s2 = 0.0;
+  for (int i = 0; i <= j; i++) {
+    s2 += S->h2[i] * S->h2[i];
+    S->h[i] += S->h2[i];
+  }
+  const double n1 = S->h2[j + 1];  // ||w1||^2
+  S->hn = n1 - s2;
+  S->renorm = (n1 > 0.0 && S->hn < 1e-8 * n1) ? 1 : 0;
+}
+// hn <- exact ||w2||^2 (in beta2 scratch) when the Pythagoras estimate was not trustworthy
+__global__ void k_cgs2_take_exact_norm(KrylovScalars* S) {
+  if (S->renorm) S->hn = S->beta2;
+}
+
 __global__ void k_back_substitute(KrylovScalars* S) {
   const int k = S->k;
   for (int i = 0; i < MAXM; i++) S->y[i] = 0.0;
@@ -154,6 +175,7 @@ struct Fgmres {
     return 0;
   }
   void release() {
+    drop_graphs();
     cudaFree(V); cudaFree(Z); cudaFree(w); cudaFree(t); cudaFree(S);
     V = Z = w = t = nullptr; S = nullptr;
   }
@@ -164,9 +186,64 @@ struct Fgmres {
     return allreduce_sum(d_out, 1);
   }
 
-  // one restart cycle, fully enqueued. x (ld entries) is updated in place.
+  // ---- CUDA graph of a restart cycle: the cycle is a fixed sequence of launches on fixed buffers, so it is
+  // captured once per (b, x, first, zero_guess) and replayed -- ~10 launches per Arnoldi step stop costing host time and
+  // inter-kernel gaps.  Not used while another capture is active (inner solvers are captured as part of the outer cycle), with
+  // more than one rank (the fused SpMV + halo kernel takes its round counter as a launch argument) or when MHD_KRYLOV_GRAPH=0.
+  struct GraphKey {
+    const double* b; double* x; bool first, zero;
+    bool operator<(const GraphKey& o) const { return std::tie(b, x, first, zero) < std::tie(o.b, o.x, o.first, o.zero); }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  bool graphs_ok = true;
+  void drop_graphs() {
+    for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+  }
+
   int cycle(const VecOp& matvec, const VecOp& precond, const double* b, double* x, double rtol, double atol, int maxiter,
             bool first, bool zero_guess) {
+    static int want = -1;
+    if (want < 0) {
+      const char* e = getenv("MHD_KRYLOV_GRAPH");
+      want = e ? atoi(e) : 1;
+    }
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(g_stream, &st);
+    if (!want || !graphs_ok || g_nranks > 1 || g_prof_on || st != cudaStreamCaptureStatusNone)
+      return enqueue_cycle(matvec, precond, b, x, rtol, atol, maxiter, first, zero_guess);
+    const GraphKey key{b, x, first, zero_guess};
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        graphs_ok = false;
+        return enqueue_cycle(matvec, precond, b, x, rtol, atol, maxiter, first, zero_guess);
+      }
+      const int rc = enqueue_cycle(matvec, precond, b, x, rtol, atol, maxiter, first, zero_guess);
+      const cudaError_t ec = cudaStreamEndCapture(g_stream, &g);
+      cudaGraphExec_t ge = nullptr;
+      if (rc != 0 || ec != cudaSuccess || g == nullptr || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
+        cudaGetLastError();  // something in the cycle cannot be captured: run it the plain way from now on
+        if (g) cudaGraphDestroy(g);
+        graphs_ok = false;
+        if (rc != 0) return rc;
+        return enqueue_cycle(matvec, precond, b, x, rtol, atol, maxiter, first, zero_guess);
+      }
+      cudaGraphDestroy(g);
+      it = graphs.emplace(key, ge).first;
+    }
+    MHD_CUDA(cudaGraphLaunch(it->second, g_stream));
+    g_launches += launches_per_cycle;
+    return 0;
+  }
+  int64_t launches_per_cycle = 0;
+
+  // one restart cycle, fully enqueued. x (ld entries) is updated in place.
+  int enqueue_cycle(const VecOp& matvec, const VecOp& precond, const double* b, double* x, double rtol, double atol, int maxiter,
+                    bool first, bool zero_guess) {
+    const int64_t l0 = g_launches;
     // r = b - A x
     if (zero_guess && first) {
       MHD_CUDA(cudaMemcpyAsync(w, b, (size_t)n * 8, cudaMemcpyDeviceToDevice, g_stream));
@@ -180,11 +257,26 @@ struct Fgmres {
     MHD_LAUNCH_CHECK();
     k_scale_to<<<vgrid(n), 256, 0, g_stream>>>(n, S, w, V);
     MHD_LAUNCH_CHECK();
+    const bool fused = gs_fused_ok(m);
     for (int j = 0; j < m; j++) {
       double* Vj = V + (int64_t)j * ld;
       double* Zj = flexible ? Z + (int64_t)j * ld : Z;
       MHD_TRY(precond(Vj, Zj));
       MHD_TRY(matvec(Zj, w));
+      if (fused) {
+        // CGS2 in 4 launches + the scalar step: h = V'w | w1 = w - V h | (h2, ||w1||^2) = (V'w1, w1'w1) | v_{j+1} = (w1 - V h2)/||.||
+        MHD_TRY(launch_gs_dots(op, n, j + 1, false, V, ld, w, S->h));
+        MHD_TRY(allreduce_sum(S->h, j + 1));
+        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h, w, nullptr, nullptr, w));
+        MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h2));
+        MHD_TRY(allreduce_sum(S->h2, j + 2));
+        k_cgs2_scalars<<<1, 1, 0, g_stream>>>(S, j);
+        MHD_LAUNCH_CHECK();
+        k_arnoldi_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
+        MHD_LAUNCH_CHECK();
+        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h2, w, &S->inv, &S->done, V + (int64_t)(j + 1) * ld));
+        continue;
+      }
       // CGS2: h = V^T w ; w -= V h ; h2 = V^T w ; w -= V h2 ; h += h2
       MHD_TRY(launch_multi_dot(op, n, j + 1, V, ld, w, S->h));
       MHD_TRY(allreduce_sum(S->h, j + 1));
@@ -211,6 +303,7 @@ struct Fgmres {
       MHD_TRY(precond(w, t));
       MHD_TRY(launch_axpy(n, 1.0, t, x));
     }
+    launches_per_cycle = g_launches - l0;
     return 0;
   }
 };
@@ -628,6 +721,10 @@ int mhd_solver_setup(mhd_solver_t* s) {
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CUDA(cudaSetDevice(g_device));
   mhd_operator* op = s->op;
+  // the captured cycles hold pointers into preconditioner data that a new setup may reallocate
+  s->outer.drop_graphs();
+  s->inner.drop_graphs();
+  s->inner2.drop_graphs();
   k_extract_dinv<<<vgrid(op->nrows), 256, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, op->d_nzval, s->d_dinv);
   MHD_LAUNCH_CHECK();
   if (s->opts.precond == MHD_PC_BLOCK_TRI && s->opts.uj_solver == MHD_UJ_DENSE_LU) {
@@ -676,11 +773,32 @@ int mhd_solver_patch_apply(mhd_solver_t* s, const double* r, double* z, double o
   return MHD_OK;
 }
 
+static int solve_impl(mhd_solver_t* s, const double* b, double* x, int32_t* iters, double* resnorm, double* res_history);
+
+// The restart cycles are replayed as CUDA graphs, and the legacy default stream cannot be captured: when the caller has not
+// set a stream (mhd_set_stream), the solve runs on a library-owned BLOCKING stream -- created with cudaStreamCreate, so it
+// is ordered against everything the caller enqueued on the legacy stream before and enqueues after (legacy-stream semantics).
 int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, double* resnorm, double* res_history) {
   MHD_CHECK(s && b && x, MHD_E_INVALID, "mhd_solve: null argument");
   MHD_CHECK(g_device >= 0, MHD_E_STATE, "mhd_init has not been called");
   MHD_CHECK(s->setup_done, MHD_E_STATE, "mhd_solve: call mhd_solver_setup after mhd_jacobian");
   MHD_CUDA(cudaSetDevice(g_device));
+  static cudaStream_t own = nullptr;
+  static int own_device = -1;
+  cudaStream_t saved = g_stream;
+  if (g_stream == 0 && g_nranks == 1) {
+    if (own_device != g_device) {
+      MHD_CUDA(cudaStreamCreate(&own));
+      own_device = g_device;
+    }
+    g_stream = own;
+  }
+  const int rc = solve_impl(s, b, x, iters, resnorm, res_history);
+  g_stream = saved;
+  return rc;
+}
+
+static int solve_impl(mhd_solver_t* s, const double* b, double* x, int32_t* iters, double* resnorm, double* res_history) {
   mhd_operator* op = s->op;
   const int64_t n = op->nrows;
   const mhd_solver_opts_t& o = s->opts;
@@ -846,6 +964,7 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
   }
   MHD_CUDA(cudaMemcpyAsync(x, s->d_x, n * 8, xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g_stream));
   MHD_CUDA(cudaStreamSynchronize(g_stream));
+  MHD_TRY(halo_check(s->op));  // a ghost exchange that timed out inside the cycles invalidates the solve
   if (hs.beta > hs.tol) {
     set_error("FGMRES stopped at %d iterations with residual %.3e > tol %.3e", total, hs.beta, hs.tol);
     return MHD_E_NOTCONV;

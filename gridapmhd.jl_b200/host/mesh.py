@@ -387,6 +387,37 @@ def read_gmsh41(path: str) -> HexMesh:
     return mesh
 
 
+def save_mesh_npz(mesh: HexMesh, path: str) -> None:
+    """Compact, reader-independent dump of an unstructured hex mesh: node coordinates, cell -> node ids (lexicographic
+    local order) and, per boundary tag, the tagged faces as sorted vertex quadruples; cell tags as masks."""
+    _, fv = entity_vertices(mesh)
+    out = {"coords": mesh.coords, "cell_nodes": mesh.cell_nodes.astype(np.int32)}
+    for name, mask in mesh.face_tags.items():
+        out["face_tag__" + name] = np.sort(fv[np.asarray(mask, dtype=bool)], axis=1).astype(np.int32)
+    for name, mask in mesh.cell_tags.items():
+        out["cell_tag__" + name] = np.asarray(mask, dtype=bool)
+    np.savez_compressed(path, **out)
+
+
+def load_mesh_npz(path: str) -> HexMesh:
+    """Inverse of `save_mesh_npz`: rebuilds the topology and re-attaches the tags (vertex / edge tags follow the faces)."""
+    d = np.load(path)
+    cn = d["cell_nodes"].astype(np.int64)
+    mesh = HexMesh(coords=d["coords"], cell_nodes=cn, cell_verts=cn.copy())
+    build_topology(mesh)
+    _, fv = entity_vertices(mesh)
+    fkey = {tuple(r): i for i, r in enumerate(np.sort(fv, axis=1).tolist())}
+    for key in d.files:
+        if key.startswith("face_tag__"):
+            mask = np.zeros(mesh.nfaces, dtype=bool)
+            for quad in d[key].tolist():
+                mask[fkey[tuple(quad)]] = True
+            tag_from_boundary_faces(mesh, key[len("face_tag__"):], mask)
+        elif key.startswith("cell_tag__"):
+            mesh.cell_tags[key[len("cell_tag__"):]] = d[key].astype(bool)
+    return mesh
+
+
 def refine_uniform(mesh: HexMesh) -> HexMesh:
     """Uniform 1:8 refinement with trilinear interpolation of the geometry (stand-in generator for the
     missing `Expansion_68k/749k.msh`). Boundary face tags are inherited."""

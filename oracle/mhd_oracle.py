@@ -170,8 +170,11 @@ def cell_residuals(T, X, state, j_sign, prm: FluidParams, solid=None, sigma_c=No
     divj = np.einsum("cqm,cm->cq", dpsi, js)
     fq = np.einsum("ql,cl->cq", Chi, fs)
     B = np.asarray(prm.B, dtype=float)
-    f = np.asarray(prm.f, dtype=float)
-    g = np.asarray(prm.g, dtype=float)
+    # body forces: constants (what the C ABI carries) or, in the oracle only, functions of the physical point
+    # (TimeSpaceFunction forcing of src/Applications/transient.jl:331-344) evaluated at the quadrature points
+    xq = np.einsum("qv,cvi->cqi", T.geo_val, X) if (callable(prm.f) or callable(prm.g)) else None
+    f = prm.f(xq) if callable(prm.f) else np.broadcast_to(np.asarray(prm.f, dtype=float), (nc, len(T.w), 3))
+    g = prm.g(xq) if callable(prm.g) else np.broadcast_to(np.asarray(prm.g, dtype=float), (nc, len(T.w), 3))
     R = np.zeros((nc, NLOC))
     # u rows
     ru = prm.beta * np.einsum("cq,cqdi,cqad->cia", w, gu, gN)
@@ -187,7 +190,7 @@ def cell_residuals(T, X, state, j_sign, prm: FluidParams, solid=None, sigma_c=No
     ru -= np.einsum("cq,cq,cqai->cia", w, pq, gN)
     jxB = _cross(jq, B)
     ru -= prm.gamma * np.einsum("cq,qa,cqi->cia", w, N, jxB)
-    ru -= np.einsum("cq,qa,i->cia", w, N, f)
+    ru -= np.einsum("cq,qa,cqi->cia", w, N, f)
     R[:, :81] = ru.reshape(nc, 81)
     # p rows
     R[:, 81:85] = -np.einsum("cq,qk,cq->ck", w, Pp, divu)
@@ -200,7 +203,7 @@ def cell_residuals(T, X, state, j_sign, prm: FluidParams, solid=None, sigma_c=No
     sgn = np.ones(nc) if solid is None else np.where(solid, -1.0, 1.0)
     rj -= sig[:, None] * np.einsum("cq,cq,cqm->cm", w, fq, dpsi)
     rj -= prm.sigma * np.einsum("cq,cqi,cqmi->cm", w, uxB, psi)
-    rj -= np.einsum("cq,i,cqmi->cm", w, g, psi)
+    rj -= np.einsum("cq,cqi,cqmi->cm", w, g, psi)
     R[:, 85:121] = rj
     # phi rows
     R[:, 121:129] = -sgn[:, None] * np.einsum("cq,ql,cq->cl", w, Chi, divj)

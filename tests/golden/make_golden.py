@@ -30,6 +30,23 @@ def main():
     print("wrote", out, os.path.getsize(out), "bytes; nnz", A.nnz)
 
 
+def main_expansion6k():
+    """BASELINE configs 3/4 stand-in: the reference's own `meshes/Expansion_6k.msh` (5 317 nodes, 4 320 non-affine
+    hexes, physical names inlet / outlet / wall / fluid) converted by host/mesh.py::read_gmsh41 into the reader-independent
+    fixture tests/golden/expansion_6k_mesh.npz -- the GPU box has no /root/reference, the mesh has to travel with the repo."""
+    from gridapmhd_jl_b200.host import mesh as M
+
+    m = M.read_gmsh41("/root/reference/meshes/Expansion_6k.msh")
+    assert m.ncells == 4320 and m.coords.shape[0] == 5317
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "expansion_6k_mesh.npz")
+    M.save_mesh_npz(m, out)
+    m2 = M.load_mesh_npz(out)
+    assert np.array_equal(m2.cell_nodes, m.cell_nodes) and np.array_equal(m2.coords, m.coords)
+    for k in m.face_tags:
+        assert np.array_equal(m2.face_tags[k], m.face_tags[k]), k
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 def main_h1h1():
     """H1-H1 formulation (oracle/mhd_oracle_h1h1.py): Hunt nc=(2,2), Ha=20, zeta_u=5, Newton convection."""
     from oracle import mhd_oracle_h1h1 as H
@@ -49,6 +66,9 @@ def main_h1h1():
     print("wrote", out, os.path.getsize(out), "bytes; nnz", A.nnz)
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "expansion6k":
+    main_expansion6k()
+    sys.exit(0)
 if __name__ == "__main__":
     main()
     main_h1h1()

@@ -206,12 +206,14 @@ def test_edge_cases_and_errors(mhdlib):
     op2.destroy()
 
 
-def test_nonuniform_and_block_layout(mhdlib):
-    """Rectangular cell counts and the badia2024 ([u,j],p,phi) block layout."""
+@pytest.mark.parametrize("solver,order", [("badia2024", ("u", "j", "p", "phi")), ("li2019", ("j", "u", "p", "phi"))])
+def test_nonuniform_and_block_layout(mhdlib, solver, order):
+    """Rectangular cell counts and the block layouts of `_multi_field_style` (src/fespaces.jl:4-9): badia2024 = ([u,j],p,phi),
+    li2019 = (j,u,p,phi)."""
     from oracle import mhd_oracle as O
 
-    params, fes = make_case(nc=(5, 3), B=(0.0, 50.0, 0.0), solver="badia2024")
-    assert fes.field_order == ("u", "j", "p", "phi")
+    params, fes = make_case(nc=(5, 3), B=(0.0, 50.0, 0.0), solver=solver)
+    assert fes.field_order == order
     op = B200FEOperator(fes, params["fluid"])
     x = np.random.default_rng(11).random(fes.ndofs)
     A = op.jacobian(x)
@@ -220,6 +222,8 @@ def test_nonuniform_and_block_layout(mhdlib):
     assert np.array_equal(rowptr, Ao.indptr) and np.array_equal(colval, Ao.indices)
     assert relerr(A.nzval(), Ao.data) < VAL_TOL
     assert relerr(op.residual(x), O.residual(fes, x, oracle_params(params["fluid"]))) < VAL_TOL
+    v = np.random.default_rng(12).standard_normal(fes.ndofs)
+    assert relerr(op.spmv(v), Ao @ v) < VAL_TOL
     op.destroy()
 
 
@@ -443,3 +447,63 @@ def test_hunt_driver_end_to_end_reproduces_published_row(mhdlib):
         assert abs(info[k] - v) / v < 1e-8, (k, info[k], v)
     assert info["time_post_process"] < 5.0
     out["op"].destroy()
+
+
+def test_hunt_nc64_ha500_device_solve_reproduces_published_row(mhdlib):
+    """BASELINE config 2 size, end to end on the device with the repo's OWN preconditioner (no vendor LU): `hunt(nc=(64,64),
+    B=(0,500,0))` on the kmap=1 mesh of the published run ha00500cx064 (analysis/gadi/results/2023_04/eaab9d14.../
+    hconv_ha00500ns100/summary.csv:2 -- 732 690 dofs, 12 288 cells): Newton + FGMRES(30) + Badia2024 block-triangular
+    preconditioner whose (u,j) block is an inner GMRES(30) preconditioned by the vertex-patch block-Jacobi smoother
+    (src/Solvers/badia2024.jl:2-48 with the smoother of gmg.jl:62-81 in place of the direct block solver), augmented
+    Lagrangian zeta = 10 (it vanishes at the discrete solution, so the published zeta = 0 norms are the target).
+    DOF counts exact; uh_l2, uh_h1, jh_l2 and the error norms against the analytical series to 1e-8 relative."""
+    from gridapmhd_jl_b200.applications import hunt
+    from gridapmhd_jl_b200.feoperator import B200SolverOptions
+
+    opts = B200SolverOptions(m=30, maxiter=120, rtol=1e-11, atol=1e-30, precond="block_tri", uj_solver="gmres_patch", uj_inner_its=30,
+                             uj_inner_restart=30, patch_its=1, patch_omega=1.0)
+    info, out = hunt(nc=(64, 64), B=(0.0, 500.0, 0.0), BL_adapted=False, solver="badia2024", zeta_u=10.0, zeta_j=10.0, nsums=100,
+                     solve=True, solver_opts=opts, newton_maxiter=3, newton_rtol=1e-10)
+    assert info["ndofs"] == 732690 and info["ndofs_u"] == 290322 and info["ndofs_j"] == 294912 and info["Ha"] == 500.0
+    log = out["newton_log"]
+    assert log[-1] <= 1e-9 * log[0], log
+    pins = dict(uh_l2=5.831116781906231e-5, uh_h1=0.0016385112887929432, jh_l2=0.0030907363432802868,
+                eu_l2=5.200746404046955e-7, eu_h1=9.23675484735579e-5, ej_l2=5.536545781986553e-5)
+    for k, v in pins.items():
+        assert abs(info[k] - v) / v < (1e-8 if k.endswith("h_l2") or k == "uh_h1" else 1e-5), (k, info[k], v)
+    out["op"].destroy()
+
+
+def test_expansion_6k_reference_mesh_assembly_and_spmv(mhdlib):
+    """BASELINE configs 3/4 on the reference's own mesh: `meshes/Expansion_6k.msh` (5 317 nodes, 4 320 NON-AFFINE hexes; shipped
+    as the reader-independent fixture tests/golden/expansion_6k_mesh.npz, written by tests/golden/make_golden.py expansion6k)
+    with the Expansion parameterisation of src/Applications/expansion.jl:40-181 (:mhd scaling, Ha = 100, N = 3740 as in
+    Turgalium_CIEMAT/sendExpansion.sh:49-56, parabolic inlet profile as Dirichlet data, Newton convection): CSR structure
+    bit-exact, Jacobian and residual <= 1e-12 against the C oracle on EVERY row, SpMV against a host product."""
+    import os
+
+    from gridapmhd_jl_b200.applications import expansion_params
+    from gridapmhd_jl_b200.host import mesh as M
+    from oracle.parity import assembly_parity, spmv_parity
+
+    m = M.load_mesh_npz(os.path.join(os.path.dirname(__file__), "golden", "expansion_6k_mesh.npz"))
+    assert m.ncells == 4320 and m.coords.shape[0] == 5317
+    params = expansion_params(Ha=100.0, N=3740.0, zeta_u=10.0, zeta_j=10.0, mesh=m)
+    fes = setup_spaces(params)
+    assert np.abs(fes.dirichlet_values["u"]).max() > 1.0  # the inlet profile is in
+    fl = params["fluid"]
+    op = B200FEOperator(fes, fl)
+    assert op.kernel_version == 7
+    x = np.random.default_rng(6).random(fes.ndofs)
+    A = op.allocate_jacobian()
+    b = np.empty(op.nrows)
+    op.residual_and_jacobian_b(b, A, x)
+    rowptr, colval = A.pattern()
+    nz = A.nzval()
+    par = assembly_parity(fes, oracle_params(fl), x, rowptr, colval, nz, b, op.nrows, ncells=m.ncells)
+    assert par["cells"] == 4320 and par["rows_checked"] == op.nrows, par
+    assert par["csr_bitexact"] and par["jac_rel"] < VAL_TOL and par["res_rel"] < VAL_TOL, par
+    v = np.random.default_rng(7).standard_normal(fes.ndofs)
+    assert spmv_parity(rowptr, colval, nz, v, op.spmv(v)) < VAL_TOL
+    assert relerr(op.residual(x), b) < 1e-13
+    op.destroy()

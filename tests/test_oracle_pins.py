@@ -172,6 +172,67 @@ def test_k2_manufactured_inspace_fields_zero_residual():
     assert np.abs(fes.split(O.residual(fes, x, bad))["u"]).max() > 1e-3
 
 
+def test_k2b_reference_manufactured_solution_with_nonconstant_velocity():
+    """The reference's own in-FE-space manufactured solution (src/Applications/transient.jl:262-270, `:stationary_fespace`):
+        u = (y, x, 0),  j = (y, 1, 0),  p = 0,  phi = 1
+    with the forcing of `_transient_solution_f` / `_transient_solution_fj` (:331-344)
+        f(x) = alpha (u.grad)u - beta lap u + grad p - gamma j x B = alpha (x, y, 0) - gamma j x B,
+        g(x) = j + sigma grad phi - sigma u x B.
+    (u.grad)u = (x, y, 0) is NOT zero here, so this pins the convection term `alpha v.((grad u)' u)` of
+    res_fluid_h1_hdiv (weakforms.jl:270, `conv` :670) independently of Hunt (fully developed: (u.grad)u = 0) and of the
+    Jacobian-vs-residual check K3.  For that field grad u is symmetric (a transposed gradient would give the same vector), so a
+    second divergence-free field with a non-symmetric gradient, u = (y, x^2, 0), is checked as well."""
+    m = M.hunt_generate_base_mesh((3, 2), Ha=10.0, BL_adapted=False, periodic_z=False)
+    M.tag_from_boundary_faces(m, "allwalls", m.face_ncells == 1)
+    B = np.array([0.3, 1.0, -0.2])
+    alpha, beta, gamma, sigma = 0.5, 0.3, 7.0, 1.9
+    cases = {
+        # name: (u, (u.grad)u with Gridap's convention sum_i u_i d_i u_c, laplacian of u)
+        "reference": (lambda X: np.stack([X[:, 1], X[:, 0], 0 * X[:, 0]], axis=1),
+                      lambda X: np.stack([X[..., 0], X[..., 1], 0 * X[..., 0]], axis=-1),
+                      lambda X: 0 * X),
+        # u = (y, x^2, 0): div u = 0, grad u not symmetric: (u.grad)u = (u_y d_y u_x, u_x d_x u_y, 0) = (x^2, 2 x y, 0), lap u = (0, 2, 0)
+        "nonsymmetric": (lambda X: np.stack([X[:, 1], X[:, 0] ** 2, 0 * X[:, 0]], axis=1),
+                         lambda X: np.stack([X[..., 0] ** 2, 2 * X[..., 0] * X[..., 1], 0 * X[..., 0]], axis=-1),
+                         lambda X: np.stack([0 * X[..., 0], 2 + 0 * X[..., 0], 0 * X[..., 0]], axis=-1)),
+    }
+    jfun = lambda X: np.stack([X[..., 1], 1 + 0 * X[..., 0], 0 * X[..., 0]], axis=-1)
+    for name, (uex, convex, lapex) in cases.items():
+        fes = F.setup_fe_spaces(m, u_tags=("allwalls",), u_values=(uex,), j_tags=("allwalls",))
+        ufield = lambda X: uex(X.reshape(-1, 3)).reshape(X.shape)
+        f = lambda X: alpha * convex(X) - beta * lapex(X) - gamma * np.cross(jfun(X), B)
+        g = lambda X: jfun(X) - sigma * np.cross(ufield(X), B)
+        # interpolate: u nodal, p = 0, phi = 1, j = cell-wise L2 projection of the (in-space) field (y, 1, 0)
+        x, _ = _interpolate(fes, uex, (0.0, 0.0, 0.0), 0.0, 1.0)
+        T = fes.tables
+        X = fes.mesh.cell_coords()
+        w, _, psi, _ = O.mapped_bases(T, X, fes.j_sign)
+        xq = np.einsum("qv,cvi->cqi", T.geo_val, X)
+        Mjj = np.einsum("cq,cqmi,cqni->cmn", w, psi, psi)
+        rhs = np.einsum("cq,cqmi,cqi->cm", w, psi, jfun(xq))
+        coef = np.linalg.solve(Mjj, rhs[..., None])[..., 0]
+        idj = fes.cell_dofs["j"]
+        off = fes.offsets
+        free = idj > 0
+        x[off["j"] + idj[free] - 1] = coef[free]
+        dirv = np.zeros(fes.ndir["j"])
+        dirv[-idj[idj < 0] - 1] = coef[idj < 0]
+        fes.dirichlet_values["j"] = dirv
+        prm = O.FluidParams(alpha=alpha, beta=beta, gamma=gamma, sigma=sigma, zeta_u=3.0, zeta_j=2.0, B=tuple(B), f=f, g=g, convection="newton")
+        r = fes.split(O.residual(fes, x, prm))
+        for k in ("u", "p", "j", "phi"):
+            assert np.abs(r[k]).max() < 1e-10, (name, k, np.abs(r[k]).max())
+        # the test is not vacuous: without the convection term, or with the transposed gradient, the momentum rows do not vanish
+        off_prm = O.FluidParams(alpha=alpha, beta=beta, gamma=gamma, sigma=sigma, B=tuple(B), f=f, g=g, convection="none")
+        assert np.abs(fes.split(O.residual(fes, x, off_prm))["u"]).max() > 1e-3, name
+    # the transposed convention (grad u)u instead of (grad u)'u differs for the non-symmetric field
+    uex, convex, _ = cases["nonsymmetric"]
+    Xs = np.array([[0.3, 0.7, 0.1]])
+    gu = np.array([[0.0, 2 * Xs[0, 0], 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0]])  # gu[i, c] = d_i u_c at Xs
+    u = uex(Xs)[0]
+    assert np.allclose(gu.T @ u, convex(Xs)[0]) and not np.allclose(gu @ u, convex(Xs)[0])
+
+
 # K3 ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("conv", ["newton", "none"])
 def test_k3_jacobian_is_derivative_of_residual(conv):
