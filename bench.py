@@ -176,7 +176,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 def cpu_baseline_leg(fes, params, seconds=12.0):
@@ -615,7 +615,7 @@ def run_ours(args):
             tr = json.load(open(traffic_file))
             line["roofline"]["traffic"] = tr.get("jacobian_kernel_dram_bytes")
             line["spmv"]["roofline"]["traffic"] = tr.get("spmv_dram_bytes")
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     barrier()  # nobody tears its inbox down while a neighbour may still push into it
     op.destroy()
     if world > 1:
@@ -624,7 +624,30 @@ def run_ours(args):
     L.finalize()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries the single JSON line and nothing else: everything libraries print to fd 1 from here on (NCCL banners of
+    the library's own dlopen'ed copy, torchrun notes, ...) is sent to stderr; emit_json() writes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -193,15 +193,32 @@ def hunt_cell_partition(mesh: HexMesh, np_xy) -> np.ndarray:
     return cartesian_partition(mesh.grid_shape, (np_xy[0], np_xy[1], 1))
 
 
-def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: int, dist=None, use_peer_memory=True):
+def default_cell_partition(mesh: HexMesh, nparts: int, np_xy=None) -> np.ndarray:
+    """cell -> part: the (px,py,1) block partition of structured Hunt meshes (hunt_mesher.jl:116-118) when `np_xy` is
+    given, else recursive coordinate bisection of the cell centroids -- the stand-in for the METIS partition GridapGmsh
+    produces for the Expansion meshes (expansion.jl:278); any other cell -> part array can be passed to
+    `distribute_operator(cell_part=...)` directly."""
+    if np_xy is not None and mesh.grid_shape is not None:
+        return hunt_cell_partition(mesh, np_xy)
+    from .mesh import rcb_partition
+
+    return rcb_partition(mesh.cell_coords().mean(axis=1), nparts)
+
+
+def distribute_operator(fes_global: FESpaces, params, np_xy, rank: int, world: int, dist=None, use_peer_memory=True, cell_part=None):
     """Create this rank's `B200FEOperator` (owned rows, ghost-cell redundant integration), install the halo plan and
-    bring up the NCCL communicator of the library (the unique id travels through torch.distributed / MPI)."""
+    bring up the NCCL communicator of the library (the unique id travels through torch.distributed / MPI).
+    `cell_part` [ncells] -> rank: an arbitrary partition (METIS-style, expansion.jl:278); default: see
+    `default_cell_partition`."""
     import ctypes as C
 
     from .. import lib as L
     from ..feoperator import B200FEOperator, B200H1H1FEOperator
 
-    cell_part = hunt_cell_partition(fes_global.mesh, np_xy)
+    if cell_part is None:
+        cell_part = default_cell_partition(fes_global.mesh, world, np_xy)
+    cell_part = np.asarray(cell_part)
+    assert cell_part.shape == (fes_global.mesh.ncells,) and cell_part.min() >= 0 and cell_part.max() < max(world, 1)
     ps = partition_fespaces(fes_global, cell_part, rank)
     lib = L.load()
     if world > 1:

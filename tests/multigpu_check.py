@@ -8,7 +8,10 @@ global matrix/residual; then the distributed SpMV (NCCL halo exchange), dot (NCC
 FGMRES are compared with the global ones.  Prints "MULTIGPU_OK <world>" on rank 0 when every rank passed.
 
 `MHD_CHECK_FORMULATION=h1h1` runs the same checks for the H1-H1 formulation (u, p, continuous Q3 phi; Jacobi-preconditioned
-FGMRES).  The H1-H1 variant has NOT been executed on GPUs yet (its host partition is covered by tests/test_partition_gloo.py).
+FGMRES).  `MHD_CHECK_CASE=expansion6k` runs them on the reference's Expansion_6k mesh (4 320 non-affine hexes, fixture
+tests/golden/expansion_6k_mesh.npz) with an ARBITRARY cell partition (recursive coordinate bisection: the stand-in for the
+METIS partition of expansion.jl:278).  `MHD_CHECK_STRESS=N` appends N back-to-back fused SpMV + halo products (arrival
+counters, double-buffered inboxes and the acquire ordering under load; N = 10000 at 8 GPUs is the stress run).
 """
 import os
 import sys
@@ -36,7 +39,19 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
     np_xy = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[world]
     h1h1 = os.environ.get("MHD_CHECK_FORMULATION", "hdiv") == "h1h1"
-    if h1h1:
+    case = os.environ.get("MHD_CHECK_CASE", "hunt")
+    cell_part = None
+    if case == "expansion6k":
+        from gridapmhd_jl_b200.applications import expansion_params
+        from gridapmhd_jl_b200.host import mesh as M
+        from gridapmhd_jl_b200.host.partition import default_cell_partition
+
+        OH = O
+        mesh = M.load_mesh_npz(os.path.join(ROOT, "tests", "golden", "expansion_6k_mesh.npz"))
+        params = expansion_params(Ha=100.0, N=3740.0, zeta_u=10.0, zeta_j=10.0, mesh=mesh, solver="badia2024")
+        cell_part = default_cell_partition(mesh, world)
+        np_xy = None
+    elif h1h1:
         from oracle import mhd_oracle_h1h1 as OH
 
         params = hunt_params(nc=(6, 4), B=(0.0, 20.0, 0.0), zeta_u=1.0, current_disc="H1")
@@ -51,7 +66,7 @@ def main():
     Ag = OH.jacobian(fes, x, prm)
     rg = OH.residual(fes, x, prm)
 
-    op, ps = distribute_operator(fes, params, np_xy, rank, world, dist)
+    op, ps = distribute_operator(fes, params, np_xy, rank, world, dist, cell_part=cell_part)
     gl = ps.local_vector_ids()
     A = op.allocate_jacobian()
     assert op.nrows == ps.nrows and op.ncols == ps.ncols
@@ -85,6 +100,19 @@ def main():
         vfull[: op.nrows] = vr
         yr = op.spmv(vfull)
         ok &= np.abs(yr.cpu().numpy() - (rep + 2) * yref).max() / np.abs(Ag @ v).max() < 1e-11
+    nstress = int(os.environ.get("MHD_CHECK_STRESS", "0"))
+    if nstress:
+        vfull = torch.zeros(op.ncols, dtype=torch.float64, device="cuda")
+        vfull[: op.nrows] = torch.from_numpy(v[gl[: op.nrows]]).cuda()
+        yy = torch.empty(op.nrows, dtype=torch.float64, device="cuda")
+        bad = 0
+        for rep in range(nstress):  # enqueued back to back: neighbours run ahead / behind each other by whole products
+            op.spmv(vfull, yy)
+            if rep % 97 == 0 or rep == nstress - 1:
+                bad += int(np.abs(yy.cpu().numpy() - yref).max() / np.abs(Ag @ v).max() >= 1e-12)
+        L.check(L.load().mhd_operator_halo_status(op.handle, C.byref(fused), C.byref(tmo)))
+        ok &= bad == 0 and tmo.value == 0
+        print(f"[rank {rank}] stress: {nstress} fused products, {bad} wrong, timed_out={tmo.value}", flush=True)
     d = op.dot(vl, vl)  # all-reduced over ranks (owned entries only)
     err_d = abs(d - v @ v) / (v @ v)
     ok &= err_d < 1e-13
@@ -97,7 +125,7 @@ def main():
     hmax, hmin = h.clone(), h.clone()
     dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
-    ok &= bool(torch.equal(hmax, hmin)) and ns.history[-1] < (1.0 if h1h1 else 0.2) * ns.history[0]
+    ok &= bool(torch.equal(hmax, hmin)) and ns.history[-1] < (1.0 if (h1h1 or case != "hunt") else 0.2) * ns.history[0]
     # true residual of the distributed solution against the global matrix
     xs = np.zeros(fes.ndofs)
     xs[gl[: op.nrows]] = dx

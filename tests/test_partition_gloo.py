@@ -41,6 +41,37 @@ def test_partition_is_a_partition_and_plans_match():
             assert len(np.unique(pr.recv_idx)) == pr.ncols - pr.nrows == len(pr.recv_idx)
 
 
+def test_arbitrary_partition_of_the_reference_expansion_mesh():
+    """An arbitrary (non-Cartesian) cell partition -- recursive coordinate bisection of the reference's Expansion_6k mesh into
+    2, 4 and 8 parts, the stand-in for the METIS partition of expansion.jl:278: every dof owned once, every ghost received
+    exactly once from its owner, send and receive lists pair up."""
+    from gridapmhd_jl_b200.applications import expansion_params
+    from gridapmhd_jl_b200.host import mesh as M
+    from gridapmhd_jl_b200.host.partition import default_cell_partition
+
+    m = M.load_mesh_npz(os.path.join(os.path.dirname(__file__), "golden", "expansion_6k_mesh.npz"))
+    params = expansion_params(Ha=100.0, N=3740.0, mesh=m, solver="badia2024")
+    fes = setup_spaces(params)
+    for nparts in (2, 4, 8):
+        cell_part = default_cell_partition(fes.mesh, nparts)
+        counts = np.bincount(cell_part, minlength=nparts)
+        assert counts.min() >= 0.9 * m.ncells / nparts and counts.max() <= 1.1 * m.ncells / nparts
+        parts = [partition_fespaces(fes, cell_part, r) for r in range(nparts)]
+        for f in ("u", "p", "j", "phi"):
+            allown = np.concatenate([p.own_global[f] for p in parts])
+            assert len(allown) == fes.nfree[f] and len(np.unique(allown)) == fes.nfree[f]
+        assert sum(p.nowned_cells for p in parts) == m.ncells
+        for r, pr in enumerate(parts):
+            gr = pr.local_vector_ids()
+            for k, s in enumerate(pr.neigh):
+                ps = parts[s]
+                ks = list(ps.neigh).index(r)
+                sent = gr[pr.send_idx[pr.send_ptr[k] : pr.send_ptr[k + 1]]]
+                recv = ps.local_vector_ids()[ps.recv_idx[ps.recv_ptr[ks] : ps.recv_ptr[ks + 1]]]
+                assert np.array_equal(sent, recv)
+            assert len(np.unique(pr.recv_idx)) == pr.ncols - pr.nrows == len(pr.recv_idx)
+
+
 def test_local_rows_reproduce_global_rows():
     """Rows assembled by a rank (owned + ghost cells) equal the same rows of the global matrix: no entry has to cross
     ranks ("fully assembled rows")."""
