@@ -370,11 +370,17 @@ MHD_7HD void phase_fields(Cell7& S, const SmallDyn& C, int tid, int nt, const Pa
 }
 
 // ------------------------------------------------------------------ phase 4: first contraction (direction d2) of every block
+// One item per call (the kernel calls it for item = tid, tid + 256, tid + 512 without a loop: inside a loop ptxas hoists the
+// constant-bank table operands of every case into registers on each call -- 850 instructions per cell in stage 1, 1 400 in
+// stage 2 -- see chunk_uj_item).
+constexpr int STAGE1_ITEMS = 189 + 81 + 54 + 54 + 27 + 324;
 template <bool ZJ>
-MHD_7HD void phase_stage1(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
+MHD_7HD void stage1_item(Cell7& S, const SmallDyn& C, const Small7& K, int it) {
   constexpr int N_UU = 189, N_UJ = N_UU + 81, N_JA = N_UJ + 54, N_JB = N_JA + 54, N_JF = N_JB + 27, N_UP = N_JF + 324;
+  static_assert(N_UP == STAGE1_ITEMS, "stage 1 item count");
   const double* F = S.r3;
-  for (int it = tid; it < N_UP; it += nt) {
+  if (it >= N_UP) return;
+  {
     if (it < N_UU) {
       // items grouped by the direction-2 derivative pattern of their field so that the pattern switch is (nearly) warp-uniform
       // and every table operand a compile-time constant: pattern 0: Newton 0..8, stiffness 9 10 12 13, convection 18 19 |
@@ -416,7 +422,7 @@ MHD_7HD void phase_stage1(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
     } else if (it < N_JB) {
       const bool typeb = it >= N_JA;
       const int i = it - (typeb ? N_JA : N_UJ), blk = i / 18, kind = (i / 9) % 2, r = i % 9;
-      if (kind == 1 && !ZJ) continue;
+      if (kind == 1 && !ZJ) return;
       int k = blk, kp = blk;
       if (typeb) jjb_pair(blk, &k, &kp);
       const int d0 = k, d1 = typeb ? kp : (k + 1) % 3, d2 = 3 - d0 - d1;
@@ -456,15 +462,22 @@ MHD_7HD void phase_stage1(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
     }
   }
 }
+template <bool ZJ>
+MHD_7HD void phase_stage1(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
+  for (int it = tid; it < STAGE1_ITEMS; it += nt) stage1_item<ZJ>(S, C, K, it);
+}
 
 // ------------------------------------------------------------------ phase 5: second contraction (direction d1)
+constexpr int STAGE2_ITEMS = 243 + 108 + 162 + 72 + 72 + 36 + 324;
 template <int CONV, bool ZJ>
-MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
+MHD_7HD void stage2_item(Cell7& S, const SmallDyn& C, const Small7& K, int it) {
   constexpr int N_N = 243, N_B = N_N + 108, N_UJ = N_B + 162, N_JA = N_UJ + 72, N_JB = N_JA + 72, N_JF = N_JB + 36, N_UP = N_JF + 324;
+  static_assert(N_UP == STAGE2_ITEMS, "stage 2 item count");
   const double* T1 = S.r1;
-  for (int it = tid; it < N_UP; it += nt) {
+  if (it >= N_UP) return;
+  {
     if (it < N_N) {
-      if (CONV != 2) continue;
+      if (CONV != 2) return;
       const int f = it / 27, p2 = (it / 3) % 9, q0 = it % 3;
       const double* x = T1 + T1_UU + f * 81 + p2 * 9 + q0;
       const double x0 = x[0], x1 = x[3], x2 = x[6];
@@ -480,35 +493,22 @@ MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
       // pattern 2 (m == ax) + (n == ax) in direction ax, convection f = 18 + n has (n == ax)); fields of one group are summed
       // before the contraction.  The loop over the pattern is NOT unrolled (27 compile-time table operands per pattern).
       const double* xb = T1 + T1_UU + p2 * 9 + q0;
-      MHD_7NOUNROLL
-      for (int pat = 0; pat < 4; pat++) {
-        int f1 = -1, f2 = -1;
-        switch (pc * 4 + pat) {
-          case 12: f1 = 9; break;
-          case 9: f1 = 10; break;
-          case 8: f1 = 11; break;
-          case 6: f1 = 12; break;
-          case 4: f1 = 15; f2 = 18; break;
-          case 3: f1 = 13; break;
-          case 2: f1 = 14; break;
-          case 1: f1 = 16; f2 = 19; break;
-          case 0: f1 = 17; f2 = 20; break;
-          default: break;
-        }
-        if (f1 < 0) continue;
-        double x0 = xb[f1 * 81], x1 = xb[f1 * 81 + 3], x2 = xb[f1 * 81 + 6];
-        if (CONV != 0 && f2 >= 0) { x0 += xb[f2 * 81]; x1 += xb[f2 * 81 + 3]; x2 += xb[f2 * 81 + 6]; }
-#define MHD_7ACC(PAT1_)                                                                                                  \
-  MHD_7UNROLL                                                                                                            \
-  for (int ab = 0; ab < 9; ab++) acc[ab] += K.Puu[1][PAT1_][ab][0] * x0 + K.Puu[1][PAT1_][ab][1] * x1 + K.Puu[1][PAT1_][ab][2] * x2
-        switch (pat) {
-          case 0: MHD_7ACC(0); break;
-          case 1: MHD_7ACC(1); break;
-          case 2: MHD_7ACC(2); break;
-          default: MHD_7ACC(3); break;
-        }
-#undef MHD_7ACC
-      }
+      // straight-line code, one block per direction-1 pattern (no loop: see stage1_item); f1 / f2 = fields of (pc, pattern)
+#define MHD_7NB(PAT_, F1_EXPR, F2_EXPR)                                                                                   \
+  do {                                                                                                                    \
+    const int f1 = (F1_EXPR), f2 = (F2_EXPR);                                                                              \
+    if (f1 >= 0) {                                                                                                        \
+      double x0 = xb[f1 * 81], x1 = xb[f1 * 81 + 3], x2 = xb[f1 * 81 + 6];                                                  \
+      if (CONV != 0 && f2 >= 0) { x0 += xb[f2 * 81]; x1 += xb[f2 * 81 + 3]; x2 += xb[f2 * 81 + 6]; }                        \
+      MHD_7UNROLL                                                                                                         \
+      for (int ab = 0; ab < 9; ab++) acc[ab] += K.Puu[1][PAT_][ab][0] * x0 + K.Puu[1][PAT_][ab][1] * x1 + K.Puu[1][PAT_][ab][2] * x2; \
+    }                                                                                                                     \
+  } while (0)
+      MHD_7NB(0, pc == 3 ? 9 : (pc == 2 ? 11 : (pc == 1 ? 15 : 17)), pc == 1 ? 18 : (pc == 0 ? 20 : -1));
+      MHD_7NB(1, pc == 2 ? 10 : (pc == 0 ? 16 : -1), pc == 0 ? 19 : -1);
+      MHD_7NB(2, pc == 1 ? 12 : (pc == 0 ? 14 : -1), -1);
+      MHD_7NB(3, pc == 0 ? 13 : -1, -1);
+#undef MHD_7NB
       double* o = S.r2 + T2_B + pc * 243 + p2 * 3 + q0;
       MHD_7UNROLL
       for (int ab = 0; ab < 9; ab++) o[ab * 27] = acc[ab];
@@ -527,7 +527,7 @@ MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
         }
     } else if (it < N_JA) {
       const int i = it - N_UJ, blk = i / 24, kind = (i / 12) % 2, p2 = (i / 3) % 4, q0 = i % 3, k = blk;
-      if (kind == 1 && !ZJ) continue;
+      if (kind == 1 && !ZJ) return;
       const double* x = T1 + T1_JA + (blk * 2 + kind) * 36 + p2 * 9 + q0;
       const double x0 = x[0], x1 = x[3], x2 = x[6];
       const double* r = C.RV[k][1][0];
@@ -538,7 +538,7 @@ MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
         for (int b = 0; b < 2; b++) o[(a * 2 + b) * 12] = r[a * 3] * r[b * 3] * x0 + r[a * 3 + 1] * r[b * 3 + 1] * x1 + r[a * 3 + 2] * r[b * 3 + 2] * x2;
     } else if (it < N_JB) {
       const int i = it - N_JA, blk = i / 24, kind = (i / 12) % 2, p2 = (i / 3) % 4, q0 = i % 3;
-      if (kind == 1 && !ZJ) continue;
+      if (kind == 1 && !ZJ) return;
       int k, kp;
       jjb_pair(blk, &k, &kp);
       const int d1 = kp;
@@ -574,6 +574,10 @@ MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid,
       for (int a = 0; a < 3; a++) o[a * 9] = tb[a * 3] * x0 + tb[a * 3 + 1] * x1 + tb[a * 3 + 2] * x2;
     }
   }
+}
+template <int CONV, bool ZJ>
+MHD_7HD void phase_stage2(Cell7& S, const SmallDyn& C, const Small7& K, int tid, int nt) {
+  for (int it = tid; it < STAGE2_ITEMS; it += nt) stage2_item<CONV, ZJ>(S, C, K, it);
 }
 
 // ------------------------------------------------------------------ phase 5b: D[k][(c, tensor node)] = int pi_k d_c N, pressure mass matrix

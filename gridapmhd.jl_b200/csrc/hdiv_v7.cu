@@ -78,9 +78,22 @@ __device__ __forceinline__ double* sm_buf() { return B == 0 ? sm_cell().r1 : sm_
 template <int CONV, bool ZJ>
 V7_NI void ni_fields(int tid, const h7::Params& P) { h7::phase_fields<CONV, ZJ>(sm_cell(), sm_small(), tid, V7_NT, P); }
 template <bool ZJ>
-V7_NI void ni_stage1(int tid) { h7::phase_stage1<ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
+V7_NI void ni_stage1_item(int item) { h7::stage1_item<ZJ>(sm_cell(), sm_small(), c_small7, item); }
+template <bool ZJ>
+__device__ __forceinline__ void ni_stage1(int tid) {  // 729 items on 256 threads: three calls, no loop (see stage1_item)
+  ni_stage1_item<ZJ>(tid);
+  ni_stage1_item<ZJ>(tid + V7_NT);
+  if (tid + 2 * V7_NT < h7::STAGE1_ITEMS) ni_stage1_item<ZJ>(tid + 2 * V7_NT);
+}
 template <int CONV, bool ZJ>
-V7_NI void ni_stage2(int tid) { h7::phase_stage2<CONV, ZJ>(sm_cell(), sm_small(), c_small7, tid, V7_NT); }
+V7_NI void ni_stage2_item(int item) { h7::stage2_item<CONV, ZJ>(sm_cell(), sm_small(), c_small7, item); }
+template <int CONV, bool ZJ>
+__device__ __forceinline__ void ni_stage2(int tid) {  // 1 017 items: four calls
+  ni_stage2_item<CONV, ZJ>(tid);
+  ni_stage2_item<CONV, ZJ>(tid + V7_NT);
+  ni_stage2_item<CONV, ZJ>(tid + 2 * V7_NT);
+  if (tid + 3 * V7_NT < h7::STAGE2_ITEMS) ni_stage2_item<CONV, ZJ>(tid + 3 * V7_NT);
+}
 // (the component / direction of a chunk is a run-time argument: ONE copy of the code -- the loop body of the kernel is several
 // times the 32 KB instruction cache and every duplicated phase shows up as no_inst stalls)
 template <int CONV, bool ZU>

@@ -175,15 +175,29 @@ spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, c
   for (int64_t row = warp0; row < nr; row += nwarps) {
     const int64_t lo = rowptr[row], hi = rowptr[row + 1];
     double s0 = 0.0, s1 = 0.0;
-    // warp-uniform trip count: the vote below is legal, and a row needs no extra load to learn that it has ghosts
+    // Pass 1, branch-free and identical to the single-GPU kernel: the LOCAL columns through the read-only path; ghost
+    // columns (sorted last in every row) contribute nothing here, the lanes only remember where the first one sits.
+    int64_t first_ghost = hi;
     for (int64_t base = lo; base < hi; base += 64) {
       const int64_t p0 = base + lane, p1 = p0 + 32;
       const bool ok0 = p0 < hi, ok1 = p1 < hi;
       const int32_t c0 = ok0 ? __ldg(colval + p0) : 0, c1 = ok1 ? __ldg(colval + p1) : 0;
       const double v0 = ok0 ? __ldg(nzval + p0) : 0.0, v1 = ok1 ? __ldg(nzval + p1) : 0.0;
       const bool g0 = c0 >= nrows, g1 = c1 >= nrows;
-      if (!arrived && __any_sync(0xffffffffu, g0 || g1)) {
-        // first ghost column met by this warp: wait (once) until every neighbour's values have landed
+      if (g0 && p0 < first_ghost) first_ghost = p0;
+      if (g1 && p1 < first_ghost) first_ghost = p1;
+      s0 = fma(g0 ? 0.0 : v0, __ldg(x + (g0 ? 0 : c0)), s0);
+      s1 = fma(g1 ? 0.0 : v1, __ldg(x + (g1 ? 0 : c1)), s1);
+    }
+    // Pass 2, interface rows only (a few per cent): wait once for the neighbours, then add the ghost tail of the row through
+    // the coherent path (ld.relaxed.sys) -- these values were written by peer GPUs during this kernel.
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int64_t other = __shfl_xor_sync(0xffffffffu, first_ghost, o);
+      first_ghost = other < first_ghost ? other : first_ghost;
+    }
+    if (first_ghost < hi) {
+      if (!arrived) {
         if (lane == 0 && ld_acquire_cta_shared(&cta_arrived) == 0u) {
           for (int k = 0; k < nn; k++) {
             const unsigned target = H->expected[k] * round;
@@ -201,18 +215,7 @@ spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, c
         __syncwarp();
         arrived = true;
       }
-      // warp-uniform choice (no divergence): chunks that touch ghost columns gather through the coherent path, all others
-      // keep the read-only path for x
-      double x0, x1;
-      if (__any_sync(0xffffffffu, g0 || g1)) {
-        x0 = ld_relaxed_sys_f64((g0 ? xg : x) + c0);
-        x1 = ld_relaxed_sys_f64((g1 ? xg : x) + c1);
-      } else {
-        x0 = __ldg(x + c0);
-        x1 = __ldg(x + c1);
-      }
-      s0 = fma(v0, x0, s0);
-      s1 = fma(v1, x1, s1);
+      for (int64_t p = first_ghost + lane; p < hi; p += 32) s0 = fma(__ldg(nzval + p), ld_relaxed_sys_f64(xg + __ldg(colval + p)), s0);
     }
     double s = s0 + s1;
 #pragma unroll
