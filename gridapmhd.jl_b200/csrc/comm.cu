@@ -153,13 +153,22 @@ int mhd_comm_finalize(void) {
   return MHD_OK;
 }
 
+// ghost_lo[r] = position of the first ghost column of row r (columns are sorted and ghost ids come last: the ghost entries are
+// the tail [ghost_lo, rowptr[r+1]) of the row; == rowptr[r+1] for rows without ghosts)
 __global__ void tag_ghost_rows(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
-                               long long* __restrict__ tagged) {
+                               long long* __restrict__ ghost_lo) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > nrows) return;
-  long long v = rowptr[r];
-  if (r < nrows && rowptr[r + 1] > rowptr[r] && colval[rowptr[r + 1] - 1] >= nrows) v |= 1ll << 62;  // sorted: ghosts are the tail
-  tagged[r] = v;
+  if (r >= nrows) {
+    if (r == nrows) ghost_lo[r] = rowptr[r];
+    return;
+  }
+  int64_t a = rowptr[r], b = rowptr[r + 1];
+  while (a < b) {  // first position with colval >= nrows
+    const int64_t m = (a + b) >> 1;
+    if (colval[m] >= nrows) b = m;
+    else a = m + 1;
+  }
+  ghost_lo[r] = a;
 }
 
 // ---- fused peer-memory halo: export this rank's inbox, connect to the neighbours' inboxes

@@ -98,7 +98,7 @@ struct Halo {
   std::vector<void*> peer_mem;          // the neighbours' ipc_mem, opened with cudaIpcOpenMemHandle
   struct HaloDev* d_dev = nullptr;      // device copy of the plan
   int32_t* d_ghost_src = nullptr;       // [nsend] destination ghost slots on the neighbours (send_dst)
-  long long* d_row_bits = nullptr;      // [nrows+1] tagged copy of rowptr (bit 62: row has ghost columns)
+  long long* d_row_bits = nullptr;      // [nrows+1] position of the first ghost column of every row (== end of the row if it has none)
   int* d_err = nullptr;
   unsigned epoch = 0;
 };
@@ -120,7 +120,7 @@ struct HaloDev {
   const int64_t* push_begin;                 // [npush] first send-list entry of each push CTA
   const unsigned* my_flags;                  // [2][HALO_MAX_NEIGH]
   const double* my_inbox[2];
-  const long long* rowptr_tagged;            // rowptr copy with bit 62 set on rows that end with ghost columns (unused by the vote kernel)
+  const long long* rowptr_tagged;            // ghost_lo[row]: first ghost entry of the row (ghost columns are sorted last)
   int* err;
 };
 

@@ -961,7 +961,7 @@ MHD_7HD void res_fields(Cell7& S, const SmallDyn& C, int tid, int nt, const Para
 template <class RAdd>
 MHD_7HD void res_stage_a(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& radd) {
   double* F = S.r3;
-  for (int it = tid; it < 152; it += nt) {
+  for (int it = tid; it < 168; it += nt) {
     if (it < 108) {
       const int c = it / 36, f = (it / 9) % 4, q01 = it % 9;
       const double* x = F + (f < 3 ? RF_G + (c * 3 + f) * 27 : RF_H + c * 27) + q01;
@@ -986,10 +986,15 @@ MHD_7HD void res_stage_a(Cell7& S, const SmallDyn& C, int tid, int nt, RAdd& rad
       F[RR_JP + ((k * 4 + i1 + 2 * i2) * 3 + qk) * 2] = pv;
       F[RR_JP + ((k * 4 + i1 + 2 * i2) * 3 + qk) * 2 + 1] = ps;
     } else {
-      const int lt = it - 144, l0 = lt & 1, l1 = (lt >> 1) & 1, l2 = lt >> 2;
+      // phi rows: 8 rows x 3 planes q2 (one 27-term sum per row kept a single warp busy while 7 waited at the barrier);
+      // the three partial sums of a row are accumulated by radd
+      const int r = it - 144, lt = r / 3, q2 = r - 3 * lt, l0 = lt & 1, l1 = (lt >> 1) & 1, l2 = lt >> 2;
       double s = 0.0;
-      for (int q = 0; q < 27; q++) s += F[RF_DJ + q] * C.XV[0][l0][q % 3] * C.XV[1][l1][(q / 3) % 3] * C.XV[2][l2][q / 9];
-      radd(OFF_F + C.t_phi[lt], S.phi_sign * s);
+      MHD_7UNROLL
+      for (int q1 = 0; q1 < 3; q1++)
+        MHD_7UNROLL
+        for (int q0 = 0; q0 < 3; q0++) s += F[RF_DJ + q0 + 3 * q1 + 9 * q2] * C.XV[0][l0][q0] * C.XV[1][l1][q1];
+      radd(OFF_F + C.t_phi[lt], S.phi_sign * C.XV[2][l2][q2] * s);
     }
   }
 }

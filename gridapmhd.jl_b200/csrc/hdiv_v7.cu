@@ -19,7 +19,11 @@ namespace mhd {
 
 namespace {
 
-constexpr int V7_NT = 256;
+#ifndef MHD_V7_NT
+#define MHD_V7_NT 256
+#endif
+constexpr int V7_NT = MHD_V7_NT;   // threads per CTA (one cell per CTA); a multiple of 32
+constexpr int V7_NW = V7_NT / 32;  // warps
 
 struct V7Args {
   const double* coords;
@@ -52,6 +56,7 @@ constexpr size_t V7_OFF_NEXT = V7_SMEM_CELL + V7_SMEM_SMALL;
 constexpr size_t V7_OFF_CODES = V7_OFF_NEXT + sizeof(NextIds);
 constexpr size_t V7_SMEM = V7_OFF_CODES + V7_CODES * sizeof(uint16_t);
 static_assert(2 * (V7_SMEM + 64 + 1024) <= 233472, "two CTAs of the v7 kernel must fit one SM");
+static_assert(V7_NT % 32 == 0 && V7_NT >= 256 && V7_NT <= 512, "LOAD_ITEMS, the 243-item chunks and fetch_next assume 256..512 threads");
 
 // The cell-independent 1-D tables exist twice: the ones looked up with thread-dependent indices in shared memory (SmallDyn C),
 // everything in constant memory (Small7 K): a table operand whose index is known at compile time (the unrolled inner loops of
@@ -81,18 +86,17 @@ template <bool ZJ>
 V7_NI void ni_stage1_item(int item) { h7::stage1_item<ZJ>(sm_cell(), sm_small(), c_small7, item); }
 template <bool ZJ>
 __device__ __forceinline__ void ni_stage1(int tid) {  // 729 items on 256 threads: three calls, no loop (see stage1_item)
-  ni_stage1_item<ZJ>(tid);
-  ni_stage1_item<ZJ>(tid + V7_NT);
-  if (tid + 2 * V7_NT < h7::STAGE1_ITEMS) ni_stage1_item<ZJ>(tid + 2 * V7_NT);
+#pragma unroll
+  for (int r = 0; r < (h7::STAGE1_ITEMS + V7_NT - 1) / V7_NT; r++)
+    if (tid + r * V7_NT < h7::STAGE1_ITEMS) ni_stage1_item<ZJ>(tid + r * V7_NT);
 }
 template <int CONV, bool ZJ>
 V7_NI void ni_stage2_item(int item) { h7::stage2_item<CONV, ZJ>(sm_cell(), sm_small(), c_small7, item); }
 template <int CONV, bool ZJ>
 __device__ __forceinline__ void ni_stage2(int tid) {  // 1 017 items: four calls
-  ni_stage2_item<CONV, ZJ>(tid);
-  ni_stage2_item<CONV, ZJ>(tid + V7_NT);
-  ni_stage2_item<CONV, ZJ>(tid + 2 * V7_NT);
-  if (tid + 3 * V7_NT < h7::STAGE2_ITEMS) ni_stage2_item<CONV, ZJ>(tid + 3 * V7_NT);
+#pragma unroll
+  for (int r = 0; r < (h7::STAGE2_ITEMS + V7_NT - 1) / V7_NT; r++)
+    if (tid + r * V7_NT < h7::STAGE2_ITEMS) ni_stage2_item<CONV, ZJ>(tid + r * V7_NT);
 }
 // (the component / direction of a chunk is a run-time argument: ONE copy of the code -- the loop body of the kernel is several
 // times the 32 KB instruction cache and every duplicated phase shows up as no_inst stalls)
@@ -104,8 +108,9 @@ V7_NI void ni_chunk_uj_item(int item, const h7::Params& P, bool ju) {
   h7::chunk_uj_item(sm_cell(), c_small7, P, ju ? sm_cell().r1 : sm_cell().r3, item, ju);
 }
 __device__ __forceinline__ void ni_chunk_uj(int tid, const h7::Params& P, bool ju) {  // 324 items on 256 threads
-  ni_chunk_uj_item(tid, P, ju);
-  if (tid < 324 - V7_NT) ni_chunk_uj_item(tid + V7_NT, P, ju);
+#pragma unroll
+  for (int r = 0; r < (324 + V7_NT - 1) / V7_NT; r++)
+    if (tid + r * V7_NT < 324) ni_chunk_uj_item(tid + r * V7_NT, P, ju);
 }
 template <bool ZJ>
 V7_NI void ni_chunk_rest(int tid) { h7::chunk_rest<ZJ>(sm_cell(), sm_small(), tid, V7_NT, sm_buf<1>()); }
@@ -140,19 +145,39 @@ __device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const ui
   if (with_map && tid * 128 < h7::NENT * 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + tid * 128));
 }
 
+// shared-memory loads through 32-bit shared addresses (no generic-address arithmetic in the sweep loops)
+__device__ __forceinline__ unsigned lds_u16(unsigned a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 // value v of an entry goes to rowbase + 8 * code: plain store (MAP_EXCL set, not MAP_SKIP) or reduction, predicated -- no branch
 __device__ __forceinline__ void scatter_one(unsigned code, unsigned long long rowbase, double v) {
-  const unsigned long long addr = rowbase + (unsigned long long)((code & 0x7FFFu) << 3);
   asm volatile(
       "{\n\t"
       ".reg .pred pst, prd;\n\t"
-      ".reg .u32 t;\n\t"
+      ".reg .u32 t, c;\n\t"
+      ".reg .u64 a;\n\t"
+      "and.b32 c, %2, 0x7FFF;\n\t"
+      "mad.wide.u32 a, c, 8, %0;\n\t"
       "xor.b32 t, %2, 0x8000;\n\t"
       "setp.lt.u32 pst, t, 0x7FFF;\n\t"   // 0x8000 <= code < 0xFFFF
       "setp.lt.u32 prd, %2, 0x8000;\n\t"
-      "@pst st.global.f64 [%0], %1;\n\t"
-      "@prd red.global.add.f64 [%0], %1;\n\t"
-      "}" ::"l"(addr), "d"(v), "r"(code)
+      "@pst st.global.f64 [a], %1;\n\t"
+      "@prd red.global.add.f64 [a], %1;\n\t"
+      "}" ::"l"(rowbase), "d"(v), "r"(code)
       : "memory");
 }
 
@@ -163,20 +188,35 @@ __device__ __forceinline__ void scatter_one(unsigned code, unsigned long long ro
 // (bufsel: 0 = Cell7::r1, 1 = Cell7::r3 -- an index, not a pointer: a pointer PARAMETER makes every staged value a generic LD)
 V7_NI void sweep_and_fetch(int bufsel, int nseg, int row0, unsigned ncol_recip, const uint16_t* __restrict__ next, int next_nseg, int tid) {
   const int w = tid >> 5, lane = tid & 31;
-  const double* buf = bufsel ? sm_cell().r3 : sm_cell().r1;
-  const uint16_t* codes = sm_codes();
-  const long long* rowbase = sm_cell().rowaddr + row0;
-#pragma unroll 3
-  for (int i = w * 32 + lane; i < nseg * 32; i += 256)
-    scatter_one(codes[i], (unsigned long long)rowbase[((unsigned)i * ncol_recip) >> 20], buf[i]);
+  const unsigned i0 = (unsigned)(w * 32 + lane), n = (unsigned)nseg * 32u;
+  const unsigned sa_codes0 = smem_u32(sm_codes());
+  unsigned sa_c = sa_codes0 + i0 * 2u;
+  unsigned sa_b = smem_u32(bufsel ? sm_cell().r3 : sm_cell().r1) + i0 * 8u;
+  const unsigned sa_r = smem_u32(sm_cell().rowaddr + row0);
+  unsigned i = i0, q = i0 * ncol_recip;  // q >> 20 = row of entry i
+  constexpr unsigned NT = (unsigned)V7_NT;
+  const unsigned dq = NT * ncol_recip;
+  // four entries per lane and iteration: all loads first, then the four predicated store / reduction pairs
+  for (; i + 3u * NT < n; i += 4u * NT, q += 4u * dq, sa_c += 8u * NT, sa_b += 32u * NT) {
+    const unsigned c0 = lds_u16(sa_c), c1 = lds_u16(sa_c + 2u * NT), c2 = lds_u16(sa_c + 4u * NT), c3 = lds_u16(sa_c + 6u * NT);
+    const double v0 = lds_f64(sa_b), v1 = lds_f64(sa_b + 8u * NT), v2 = lds_f64(sa_b + 16u * NT), v3 = lds_f64(sa_b + 24u * NT);
+    const unsigned long long r0 = lds_u64(sa_r + ((q >> 20) << 3)), r1 = lds_u64(sa_r + (((q + dq) >> 20) << 3)),
+                             r2 = lds_u64(sa_r + (((q + 2u * dq) >> 20) << 3)), r3 = lds_u64(sa_r + (((q + 3u * dq) >> 20) << 3));
+    scatter_one(c0, r0, v0);
+    scatter_one(c1, r1, v1);
+    scatter_one(c2, r2, v2);
+    scatter_one(c3, r3, v3);
+  }
+  for (; i < n; i += NT, q += dq, sa_c += 2u * NT, sa_b += 8u * NT)
+    scatter_one(lds_u16(sa_c), lds_u64(sa_r + ((q >> 20) << 3)), lds_f64(sa_b));
   __syncwarp();
-  // lane l copies 16 bytes of segment w + 8 (l / 4) (+ 64 per round): one instruction moves eight of the warp's segments
-  int seg = w + 8 * (lane >> 2);
+  // lane l copies 16 bytes of segment w + NW (l / 4) (+ 8 NW per round): one instruction moves eight of the warp's segments
+  int seg = w + V7_NW * (lane >> 2);
   const int off = seg * 64 + (lane & 3) * 16;
-  unsigned dst = (unsigned)__cvta_generic_to_shared(sm_codes()) + (unsigned)off;
+  unsigned dst = sa_codes0 + (unsigned)off;
   const char* src = reinterpret_cast<const char*>(next) + off;
 #pragma unroll 1
-  for (; seg < next_nseg; seg += 64, dst += 4096, src += 4096)
+  for (; seg < next_nseg; seg += 8 * V7_NW, dst += 512 * V7_NW, src += 512 * V7_NW)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -192,7 +232,7 @@ V7_NI void sweep_rest(int tid) {
   const uint16_t* codes = sm_codes();
   const long long* rowbase = sm_cell().rowaddr;
 #pragma unroll 2
-  for (int seg = w; seg < NSEG; seg += 8) {
+  for (int seg = w; seg < NSEG; seg += V7_NW) {
     const int i = seg * 32 + lane;
     int row;
     if (i < R_JF) row = OFF_J + i / 36;

@@ -172,31 +172,23 @@ spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, c
   __shared__ unsigned cta_arrived;
   if (threadIdx.x == 0) cta_arrived = 0u;
   __syncthreads();
+  const long long* __restrict__ ghost_lo = H->rowptr_tagged;
   for (int64_t row = warp0; row < nr; row += nwarps) {
-    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    const int64_t lo = rowptr[row], hi = rowptr[row + 1], gl = ghost_lo[row];
     double s0 = 0.0, s1 = 0.0;
-    // Pass 1, branch-free and identical to the single-GPU kernel: the LOCAL columns through the read-only path; ghost
-    // columns (sorted last in every row) contribute nothing here, the lanes only remember where the first one sits.
-    int64_t first_ghost = hi;
-    for (int64_t base = lo; base < hi; base += 64) {
+    // Pass 1 = the single-GPU kernel on the LOCAL columns [lo, gl) (read-only path, no votes, no selects): ghost columns are
+    // sorted last in every row and their start is known from the symbolic phase.
+    for (int64_t base = lo; base < gl; base += 64) {
       const int64_t p0 = base + lane, p1 = p0 + 32;
-      const bool ok0 = p0 < hi, ok1 = p1 < hi;
+      const bool ok0 = p0 < gl, ok1 = p1 < gl;
       const int32_t c0 = ok0 ? __ldg(colval + p0) : 0, c1 = ok1 ? __ldg(colval + p1) : 0;
       const double v0 = ok0 ? __ldg(nzval + p0) : 0.0, v1 = ok1 ? __ldg(nzval + p1) : 0.0;
-      const bool g0 = c0 >= nrows, g1 = c1 >= nrows;
-      if (g0 && p0 < first_ghost) first_ghost = p0;
-      if (g1 && p1 < first_ghost) first_ghost = p1;
-      s0 = fma(g0 ? 0.0 : v0, __ldg(x + (g0 ? 0 : c0)), s0);
-      s1 = fma(g1 ? 0.0 : v1, __ldg(x + (g1 ? 0 : c1)), s1);
+      s0 = fma(v0, __ldg(x + c0), s0);
+      s1 = fma(v1, __ldg(x + c1), s1);
     }
     // Pass 2, interface rows only (a few per cent): wait once for the neighbours, then add the ghost tail of the row through
     // the coherent path (ld.relaxed.sys) -- these values were written by peer GPUs during this kernel.
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int64_t other = __shfl_xor_sync(0xffffffffu, first_ghost, o);
-      first_ghost = other < first_ghost ? other : first_ghost;
-    }
-    if (first_ghost < hi) {
+    if (gl < hi) {
       if (!arrived) {
         if (lane == 0 && ld_acquire_cta_shared(&cta_arrived) == 0u) {
           for (int k = 0; k < nn; k++) {
@@ -215,7 +207,7 @@ spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, c
         __syncwarp();
         arrived = true;
       }
-      for (int64_t p = first_ghost + lane; p < hi; p += 32) s0 = fma(__ldg(nzval + p), ld_relaxed_sys_f64(xg + __ldg(colval + p)), s0);
+      for (int64_t p = gl + lane; p < hi; p += 32) s0 = fma(__ldg(nzval + p), ld_relaxed_sys_f64(xg + __ldg(colval + p)), s0);
     }
     double s = s0 + s1;
 #pragma unroll
