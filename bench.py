@@ -446,6 +446,10 @@ def run_ours(args):
     ms_spmv = timed(lambda: op.spmv(v_dev, y_dev), max(args.steps, 20), max(args.warmup, 3))
     spmv_ms, spmv_n = L.profile_get("spmv")
     L.load().mhd_profile_enable(0)
+    if os.environ.get("MHD_HALO_DEBUG") and world > 1:  # spin / interface statistics of the fused exchange (stderr)
+        import ctypes as C
+        fused, tmo = C.c_int32(0), C.c_int32(0)
+        L.check(L.load().mhd_operator_halo_status(op.handle, C.byref(fused), C.byref(tmo)))
     # Krylov leg (single GPU): one FGMRES(15) cycle of the reference's configuration (badia2024.jl:40: m = maxiter = 15) on
     # the assembled matrix, enqueued as a whole on the stream (SpMV, fused CGS2 Gram-Schmidt, Givens on the device; the
     # host reads the scalars once per cycle).  Point-Jacobi preconditioner: the block preconditioner's (u,j) solve is

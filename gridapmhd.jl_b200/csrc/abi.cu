@@ -410,6 +410,7 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->halo.d_dev);
   cudaFree(op->halo.d_ghost_src);
   cudaFree(op->halo.d_row_bits);
+  cudaFree(op->halo.d_if_rows);
   cudaFree(op->halo.d_err);
   cudaFree(op->halo.d_send_idx);
   cudaFree(op->halo.d_recv_idx);

@@ -235,11 +235,11 @@ int mhd_operator_halo_ipc_connect(mhd_operator_t* op, const void* handles, const
   MHD_TRY(dev_alloc(&d_push_neigh, (int64_t)push_neigh.size()));
   MHD_TRY(dev_alloc(&d_push_begin, (int64_t)push_begin.size()));
   MHD_TRY(dev_alloc(&h.d_ghost_src, h.nsend));
-  MHD_TRY(dev_alloc(&h.d_err, 1));
+  MHD_TRY(dev_alloc(&h.d_err, 8));  // [0] time-out flag, [1..4] MHD_HALO_DEBUG statistics
   MHD_TRY(h2d(d_push_neigh, push_neigh.data(), (int64_t)push_neigh.size()));
   MHD_TRY(h2d(d_push_begin, push_begin.data(), (int64_t)push_begin.size()));
   MHD_TRY(h2d(h.d_ghost_src, send_dst, h.nsend));
-  MHD_CUDA(cudaMemsetAsync(h.d_err, 0, sizeof(int), g_stream));
+  MHD_CUDA(cudaMemsetAsync(h.d_err, 0, 8 * sizeof(int), g_stream));
   hd.send_idx = h.d_send_idx;
   hd.push_neigh = d_push_neigh;
   hd.push_begin = d_push_begin;
@@ -250,8 +250,27 @@ int mhd_operator_halo_ipc_connect(mhd_operator_t* op, const void* handles, const
   MHD_TRY(dev_alloc(&h.d_row_bits, op->nrows + 1));
   tag_ghost_rows<<<(unsigned)((op->nrows + 256) / 256), 256, 0, g_stream>>>(op->nrows, op->d_rowptr, op->d_colval, h.d_row_bits);
   MHD_LAUNCH_CHECK();
+  {  // interface rows = rows with a non-empty ghost tail (setup-time host pass)
+    std::vector<long long> gl((size_t)op->nrows + 1), rp((size_t)op->nrows + 1);
+    MHD_CUDA(cudaMemcpyAsync(gl.data(), h.d_row_bits, gl.size() * sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+    MHD_CUDA(cudaMemcpyAsync(rp.data(), op->d_rowptr, rp.size() * sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+    MHD_CUDA(cudaStreamSynchronize(g_stream));
+    std::vector<int32_t> ifr;
+    for (int64_t r = 0; r < op->nrows; r++)
+      if (gl[(size_t)r] < rp[(size_t)r + 1]) ifr.push_back((int32_t)r);
+    cudaFree(h.d_if_rows);
+    h.d_if_rows = nullptr;
+    h.n_if_rows = (int64_t)ifr.size();
+    if (h.n_if_rows > 0) {
+      MHD_TRY(dev_alloc(&h.d_if_rows, h.n_if_rows));
+      MHD_TRY(h2d(h.d_if_rows, ifr.data(), h.n_if_rows));
+    }
+  }
   hd.send_dst = h.d_ghost_src;
   hd.rowptr_tagged = h.d_row_bits;
+  h.inbox[0] = hd.my_inbox[0];
+  h.inbox[1] = hd.my_inbox[1];
+  h.flags = hd.my_flags;
   hd.err = h.d_err;
   MHD_TRY(dev_alloc(&h.d_dev, 1));
   MHD_CUDA(cudaMemcpyAsync(h.d_dev, &hd, sizeof(HaloDev), cudaMemcpyHostToDevice, g_stream));
@@ -267,9 +286,12 @@ int mhd_operator_halo_status(mhd_operator_t* op, int32_t* fused, int32_t* timed_
   if (timed_out) {
     *timed_out = 0;
     if (op->halo.d_err) {
-      int e = 0;
-      MHD_CUDA(cudaMemcpy(&e, op->halo.d_err, sizeof(int), cudaMemcpyDeviceToHost));
-      *timed_out = e;
+      int e[8];
+      MHD_CUDA(cudaMemcpy(e, op->halo.d_err, sizeof(e), cudaMemcpyDeviceToHost));
+      *timed_out = e[0];
+      if (getenv("MHD_HALO_DEBUG"))
+        fprintf(stderr, "[mhd halo rank %d] products %u  max spin clocks %d  waiting CTAs (all products) %d  interface rows %lld  max push-CTA clocks %d\n", g_rank,
+                op->halo.epoch, e[1], e[2], (long long)op->halo.n_if_rows, e[5]);
     }
   }
   return MHD_OK;

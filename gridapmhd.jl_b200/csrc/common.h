@@ -99,7 +99,11 @@ struct Halo {
   struct HaloDev* d_dev = nullptr;      // device copy of the plan
   int32_t* d_ghost_src = nullptr;       // [nsend] destination ghost slots on the neighbours (send_dst)
   long long* d_row_bits = nullptr;      // [nrows+1] position of the first ghost column of every row (== end of the row if it has none)
+  int32_t* d_if_rows = nullptr;         // [n_if_rows] interface rows (rows with at least one ghost column), ascending
+  int64_t n_if_rows = 0;
   int* d_err = nullptr;
+  const double* inbox[2] = {nullptr, nullptr};  // this rank's inboxes and arrival counters (inside ipc_mem): kernel parameters
+  const unsigned* flags = nullptr;
   unsigned epoch = 0;
 };
 

@@ -39,6 +39,33 @@ int ensure_red(mhd_operator* op, int64_t n) {
 // x gathered through the read-only path (x is tiny next to A and stays L2 resident).
 constexpr int SPMV_WARPS = 8;
 
+// sum over the entries [lo, hi) of one row, this lane's share: U x 32 entries in flight per warp, all (col,val) loads issued
+// before the dependent x gathers (unpredicated main loop + tail: predicated loads made ptxas serialise col -> x -> fma)
+template <int U>
+__device__ __forceinline__ double warp_row_partial(const int32_t* __restrict__ colval, const double* __restrict__ nzval,
+                                                   const double* __restrict__ x, int64_t lo, int64_t hi, int lane) {
+  double s[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) s[u] = 0.0;
+  int64_t p = lo + lane;
+  for (; p + 32 * (U - 1) < hi; p += 32 * U) {
+    int32_t c[U];
+    double v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      c[u] = __ldg(colval + p + 32 * u);
+      v[u] = __ldg(nzval + p + 32 * u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) s[u] = fma(v[u], __ldg(x + c[u]), s[u]);
+  }
+  for (; p < hi; p += 32) s[0] = fma(__ldg(nzval + p), __ldg(x + __ldg(colval + p)), s[0]);
+  double t = s[0];
+#pragma unroll
+  for (int u = 1; u < U; u++) t += s[u];
+  return t;
+}
+
 template <int U>
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
 spmv_warp_row(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
@@ -47,27 +74,7 @@ spmv_warp_row(int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* 
   const int64_t warp0 = (int64_t)blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * SPMV_WARPS;
   for (int64_t row = warp0; row < nrows; row += nwarps) {
-    const int64_t lo = rowptr[row], hi = rowptr[row + 1];
-    double s[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) s[u] = 0.0;
-    int64_t p = lo + lane;
-    // U x 32 entries in flight per warp: all (col,val) loads are issued before the dependent x gathers
-    for (; p + 32 * (U - 1) < hi; p += 32 * U) {
-      int32_t c[U];
-      double v[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        c[u] = __ldg(colval + p + 32 * u);
-        v[u] = __ldg(nzval + p + 32 * u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) s[u] = fma(v[u], __ldg(x + c[u]), s[u]);
-    }
-    for (; p < hi; p += 32) s[0] = fma(__ldg(nzval + p), __ldg(x + __ldg(colval + p)), s[0]);
-    double t = s[0];
-#pragma unroll
-    for (int u = 1; u < U; u++) t += s[u];
+    double t = warp_row_partial<U>(colval, nzval, x, rowptr[row], rowptr[row + 1], lane);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
     if (lane == 0) y[row] = t;
@@ -101,19 +108,19 @@ int launch_spmv(mhd_operator* op, const double* d_x, double* d_y) {
 }
 
 // ---------------------------------------------------------------- fused SpMV + ghost exchange over NVLink peer memory
-// ONE kernel per product (replaces pack -> ncclSend/ncclRecv -> unpack -> SpMV):
-//   * the first `npush` CTAs store this rank's interface values straight into the neighbours' inboxes (peer-mapped
-//     memory, st.global over NVLink), fence, and bump an arrival counter inside the neighbour's memory;
-//   * all other CTAs run the warp-per-row SpMV.  Columns are sorted and ghost ids come last, so a row is computed from
-//     local x first and touches the inbox only at its tail; a warp waits (once) for the neighbours' counters when it
-//     meets its first ghost column.  Interior rows never wait: the exchange is overlapped with the bulk of the product.
+// Replaces pack -> ncclSend/ncclRecv -> unpack -> SpMV by two launches per product:
+//   * product kernel: the first `npush` CTAs store this rank's interface values straight into the neighbours' inboxes (peer-mapped
+//     memory, st.global over NVLink), fence, and bump an arrival counter inside the neighbour's memory; all other CTAs run the
+//     warp-per-row product on the LOCAL columns.  Columns are sorted and ghost ids come last, so that is a prefix of every row
+//     and the whole exchange is overlapped with it;
+//   * tail kernel (interface rows only): waits for the neighbours' counters and adds the ghost entries of those rows.
 //   Inboxes are double-buffered by the parity of the product count and the counters are monotone (target = expected
 //   CTAs x use count), so nothing is ever reset and a fast neighbour cannot overwrite data still being read.
 // Memory model of the exchange (PTX ISA "memory consistency model"): the pusher's value stores, fence.sc.sys
-// (__threadfence_system) and relaxed system-scope atomic on the counter form a release pattern; the consumer polls the counter
-// with ld.relaxed.sys and, once it has seen the target, performs ONE ld.acquire.sys -- an acquire pattern that synchronises with
-// the release, so every later load of the warp (ordered behind lane 0 by __syncwarp) observes the pushed values.  The ghost
-// values themselves are read with ld.relaxed.sys (coherent, served by L2): the non-coherent path (__ldg / ld.global.nc) is
+// (__threadfence_system) and relaxed system-scope atomic on the counter form a release pattern; thread 0 of a tail CTA polls the
+// counter with ld.relaxed.sys and, once it has seen the target, performs ONE ld.acquire.sys -- an acquire pattern that synchronises
+// with the release; the CTA barrier behind it orders every other thread of the CTA after that acquire (causality order).  The
+// ghost values themselves are read with ld.relaxed.sys (coherent, served by L2): the non-coherent path (__ldg / ld.global.nc) is
 // only legal for data no one writes during the kernel, which is true for x and the matrix but not for the inbox.
 __device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
   unsigned v;
@@ -125,94 +132,92 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// CTA-scope hand-over of "the neighbours' values have arrived": the first warp of a CTA that meets a ghost column performs the
-// system-scope acquire (which costs an L1 invalidation on the SM -- 12 % of the product when every warp did it) and releases a
-// shared flag; the other warps of the CTA acquire that flag at CTA scope and are ordered behind it by causality.
-__device__ __forceinline__ unsigned ld_acquire_cta_shared(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_cta_shared(unsigned* p, unsigned v) {
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
 __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   double v;
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
+// The exchange lives in three out-of-line functions so that the row loop of the kernel below compiles to the same code as the
+// single-GPU product (inlined, their live values cost the loop its load batching: ptxas serialised col -> x -> fma, +40..100 %).
+__device__ __noinline__ void halo_push_cta(const HaloDev* __restrict__ H, const double* __restrict__ x, int parity, bool dbg) {
+  const long long tp0 = dbg ? clock64() : 0;
+  const int k = H->push_neigh[blockIdx.x];
+  const int64_t b0 = H->push_begin[blockIdx.x];
+  const int64_t kend = H->send_begin[k + 1];
+  const int64_t b1 = b0 + HALO_CHUNK < kend ? b0 + HALO_CHUNK : kend;
+  double* dst = H->peer_inbox[parity][k];
+  // each value goes straight to its final ghost slot of the neighbour (send_dst = ghost id - nrows over there)
+  for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[H->send_dst[i]] = x[H->send_idx[i]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd_system(H->peer_flag[parity][k], 1u);
+  if (dbg && threadIdx.x == 0) atomicMax(H->err + 5, (int)(clock64() - tp0));
+}
+
+// thread 0 of a tail CTA: wait for every neighbour's counter, then acquire
+__device__ __noinline__ void halo_wait(const HaloDev* __restrict__ H, const unsigned* fl, int nn, unsigned round, bool dbg) {
+  const long long t0 = dbg ? clock64() : 0;
+  for (int k = 0; k < nn; k++) {
+    const unsigned target = H->expected[k] * round;
+    unsigned spins = 0;
+    while (ld_relaxed_sys_u32(fl + k) < target) {
+      if (++spins > (1u << 28)) {  // never hang the GPU: flag the error (the host turns it into MHD_E_COMM) and go on
+        atomicExch(H->err, 1);
+        break;
+      }
+    }
+    (void)ld_acquire_sys_u32(fl + k);  // synchronises with the pusher's fence + atomic: its values are visible from here on
+  }
+  if (dbg) {
+    atomicMax(H->err + 1, (int)(clock64() - t0));
+    atomicAdd(H->err + 2, 1);
+  }
+}
+
+// Product kernel: the first `npush` CTAs push; all others are the single-GPU product restricted to the LOCAL columns of each row
+// (columns are sorted and ghost ids come last, their start ghost_lo[row] is known from the symbolic phase).  No wait code in here:
+// with it inlined ptxas either serialised the loads of the row loop (32 registers) or lost occupancy (40 registers, +20 %).
 __global__ void __launch_bounds__(SPMV_WARPS * 32)
-spmv_fused_halo(int64_t nr, int64_t nrows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colval,
+spmv_fused_halo(int64_t nr, const int64_t* __restrict__ rowptr, const long long* __restrict__ ghost_lo, const int32_t* __restrict__ colval,
                 const double* __restrict__ nzval, const double* __restrict__ x, double* __restrict__ y,
-                const HaloDev* __restrict__ H, int parity, unsigned round, int nowait) {
-  const int npush = H->npush;
+                const HaloDev* __restrict__ H, int parity, int npush, int dbg) {
   if ((int)blockIdx.x < npush) {
-    // ---- push CTA: one chunk of the send list of one neighbour
-    const int k = H->push_neigh[blockIdx.x];
-    const int64_t b0 = H->push_begin[blockIdx.x];
-    const int64_t kend = H->send_begin[k + 1];
-    const int64_t b1 = b0 + HALO_CHUNK < kend ? b0 + HALO_CHUNK : kend;
-    double* dst = H->peer_inbox[parity][k];
-    // each value goes straight to its final ghost slot of the neighbour (send_dst = ghost id - nrows over there)
-    for (int64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[H->send_dst[i]] = x[H->send_idx[i]];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd_system(H->peer_flag[parity][k], 1u);
+    halo_push_cta(H, x, parity, dbg != 0);  // one chunk of the send list of one neighbour
     return;
   }
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)(blockIdx.x - npush) * SPMV_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)(gridDim.x - npush) * SPMV_WARPS;
-  // ghost column c lives at inbox[c - nrows]: one pointer select, one load, no branch in the gather
-  const double* xg = H->my_inbox[parity] - nrows;
-  const unsigned* fl = H->my_flags + parity * HALO_MAX_NEIGH;
-  const int nn = nowait ? 0 : H->nneigh;
-  bool arrived = false;
-  __shared__ unsigned cta_arrived;
-  if (threadIdx.x == 0) cta_arrived = 0u;
-  __syncthreads();
-  const long long* __restrict__ ghost_lo = H->rowptr_tagged;
   for (int64_t row = warp0; row < nr; row += nwarps) {
-    const int64_t lo = rowptr[row], hi = rowptr[row + 1], gl = ghost_lo[row];
-    double s0 = 0.0, s1 = 0.0;
-    // Pass 1 = the single-GPU kernel on the LOCAL columns [lo, gl) (read-only path, no votes, no selects): ghost columns are
-    // sorted last in every row and their start is known from the symbolic phase.
-    for (int64_t base = lo; base < gl; base += 64) {
-      const int64_t p0 = base + lane, p1 = p0 + 32;
-      const bool ok0 = p0 < gl, ok1 = p1 < gl;
-      const int32_t c0 = ok0 ? __ldg(colval + p0) : 0, c1 = ok1 ? __ldg(colval + p1) : 0;
-      const double v0 = ok0 ? __ldg(nzval + p0) : 0.0, v1 = ok1 ? __ldg(nzval + p1) : 0.0;
-      s0 = fma(v0, __ldg(x + c0), s0);
-      s1 = fma(v1, __ldg(x + c1), s1);
-    }
-    // Pass 2, interface rows only (a few per cent): wait once for the neighbours, then add the ghost tail of the row through
-    // the coherent path (ld.relaxed.sys) -- these values were written by peer GPUs during this kernel.
-    if (gl < hi) {
-      if (!arrived) {
-        if (lane == 0 && ld_acquire_cta_shared(&cta_arrived) == 0u) {
-          for (int k = 0; k < nn; k++) {
-            const unsigned target = H->expected[k] * round;
-            unsigned spins = 0;
-            while (ld_relaxed_sys_u32(fl + k) < target) {
-              if (++spins > (1u << 28)) {  // never hang the GPU: flag the error (the host turns it into MHD_E_COMM) and go on
-                atomicExch(H->err, 1);
-                break;
-              }
-            }
-            (void)ld_acquire_sys_u32(fl + k);  // synchronises with the pusher's fence + atomic: its values are visible from here on
-          }
-          st_release_cta_shared(&cta_arrived, 1u);
-        }
-        __syncwarp();
-        arrived = true;
-      }
-      for (int64_t p = gl + lane; p < hi; p += 32) s0 = fma(__ldg(nzval + p), ld_relaxed_sys_f64(xg + __ldg(colval + p)), s0);
-    }
-    double s = s0 + s1;
+    double t = warp_row_partial<2>(colval, nzval, x, rowptr[row], ghost_lo[row], lane);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) y[row] = t;
+  }
+}
+
+// Tail kernel, interface rows only (a few per cent of the rows, launched right behind the product kernel): wait for the
+// neighbours' counters -- normally long there, their push CTAs ran at the START of the neighbours' product kernels -- and add
+// the ghost entries [ghost_lo, row end) through the coherent path (ld.relaxed.sys; values written by peer GPUs).
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
+spmv_ghost_tail(int64_t nif, int64_t nr, const int32_t* __restrict__ if_rows, int64_t nrows, const int64_t* __restrict__ rowptr,
+                const long long* __restrict__ ghost_lo, const int32_t* __restrict__ colval, const double* __restrict__ nzval,
+                double* __restrict__ y, const HaloDev* __restrict__ H, const double* inbox, const unsigned* flags, int nn,
+                unsigned round, int dbg) {
+  if (threadIdx.x == 0) halo_wait(H, flags, nn, round, dbg != 0);
+  __syncthreads();  // CTA-scope hand-over of thread 0's system-scope acquire (causality order)
+  const int lane = threadIdx.x & 31;
+  const double* xg = inbox - nrows;  // ghost column c lives at inbox[c - nrows]
+  for (int64_t i = (int64_t)blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5); i < nif; i += (int64_t)gridDim.x * SPMV_WARPS) {
+    const int64_t row = if_rows[i];
+    if (row >= nr) continue;  // block-row products (nr < nrows)
+    double s = 0.0;
+    for (int64_t p = ghost_lo[row] + lane, hi = rowptr[row + 1]; p < hi; p += 32)
+      s = fma(__ldg(nzval + p), ld_relaxed_sys_f64(xg + __ldg(colval + p)), s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[row] = s;
+    if (lane == 0) y[row] += s;
   }
 }
 
@@ -258,10 +263,18 @@ int spmv_with_halo(mhd_operator* op, int64_t nr, double* d_x, double* d_y) {
     const int parity = (int)(h.epoch & 1u);
     const unsigned round = h.epoch / 2u + 1u;
     h.epoch++;
+    const int dbg = getenv("MHD_HALO_DEBUG") ? 1 : 0;
     prof_begin(PROF_SPMV);
-    spmv_fused_halo<<<(unsigned)(blocks + npush), SPMV_WARPS * 32, 0, g_stream>>>(nr, op->nrows, op->d_rowptr, op->d_colval,
-                                                                                  op->d_nzval, d_x, d_y, h.d_dev, parity, round,
-                                                                                  getenv("MHD_FUSED_NOWAIT") ? 1 : 0);
+    spmv_fused_halo<<<(unsigned)(blocks + npush), SPMV_WARPS * 32, 0, g_stream>>>(nr, op->d_rowptr, h.d_row_bits, op->d_colval, op->d_nzval,
+                                                                                  d_x, d_y, h.d_dev, parity, npush, dbg);
+    if (h.n_if_rows > 0) {
+      int64_t tb = (h.n_if_rows + SPMV_WARPS - 1) / SPMV_WARPS;
+      if (tb > (int64_t)sms() * 8) tb = (int64_t)sms() * 8;
+      spmv_ghost_tail<<<(unsigned)tb, SPMV_WARPS * 32, 0, g_stream>>>(h.n_if_rows, nr, h.d_if_rows, op->nrows, op->d_rowptr, h.d_row_bits,
+                                                                      op->d_colval, op->d_nzval, d_y, h.d_dev, h.inbox[parity],
+                                                                      h.flags + parity * HALO_MAX_NEIGH,
+                                                                      getenv("MHD_FUSED_NOWAIT") ? 0 : h.nneigh, round, dbg);
+    }
     prof_end(PROF_SPMV);
     MHD_LAUNCH_CHECK();
     return 0;
