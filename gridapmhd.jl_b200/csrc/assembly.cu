@@ -401,7 +401,7 @@ __device__ __forceinline__ void cell_prep(CellCtx& cx, int64_t cell, int64_t nex
       for (int i = 0; i < 3; i++) {
         const double xv = sm[S_X + v * 3 + i];
 #pragma unroll
-        for (int k = 0; k < 3; k++) J[i][k] = fma(xv, gk[k], J[i][k]);
+        for (int k = 0; k < 3; k++) J[i][k] = __dadd_rn(__dmul_rn(xv, gk[k]), J[i][k]);  // rounded like the reference: hdiv7_cell.h
       }
     }
     const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];

@@ -20,6 +20,14 @@
 #define MHD_UNROLL
 #endif
 
+// product and sum rounded separately, like the reference (see hdiv7_cell.h): the Jacobian-matrix sum cancels |X| / h digits
+#ifndef MHD_MULADD_REF
+#ifdef __CUDA_ARCH__
+#define MHD_MULADD_REF(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#else
+#define MHD_MULADD_REF(a, b, c) ((a) * (b) + (c))
+#endif
+#endif
 namespace mhd {
 namespace h1 {
 
@@ -123,7 +131,7 @@ MHD_HD void phase_geometry(Shared& S, int tid, int nt, const double* tab) {
     for (int i = 0; i < 9; i++) J[i] = 0.0;
     for (int v = 0; v < 8; v++)
       for (int i = 0; i < 3; i++)
-        for (int k = 0; k < 3; k++) J[i * 3 + k] += S.X[v * 3 + i] * tab[T_GG + (q * 8 + v) * 3 + k];
+        for (int k = 0; k < 3; k++) J[i * 3 + k] = MHD_MULADD_REF(S.X[v * 3 + i], tab[T_GG + (q * 8 + v) * 3 + k], J[i * 3 + k]);
     const double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
     const double det = J[0] * c00 + J[1] * c01 + J[2] * c02;
     const double id = 1.0 / det;

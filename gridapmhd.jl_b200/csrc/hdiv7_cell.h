@@ -20,6 +20,15 @@
 
 #include "hdiv7_tables.h"
 
+// d x / d xi = sum_v X_v (x) grad N_v cancels |X| / h leading digits (1e4 on the boundary-layer cells of the Hunt meshes), so
+// its ROUNDING decides the 13th digit of every matrix entry.  The reference rounds the product and the sum separately (Julia
+// never contracts a * b + c on its own; oracle/mhd_oracle.py does the same): do that here too instead of the FMA nvcc would
+// emit -- with the FMA the device sits 3e-13 (cfg2) .. 1.1e-12 (256 x 128 mesh) from the oracle, without it 4e-14.
+#ifdef __CUDA_ARCH__
+#define MHD_MULADD_REF(a, b, c) __dadd_rn(__dmul_rn((a), (b)), (c))
+#else
+#define MHD_MULADD_REF(a, b, c) ((a) * (b) + (c))
+#endif
 #ifdef __CUDACC__
 #define MHD_7HD __host__ __device__ __forceinline__
 #define MHD_7UNROLL _Pragma("unroll")
@@ -229,7 +238,7 @@ MHD_7HD void phase_geom_a(Cell7& S, const SmallDyn& C, int tid, int nt, const do
       const int q = it / 9, i = (it / 3) % 3, k = it % 3;
       double s = 0.0;
       MHD_7UNROLL
-      for (int v = 0; v < 8; v++) s += S.X[v * 3 + i] * gg[q * 24 + v * 3 + k];
+      for (int v = 0; v < 8; v++) s = MHD_MULADD_REF(S.X[v * 3 + i], gg[q * 24 + v * 3 + k], s);
       S.J[q][i * 3 + k] = s;
     } else {
       // A1[var][c][q0 + 3 a12] = sum_a0 (var ? LD : LV)[0][a0][q0] ut[c][a0 + 3 a12]

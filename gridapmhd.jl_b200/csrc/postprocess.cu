@@ -96,7 +96,7 @@ hunt_norms_kernel(int64_t ncells, int nq, const double* __restrict__ w, const do
     double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int v = 0; v < 8; v++)
       for (int i = 0; i < 3; i++)
-        for (int k = 0; k < 3; k++) J[i][k] = fma(X[v * 3 + i], geo_grad[(q * 8 + v) * 3 + k], J[i][k]);
+        for (int k = 0; k < 3; k++) J[i][k] = __dadd_rn(__dmul_rn(X[v * 3 + i], geo_grad[(q * 8 + v) * 3 + k]), J[i][k]);  // see hdiv7_cell.h
     const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
                  c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
     const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, id = 1.0 / det;

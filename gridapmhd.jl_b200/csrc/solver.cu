@@ -503,7 +503,7 @@ k_h1h1_mass_inverse_p(int64_t ncells, const double* __restrict__ tab, const doub
     double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int v = 0; v < 8; v++)
       for (int i = 0; i < 3; i++)
-        for (int k = 0; k < 3; k++) J[i][k] += X[v][i] * tab[h1::T_GG + (q * 8 + v) * 3 + k];
+        for (int k = 0; k < 3; k++) J[i][k] = __dadd_rn(__dmul_rn(X[v][i], tab[h1::T_GG + (q * 8 + v) * 3 + k]), J[i][k]);  // see hdiv7_cell.h
     const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
                        J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
     const double w = tab[h1::T_W + q] * fabs(det);

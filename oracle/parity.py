@@ -89,10 +89,19 @@ def assembly_parity(fes, prm, x_lib, rowptr, colval, nzval, r_lib, nrows, nowned
     bitexact = bool(len(rd) == len(ro) and np.array_equal(rd, ro) and np.array_equal(cd, co_))
     scale = float(np.abs(vo).max()) if len(vo) else 1.0
     jac_rel = float(np.abs(vd - vo).max() / scale) if bitexact and len(vo) else float("inf")
+    worst = None
+    if bitexact and len(vo):  # where the largest deviation sits (field block of the entry, both values): diagnostics only
+        k = int(np.abs(vd - vo).argmax())
+        inv = np.empty(len(lof), dtype=np.int64)
+        inv[lof] = np.arange(len(lof))
+        names = list(fes.offsets.keys())
+        offs = np.array([fes.offsets[f] for f in names])
+        fld = lambda g: names[int(np.searchsorted(offs, g, side="right") - 1)]
+        worst = {"row_field": fld(inv[ro[k]]), "col_field": fld(inv[co_[k]]), "device": float(vd[k]), "oracle": float(vo[k]), "scale": scale}
     rr = np.asarray(r_lib)[rows_lib]
     res_rel = float(np.abs(rr - r[rows_fes]).max() / np.abs(r[rows_fes]).max()) if len(rows_fes) else float("inf")
     return {"jac_rel": jac_rel, "res_rel": res_rel, "csr_bitexact": bitexact, "rows_checked": int(len(rows_fes)),
-            "entries_checked": int(len(vo)), "cells": int(len(cells))}
+            "entries_checked": int(len(vo)), "cells": int(len(cells)), "worst_entry": worst}
 
 
 def spmv_parity(rowptr, colval, nzval, v_lib, y_dev):
