@@ -1255,7 +1255,7 @@ static cudaStream_t s_clear_stream = nullptr;
 static cudaEvent_t s_ev_in = nullptr, s_ev_done = nullptr;
 static int s_clear_device = -1;
 
-int begin_clear(mhd_operator* op, double* d_r) {
+int begin_clear(mhd_operator* op, double* d_r, bool matrix) {
   if (s_clear_device != g_device) {  // (re)created per mhd_init
     MHD_CUDA(cudaStreamCreateWithFlags(&s_clear_stream, cudaStreamNonBlocking));
     MHD_CUDA(cudaEventCreateWithFlags(&s_ev_in, cudaEventDisableTiming));
@@ -1264,10 +1264,18 @@ int begin_clear(mhd_operator* op, double* d_r) {
   }
   MHD_CUDA(cudaEventRecord(s_ev_in, g_stream));
   MHD_CUDA(cudaStreamWaitEvent(s_clear_stream, s_ev_in, 0));
-  MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), s_clear_stream));
+  if (matrix) {
+    if (op->jac_version == 7) MHD_TRY(v7_zero_shared(op, s_clear_stream));  // only the sectors that hold shared nnz
+    else MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), s_clear_stream));
+  }
   if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), s_clear_stream));
   MHD_CUDA(cudaEventRecord(s_ev_done, s_clear_stream));
   op->clear_pending = true;
+  return 0;
+}
+
+int end_clear() {  // the compute stream waits for the clearing started by begin_clear
+  MHD_CUDA(cudaStreamWaitEvent(g_stream, s_ev_done, 0));
   return 0;
 }
 
@@ -1284,7 +1292,7 @@ void assembly_finalize() {
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
   if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r));
   op->clear_pending = false;
-  MHD_CUDA(cudaStreamWaitEvent(g_stream, s_ev_done, 0));
+  MHD_TRY(end_clear());
   KParams P = make_kparams(op->prm);
   P.cell_solid = op->d_cell_solid;
   P.cell_sigma = op->d_cell_sigma;

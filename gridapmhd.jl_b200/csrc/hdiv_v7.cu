@@ -463,11 +463,11 @@ int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib) {
   return 0;
 }
 
-int v7_zero_shared(mhd_operator* op) {
+int v7_zero_shared(mhd_operator* op, cudaStream_t stream) {
   const int64_t nsectors = (op->nnz + 3) / 4;
   const int64_t want = (nsectors + 255) / 256;
   const int64_t cap = (int64_t)sm_count7() * 64;
-  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, g_stream>>>(nsectors, op->d_shared_mask, op->d_nzval, op->nnz);
+  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(nsectors, op->d_shared_mask, op->d_nzval, op->nnz);
   MHD_LAUNCH_CHECK();
   return 0;
 }
@@ -477,7 +477,11 @@ int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode) {
   MHD_CHECK(op->jac_version == 7 && op->d_tab7 != nullptr && (mode == 2 || op->d_shared_mask != nullptr), MHD_E_STATE,
             "v7 kernel is not enabled on this operator");
   if (mode == 0) d_r = nullptr;
-  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), g_stream));
+  // clearing (shared sectors of nzval, the residual) runs on the side stream of begin_clear: when the caller passes host vectors
+  // it was started BEFORE the copy of the state was enqueued and overlaps it (abi.cu)
+  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r, mode != 2));
+  op->clear_pending = false;
+  MHD_TRY(end_clear());
   h7::Params P;
   P.alpha = op->prm.alpha; P.beta = op->prm.beta; P.gamma = op->prm.gamma; P.sigma = op->prm.sigma;
   P.zeta_u = op->prm.zeta_u; P.zeta_j = op->prm.zeta_j;
@@ -513,7 +517,6 @@ int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode) {
 #define VKJ(C, U) do { if (zj) VK(C, U, true); else VK(C, U, false); } while (0)
 #define VKU(C) do { if (zu) VKJ(C, true); else VKJ(C, false); } while (0)
 #define VKC() do { if (conv == 0) VKU(0); else if (conv == 1) VKU(1); else VKU(2); } while (0)
-  if (mode != 2) MHD_TRY(v7_zero_shared(op));
   prof_begin(mode == 2 ? PROF_RES : PROF_JAC);
   if (op->deterministic && op->d_color_cells != nullptr) {
     // one launch per colour: cells of a colour share no dof, colours run in stream order => a fixed summation order

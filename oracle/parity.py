@@ -54,9 +54,12 @@ def lib_of_fes_map(fes, nowned: dict | None = None) -> np.ndarray:
     return out
 
 
-def assembly_parity(fes, prm, x_lib, rowptr, colval, nzval, r_lib, nrows, nowned=None, ncells=2048, seed_cell=0):
+def assembly_parity(fes, prm, x_lib, rowptr, colval, nzval, r_lib, nrows, nowned=None, ncells=2048, seed_cell=0, gather=None, v_lib=None):
     """Device CSR (library numbering, owned rows) and residual against the C oracle on a block of >= ncells cells.
-    Returns {"jac_rel", "res_rel", "csr_bitexact", "rows_checked", "entries_checked", "cells"}."""
+    Returns {"jac_rel", "res_rel", "csr_bitexact", "rows_checked", "entries_checked", "cells"}.
+    `gather(idx) -> (colval[idx], nzval[idx])`: for matrices too large to copy to the host the caller keeps colval / nzval on
+    the device and hands over only the entries of the sampled rows (colval and nzval arguments are then ignored).  With `v_lib`
+    the result also carries "rows_lib" and "y_rows" = (A v) on the sampled rows from those entries (for the SpMV check)."""
     cells = sample_block(fes.mesh.cell_nodes, ncells, seed_cell)
     lof = lib_of_fes_map(fes, nowned)
     x_fes = np.ascontiguousarray(np.asarray(x_lib)[lof])
@@ -84,8 +87,12 @@ def assembly_parity(fes, prm, x_lib, rowptr, colval, nzval, r_lib, nrows, nowned
     cnt_d = rowptr[rl + 1] - rowptr[rl]
     idx_d = np.repeat(rowptr[rl] - np.concatenate([[0], np.cumsum(cnt_d)[:-1]]), cnt_d) + np.arange(cnt_d.sum())
     rd = np.repeat(rl, cnt_d)
-    cd = np.asarray(colval)[idx_d].astype(np.int64)
-    vd = np.asarray(nzval)[idx_d]
+    if gather is not None:
+        cd, vd = gather(idx_d)
+        cd, vd = np.asarray(cd).astype(np.int64), np.asarray(vd)
+    else:
+        cd = np.asarray(colval)[idx_d].astype(np.int64)
+        vd = np.asarray(nzval)[idx_d]
     bitexact = bool(len(rd) == len(ro) and np.array_equal(rd, ro) and np.array_equal(cd, co_))
     scale = float(np.abs(vo).max()) if len(vo) else 1.0
     jac_rel = float(np.abs(vd - vo).max() / scale) if bitexact and len(vo) else float("inf")
@@ -100,8 +107,13 @@ def assembly_parity(fes, prm, x_lib, rowptr, colval, nzval, r_lib, nrows, nowned
         worst = {"row_field": fld(inv[ro[k]]), "col_field": fld(inv[co_[k]]), "device": float(vd[k]), "oracle": float(vo[k]), "scale": scale}
     rr = np.asarray(r_lib)[rows_lib]
     res_rel = float(np.abs(rr - r[rows_fes]).max() / np.abs(r[rows_fes]).max()) if len(rows_fes) else float("inf")
-    return {"jac_rel": jac_rel, "res_rel": res_rel, "csr_bitexact": bitexact, "rows_checked": int(len(rows_fes)),
-            "entries_checked": int(len(vo)), "cells": int(len(cells)), "worst_entry": worst}
+    out = {"jac_rel": jac_rel, "res_rel": res_rel, "csr_bitexact": bitexact, "rows_checked": int(len(rows_fes)),
+           "entries_checked": int(len(vo)), "cells": int(len(cells)), "worst_entry": worst}
+    if v_lib is not None:  # host product of the sampled rows with the device's own entries
+        seg = np.concatenate([[0], np.cumsum(cnt_d)])
+        out["rows_lib"] = rl
+        out["y_rows"] = np.add.reduceat(vd * np.asarray(v_lib)[cd], seg[:-1]) if len(vd) else np.zeros(0)
+    return out
 
 
 def spmv_parity(rowptr, colval, nzval, v_lib, y_dev):

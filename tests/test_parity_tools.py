@@ -52,3 +52,24 @@ def test_sampler_on_a_partition_uses_the_library_numbering():
         assert out["csr_bitexact"] and out["jac_rel"] < 1e-13 and out["res_rel"] < 1e-13 and out["rows_checked"] > 200
         y = Aloc @ x[gl]
         assert P.spmv_parity(Aloc.indptr, Aloc.indices, Aloc.data, x[gl], y) < 1e-15
+
+
+def test_sampler_with_a_gather_callback_and_the_row_product():
+    """Large matrices stay on the device: the sampler then receives only the entries of its rows through `gather` and returns
+    the product of those rows (bench.py --nc-global)."""
+    fes, prm, x = _case()
+    A = O.jacobian(fes, x, prm)
+    r = O.residual(fes, x, prm)
+    v = np.cos(0.37 * np.arange(fes.ndofs))
+    calls = []
+
+    def gather(idx):
+        calls.append(len(idx))
+        return A.indices[idx], A.data[idx]
+
+    out = P.assembly_parity(fes, prm, x, A.indptr, None, None, r, fes.ndofs, ncells=30, gather=gather, v_lib=v)
+    ref = P.assembly_parity(fes, prm, x, A.indptr, A.indices, A.data, r, fes.ndofs, ncells=30)
+    assert calls == [out["entries_checked"]] and out["csr_bitexact"]
+    assert out["jac_rel"] == ref["jac_rel"] and out["res_rel"] == ref["res_rel"]
+    y = A @ v
+    assert np.abs(out["y_rows"] - y[out["rows_lib"]]).max() <= 1e-13 * np.abs(y).max()
