@@ -392,6 +392,7 @@ int mhd_operator_destroy(mhd_operator_t* op) {
   cudaFree(op->d_tab7);
   cudaFree(op->d_shared_mask);
   cudaFree(op->d_color_cells);
+  cudaFree(op->d_cell_order);
   cudaFree(op->d_rowptr);
   cudaFree(op->d_colval);
   cudaFree(op->d_nzval);

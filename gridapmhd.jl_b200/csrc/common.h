@@ -144,6 +144,8 @@ struct mhd_operator {
   uint32_t* d_shared_mask = nullptr;  // v7: bit s set <=> the 32-byte sector s of nzval holds an nnz with != 1 contributions (cleared before an assembly)
   bool deterministic = false;      // v7: one launch per colour => run-to-run identical bits
   int32_t* d_color_cells = nullptr;   // cells sorted by colour
+  int32_t* d_cell_order = nullptr;    // v7: traversal order of the cells (breadth-first over face neighbours), see v7_build_cell_order
+  bool cell_order_tried = false;
   std::vector<int64_t> color_ptr;  // [ncolors + 1]
   std::vector<double> h_tables;    // host copy of the packed reference tables (T_* layout)
   int64_t ncells = 0, nnodes = 0;
@@ -264,6 +266,7 @@ int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
 void v7_entry_order(std::vector<uint16_t>& ord);
 int v7_try_enable(mhd_operator* op);                                  // at operator creation: discovers the tensor structure of the tables
 int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib); // end of the symbolic phase
+int v7_build_cell_order(mhd_operator* op);                            // lazily, before the first launch
 int v7_zero_shared(mhd_operator* op, cudaStream_t stream);             // clears the sectors of nzval that hold shared nnz
 int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode /* 0: Jacobian, 1: residual + Jacobian, 2: residual */);
 // h1h1.cu
