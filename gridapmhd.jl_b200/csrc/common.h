@@ -291,9 +291,10 @@ int launch_multi_axpy(int64_t n, int k, const double* d_V, int64_t ldv, const do
 int ensure_red(mhd_operator* op, int64_t ndoubles);
 // fused Gram-Schmidt building blocks of FGMRES (one launch each; k + 1 <= 18)
 bool gs_fused_ok(int k);
-int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out);
+int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out,
+                   const int* d_run_if = nullptr);
 int launch_gs_update(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, const double* d_w, const double* d_scale,
-                     const int* d_dead, double* d_out);
+                     const int* d_dead, double* d_out, const int* d_reorth = nullptr, int pass = 0, double* d_plain_out = nullptr);
 // postprocess.cu
 int hunt_error_norms(mhd_operator* op, const double* d_x, const mhd_tables_t* t, const mhd_hunt_post_t* p, double* out6);
 // comm.cu

@@ -368,7 +368,9 @@ int launch_multi_dot(mhd_operator* op, int64_t n, int k, const double* d_V, int6
 template <int KB>
 __global__ void __launch_bounds__(RED_T)
 gs_dots_kernel(int64_t n, int k, int with_norm, const double* __restrict__ V, int64_t ldv, const double* __restrict__ w,
-               double* __restrict__ partial, int pstride, unsigned* __restrict__ ticket, double* __restrict__ out) {
+               double* __restrict__ partial, int pstride, unsigned* __restrict__ ticket, double* __restrict__ out,
+               const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;  // conditional second Gram-Schmidt pass: every block takes the same exit
   __shared__ double sh[RED_T / 32];
   __shared__ bool last;
   double acc[KB];
@@ -408,28 +410,39 @@ constexpr int GS_KB = 18;  // m <= 16: h[0..j] and the norm in one pass
 
 bool gs_fused_ok(int k) { return k + 1 <= GS_KB; }
 
-int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out) {
+int launch_gs_dots(mhd_operator* op, int64_t n, int k, bool with_norm, const double* d_V, int64_t ldv, const double* d_w, double* d_out,
+                   const int* d_run_if) {
   MHD_CHECK(gs_fused_ok(k), MHD_E_INVALID, "launch_gs_dots: k = %d exceeds the fused kernel", k);
   const int nb = red_blocks(n);
   MHD_TRY(ensure_red(op, 4096 + (int64_t)GS_KB * RED_MAXB));
   double* partial = op->d_red + 4096;
   unsigned* ticket = reinterpret_cast<unsigned*>(op->d_red + 4000);  // zeroed by ensure_red, reset by the kernel
-  gs_dots_kernel<GS_KB><<<nb, RED_T, 0, g_stream>>>(n, k, with_norm ? 1 : 0, d_V, ldv, d_w, partial, RED_MAXB, ticket, d_out);
+  gs_dots_kernel<GS_KB><<<nb, RED_T, 0, g_stream>>>(n, k, with_norm ? 1 : 0, d_V, ldv, d_w, partial, RED_MAXB, ticket, d_out, d_run_if);
   MHD_LAUNCH_CHECK();
   return 0;
 }
 
-// out = scale * (w - sum_j h[j] V_j): the second Gram-Schmidt update fused with the normalisation of the next basis vector
-// (scale_ptr == nullptr: out = w - V h, plain update; dead_ptr != nullptr && *dead_ptr: out = 0)
+// out = scale * (w - sum_j h[j] V_j): a Gram-Schmidt update fused with the normalisation of the next basis vector
+// (scale_ptr == nullptr: out = w - V h, plain update; dead_ptr != nullptr && *dead_ptr: out = 0).
+// Conditional re-orthogonalisation (reorth != nullptr): pass 1 -- *reorth ? plain update into `plain_out` : normalised update into
+// `out`; pass 2 -- runs only if *reorth.  (w and plain_out may alias: no __restrict__ on them)
 template <int KB>
 __global__ void __launch_bounds__(256)
-gs_update_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv, const double* __restrict__ h, const double* __restrict__ w,
-                 const double* __restrict__ scale_ptr, const int* __restrict__ dead_ptr, double* __restrict__ out) {
+gs_update_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv, const double* __restrict__ h, const double* w,
+                 const double* __restrict__ scale_ptr, const int* __restrict__ dead_ptr, double* out, const int* __restrict__ reorth,
+                 int pass, double* plain_out) {
+  bool plain = false;
+  if (reorth != nullptr) {
+    const int r = *reorth;
+    if (pass == 2 && r == 0) return;
+    if (pass == 1 && r != 0) plain = true;
+  }
   double hh[KB];
 #pragma unroll
   for (int j = 0; j < KB; j++) hh[j] = j < k ? h[j] : 0.0;
-  const bool dead = dead_ptr != nullptr && *dead_ptr != 0;
-  const double sc = dead ? 0.0 : (scale_ptr ? *scale_ptr : 1.0);
+  const bool dead = !plain && dead_ptr != nullptr && *dead_ptr != 0;
+  const double sc = dead ? 0.0 : ((scale_ptr && !plain) ? *scale_ptr : 1.0);
+  if (plain) out = plain_out;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     double s = w[i];
 #pragma unroll
@@ -440,13 +453,13 @@ gs_update_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv, co
 }
 
 int launch_gs_update(int64_t n, int k, const double* d_V, int64_t ldv, const double* d_h, const double* d_w, const double* d_scale,
-                     const int* d_dead, double* d_out) {
+                     const int* d_dead, double* d_out, const int* d_reorth, int pass, double* d_plain_out) {
   if (n == 0) return 0;
   MHD_CHECK(k <= GS_KB, MHD_E_INVALID, "launch_gs_update: k = %d exceeds the fused kernel", k);
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)sms() * 8;
   if (b > cap) b = cap;
-  gs_update_kernel<GS_KB><<<(unsigned)b, 256, 0, g_stream>>>(n, k, d_V, ldv, d_h, d_w, d_scale, d_dead, d_out);
+  gs_update_kernel<GS_KB><<<(unsigned)b, 256, 0, g_stream>>>(n, k, d_V, ldv, d_h, d_w, d_scale, d_dead, d_out, d_reorth, pass, d_plain_out);
   MHD_LAUNCH_CHECK();
   return 0;
 }

@@ -36,7 +36,7 @@ struct KrylovScalars {  // lives in device memory
   double tol;
   double inv;           // scaling for the next basis vector
   double hist[4 * MAXM + 2];
-  int renorm;           // fused CGS2: the Pythagoras norm lost too many digits, use the explicitly computed one
+  int reorth;           // this Arnoldi step needs the second Gram-Schmidt pass (DGKS criterion), see k_dgks_scalars
   int done;             // converged (or breakdown): later steps of the cycle become no-ops
   int k;                // Arnoldi steps taken in this cycle
   int iters;            // total iterations
@@ -73,7 +73,7 @@ __global__ void k_add_h(KrylovScalars* S, int j) {
 }
 
 // one Arnoldi step's scalar work: new Hessenberg column, Givens rotations, residual estimate
-__global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
+__device__ void arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
   if (S->done) return;
   double* H = S->H;
   const double hn = sqrt(fmax(S->hn, 0.0));
@@ -104,22 +104,35 @@ __global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
   if (S->beta <= S->tol || hn == 0.0 || S->iters >= maxiter) S->done = 1;
 }
 
-// fused CGS2 step: h (pass 1) and h2 | ||w1||^2 (pass 2, w1 = w - V h) are in; the norm of w2 = w1 - V h2 follows from
-// Pythagoras (V orthonormal): ||w2||^2 = ||w1||^2 - ||h2||^2, unless cancellation eats more than ~8 digits -- then the flag
-// `renorm` asks the host-free slow path (one extra reduction) to recompute it.  Leaves h += h2 and hn in place.
-__global__ void k_cgs2_scalars(KrylovScalars* S, int j) {
+__global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) { arnoldi_scalars(S, j, m, maxiter); }
+
+// Pass 1 of the fused Gram-Schmidt step is in: h = V'w and h[j+1] = ||w||^2.  ||w1||^2 = ||w||^2 - ||h||^2 (Pythagoras, V
+// orthonormal).  Daniel-Gragg-Kaufman-Stewart criterion: the second pass is needed only when the projection removed more than half
+// of w (||w1||^2 < ||w||^2 / 2) -- otherwise w1 is orthogonal to V to working precision, the Pythagoras norm has lost at most one
+// bit, and the step is finished here: Hessenberg column, rotations, scaling of v_{j+1}.  (always = 1: classical CGS2, the A/B switch)
+__global__ void k_dgks_scalars(KrylovScalars* S, int j, int m, int maxiter, int always) {
+  S->reorth = 0;
+  if (S->done) return;
+  double s1 = 0.0;
+  for (int i = 0; i <= j; i++) s1 += S->h[i] * S->h[i];
+  const double n0 = S->h[j + 1], n1 = n0 - s1;
+  if (always || !(n1 >= 0.5 * n0)) {
+    S->reorth = 1;
+    return;
+  }
+  S->hn = n1;
+  arnoldi_scalars(S, j, m, maxiter);
+}
+// second pass (only when reorth): h += h2, ||w2||^2 by Pythagoras from ||w1||^2 (computed, not estimated, in pass 2), then the step
+__global__ void k_cgs2_finish(KrylovScalars* S, int j, int m, int maxiter) {
+  if (!S->reorth || S->done) return;
   double s2 = 0.0;
   for (int i = 0; i <= j; i++) {
     s2 += S->h2[i] * S->h2[i];
     S->h[i] += S->h2[i];
   }
-  const double n1 = S->h2[j + 1];  // ||w1||^2
-  S->hn = n1 - s2;
-  S->renorm = (n1 > 0.0 && S->hn < 1e-8 * n1) ? 1 : 0;
-}
-// hn <- exact ||w2||^2 (in beta2 scratch) when the Pythagoras estimate was not trustworthy
-__global__ void k_cgs2_take_exact_norm(KrylovScalars* S) {
-  if (S->renorm) S->hn = S->beta2;
+  S->hn = S->h2[j + 1] - s2;
+  arnoldi_scalars(S, j, m, maxiter);
 }
 
 __global__ void k_back_substitute(KrylovScalars* S) {
@@ -265,16 +278,28 @@ struct Fgmres {
       MHD_TRY(matvec(Zj, w));
       if (fused) {
         // CGS2 in 4 launches + the scalar step: h = V'w | w1 = w - V h | (h2, ||w1||^2) = (V'w1, w1'w1) | v_{j+1} = (w1 - V h2)/||.||
-        MHD_TRY(launch_gs_dots(op, n, j + 1, false, V, ld, w, S->h));
-        MHD_TRY(allreduce_sum(S->h, j + 1));
-        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h, w, nullptr, nullptr, w));
-        MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h2));
+        // Pass 1: (h, ||w||^2) = (V'w, w'w) in one sweep; the scalar kernel decides whether a second pass is needed (always, unless
+        // MHD_KRYLOV_DGKS=1).  If not, the first update already writes v_{j+1} = (w - V h) / ||.|| and the three launches of the
+        // second pass return at once (they read S->reorth); with more than one rank its all-reduce still runs, on unused data.
+        static int always = -1;
+        if (always < 0) {
+          // default: always re-orthogonalise (classical CGS2).  MHD_KRYLOV_DGKS=1 makes the second pass conditional: measured on
+          // cfg2 it almost never saves the pass (a preconditioned operator is close to the identity, so the projection on v_j
+          // removes most of w and the criterion fires) -- 0.424 against 0.427 ms per iteration, 100 against 96 outer iterations.
+          const char* e = getenv("MHD_KRYLOV_DGKS");
+          always = (e && atoi(e) != 0) ? 0 : 1;
+        }
+        double* Vn = V + (int64_t)(j + 1) * ld;
+        MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h, nullptr));
+        MHD_TRY(allreduce_sum(S->h, j + 2));
+        k_dgks_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter, always);
+        MHD_LAUNCH_CHECK();
+        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h, w, &S->inv, &S->done, Vn, &S->reorth, 1, w));
+        MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h2, &S->reorth));
         MHD_TRY(allreduce_sum(S->h2, j + 2));
-        k_cgs2_scalars<<<1, 1, 0, g_stream>>>(S, j);
+        k_cgs2_finish<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
         MHD_LAUNCH_CHECK();
-        k_arnoldi_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
-        MHD_LAUNCH_CHECK();
-        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h2, w, &S->inv, &S->done, V + (int64_t)(j + 1) * ld));
+        MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h2, w, &S->inv, &S->done, Vn, &S->reorth, 2, nullptr));
         continue;
       }
       // CGS2: h = V^T w ; w -= V h ; h2 = V^T w ; w -= V h2 ; h += h2
