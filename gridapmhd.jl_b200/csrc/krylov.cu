@@ -397,11 +397,14 @@ gs_dots_kernel(int64_t n, int k, int with_norm, const double* __restrict__ V, in
   __syncthreads();
   if (!last) return;
   __threadfence();
-  for (int j = 0; j < nout; j++) {
+  // one warp per output, all outputs at once (the serial loop over outputs with a block reduction each cost ~1.5 us per output:
+  // 15 of the kernel's 27 us at k = 8); fixed summation order: lane-strided partial sums, then the shuffle tree
+  for (int j = threadIdx.x >> 5; j < nout; j += RED_T / 32) {
     double s = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_T) s += __ldcg(partial + (int64_t)j * pstride + i);
-    const double r = block_sum(s, sh);
-    if (threadIdx.x == 0) out[j] = r;
+    for (int i = threadIdx.x & 31; i < (int)gridDim.x; i += 32) s += __ldcg(partial + (int64_t)j * pstride + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) out[j] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -443,12 +446,21 @@ gs_update_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv, co
   const bool dead = !plain && dead_ptr != nullptr && *dead_ptr != 0;
   const double sc = dead ? 0.0 : ((scale_ptr && !plain) ? *scale_ptr : 1.0);
   if (plain) out = plain_out;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    double s = w[i];
+  // two elements per thread and iteration: 2 (k + 1) independent loads in flight before the first fma
+  for (int64_t i0 = (int64_t)blockIdx.x * 512 + threadIdx.x; i0 < n; i0 += (int64_t)gridDim.x * 512) {
+    const int64_t i1 = i0 + 256;
+    const bool two = i1 < n;
+    double s0 = w[i0], s1 = two ? w[i1] : 0.0;
 #pragma unroll
     for (int j = 0; j < KB; j++)
-      if (j < k) s = fma(-hh[j], V[(int64_t)j * ldv + i], s);
-    out[i] = dead ? 0.0 : sc * s;
+      if (j < k) {
+        const double* Vj = V + (int64_t)j * ldv;
+        const double a = Vj[i0], b = two ? Vj[i1] : 0.0;
+        s0 = fma(-hh[j], a, s0);
+        s1 = fma(-hh[j], b, s1);
+      }
+    out[i0] = dead ? 0.0 : sc * s0;
+    if (two) out[i1] = dead ? 0.0 : sc * s1;
   }
 }
 
@@ -456,8 +468,8 @@ int launch_gs_update(int64_t n, int k, const double* d_V, int64_t ldv, const dou
                      const int* d_dead, double* d_out, const int* d_reorth, int pass, double* d_plain_out) {
   if (n == 0) return 0;
   MHD_CHECK(k <= GS_KB, MHD_E_INVALID, "launch_gs_update: k = %d exceeds the fused kernel", k);
-  int64_t b = (n + 255) / 256;
-  const int64_t cap = (int64_t)sms() * 8;
+  int64_t b = (n + 511) / 512;  // one pass: every thread owns two elements
+  const int64_t cap = (int64_t)sms() * 32;
   if (b > cap) b = cap;
   gs_update_kernel<GS_KB><<<(unsigned)b, 256, 0, g_stream>>>(n, k, d_V, ldv, d_h, d_w, d_scale, d_dead, d_out, d_reorth, pass, d_plain_out);
   MHD_LAUNCH_CHECK();

@@ -72,66 +72,102 @@ __global__ void k_add_h(KrylovScalars* S, int j) {
   if (i <= j) S->h[i] += S->h2[i];
 }
 
-// one Arnoldi step's scalar work: new Hessenberg column, Givens rotations, residual estimate
+// one Arnoldi step's scalar work: new Hessenberg column, Givens rotations, residual estimate.  Called by ALL threads of a
+// SCALAR_T-thread block (uniform control flow): the column and the rotations are staged in shared memory in parallel and thread 0
+// walks the dependent chain there -- as a single thread on global memory the chain of L2 round trips cost 5.6 us per step.
+constexpr int SCALAR_T = 96;  // >= MAXM + 2
 __device__ void arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) {
+  __shared__ double col[MAXM + 2], cs[MAXM], sn[MAXM];
   if (S->done) return;
-  double* H = S->H;
-  const double hn = sqrt(fmax(S->hn, 0.0));
-  for (int i = 0; i <= j; i++) H[i * MAXM + j] = S->h[i];
-  H[(j + 1) * MAXM + j] = hn;
-  for (int i = 0; i < j; i++) {
-    const double t = S->cs[i] * H[i * MAXM + j] + S->sn[i] * H[(i + 1) * MAXM + j];
-    H[(i + 1) * MAXM + j] = -S->sn[i] * H[i * MAXM + j] + S->cs[i] * H[(i + 1) * MAXM + j];
-    H[i * MAXM + j] = t;
+  const int tid = threadIdx.x;
+  if (tid <= j) col[tid] = S->h[tid];
+  if (tid < j) {
+    cs[tid] = S->cs[tid];
+    sn[tid] = S->sn[tid];
   }
-  const double a = H[j * MAXM + j], b = H[(j + 1) * MAXM + j];
-  const double d = hypot(a, b);
-  if (d == 0.0) {  // exact breakdown: stop
-    S->done = 1;
-    return;
+  __syncthreads();
+  if (tid == 0) {
+    const double hn = sqrt(fmax(S->hn, 0.0));
+    col[j + 1] = hn;
+    for (int i = 0; i < j; i++) {
+      const double t = cs[i] * col[i] + sn[i] * col[i + 1];
+      col[i + 1] = -sn[i] * col[i] + cs[i] * col[i + 1];
+      col[i] = t;
+    }
+    const double a = col[j], b = col[j + 1];
+    const double d = hypot(a, b);
+    if (d == 0.0) {  // exact breakdown: stop
+      S->done = 1;
+    } else {
+      const double c = a / d, sj = b / d;
+      S->cs[j] = c;
+      S->sn[j] = sj;
+      col[j] = d;
+      col[j + 1] = 0.0;
+      const double gj = S->g[j];
+      S->g[j + 1] = -sj * gj;
+      S->g[j] = c * gj;
+      const double beta = fabs(sj * gj);
+      S->beta = beta;
+      S->k = j + 1;
+      const int it = S->iters + 1;
+      S->iters = it;
+      if (it < 4 * MAXM + 2) S->hist[it] = beta;
+      S->inv = hn > 0.0 ? 1.0 / hn : 0.0;
+      if (beta <= S->tol || hn == 0.0 || it >= maxiter) S->done = 1;
+    }
   }
-  S->cs[j] = a / d;
-  S->sn[j] = b / d;
-  H[j * MAXM + j] = d;
-  H[(j + 1) * MAXM + j] = 0.0;
-  S->g[j + 1] = -S->sn[j] * S->g[j];
-  S->g[j] = S->cs[j] * S->g[j];
-  S->beta = fabs(S->g[j + 1]);
-  S->k = j + 1;
-  S->iters += 1;
-  if (S->iters < 4 * MAXM + 2) S->hist[S->iters] = S->beta;
-  S->inv = hn > 0.0 ? 1.0 / hn : 0.0;
-  if (S->beta <= S->tol || hn == 0.0 || S->iters >= maxiter) S->done = 1;
+  __syncthreads();
+  if (tid <= j + 1) S->H[tid * MAXM + j] = col[tid];
 }
-
-__global__ void k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) { arnoldi_scalars(S, j, m, maxiter); }
+__global__ void __launch_bounds__(SCALAR_T) k_arnoldi_scalars(KrylovScalars* S, int j, int m, int maxiter) { arnoldi_scalars(S, j, m, maxiter); }
 
 // Pass 1 of the fused Gram-Schmidt step is in: h = V'w and h[j+1] = ||w||^2.  ||w1||^2 = ||w||^2 - ||h||^2 (Pythagoras, V
 // orthonormal).  Daniel-Gragg-Kaufman-Stewart criterion: the second pass is needed only when the projection removed more than half
 // of w (||w1||^2 < ||w||^2 / 2) -- otherwise w1 is orthogonal to V to working precision, the Pythagoras norm has lost at most one
-// bit, and the step is finished here: Hessenberg column, rotations, scaling of v_{j+1}.  (always = 1: classical CGS2, the A/B switch)
-__global__ void k_dgks_scalars(KrylovScalars* S, int j, int m, int maxiter, int always) {
-  S->reorth = 0;
-  if (S->done) return;
-  double s1 = 0.0;
-  for (int i = 0; i <= j; i++) s1 += S->h[i] * S->h[i];
-  const double n0 = S->h[j + 1], n1 = n0 - s1;
-  if (always || !(n1 >= 0.5 * n0)) {
-    S->reorth = 1;
-    return;
+// bit, and the step is finished here: Hessenberg column, rotations, scaling of v_{j+1}.  (always = 1: classical CGS2, the default)
+__global__ void __launch_bounds__(SCALAR_T) k_dgks_scalars(KrylovScalars* S, int j, int m, int maxiter, int always) {
+  __shared__ int go;
+  if (threadIdx.x == 0) {
+    go = 0;
+    int reorth = 0;
+    if (!S->done) {
+      if (always) {
+        reorth = 1;
+      } else {
+        double s1 = 0.0;
+        for (int i = 0; i <= j; i++) s1 += S->h[i] * S->h[i];
+        const double n0 = S->h[j + 1], n1 = n0 - s1;
+        if (!(n1 >= 0.5 * n0)) {
+          reorth = 1;
+        } else {
+          S->hn = n1;
+          go = 1;
+        }
+      }
+    }
+    S->reorth = reorth;
   }
-  S->hn = n1;
-  arnoldi_scalars(S, j, m, maxiter);
+  __syncthreads();
+  if (go) arnoldi_scalars(S, j, m, maxiter);
 }
 // second pass (only when reorth): h += h2, ||w2||^2 by Pythagoras from ||w1||^2 (computed, not estimated, in pass 2), then the step
-__global__ void k_cgs2_finish(KrylovScalars* S, int j, int m, int maxiter) {
+__global__ void __launch_bounds__(SCALAR_T) k_cgs2_finish(KrylovScalars* S, int j, int m, int maxiter) {
+  __shared__ double sq[MAXM + 2];
   if (!S->reorth || S->done) return;
-  double s2 = 0.0;
-  for (int i = 0; i <= j; i++) {
-    s2 += S->h2[i] * S->h2[i];
-    S->h[i] += S->h2[i];
+  const int tid = threadIdx.x;
+  if (tid <= j) {
+    const double h2 = S->h2[tid];
+    sq[tid] = h2 * h2;
+    S->h[tid] += h2;
   }
-  S->hn = S->h2[j + 1] - s2;
+  __syncthreads();
+  if (tid == 0) {
+    double s2 = 0.0;
+    for (int i = 0; i <= j; i++) s2 += sq[i];
+    S->hn = S->h2[j + 1] - s2;
+  }
+  __syncthreads();  // also makes this block's writes to S->h / S->hn visible to its own later reads
   arnoldi_scalars(S, j, m, maxiter);
 }
 
@@ -292,12 +328,12 @@ struct Fgmres {
         double* Vn = V + (int64_t)(j + 1) * ld;
         MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h, nullptr));
         MHD_TRY(allreduce_sum(S->h, j + 2));
-        k_dgks_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter, always);
+        k_dgks_scalars<<<1, SCALAR_T, 0, g_stream>>>(S, j, m, maxiter, always);
         MHD_LAUNCH_CHECK();
         MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h, w, &S->inv, &S->done, Vn, &S->reorth, 1, w));
         MHD_TRY(launch_gs_dots(op, n, j + 1, true, V, ld, w, S->h2, &S->reorth));
         MHD_TRY(allreduce_sum(S->h2, j + 2));
-        k_cgs2_finish<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
+        k_cgs2_finish<<<1, SCALAR_T, 0, g_stream>>>(S, j, m, maxiter);
         MHD_LAUNCH_CHECK();
         MHD_TRY(launch_gs_update(n, j + 1, V, ld, S->h2, w, &S->inv, &S->done, Vn, &S->reorth, 2, nullptr));
         continue;
@@ -312,7 +348,7 @@ struct Fgmres {
       k_add_h<<<1, 64, 0, g_stream>>>(S, j);
       MHD_LAUNCH_CHECK();
       MHD_TRY(norm2(w, &S->hn));
-      k_arnoldi_scalars<<<1, 1, 0, g_stream>>>(S, j, m, maxiter);
+      k_arnoldi_scalars<<<1, SCALAR_T, 0, g_stream>>>(S, j, m, maxiter);
       MHD_LAUNCH_CHECK();
       k_scale_to<<<vgrid(n), 256, 0, g_stream>>>(n, S, w, V + (int64_t)(j + 1) * ld);
       MHD_LAUNCH_CHECK();
@@ -818,7 +854,48 @@ int mhd_solve(mhd_solver_t* s, const double* b, double* x, int32_t* iters, doubl
     }
     g_stream = own;
   }
+  // Keep the Krylov basis of the outer FGMRES in L2 across the SpMVs: every product streams the whole matrix (1.8 GB at cfg2)
+  // through the 126 MB L2 and evicts the basis, which the two Gram-Schmidt passes of the next step then fetch from HBM again.
+  // A persisting access-policy window over V (hit ratio scaled to the set-aside the device allows) keeps it resident; the
+  // window travels into the captured cycle graphs as a kernel-node attribute.  OFF by default (MHD_KRYLOV_L2=1 enables): measured
+  // on cfg2 it LOSES -- 0.430 against 0.405 ms per iteration, the cfg2 solve 6.2 s against 4.6 s: the 94 MB set-aside takes the
+  // L2 away from the x gathers of the SpMV and from the patch smoother's inverses.
+  static int l2_want = -1;
+  if (l2_want < 0) {
+    const char* e = getenv("MHD_KRYLOV_L2");
+    l2_want = e ? atoi(e) : 0;
+  }
+  bool window = false;
+  if (l2_want && s->outer.V != nullptr) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g_device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g_device);
+    const size_t vbytes = (size_t)(s->outer.m + 1) * (size_t)s->outer.ld * sizeof(double);
+    if (max_persist > 0 && max_window > 0) {
+      const size_t setaside = vbytes < (size_t)max_persist ? vbytes : (size_t)max_persist;
+      const size_t wbytes = vbytes < (size_t)max_window ? vbytes : (size_t)max_window;
+      cudaStreamAttrValue a;
+      memset(&a, 0, sizeof(a));
+      a.accessPolicyWindow.base_ptr = s->outer.V;
+      a.accessPolicyWindow.num_bytes = wbytes;
+      a.accessPolicyWindow.hitRatio = setaside >= wbytes ? 1.0f : (float)((double)setaside / (double)wbytes);
+      a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside) == cudaSuccess &&
+          cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &a) == cudaSuccess)
+        window = true;
+      else
+        cudaGetLastError();  // optional optimisation: carry on without it
+    }
+  }
   const int rc = solve_impl(s, b, x, iters, resnorm, res_history);
+  if (window) {
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &a);
+    cudaCtxResetPersistingL2Cache();
+    cudaGetLastError();
+  }
   g_stream = saved;
   return rc;
 }
