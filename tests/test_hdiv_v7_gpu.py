@@ -108,6 +108,34 @@ def test_both_kernels_agree_entry_by_entry(mhdlib):
     assert relerr(v7, v5) < VAL_TOL
 
 
+def test_cell_traversal_order_does_not_change_the_result(mhdlib):
+    """The kernel walks the cells breadth-first over face neighbours (L2 locality of shared sectors, hdiv_v7.cu
+    v7_build_cell_order); MHD_V7_ORDER=0 keeps the mesh order.  Same matrix and residual either way (summation order of the
+    shared entries aside), both within tolerance of the oracle -- on a mesh with more cells than one wave of the grid."""
+    p = hunt_params(nc=(12, 10), B=(0.0, 30.0, 0.0))
+    fes = setup_spaces(p)
+    _, fl = small_case()
+    x = np.random.default_rng(5).random(fes.ndofs)
+    out = {}
+    for order in ("1", "0"):
+        os.environ["MHD_V7_ORDER"] = order
+        try:
+            op = B200FEOperator(fes, fl)
+            A = op.allocate_jacobian()
+            b = np.empty(op.nrows)
+            op.residual_and_jacobian_b(b, A, x)
+            out[order] = (A.nzval().copy(), b.copy())
+            op.destroy()
+        finally:
+            del os.environ["MHD_V7_ORDER"]
+    Ao = O.jacobian(fes, x, oprm(fl))
+    ro = O.residual(fes, x, oprm(fl))
+    for order in ("1", "0"):
+        assert relerr(out[order][0], Ao.data) < VAL_TOL
+        assert relerr(out[order][1], ro) < VAL_TOL
+    assert relerr(out["1"][0], out["0"][0]) < 1e-14
+
+
 def test_deterministic_mode_is_bit_reproducible_and_matches_the_oracle(mhdlib):
     fes, fl = small_case()
     op = B200FEOperator(fes, fl)
