@@ -73,3 +73,16 @@ def test_sampler_with_a_gather_callback_and_the_row_product():
     assert out["jac_rel"] == ref["jac_rel"] and out["res_rel"] == ref["res_rel"]
     y = A @ v
     assert np.abs(out["y_rows"] - y[out["rows_lib"]]).max() <= 1e-13 * np.abs(y).max()
+
+
+def test_bench_parses_the_ncu_dram_csv_of_a_committed_capture():
+    """bench.py measures `roofline.traffic` through an ncu child run; its CSV parser is checked here on a capture kept in profiles/"""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    out = bench.parse_ncu_dram_csv(os.path.join(root, "profiles", "r2_dram_bytes_bfs_order.csv"))
+    assert out == {"jacobian": 952693760 + 1194133248}
