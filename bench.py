@@ -713,6 +713,8 @@ def measure_traffic_with_ncu():
     ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
     if ncu is None or os.environ.get("MHD_BENCH_NO_NCU"):
         return None
+    if any(k in os.environ for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NSYS_PROFILING_SESSION_ID")):
+        return None  # this process is itself running under a profiler: do not nest another one
     with tempfile.TemporaryDirectory() as tmp:
         log = os.path.join(tmp, "dram.csv")
         cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
@@ -720,7 +722,7 @@ def measure_traffic_with_ncu():
                sys.executable, os.path.abspath(__file__), "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-parity", "--no-extra"]
         env = dict(os.environ, MHD_BENCH_NO_NCU="1")
         try:
-            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240, env=env, check=False)
+            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=150, env=env, check=False)
             out = parse_ncu_dram_csv(log)
         except Exception:
             return None
