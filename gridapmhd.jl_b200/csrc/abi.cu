@@ -554,11 +554,11 @@ int mhd_jacobian(mhd_operator_t* op, const double* x, double* nzval_out) {
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
   } else if (op->jac_version == 7) {
-    MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
+    if (!is_device_ptr(x)) MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(v7_launch(op, dx, nullptr, 0));
   } else {
-    MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
+    if (!is_device_ptr(x)) MHD_TRY(begin_clear(op, nullptr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(launch_jacobian(op, dx, nullptr));
   }
@@ -590,11 +590,11 @@ int mhd_residual_and_jacobian(mhd_operator_t* op, const double* x, double* r_out
       MHD_TRY(h1h1_launch_jacobian(op, dx, nullptr));
     }
   } else if (op->jac_version == 7) {
-    MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
+    if (!is_device_ptr(x)) MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(v7_launch(op, dx, dr, 1));
   } else {
-    MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
+    if (!is_device_ptr(x)) MHD_TRY(begin_clear(op, dr));  // overlaps the copy of x
     MHD_TRY(in_vec(op, x, op->ncols, op->d_x, &dx));
     MHD_TRY(launch_jacobian(op, dx, dr));
   }

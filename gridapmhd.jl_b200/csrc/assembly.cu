@@ -1255,27 +1255,39 @@ static cudaStream_t s_clear_stream = nullptr;
 static cudaEvent_t s_ev_in = nullptr, s_ev_done = nullptr;
 static int s_clear_device = -1;
 
-int begin_clear(mhd_operator* op, double* d_r, bool matrix) {
-  if (s_clear_device != g_device) {  // (re)created per mhd_init
-    MHD_CUDA(cudaStreamCreateWithFlags(&s_clear_stream, cudaStreamNonBlocking));
-    MHD_CUDA(cudaEventCreateWithFlags(&s_ev_in, cudaEventDisableTiming));
-    MHD_CUDA(cudaEventCreateWithFlags(&s_ev_done, cudaEventDisableTiming));
-    s_clear_device = g_device;
+static bool s_clear_on_side = false;
+
+// side = true: on the side stream (the caller is about to enqueue a host->device copy on the library stream and wants the
+// clearing to overlap it); side = false: in line on the library stream -- no cross-stream hand-over, which costs ~10 us per
+// assembly when there is nothing to overlap (device-resident callers)
+int begin_clear(mhd_operator* op, double* d_r, bool matrix, bool side) {
+  cudaStream_t st = g_stream;
+  if (side) {
+    if (s_clear_device != g_device) {  // (re)created per mhd_init
+      MHD_CUDA(cudaStreamCreateWithFlags(&s_clear_stream, cudaStreamNonBlocking));
+      MHD_CUDA(cudaEventCreateWithFlags(&s_ev_in, cudaEventDisableTiming));
+      MHD_CUDA(cudaEventCreateWithFlags(&s_ev_done, cudaEventDisableTiming));
+      s_clear_device = g_device;
+    }
+    MHD_CUDA(cudaEventRecord(s_ev_in, g_stream));
+    MHD_CUDA(cudaStreamWaitEvent(s_clear_stream, s_ev_in, 0));
+    st = s_clear_stream;
   }
-  MHD_CUDA(cudaEventRecord(s_ev_in, g_stream));
-  MHD_CUDA(cudaStreamWaitEvent(s_clear_stream, s_ev_in, 0));
-  if (matrix) {
-    if (op->jac_version == 7) MHD_TRY(v7_zero_shared(op, s_clear_stream));  // only the sectors that hold shared nnz
-    else MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), s_clear_stream));
+  if (matrix && op->jac_version == 7) {
+    MHD_TRY(v7_zero_shared(op, st, d_r));  // only the sectors that hold shared nnz (+ the residual, same launch)
+  } else {
+    if (matrix) MHD_CUDA(cudaMemsetAsync(op->d_nzval, 0, (size_t)op->nnz * sizeof(double), st));
+    if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), st));
   }
-  if (d_r) MHD_CUDA(cudaMemsetAsync(d_r, 0, (size_t)op->nrows * sizeof(double), s_clear_stream));
-  MHD_CUDA(cudaEventRecord(s_ev_done, s_clear_stream));
+  if (side) MHD_CUDA(cudaEventRecord(s_ev_done, s_clear_stream));
+  s_clear_on_side = side;
   op->clear_pending = true;
   return 0;
 }
 
-int end_clear() {  // the compute stream waits for the clearing started by begin_clear
-  MHD_CUDA(cudaStreamWaitEvent(g_stream, s_ev_done, 0));
+int end_clear() {  // the compute stream waits for the clearing started by begin_clear (nothing to do when it ran in line)
+  if (s_clear_on_side) MHD_CUDA(cudaStreamWaitEvent(g_stream, s_ev_done, 0));
+  s_clear_on_side = false;
   return 0;
 }
 
@@ -1290,7 +1302,7 @@ void assembly_finalize() {
 
 // d_r != nullptr: fused residual + Jacobian (residual_and_jacobian!)
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r) {
-  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r));
+  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r, true, false));
   op->clear_pending = false;
   MHD_TRY(end_clear());
   KParams P = make_kparams(op->prm);

@@ -258,7 +258,7 @@ void entry_order(std::vector<uint16_t>& ord);  // [NENT] (row slot << 8 | col sl
 // assembly.cu
 int pack_tables(mhd_operator* op, const mhd_tables_t* t);
 int launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);
-int begin_clear(mhd_operator* op, double* d_r /* nullable */, bool matrix = true);
+int begin_clear(mhd_operator* op, double* d_r /* nullable */, bool matrix = true, bool side = true);
 int end_clear();  // optional: start clearing before the state is copied in
 void assembly_finalize();
 int launch_residual(mhd_operator* op, const double* d_x, double* d_r);
@@ -267,7 +267,7 @@ void v7_entry_order(std::vector<uint16_t>& ord);
 int v7_try_enable(mhd_operator* op);                                  // at operator creation: discovers the tensor structure of the tables
 int v7_build_shared_mask(mhd_operator* op, const uint8_t* d_contrib); // end of the symbolic phase
 int v7_build_cell_order(mhd_operator* op);                            // lazily, before the first launch
-int v7_zero_shared(mhd_operator* op, cudaStream_t stream);             // clears the sectors of nzval that hold shared nnz
+int v7_zero_shared(mhd_operator* op, cudaStream_t stream, double* d_r /* nullable: residual cleared by the same launch */);             // clears the sectors of nzval that hold shared nnz
 int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode /* 0: Jacobian, 1: residual + Jacobian, 2: residual */);
 // h1h1.cu
 int h1h1_launch_jacobian(mhd_operator* op, const double* d_x, double* d_r /* nullable: fused residual */);

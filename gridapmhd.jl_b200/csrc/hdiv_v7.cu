@@ -383,7 +383,10 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
 // the L2 has to fill from DRAM), so whole SECTORS are cleared: bit s of the mask <=> sector s (nnz 4 s .. 4 s + 3) holds a
 // shared nnz.  Exclusive nnz inside a cleared sector are overwritten by their plain store later in the same assembly.
 __global__ void __launch_bounds__(256)
-zero_shared_kernel(int64_t nsectors, const uint32_t* __restrict__ mask, double* __restrict__ nz, int64_t nnz) {
+zero_shared_kernel(int64_t nsectors, const uint32_t* __restrict__ mask, double* __restrict__ nz, int64_t nnz, double* __restrict__ r,
+                   int64_t nr) {
+  // the residual of a fused assembly is cleared by the same launch (r == nullptr: none)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (int64_t)gridDim.x * blockDim.x) r[i] = 0.0;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsectors; s += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t wd = __ldg(mask + (s >> 5));  // one word per warp: broadcast load
     if (!((wd >> (s & 31)) & 1u)) continue;
@@ -519,11 +522,12 @@ int v7_build_cell_order(mhd_operator* op) {
   return 0;
 }
 
-int v7_zero_shared(mhd_operator* op, cudaStream_t stream) {
+int v7_zero_shared(mhd_operator* op, cudaStream_t stream, double* d_r) {
   const int64_t nsectors = (op->nnz + 3) / 4;
   const int64_t want = (nsectors + 255) / 256;
   const int64_t cap = (int64_t)sm_count7() * 64;
-  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(nsectors, op->d_shared_mask, op->d_nzval, op->nnz);
+  zero_shared_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(nsectors, op->d_shared_mask, op->d_nzval, op->nnz, d_r,
+                                                                               d_r ? op->nrows : 0);
   MHD_LAUNCH_CHECK();
   return 0;
 }
@@ -533,9 +537,9 @@ int v7_launch(mhd_operator* op, const double* d_x, double* d_r, int mode) {
   MHD_CHECK(op->jac_version == 7 && op->d_tab7 != nullptr && (mode == 2 || op->d_shared_mask != nullptr), MHD_E_STATE,
             "v7 kernel is not enabled on this operator");
   if (mode == 0) d_r = nullptr;
-  // clearing (shared sectors of nzval, the residual) runs on the side stream of begin_clear: when the caller passes host vectors
-  // it was started BEFORE the copy of the state was enqueued and overlaps it (abi.cu)
-  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r, mode != 2));
+  // clearing (shared sectors of nzval, the residual): when the caller passes host vectors it was started on a side stream BEFORE
+  // the copy of the state was enqueued and overlaps it (abi.cu); otherwise it runs here, in line
+  if (!op->clear_pending) MHD_TRY(begin_clear(op, d_r, mode != 2, false));
   op->clear_pending = false;
   MHD_TRY(end_clear());
   h7::Params P;
