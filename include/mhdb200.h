@@ -157,8 +157,9 @@ int mhd_operator_set_halo(mhd_operator_t*, int32_t nneigh, const int32_t* neigh_
 /* Fused SpMV + ghost exchange over NVLink peer memory (CUDA IPC; same-node ranks): every rank exports the handle of its
  * inbox, the host exchanges the 64-byte handles (MPI / torch.distributed) and hands each rank its neighbours' handles
  * plus: for every entry of the send list the ghost slot it fills on its neighbour (the neighbour's recv_idx entry minus
- * the neighbour's row count), and per neighbour k this rank's position in k's neighbour list and k's ghost count.  Afterwards mhd_spmv / mhd_solve use ONE kernel per
- * product that pushes interface values into the neighbours' inboxes and multiplies (interior rows never wait).
+ * the neighbour's row count), and per neighbour k this rank's position in k's neighbour list and k's ghost count.  Afterwards mhd_spmv / mhd_solve run every
+ * product as two launches: a product kernel whose first CTAs push the interface values into the neighbours' inboxes while the
+ * others multiply the local columns, and a tail kernel over the interface rows that waits for the arrivals and adds the ghost part.
  * Without it the exchange runs as pack -> ncclSend/ncclRecv -> unpack. */
 int mhd_operator_halo_ipc_export(mhd_operator_t*, void* handle64 /* 64 bytes out */);
 int mhd_operator_halo_ipc_connect(mhd_operator_t*, const void* handles /* nneigh x 64 B */, const int32_t* send_dst /* [nsend] */,

@@ -340,6 +340,70 @@ function Algebra.solve!(x::AbstractVector, ns::B200NumericalSetup, b::AbstractVe
   x
 end
 
+# ---------------------------------------------------------------------------------------------------------------
+# distributed runs: one MPI rank per GPU, as the reference runs under PartitionedArrays (src/Applications/hunt.jl:18-25,
+# with_mpi).  The operator of a rank is built by b200_operator on its LOCAL spaces (own + ghost cells, local dof numbering with the
+# owned dofs first -- `layout.nowned` says how many per field); what the library needs on top is (1) a communicator, (2) the
+# ghost-exchange plan of the dof partition and (3), on one node, the peer-memory connection of the inboxes.  The plan is what
+# PartitionedArrays keeps in the cache of the column PRange of the assembled matrix (`assembly_neighbors`, `assembly_local_indices`):
+# for every neighbouring rank the local ids this rank sends (owned here, ghost there) and receives (ghost here), the two lists of a
+# pair of ranks in the same order.  Python counterpart, executed in this repository on 2-8 GPUs: host/partition.py:distribute_operator.
+import MPI
+
+function comm_init(comm::MPI.Comm)
+  rank, nranks = MPI.Comm_rank(comm), MPI.Comm_size(comm)
+  id = zeros(UInt8, 128)                                       # ncclUniqueId travels through the host
+  rank == 0 && @check ccall((:mhd_comm_get_unique_id, libmhd), Cint, (Ptr{UInt8},), id)
+  MPI.Bcast!(id, 0, comm)
+  @check ccall((:mhd_comm_init, libmhd), Cint, (Cint, Cint, Ptr{UInt8}), rank, nranks, id)
+end
+comm_finalize() = ccall((:mhd_comm_finalize, libmhd), Cint, ())
+
+# neigh: ranks of the neighbours; send_ptr/recv_ptr: [nneigh+1] offsets into send_idx/recv_idx (0-based local dof ids)
+function set_halo!(op::B200FEOperator, neigh::Vector{Int32}, send_ptr::Vector{Int64}, send_idx::Vector{Int32},
+                   recv_ptr::Vector{Int64}, recv_idx::Vector{Int32})
+  @check ccall((:mhd_operator_set_halo, libmhd), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}),
+               op.handle, length(neigh), neigh, send_ptr, send_idx, recv_ptr, recv_idx)
+end
+
+# SpMV + ghost exchange over NVLink peer memory (ranks of ONE node; without this call the exchange runs through NCCL send/recv):
+# every rank exports its inbox (CUDA IPC handle, 64 bytes), the handles and the receive lists are gathered through MPI, and each
+# rank tells the library, for every value it sends, the ghost slot that value fills on its neighbour.
+function connect_peer_memory!(op::B200FEOperator, comm::MPI.Comm, neigh::Vector{Int32}, send_ptr::Vector{Int64},
+                              recv_ptr::Vector{Int64}, recv_idx::Vector{Int32}, nrows::Int, ncols::Int)
+  isempty(neigh) && return
+  rank = MPI.Comm_rank(comm)
+  handle = zeros(UInt8, 64)
+  @check ccall((:mhd_operator_halo_ipc_export, libmhd), Cint, (Ptr{Cvoid}, Ptr{UInt8}), op.handle, handle)
+  mine = (handle=handle, neigh=neigh, recv_ptr=recv_ptr, recv_idx=recv_idx, nrows=nrows, ncols=ncols)
+  all = MPI.deserialize.(MPI.Allgather(MPI.serialize(mine), comm))   # small host-side metadata, once per mesh
+  handles = reduce(vcat, (all[s+1].handle for s in neigh))
+  slot = Int32[findfirst(==(Int32(rank)), all[s+1].neigh) - 1 for s in neigh]          # my position in the neighbour's list
+  nghost = Int64[all[s+1].ncols - all[s+1].nrows for s in neigh]
+  send_dst = Int32[]
+  for (k, s) in enumerate(neigh)
+    info = all[s+1]; kk = slot[k] + 1
+    seg = info.recv_idx[info.recv_ptr[kk]+1:info.recv_ptr[kk+1]] .- Int32(info.nrows)   # ghost slot = ghost id - row count, over there
+    @assert length(seg) == send_ptr[k+1] - send_ptr[k]
+    append!(send_dst, seg)
+  end
+  @check ccall((:mhd_operator_halo_ipc_connect, libmhd), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}),
+               op.handle, handles, send_dst, slot, nghost)
+  MPI.Barrier(comm)
+end
+
+# bit-reproducible assembly (coloured launches; SURVEY 5.2) and which assembly kernel the tables selected (7 = sum-factorised)
+function set_deterministic!(op::B200FEOperator, on::Bool=true)
+  ncolors = Ref{Int32}(0)
+  @check ccall((:mhd_operator_set_deterministic, libmhd), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}), op.handle, on ? 1 : 0, ncolors)
+  Int(ncolors[])
+end
+function kernel_version(op::B200FEOperator)
+  v = Ref{Int32}(0)
+  @check ccall((:mhd_operator_get_kernel_version, libmhd), Cint, (Ptr{Cvoid}, Ref{Int32}), op.handle, v)
+  Int(v[])
+end
+
 # what GridapMHD itself needs (one more symbol, SURVEY.md 5.6):
 #   _multi_field_style(::Val{:b200}) = BlockMultiFieldStyle(3,(2,1,1),(1,3,2,4))            # ([u,j],p,φ), fespaces.jl:8
 #   uses_petsc(::Val{:b200}) = false ; space_uses_multigrid(::Val{:b200},solver) = fill(false,4)
