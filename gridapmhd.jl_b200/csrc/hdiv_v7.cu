@@ -146,9 +146,10 @@ __device__ __forceinline__ void fetch_next(NextIds& N, const V7Args& A, const ui
 }
 
 // shared-memory loads through 32-bit shared addresses (no generic-address arithmetic in the sweep loops)
-__device__ __forceinline__ unsigned lds_u16(unsigned a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+// a map code, sign-extended: >= 0 RED at position code | -1 (MAP_SKIP) nothing | < -1 plain store at position code & 0x7FFF
+__device__ __forceinline__ int lds_code(unsigned a) {
+  int v;
+  asm volatile("{\n\t.reg .s16 h;\n\tld.shared.s16 h, [%1];\n\tcvt.s32.s16 %0, h;\n\t}" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ double lds_f64(unsigned a) {
@@ -164,17 +165,16 @@ __device__ __forceinline__ unsigned long long lds_u64(unsigned a) {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // value v of an entry goes to rowbase + 8 * code: plain store (MAP_EXCL set, not MAP_SKIP) or reduction, predicated -- no branch
-__device__ __forceinline__ void scatter_one(unsigned code, unsigned long long rowbase, double v) {
+__device__ __forceinline__ void scatter_one(int code, unsigned long long rowbase, double v) {
   asm volatile(
       "{\n\t"
       ".reg .pred pst, prd;\n\t"
-      ".reg .u32 t, c;\n\t"
+      ".reg .u32 c;\n\t"
       ".reg .u64 a;\n\t"
       "and.b32 c, %2, 0x7FFF;\n\t"
       "mad.wide.u32 a, c, 8, %0;\n\t"
-      "xor.b32 t, %2, 0x8000;\n\t"
-      "setp.lt.u32 pst, t, 0x7FFF;\n\t"   // 0x8000 <= code < 0xFFFF
-      "setp.lt.u32 prd, %2, 0x8000;\n\t"
+      "setp.lt.s32 pst, %2, -1;\n\t"   // 0x8000 <= code < 0xFFFF as u16
+      "setp.ge.s32 prd, %2, 0;\n\t"
       "@pst st.global.f64 [a], %1;\n\t"
       "@prd red.global.add.f64 [a], %1;\n\t"
       "}" ::"l"(rowbase), "d"(v), "r"(code)
@@ -198,7 +198,7 @@ V7_NI void sweep_and_fetch(int bufsel, int nseg, int row0, unsigned ncol_recip, 
   const unsigned dq = NT * ncol_recip;
   // four entries per lane and iteration: all loads first, then the four predicated store / reduction pairs
   for (; i + 3u * NT < n; i += 4u * NT, q += 4u * dq, sa_c += 8u * NT, sa_b += 32u * NT) {
-    const unsigned c0 = lds_u16(sa_c), c1 = lds_u16(sa_c + 2u * NT), c2 = lds_u16(sa_c + 4u * NT), c3 = lds_u16(sa_c + 6u * NT);
+    const int c0 = lds_code(sa_c), c1 = lds_code(sa_c + 2u * NT), c2 = lds_code(sa_c + 4u * NT), c3 = lds_code(sa_c + 6u * NT);
     const double v0 = lds_f64(sa_b), v1 = lds_f64(sa_b + 8u * NT), v2 = lds_f64(sa_b + 16u * NT), v3 = lds_f64(sa_b + 24u * NT);
     const unsigned long long r0 = lds_u64(sa_r + ((q >> 20) << 3)), r1 = lds_u64(sa_r + (((q + dq) >> 20) << 3)),
                              r2 = lds_u64(sa_r + (((q + 2u * dq) >> 20) << 3)), r3 = lds_u64(sa_r + (((q + 3u * dq) >> 20) << 3));
@@ -208,7 +208,7 @@ V7_NI void sweep_and_fetch(int bufsel, int nseg, int row0, unsigned ncol_recip, 
     scatter_one(c3, r3, v3);
   }
   for (; i < n; i += NT, q += dq, sa_c += 2u * NT, sa_b += 8u * NT)
-    scatter_one(lds_u16(sa_c), lds_u64(sa_r + ((q >> 20) << 3)), lds_f64(sa_b));
+    scatter_one(lds_code(sa_c), lds_u64(sa_r + ((q >> 20) << 3)), lds_f64(sa_b));
   __syncwarp();
   // lane l copies 16 bytes of segment w + NW (l / 4) (+ 8 NW per round): one instruction moves eight of the warp's segments
   int seg = w + V7_NW * (lane >> 2);
@@ -222,26 +222,46 @@ V7_NI void sweep_and_fetch(int bufsel, int nseg, int row0, unsigned ncol_recip, 
 }
 __host__ __device__ constexpr unsigned recip20(int n) { return (unsigned)(((1u << 20) + n - 1) / n); }
 static_assert((2943u * recip20(81)) >> 20 == 2943u / 81 && (2943u * recip20(36)) >> 20 == 2943u / 36, "reciprocal division");
-// the last chunk holds five sections: jj | j-phi | phi-j | up | pu
-V7_NI void sweep_rest(int tid) {
-  const double* buf = sm_cell().r3;
-  constexpr int NSEG = h7::CH_REST_PAD / 32;
+// the last chunk holds five sections: jj | j-phi | phi-j | up | pu.  The row of entry i is cell-independent: rest_row(i)
+__device__ __forceinline__ int rest_row(int i) {
   constexpr int R_JF = h7::R_JF, R_FJ = h7::R_FJ, R_UP = h7::R_UP, R_PU = h7::R_PU;
   constexpr int OFF_P = h7::OFF_P, OFF_J = h7::OFF_J, OFF_F = h7::OFF_F, NLOC = h7::NLOC;
+  int row;
+  if (i < R_JF) row = OFF_J + i / 36;
+  else if (i < R_FJ) row = OFF_J + (i - R_JF) / 8;
+  else if (i < R_UP) row = OFF_F + (i - R_FJ) / 36;
+  else if (i < R_PU) row = (i - R_UP) / 4;
+  else row = OFF_P + (i - R_PU) / 81;
+  return row > NLOC - 1 ? NLOC - 1 : row;
+}
+// Warp w sweeps the segments w, w + NW, ...; a lane's rows (one byte each, at most 12) are computed ONCE per kernel and travel
+// in three registers -- the if-chain with its divisions cost 12 instructions per entry (950 per cell).
+constexpr int REST_SEGS = h7::CH_REST_PAD / 32, REST_ROUNDS = (REST_SEGS + V7_NW - 1) / V7_NW;
+static_assert(REST_ROUNDS <= 12 && h7::NLOC <= 256, "packed row table of sweep_rest");
+struct RestRows { unsigned w[3]; };
+__device__ __forceinline__ RestRows rest_rows_of_lane(int tid) {
+  RestRows R{{0u, 0u, 0u}};
   const int w = tid >> 5, lane = tid & 31;
-  const uint16_t* codes = sm_codes();
-  const long long* rowbase = sm_cell().rowaddr;
-#pragma unroll 2
-  for (int seg = w; seg < NSEG; seg += V7_NW) {
-    const int i = seg * 32 + lane;
-    int row;
-    if (i < R_JF) row = OFF_J + i / 36;
-    else if (i < R_FJ) row = OFF_J + (i - R_JF) / 8;
-    else if (i < R_UP) row = OFF_F + (i - R_FJ) / 36;
-    else if (i < R_PU) row = (i - R_UP) / 4;
-    else row = OFF_P + (i - R_PU) / 81;
-    if (row > NLOC - 1) row = NLOC - 1;
-    scatter_one(codes[i], (unsigned long long)rowbase[row], buf[i]);
+#pragma unroll
+  for (int k = 0; k < REST_ROUNDS; k++) {
+    const int seg = w + V7_NW * k;
+    const unsigned row = seg < REST_SEGS ? (unsigned)rest_row(seg * 32 + lane) : 0u;
+    R.w[k >> 2] |= row << (8 * (k & 3));
+  }
+  return R;
+}
+V7_NI void sweep_rest(int tid, unsigned rw0, unsigned rw1, unsigned rw2) {
+  const int w = tid >> 5, lane = tid & 31;
+  const unsigned sa_codes = smem_u32(sm_codes()), sa_buf = smem_u32(sm_cell().r3), sa_r = smem_u32(sm_cell().rowaddr);
+#pragma unroll
+  for (int k = 0; k < REST_ROUNDS; k++) {
+    const int seg = w + V7_NW * k;
+    if (seg < REST_SEGS) {
+      const unsigned i = (unsigned)(seg * 32 + lane);
+      const unsigned word = (k >> 2) == 0 ? rw0 : ((k >> 2) == 1 ? rw1 : rw2);
+      const unsigned row = (word >> (8 * (k & 3))) & 0xFFu;
+      scatter_one(lds_code(sa_codes + 2u * i), lds_u64(sa_r + 8u * row), lds_f64(sa_buf + 8u * i));
+    }
   }
 }
 
@@ -276,6 +296,7 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     for (int i = 0; i < 7; i++) clk_acc[i] = 0;
     clk_acc[7] = (unsigned long long)clock64();
   }
+  const RestRows rest_rows = rest_rows_of_lane(threadIdx.x);  // cell-independent: rows of this lane's entries in the last sweep
   double v_pre = 0.0;  // this thread's gathered value (state / vertex coordinate) of the cell about to start
   if ((int64_t)blockIdx.x < ncells) {
     fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[blockIdx.x] : (int64_t)blockIdx.x, threadIdx.x, JAC);
@@ -371,7 +392,7 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     __syncthreads();
     // the next cell's ids landed before the barrier above: gather its state now, behind the last sweep
     if (it + gridDim.x < ncells && tid < LOAD_ITEMS) v_pre = load_gather(tid, A.coords, N.nodes, N.gid, A.dir, x, WU != 0, RES);
-    sweep_rest(tid);
+    sweep_rest(tid, rest_rows.w[0], rest_rows.w[1], rest_rows.w[2]);
     V7_CLK(6);
   }
   if (A.clk != nullptr && threadIdx.x == 0)
