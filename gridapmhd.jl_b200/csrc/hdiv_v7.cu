@@ -298,20 +298,26 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
   }
   const RestRows rest_rows = rest_rows_of_lane(threadIdx.x);  // cell-independent: rows of this lane's entries in the last sweep
   double v_pre = 0.0;  // this thread's gathered value (state / vertex coordinate) of the cell about to start
+  // cell ids of this CTA's current / next / next-but-one cell: with a cell list (traversal order, colours) the id is a global
+  // load, issued two cells ahead so that neither the loop top nor fetch_next ever waits for it (it cost ~400 cycles per cell)
+  const int64_t stride = (int64_t)gridDim.x;
+  auto cell_at = [&](int64_t i) -> int64_t { return i < ncells ? (A.cell_list ? (int64_t)A.cell_list[i] : i) : 0; };
+  int64_t cell_cur = cell_at(blockIdx.x), cell_n1 = cell_at(blockIdx.x + stride), cell_n2 = 0;
   if ((int64_t)blockIdx.x < ncells) {
-    fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[blockIdx.x] : (int64_t)blockIdx.x, threadIdx.x, JAC);
+    fetch_next(N, A, map, cell_cur, threadIdx.x, JAC);
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < LOAD_ITEMS) v_pre = load_gather(threadIdx.x, A.coords, N.nodes, N.gid, A.dir, x, WU != 0, RES);
   }
   DevRAdd radd{rout, nrows};
-  for (int64_t it = blockIdx.x; it < ncells; it += gridDim.x) {
+  for (int64_t it = blockIdx.x; it < ncells; it += gridDim.x, cell_cur = cell_n1, cell_n1 = cell_n2) {
     // re-read the thread id inside the loop: keeps the index arithmetic of the phases from being hoisted out of the cell
     // loop (and spilled) -- it is a handful of integer instructions per phase
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    const int64_t cell = A.cell_list ? (int64_t)A.cell_list[it] : it;
+    const int64_t cell = cell_cur;
+    cell_n2 = cell_at(it + 2 * stride);  // consumed two iterations from now
     const uint16_t* m = map + cell * h7::NENT;
     const bool solid = A.cell_solid != nullptr && A.cell_solid[cell] != 0;
     __syncthreads();  // the previous cell's sweeps are done with S (the ids of this cell landed in N long ago)
@@ -319,7 +325,7 @@ hdiv_v7_jacobian_kernel(int64_t ncells, int64_t nrows, V7Args A, const double* _
     if (tid < LOAD_ITEMS) load_scatter(S, C, tid, v_pre, N.perm, RES);
     __syncthreads();
     if (it + gridDim.x < ncells) {
-      fetch_next(N, A, map, A.cell_list ? (int64_t)A.cell_list[it + gridDim.x] : it + gridDim.x, tid, JAC);
+      fetch_next(N, A, map, cell_n1, tid, JAC);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
     V7_CLK(0);
