@@ -1,15 +1,21 @@
-// "v7" Jacobian kernel of the H1-HDiv formulation (jac_fluid_h1_hdiv / jac_solid_h1_hdiv, src/weakforms.jl:283-312,:327-338):
-// the fully sum-factorised cell code of hdiv7_cell.h run by one CTA of 256 threads per cell on a persistent grid (2 CTAs per
-// SM).  ~0.13 M FMA per cell instead of 0.43 M, operands of a few hundred bytes instead of 27 x 27 panels, so the kernel's
-// time goes where the roofline says it should: into streaming the 14 913 values of a cell out through the u16 scatter map.
+// "v7" kernel of the H1-HDiv formulation (jac_fluid_h1_hdiv / jac_solid_h1_hdiv, res_fluid_h1_hdiv / res_solid_h1_hdiv,
+// src/weakforms.jl:255-338): the fully sum-factorised cell code of hdiv7_cell.h run by one CTA of 256 threads per cell on a
+// persistent grid (2 CTAs per SM).  ~0.13 M FMA per cell instead of 0.43 M, operands of a few hundred bytes instead of 27 x 27
+// panels.  MODE 0 = jacobian!, 1 = residual_and_jacobian! (the residual phases ride in the barrier intervals of the Jacobian
+// phases), 2 = residual! alone.
 //
 // * The 1-D factors are DISCOVERED from the plain tables of mhd_tables_t when the operator is created (hdiv7_tables.h); an
 //   operator whose tables lack the tensor structure keeps the generic tensor-core kernel of assembly.cu.
 // * Values are staged in shared memory in destination order (permuted local numbering: every field sorted by global id),
 //   chunk by chunk in two buffers; while chunk n+1 is computed, chunk n is swept out 32 consecutive map entries per
-//   instruction.  The map codes of a chunk are fetched into registers one barrier interval before they are needed.
+//   instruction.  The u16 map codes of a chunk arrive in shared memory by cp.async one barrier interval before they are needed,
+//   the ids / row starts of the next cell likewise, its state values one interval early in a register.
 // * nnz that receive exactly one contribution (67 % on Hunt meshes) are stored plainly; the others are accumulated with
-//   RED.ADD.F64 after `zero_shared` cleared just those (a bit mask from the symbolic phase) -- no 1.2 GB memset.
+//   RED.ADD.F64 after `zero_shared_kernel` cleared just the 32-byte sectors that hold them (a bit mask from the symbolic phase)
+//   -- no 1.2 GB memset.
+// * Cells are walked breadth-first over face neighbours (v7_build_cell_order) so that cells sharing sectors meet in L2:
+//   DRAM traffic 1.12x the algorithmic bytes.  Deterministic mode: one launch per colour of a cell colouring.
+// What bounds it (ncu, profiles/r2_*): the shared-memory data pipe (64 %) and instruction issue (46 %), not HBM -- DESIGN.md 4.2b, 7.
 #include <stdlib.h>
 
 #include "common.h"
