@@ -369,21 +369,32 @@ end
 # SpMV + ghost exchange over NVLink peer memory (ranks of ONE node; without this call the exchange runs through NCCL send/recv):
 # every rank exports its inbox (CUDA IPC handle, 64 bytes), the handles and the receive lists are gathered through MPI, and each
 # rank tells the library, for every value it sends, the ghost slot that value fills on its neighbour.
+# every rank's vector, as a vector of vectors (counts first, then MPI.Allgatherv!)
+function _allgatherv(v::Vector{T}, comm::MPI.Comm) where T
+  counts = MPI.Allgather(Int32[length(v)], comm)
+  out = Vector{T}(undef, sum(counts))
+  MPI.Allgatherv!(v, MPI.VBuffer(out, counts), comm)
+  ptr = cumsum([0; Int.(counts)])
+  [out[ptr[r]+1:ptr[r+1]] for r in 1:length(counts)]
+end
+
 function connect_peer_memory!(op::B200FEOperator, comm::MPI.Comm, neigh::Vector{Int32}, send_ptr::Vector{Int64},
                               recv_ptr::Vector{Int64}, recv_idx::Vector{Int32}, nrows::Int, ncols::Int)
-  isempty(neigh) && return
   rank = MPI.Comm_rank(comm)
   handle = zeros(UInt8, 64)
-  @check ccall((:mhd_operator_halo_ipc_export, libmhd), Cint, (Ptr{Cvoid}, Ptr{UInt8}), op.handle, handle)
-  mine = (handle=handle, neigh=neigh, recv_ptr=recv_ptr, recv_idx=recv_idx, nrows=nrows, ncols=ncols)
-  all = MPI.deserialize.(MPI.Allgather(MPI.serialize(mine), comm))   # small host-side metadata, once per mesh
-  handles = reduce(vcat, (all[s+1].handle for s in neigh))
-  slot = Int32[findfirst(==(Int32(rank)), all[s+1].neigh) - 1 for s in neigh]          # my position in the neighbour's list
-  nghost = Int64[all[s+1].ncols - all[s+1].nrows for s in neigh]
+  isempty(neigh) || @check ccall((:mhd_operator_halo_ipc_export, libmhd), Cint, (Ptr{Cvoid}, Ptr{UInt8}), op.handle, handle)
+  # small host-side metadata, gathered once per mesh (collective: ranks without neighbours take part too)
+  handles_all = reshape(MPI.Allgather(handle, comm), 64, :)
+  sizes_all   = reshape(MPI.Allgather(Int64[nrows, ncols], comm), 2, :)
+  neigh_all, rptr_all, ridx_all = _allgatherv(neigh, comm), _allgatherv(recv_ptr, comm), _allgatherv(recv_idx, comm)
+  isempty(neigh) && return
+  handles = reduce(vcat, (handles_all[:, s+1] for s in neigh))
+  slot = Int32[findfirst(==(Int32(rank)), neigh_all[s+1]) - 1 for s in neigh]          # my position in the neighbour's list
+  nghost = Int64[sizes_all[2, s+1] - sizes_all[1, s+1] for s in neigh]
   send_dst = Int32[]
   for (k, s) in enumerate(neigh)
-    info = all[s+1]; kk = slot[k] + 1
-    seg = info.recv_idx[info.recv_ptr[kk]+1:info.recv_ptr[kk+1]] .- Int32(info.nrows)   # ghost slot = ghost id - row count, over there
+    kk = slot[k] + 1
+    seg = ridx_all[s+1][rptr_all[s+1][kk]+1:rptr_all[s+1][kk+1]] .- Int32(sizes_all[1, s+1])  # ghost slot = ghost id - row count, over there
     @assert length(seg) == send_ptr[k+1] - send_ptr[k]
     append!(send_dst, seg)
   end
