@@ -90,19 +90,39 @@ template <int CONV, bool ZJ>
 V7_NI void ni_fields(int tid, const h7::Params& P) { h7::phase_fields<CONV, ZJ>(sm_cell(), sm_small(), tid, V7_NT, P); }
 template <bool ZJ>
 V7_NI void ni_stage1_item(int item) { h7::stage1_item<ZJ>(sm_cell(), sm_small(), c_small7, item); }
+// Which 32-item group ("warp item") a warp takes in each round.  The item classes of the stage contractions differ in cost by 4x
+// (a Newton-base item sums up to four field groups, a u-p item has three outputs) and sit in index order, so with item = tid +
+// 256 r the heavy classes pile up on warps 0-2 (max / mean = 1.28 in stage 2, 1.26 in stage 1: barrier stalls).  The tables
+// deal the groups to the 8 warps by estimated cost, longest first; slot [w + 8 r] = group of warp w in round r.
+__constant__ unsigned char c_stage1_group[24] = {5, 8, 11, 10, 12, 6, 7, 0, 17, 14, 13, 9, 4, 2, 3, 1, 23, 21, 15, 18, 22, 19, 20, 16};
+__constant__ unsigned char c_stage2_group[32] = {10, 7, 8, 9, 16, 20, 18, 21, 19, 5, 15, 0, 14, 13, 12, 11,
+                                                 27, 28, 17, 6, 4, 3, 2, 1, 30, 31, 26, 29, 25, 24, 23, 22};
+template <int ROUNDS>
+__device__ __forceinline__ int dealt_item(const unsigned char* group, int tid, int r) {
+  if (V7_NT != 256) return tid + r * V7_NT;  // the tables are made for 8 warps
+  return (int)group[(tid >> 5) + 8 * r] * 32 + (tid & 31);
+}
 template <bool ZJ>
 __device__ __forceinline__ void ni_stage1(int tid) {  // 729 items on 256 threads: three calls, no loop (see stage1_item)
+  constexpr int R = (h7::STAGE1_ITEMS + V7_NT - 1) / V7_NT;
+  static_assert(V7_NT != 256 || R * 8 == 24, "c_stage1_group");
 #pragma unroll
-  for (int r = 0; r < (h7::STAGE1_ITEMS + V7_NT - 1) / V7_NT; r++)
-    if (tid + r * V7_NT < h7::STAGE1_ITEMS) ni_stage1_item<ZJ>(tid + r * V7_NT);
+  for (int r = 0; r < R; r++) {
+    const int item = dealt_item<R>(c_stage1_group, tid, r);
+    if (item < h7::STAGE1_ITEMS) ni_stage1_item<ZJ>(item);
+  }
 }
 template <int CONV, bool ZJ>
 V7_NI void ni_stage2_item(int item) { h7::stage2_item<CONV, ZJ>(sm_cell(), sm_small(), c_small7, item); }
 template <int CONV, bool ZJ>
 __device__ __forceinline__ void ni_stage2(int tid) {  // 1 017 items: four calls
+  constexpr int R = (h7::STAGE2_ITEMS + V7_NT - 1) / V7_NT;
+  static_assert(V7_NT != 256 || R * 8 == 32, "c_stage2_group");
 #pragma unroll
-  for (int r = 0; r < (h7::STAGE2_ITEMS + V7_NT - 1) / V7_NT; r++)
-    if (tid + r * V7_NT < h7::STAGE2_ITEMS) ni_stage2_item<CONV, ZJ>(tid + r * V7_NT);
+  for (int r = 0; r < R; r++) {
+    const int item = dealt_item<R>(c_stage2_group, tid, r);
+    if (item < h7::STAGE2_ITEMS) ni_stage2_item<CONV, ZJ>(item);
+  }
 }
 // (the component / direction of a chunk is a run-time argument: ONE copy of the code -- the loop body of the kernel is several
 // times the 32 KB instruction cache and every duplicated phase shows up as no_inst stalls)
